@@ -1,0 +1,522 @@
+// spectral.cu — fused spectral ("decomposable") operator family: MRI and BlurFFT.
+//
+// Replaces the bodies of (reference, relative to the deepinv tree):
+//   MRIMixin.to_torch_complex/from_torch_complex/fft/ifft   deepinv/utils/mixins.py:148-206
+//   DecomposablePhysics.A/A_adjoint/A_adjoint_A/prox_l2/A_dagger  deepinv/physics/forward.py:1080-1252
+//   MultiCoilMRI.A/A_adjoint                                 deepinv/physics/mri.py:254-324
+//   BlurFFT.U/V/...                                          deepinv/physics/blur.py:639-692
+//   L2.grad + fStepPGD (fused data step)                     deepinv/optim/data_fidelity.py:335-336, optim_iterators/pgd.py:137-139
+//
+// Data movement: a 2-D transform is two tile passes over HBM-resident images:
+//   COL pass: one CTA owns a strip of Wc columns x all H rows of one image (coalesced Wc*4-byte
+//             row segments), transforms along H in shared memory.
+//   ROW pass: one CTA owns L full rows (fully contiguous), transforms along W; the mask / spectral
+//             multiplier, and for A^T A / prox the inverse row transform, are fused into this pass.
+// The intermediate between the two passes is an interleaved complex workspace written once and read
+// once; for the cfg2 batch (33.5 MB) it stays resident in the 126 MB L2.  When the multiplier does
+// not depend on h (Cartesian line masks, mask_sh == 0) and both transforms run, the H-direction
+// transforms cancel algebraically and a single ROW pass does the whole operator.
+#include "common.cuh"
+#include "fft_core.cuh"
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <vector>
+
+namespace dinvk {
+
+// ---------------------------------------------------------------------------------------------
+// pass description
+// ---------------------------------------------------------------------------------------------
+struct PassParams {
+  int B, H, W;          // B = number of complex images handled by this pass
+  int lines;            // rows per CTA (ROW) or columns per CTA (COL)
+  // source
+  const float* p0; const float* p1; float a0, a1;
+  int src_nc;           // planar source: number of coil planes interleaved per batch sample (>=1)
+  int src_div;          // planar source batch index = image / src_div (coil broadcast of x)
+  const float2* tin;    // interleaved source (B,H,W) if non-null
+  const float2* coil;   // multiply source by coil map if non-null  (index by image/ncoil, image%ncoil)
+  long long coil_sb; int ncoil;
+  // transforms along this pass's axis
+  int dir1, dir2;       // 0 none, -1 forward, +1 inverse
+  // pointwise multiplier
+  int gmode; int g_at_load; int g_after;
+  const float* g; long long gsb, gsc, gsh; float gc; const float* gcb;
+  // destination
+  float* out; int dst_nc; float2* tout;
+  const float* q0; const float* q1; float e0, e1, e2;
+  // tables for this axis
+  const float2* tw; const float2* pre; const float2* post;
+  FftPlanDev plan;
+};
+
+__device__ __forceinline__ float2 apply_g(const PassParams& P, float2 v, int img, int h, int w) {
+  const int mb = img / P.ncoil;
+  if (P.gmode == DINVK_G_CMUL || P.gmode == DINVK_G_CMUL_CONJ) {
+    const float2 m = __ldg(reinterpret_cast<const float2*>(P.g) + (long long)mb * P.gsb + (long long)h * P.gsh + w);
+    return P.gmode == DINVK_G_CMUL ? cmul(v, m) : cmul_conj(v, m);
+  }
+  const long long o = (long long)mb * P.gsb + (long long)h * P.gsh + w;
+  float m0 = __ldg(P.g + o), m1 = __ldg(P.g + o + P.gsc);
+  switch (P.gmode) {
+    case DINVK_G_MASK: break;
+    case DINVK_G_SQ: m0 = m0 * m0; m1 = m1 * m1; break;
+    case DINVK_G_INV_SQ_PLUS_C: {
+      const float c = P.gcb ? __ldg(P.gcb + mb) : P.gc;
+      m0 = 1.0f / (m0 * m0 + c);
+      m1 = 1.0f / (m1 * m1 + c);
+      break;
+    }
+    case DINVK_G_PINV:
+      m0 = m0 > 1e-5f ? 1.0f / m0 : 0.0f;
+      m1 = m1 > 1e-5f ? 1.0f / m1 : 0.0f;
+      break;
+    default: break;
+  }
+  return make_float2(v.x * m0, v.y * m1);
+}
+
+// planar addressing of image `img` in a (batch, 2, nc, H, W) tensor: returns offset of the real plane,
+// the imaginary plane is +cs
+__device__ __forceinline__ long long planar_base(int img, int nc, long long HW, long long& cs) {
+  cs = (long long)nc * HW;
+  return (long long)(img / nc) * 2 * cs + (long long)(img % nc) * HW;
+}
+
+#ifdef DINVK_EMUL
+#define DINVK_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(::emul::dyn_smem())
+#else
+#define DINVK_DYN_SMEM(type, name)                                      \
+  extern __shared__ __align__(16) unsigned char dinvk_dyn_smem_raw[];   \
+  type* name = reinterpret_cast<type*>(dinvk_dyn_smem_raw)
+#endif
+
+template <bool COLS, int NTHR>
+__global__ void __launch_bounds__(NTHR, 1024 / NTHR) spectral_pass_kernel(const PassParams P) {
+  DINVK_DYN_SMEM(float2, buf);
+  const int tid = threadIdx.x;
+  constexpr int nthr = NTHR;
+  const int N = COLS ? P.H : P.W;          // transform length of this pass
+  const long long HW = (long long)P.H * P.W;
+
+  // tile geometry
+  int img0 = 0, c0 = 0;
+  long long row0 = 0;
+  int nlines = P.lines;
+  if (COLS) {
+    const int strips = (P.W + P.lines - 1) / P.lines;
+    img0 = blockIdx.x / strips;
+    c0 = (blockIdx.x % strips) * P.lines;
+    nlines = min(P.lines, P.W - c0);
+  } else {
+    row0 = (long long)blockIdx.x * P.lines;
+    const long long rows_total = (long long)P.B * P.H;
+    nlines = (int)min((long long)P.lines, rows_total - row0);
+  }
+  RowLayout RL; RL.ls = row_line_stride(N);
+  ColLayout CL; CL.lines = P.lines;
+  const int telems = nlines * N;
+
+  // ---- LOAD -----------------------------------------------------------------------------------
+  for (int e = tid; e < telems; e += nthr) {
+    int line, n, img, h, w;
+    if (COLS) { n = e / nlines; line = e - n * nlines; img = img0; h = n; w = c0 + line; }
+    else { line = e / N; n = e - line * N; const long long gr = row0 + line; img = (int)(gr / P.H); h = (int)(gr - (long long)img * P.H); w = n; }
+    float2 v;
+    if (P.tin) {
+      v = P.tin[(long long)img * HW + (long long)h * P.W + w];
+    } else {
+      long long cs;
+      const long long o = planar_base(img / P.src_div, P.src_nc, HW, cs) + (long long)h * P.W + w;
+      v = make_float2(P.a0 * __ldg(P.p0 + o), P.a0 * __ldg(P.p0 + o + cs));
+      if (P.p1) { v.x += P.a1 * __ldg(P.p1 + o); v.y += P.a1 * __ldg(P.p1 + o + cs); }
+    }
+    if (P.coil) {
+      const float2 s = __ldg(P.coil + (long long)(img / P.ncoil) * P.coil_sb + (long long)(img % P.ncoil) * HW + (long long)h * P.W + w);
+      v = cmul(v, s);
+    }
+    if (P.g_at_load) v = apply_g(P, v, img, h, w);
+    if (P.dir1 != 0) {
+      if (P.dir1 > 0) v = cconj(v);
+      v = cmul(v, __ldg(P.pre + n));
+    }
+    buf[COLS ? CL.idx(line, n) : RL.idx(line, n)] = v;
+  }
+  __syncthreads();
+
+  // ---- transform 1 ----------------------------------------------------------------------------
+  if (P.dir1 != 0) {
+    if (COLS) fft_tile(buf, P.tw, P.plan, P.lines, tid, nthr, CL);
+    else fft_tile(buf, P.tw, P.plan, nlines, tid, nthr, RL);
+  }
+
+  // ---- fused middle: post-phase of transform 1, multiplier, pre-phase of transform 2 ----------
+  if (P.dir2 != 0) {
+    for (int e = tid; e < telems; e += nthr) {
+      int line, n, img, h, w;
+      if (COLS) { n = e / nlines; line = e - n * nlines; img = img0; h = n; w = c0 + line; }
+      else { line = e / N; n = e - line * N; const long long gr = row0 + line; img = (int)(gr / P.H); h = (int)(gr - (long long)img * P.H); w = n; }
+      const int si = COLS ? CL.idx(line, n) : RL.idx(line, n);
+      float2 v = buf[si];
+      if (P.dir1 != 0) { v = cmul(v, __ldg(P.post + n)); if (P.dir1 > 0) v = cconj(v); }
+      if (P.g_after) v = apply_g(P, v, img, h, w);
+      if (P.dir2 > 0) v = cconj(v);
+      v = cmul(v, __ldg(P.pre + n));
+      buf[si] = v;
+    }
+    __syncthreads();
+    if (COLS) fft_tile(buf, P.tw, P.plan, P.lines, tid, nthr, CL);
+    else fft_tile(buf, P.tw, P.plan, nlines, tid, nthr, RL);
+  }
+
+  // ---- STORE ----------------------------------------------------------------------------------
+  const int last_dir = P.dir2 != 0 ? P.dir2 : P.dir1;
+  for (int e = tid; e < telems; e += nthr) {
+    int line, n, img, h, w;
+    if (COLS) { n = e / nlines; line = e - n * nlines; img = img0; h = n; w = c0 + line; }
+    else { line = e / N; n = e - line * N; const long long gr = row0 + line; img = (int)(gr / P.H); h = (int)(gr - (long long)img * P.H); w = n; }
+    float2 v = buf[COLS ? CL.idx(line, n) : RL.idx(line, n)];
+    if (last_dir != 0) { v = cmul(v, __ldg(P.post + n)); if (last_dir > 0) v = cconj(v); }
+    if (P.dir2 == 0 && P.g_after) v = apply_g(P, v, img, h, w);
+    if (P.tout) {
+      P.tout[(long long)img * HW + (long long)h * P.W + w] = v;
+    } else {
+      long long cs;
+      const long long o = planar_base(img, P.dst_nc, HW, cs) + (long long)h * P.W + w;
+      float re = P.e0 * v.x, im = P.e0 * v.y;
+      if (P.q0) { re += P.e1 * __ldg(P.q0 + o); im += P.e1 * __ldg(P.q0 + o + cs); }
+      if (P.q1) { re += P.e2 * __ldg(P.q1 + o); im += P.e2 * __ldg(P.q1 + o + cs); }
+      P.out[o] = re;
+      P.out[o + cs] = im;
+    }
+  }
+}
+
+// O(N^2) DFT along one axis of an interleaved (B,H,W) tensor — sizes with prime factors > 5.
+// out[k] = N^-1/2 * sum_n in[n] * w^{(k-c)(n-c)}  (c = N/2 when centred, else 0); dir = -1 fwd / +1 inv
+__global__ void dft_axis_naive_kernel(const float2* __restrict__ in, float2* __restrict__ out, int B, int H, int W,
+                                      int axis_w, int dir, int centered, const float2* __restrict__ tw) {
+  const long long total = (long long)B * H * W;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid < total) {
+    const int w = (int)(gid % W);
+    const int h = (int)((gid / W) % H);
+    const long long img = gid / ((long long)W * H);
+    const int N = axis_w ? W : H;
+    const int k = axis_w ? w : h;
+    const int c = centered ? N / 2 : 0;
+    const long long base = img * (long long)H * W + (axis_w ? (long long)h * W : w);
+    const long long stride = axis_w ? 1 : W;
+    float2 acc = make_float2(0.f, 0.f);
+    long long kk = ((long long)(k - c) % N + N) % N;
+    for (int n = 0; n < N; ++n) {
+      const long long nn = ((long long)(n - c) % N + N) % N;
+      const int ti = (int)((kk * nn) % N);
+      float2 t = __ldg(tw + ti);
+      if (dir > 0) t.y = -t.y;
+      const float2 x = in[base + n * stride];
+      acc.x += x.x * t.x - x.y * t.y;
+      acc.y += x.x * t.y + x.y * t.x;
+    }
+    const float sc = 1.0f / sqrtf((float)N);
+    out[gid] = make_float2(acc.x * sc, acc.y * sc);
+  }
+}
+
+// coil combination after the per-coil inverse transforms (deepinv/physics/mri.py:313-322):
+// mode 2: out[b] = sum_n conj(S[b,n]) * v[b,n]   (planar (batch,2,H,W))
+// mode 3: out[b] = sqrt(sum_n |v[b,n]|^2)        ((batch,1,H,W))
+__global__ void coil_combine_kernel(const float2* __restrict__ v, const float2* __restrict__ S, long long coil_sb,
+                                    float* __restrict__ out, int batch, int ncoil, long long HW, int mode, float e0) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid < (long long)batch * HW) {
+    const long long b = gid / HW, p = gid - b * HW;
+    float re = 0.f, im = 0.f;
+    for (int n = 0; n < ncoil; ++n) {
+      const float2 x = v[(b * ncoil + n) * HW + p];
+      if (mode == 2) {
+        const float2 s = __ldg(S + b * coil_sb + (long long)n * HW + p);
+        re += x.x * s.x + x.y * s.y;
+        im += x.y * s.x - x.x * s.y;
+      } else {
+        re += x.x * x.x + x.y * x.y;
+      }
+    }
+    if (mode == 2) { out[b * 2 * HW + p] = e0 * re; out[b * 2 * HW + HW + p] = e0 * im; }
+    else out[b * HW + p] = sqrtf(re);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: table cache
+// ---------------------------------------------------------------------------------------------
+struct Tables { float2* tw; float2* pre; float2* post; };
+
+static void unit_root(long long num, long long den, double* c, double* s) {
+  // exp(2*pi*i*num/den) with exact values on the axes
+  num %= den; if (num < 0) num += den;
+  if ((4 * num) % den == 0) {
+    const long long q = 4 * num / den;
+    const double cc[4] = {1, 0, -1, 0}, ss[4] = {0, 1, 0, -1};
+    *c = cc[q]; *s = ss[q];
+    return;
+  }
+  const double a = 2.0 * 3.14159265358979323846264338327950288 * (double)num / (double)den;
+  *c = cos(a); *s = sin(a);
+}
+
+static std::mutex g_tab_mu;
+static std::map<std::vector<int>, Tables> g_tab;
+
+static int get_tables(int n, int centered, Tables* out) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_tab_mu);
+  std::vector<int> key = {dev, n, centered};
+  auto it = g_tab.find(key);
+  if (it != g_tab.end()) { *out = it->second; return 0; }
+  std::vector<float2> tw(n), pre(n), post(n);
+  const long long c = centered ? n / 2 : 0;
+  const double sc = 1.0 / sqrt((double)n);
+  for (int k = 0; k < n; ++k) {
+    double cr, ci;
+    unit_root(-(long long)k, n, &cr, &ci);
+    tw[k] = make_float2((float)cr, (float)ci);
+    unit_root(c * k, n, &cr, &ci);                     // exp(+2*pi*i*c*n/N)
+    pre[k] = make_float2((float)cr, (float)ci);
+    unit_root(c * k - c * c, n, &cr, &ci);             // exp(+2*pi*i*c*k/N - 2*pi*i*c^2/N) / sqrt(N)
+    post[k] = make_float2((float)(cr * sc), (float)(ci * sc));
+  }
+  Tables t;
+  float2* base = nullptr;
+  if (cudaMalloc((void**)&base, sizeof(float2) * 3 * (size_t)n) != cudaSuccess)
+    return set_error(DINVK_ECUDA, "cudaMalloc of FFT tables (n=%d) failed", n);
+  t.tw = base; t.pre = base + n; t.post = base + 2 * (size_t)n;
+  cudaMemcpy(t.tw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice);
+  cudaMemcpy(t.pre, pre.data(), sizeof(float2) * n, cudaMemcpyHostToDevice);
+  cudaMemcpy(t.post, post.data(), sizeof(float2) * n, cudaMemcpyHostToDevice);
+  g_tab[key] = t;
+  *out = t;
+  return 0;
+}
+
+static int pow2floor(int x) { int p = 1; while (2 * p <= x) p *= 2; return p; }
+
+struct TileCfg { int lines; int nthr; size_t smem; };
+
+// tiles hold at most 16 complex elements per thread (15 when a radix-3/5 stage is present: a thread
+// owns floor(16/R) butterflies, see stage_load)
+static int tile_budget(const FftPlan& p, int nthr) {
+  for (int s = 0; s < p.nstages; ++s)
+    if (p.radix[s] == 3 || p.radix[s] == 5) return 15 * nthr;
+  return 16 * nthr;
+}
+static bool row_cfg(const FftPlan& pW, int W, TileCfg* c) {
+  int nthr = 256;
+  while ((long long)W > tile_budget(pW, nthr) && nthr < 1024) nthr *= 2;
+  if ((long long)W > tile_budget(pW, nthr)) return false;
+  int lines = tile_budget(pW, nthr) / W;
+  if (lines < 1) lines = 1;
+  if (lines > 64) lines = 64;
+  c->lines = lines; c->nthr = nthr;
+  c->smem = (size_t)lines * row_line_stride(W) * sizeof(float2);
+  return true;
+}
+static bool col_cfg(const FftPlan& pH, int H, int W, TileCfg* c) {
+  // prefer 16-column strips (64-byte row segments x 2 planes); never narrower than 4 columns
+  int nthr = 256;
+  while ((long long)H * 16 > tile_budget(pH, nthr) && nthr < 1024) nthr *= 2;
+  int wc = pow2floor((int)std::min<long long>(16, std::max(1, tile_budget(pH, nthr) / H)));
+  if ((long long)wc * H > tile_budget(pH, nthr)) return false;
+  if (wc < 4 && wc < W) return false;
+  if (wc > W) wc = W;
+  c->lines = wc; c->nthr = nthr;
+  c->smem = (size_t)wc * H * sizeof(float2);
+  return true;
+}
+
+template <bool COLS, int NTHR>
+static int launch_pass_t(PassParams& P, const TileCfg& cfg, void* stream) {
+  int rc;
+  if ((rc = allow_smem(spectral_pass_kernel<COLS, NTHR>, cfg.smem))) return rc;
+  unsigned grid;
+  if (COLS) grid = (unsigned)P.B * (unsigned)ceil_div(P.W, cfg.lines);
+  else grid = (unsigned)ceil_div((long long)P.B * P.H, cfg.lines);
+  auto kern = spectral_pass_kernel<COLS, NTHR>;
+  DINVK_LAUNCH(kern, dim3(grid), dim3(NTHR), cfg.smem, stream, P);
+  return DINVK_POST_LAUNCH();
+}
+static int launch_pass(bool cols, PassParams& P, const TileCfg& cfg, void* stream) {
+  P.lines = cfg.lines;
+  if (cols) {
+    switch (cfg.nthr) {
+      case 256: return launch_pass_t<true, 256>(P, cfg, stream);
+      case 512: return launch_pass_t<true, 512>(P, cfg, stream);
+      default: return launch_pass_t<true, 1024>(P, cfg, stream);
+    }
+  }
+  switch (cfg.nthr) {
+    case 256: return launch_pass_t<false, 256>(P, cfg, stream);
+    case 512: return launch_pass_t<false, 512>(P, cfg, stream);
+    default: return launch_pass_t<false, 1024>(P, cfg, stream);
+  }
+}
+
+static void init_pass(PassParams& P, const dinvk_spectral_args& a) {
+  P = PassParams();
+  P.B = a.B; P.H = a.H; P.W = a.W;
+  P.src_nc = 1; P.src_div = 1; P.dst_nc = 1; P.ncoil = a.ncoil > 1 ? a.ncoil : 1;
+  P.a0 = 1.f; P.a1 = 0.f; P.e0 = 1.f; P.e1 = 0.f; P.e2 = 0.f;
+  P.gmode = DINVK_G_NONE;
+}
+static void set_source(PassParams& P, const dinvk_spectral_args& a) {
+  P.p0 = a.p0; P.p1 = a.p1; P.a0 = a.a0; P.a1 = a.p1 ? a.a1 : 0.f;
+  if (a.ncoil > 1 && a.coil_mode == 1) {  // x (batch,2,H,W) broadcast over coils and multiplied by the maps
+    P.src_nc = 1; P.src_div = a.ncoil;
+    P.coil = reinterpret_cast<const float2*>(a.coil_maps); P.coil_sb = a.coil_sb;
+  } else if (a.ncoil > 1) {               // y (batch,2,ncoil,H,W)
+    P.src_nc = a.ncoil; P.src_div = 1;
+  }
+}
+static void set_mult(PassParams& P, const dinvk_spectral_args& a, bool at_load) {
+  P.gmode = a.gmode;
+  if (a.gmode == DINVK_G_NONE) return;
+  P.g = a.mask; P.gsb = a.mask_sb; P.gsc = a.mask_sc; P.gsh = a.mask_sh; P.gc = a.c; P.gcb = a.c_batch;
+  P.g_at_load = at_load ? 1 : 0; P.g_after = at_load ? 0 : 1;
+}
+// destination = user output with epilogue, or the interleaved workspace when a coil reduction follows
+static void set_dest(PassParams& P, const dinvk_spectral_args& a, float2* coil_ws) {
+  if (coil_ws) { P.tout = coil_ws; return; }
+  P.out = a.out; P.q0 = a.q0; P.q1 = a.q1; P.e0 = a.e0; P.e1 = a.q0 ? a.e1 : 0.f; P.e2 = a.q1 ? a.e2 : 0.f;
+  P.dst_nc = (a.ncoil > 1 && a.coil_mode == 1) ? a.ncoil : 1;
+}
+static void set_axis(PassParams& P, const Tables& t, const FftPlan& plan) { P.tw = t.tw; P.pre = t.pre; P.post = t.post; P.plan = pack_plan(plan); }
+
+}  // namespace dinvk
+
+using namespace dinvk;
+
+extern "C" size_t dinvk_spectral_workspace_bytes(int B, int H, int W) {
+  return 2 * (size_t)B * (size_t)H * (size_t)W * sizeof(float2) + 256;
+}
+
+extern "C" int dinvk_fft_prepare(int n, int centered) {
+  DINVK_CHECK_ARG(n >= 1, "dinvk_fft_prepare: n=%d", n);
+  Tables t;
+  return get_tables(n, centered ? 1 : 0, &t);
+}
+
+extern "C" int dinvk_spectral(const dinvk_spectral_args* ap, void* workspace, size_t workspace_bytes, void* stream) {
+  DINVK_CHECK_ARG(ap != nullptr, "dinvk_spectral: null args");
+  const dinvk_spectral_args& a = *ap;
+  DINVK_CHECK_ARG(a.B >= 0 && a.H >= 1 && a.W >= 1, "dinvk_spectral: bad shape B=%d H=%d W=%d", a.B, a.H, a.W);
+  DINVK_CHECK_ARG(a.p0 && a.out, "dinvk_spectral: p0/out must not be null");
+  DINVK_CHECK_ARG(a.gmode >= DINVK_G_NONE && a.gmode <= DINVK_G_CMUL_CONJ, "dinvk_spectral: bad gmode %d", a.gmode);
+  DINVK_CHECK_ARG(a.gmode == DINVK_G_NONE || a.mask, "dinvk_spectral: gmode %d needs a mask", a.gmode);
+  const int nc = a.ncoil > 1 ? a.ncoil : 1;
+  if (nc > 1) {
+    DINVK_CHECK_ARG(a.coil_mode >= 1 && a.coil_mode <= 3, "dinvk_spectral: ncoil=%d needs coil_mode 1..3", nc);
+    DINVK_CHECK_ARG(a.B % nc == 0, "dinvk_spectral: B=%d not a multiple of ncoil=%d", a.B, nc);
+    DINVK_CHECK_ARG(a.coil_mode == 3 || a.coil_maps, "dinvk_spectral: coil maps missing");
+    DINVK_CHECK_ARG(!(a.coil_mode == 1) || (a.fwd && !a.inv), "dinvk_spectral: coil_mode 1 is the forward operator");
+    DINVK_CHECK_ARG(!(a.coil_mode >= 2) || (!a.fwd && a.inv), "dinvk_spectral: coil_mode 2/3 is the adjoint operator");
+    DINVK_CHECK_ARG(!(a.coil_mode >= 2) || (!a.q0 && !a.q1), "dinvk_spectral: epilogue terms unsupported with coil reduction");
+  }
+  if (a.B == 0) return DINVK_OK;
+  const size_t need = dinvk_spectral_workspace_bytes(a.B, a.H, a.W);
+  DINVK_CHECK_ARG(workspace != nullptr || (!a.fwd && !a.inv), "dinvk_spectral: workspace is null");
+  if (workspace_bytes < need && (a.fwd || a.inv)) return set_error(DINVK_EWORKSPACE, "dinvk_spectral: workspace %zu < %zu", workspace_bytes, need);
+  const long long HW = (long long)a.H * a.W;
+  uintptr_t wsp = ((uintptr_t)workspace + 127) & ~(uintptr_t)127;
+  float2* T1 = reinterpret_cast<float2*>(wsp);
+  float2* T2 = T1 + (size_t)a.B * HW;
+  const bool coil_reduce = nc > 1 && a.coil_mode >= 2;
+
+  Tables tH, tW;
+  FftPlan pH, pW;
+  int rc;
+  const int cen = a.centered ? 1 : 0;
+  if ((rc = get_tables(a.H, cen, &tH))) return rc;
+  if ((rc = get_tables(a.W, cen, &tW))) return rc;
+  TileCfg rcfg, ccfg;
+  const bool fast = make_fft_plan(a.H, &pH) && make_fft_plan(a.W, &pW) && row_cfg(pW, a.W, &rcfg) && col_cfg(pH, a.H, a.W, &ccfg);
+  PassParams P;
+
+  if (!a.fwd && !a.inv) {  // pure elementwise
+    TileCfg ecfg; ecfg.nthr = 256; ecfg.lines = std::max(1, 4096 / a.W); ecfg.smem = (size_t)ecfg.lines * row_line_stride(a.W) * sizeof(float2);
+    init_pass(P, a); set_source(P, a); set_mult(P, a, true); set_dest(P, a, nullptr);
+    set_axis(P, tW, pW);
+    return launch_pass(false, P, ecfg, stream);
+  }
+
+  if (fast) {
+    if (a.fwd && !a.inv) {
+      // A: COL(fwd) planar -> T1 ; ROW(fwd, multiplier) T1 -> out
+      init_pass(P, a); set_source(P, a); P.dir1 = -1; P.tout = T1; set_axis(P, tH, pH);
+      if ((rc = launch_pass(true, P, ccfg, stream))) return rc;
+      init_pass(P, a); P.tin = T1; P.dir1 = -1; set_mult(P, a, false); set_dest(P, a, nullptr); set_axis(P, tW, pW);
+      return launch_pass(false, P, rcfg, stream);
+    }
+    if (!a.fwd && a.inv) {
+      // A^T: ROW(multiplier at load, inv) planar -> T1 ; COL(inv) T1 -> out (or coil workspace)
+      init_pass(P, a); set_source(P, a); set_mult(P, a, true); P.dir1 = +1; P.tout = T1; set_axis(P, tW, pW);
+      if ((rc = launch_pass(false, P, rcfg, stream))) return rc;
+      init_pass(P, a); P.tin = T1; P.dir1 = +1; set_dest(P, a, coil_reduce ? T2 : nullptr); set_axis(P, tH, pH);
+      if ((rc = launch_pass(true, P, ccfg, stream))) return rc;
+    } else {
+      const bool complex_mult = a.gmode == DINVK_G_CMUL || a.gmode == DINVK_G_CMUL_CONJ;
+      if (a.gmode == DINVK_G_NONE || (a.mask_sh == 0 && (complex_mult || a.mask_sc == 0))) {
+        // multiplier independent of h and acting as a complex scalar (same factor on the real and
+        // imaginary planes): it commutes with the H-direction transform, F_H^-1 F_H cancels
+        // -> one fused ROW pass
+        init_pass(P, a); set_source(P, a); P.dir1 = -1; P.dir2 = +1; set_mult(P, a, false); set_dest(P, a, nullptr); set_axis(P, tW, pW);
+        return launch_pass(false, P, rcfg, stream);
+      }
+      init_pass(P, a); set_source(P, a); P.dir1 = -1; P.tout = T1; set_axis(P, tH, pH);
+      if ((rc = launch_pass(true, P, ccfg, stream))) return rc;
+      init_pass(P, a); P.tin = T1; P.dir1 = -1; P.dir2 = +1; set_mult(P, a, false); P.tout = T2; set_axis(P, tW, pW);
+      if ((rc = launch_pass(false, P, rcfg, stream))) return rc;
+      init_pass(P, a); P.tin = T2; P.dir1 = +1; set_dest(P, a, nullptr); set_axis(P, tH, pH);
+      return launch_pass(true, P, ccfg, stream);
+    }
+  } else {
+    // generic sizes: elementwise prologue -> naive axis DFTs -> elementwise epilogue
+    TileCfg ecfg; ecfg.nthr = 256; ecfg.lines = std::max(1, 4096 / a.W); ecfg.smem = (size_t)ecfg.lines * row_line_stride(a.W) * sizeof(float2);
+    const long long total = (long long)a.B * HW;
+    const dim3 ngrid((unsigned)ceil_div(total, 256));
+    float2 *cur = T1, *oth = T2;
+    init_pass(P, a); set_source(P, a); if (!a.fwd) set_mult(P, a, true); P.tout = cur; set_axis(P, tW, pW);
+    if ((rc = launch_pass(false, P, ecfg, stream))) return rc;
+    if (a.fwd) {
+      DINVK_LAUNCH(dft_axis_naive_kernel, ngrid, dim3(256), 0, stream, cur, oth, a.B, a.H, a.W, 0, -1, cen, tH.tw);
+      DINVK_LAUNCH(dft_axis_naive_kernel, ngrid, dim3(256), 0, stream, oth, cur, a.B, a.H, a.W, 1, -1, cen, tW.tw);
+      if ((rc = DINVK_POST_LAUNCH())) return rc;
+      if (a.inv) {  // multiplier in the middle
+        init_pass(P, a); P.tin = cur; set_mult(P, a, true); P.tout = oth; set_axis(P, tW, pW);
+        if ((rc = launch_pass(false, P, ecfg, stream))) return rc;
+        float2* t = cur; cur = oth; oth = t;
+      }
+    }
+    if (a.inv) {
+      DINVK_LAUNCH(dft_axis_naive_kernel, ngrid, dim3(256), 0, stream, cur, oth, a.B, a.H, a.W, 1, +1, cen, tW.tw);
+      DINVK_LAUNCH(dft_axis_naive_kernel, ngrid, dim3(256), 0, stream, oth, cur, a.B, a.H, a.W, 0, +1, cen, tH.tw);
+      if ((rc = DINVK_POST_LAUNCH())) return rc;
+    }
+    if (coil_reduce) {
+      if (cur != T2) { cudaMemcpyAsync(T2, cur, sizeof(float2) * (size_t)total, cudaMemcpyDeviceToDevice, (cudaStream_t)stream); }
+    } else {
+      init_pass(P, a); P.tin = cur; if (a.fwd && !a.inv) set_mult(P, a, true); set_dest(P, a, nullptr); set_axis(P, tW, pW);
+      return launch_pass(false, P, ecfg, stream);
+    }
+  }
+  if (coil_reduce) {
+    const int batch = a.B / nc;
+    DINVK_LAUNCH(coil_combine_kernel, dim3((unsigned)ceil_div((long long)batch * HW, 256)), dim3(256), 0, stream,
+                 (const float2*)T2, reinterpret_cast<const float2*>(a.coil_maps), (long long)a.coil_sb, a.out, batch, nc, HW,
+                 a.coil_mode, a.e0);
+    return DINVK_POST_LAUNCH();
+  }
+  return DINVK_OK;
+}
