@@ -101,18 +101,28 @@ __global__ void __launch_bounds__(256) batched_dot_final_kernel(float* __restric
 
 __global__ void cg_scalars_kernel(int mode, float* __restrict__ out0, const float* __restrict__ num,
                                   const float* __restrict__ den, float eps, const float* __restrict__ bnorm2,
-                                  float tol2, int* __restrict__ all_done, int B) {
-  // single block; all_done must be pre-set to 1 by the caller before a mode-1 call
+                                  float tol2, int* __restrict__ done, int B) {
+  // single block.  `done` is a sticky device flag (caller zero-initialises it once per solve):
+  //   mode 0 (alpha): a converged solve gets alpha = 0, so iterations issued after convergence do not
+  //                   move x or r — the host may poll the flag lazily without changing the result;
+  //   mode 1 (beta + stopping test): done <- 1 when every sample satisfies r.r < tol^2 * b.b.
+  __shared__ int s_not_done;
+  if (threadIdx.x == 0) s_not_done = 0;
+  __syncthreads();
+  const int frozen = done ? *done : 0;
   int not_done = 0;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    out0[b] = num[b] / (den[b] + eps);
+    const float v = num[b] / (den[b] + eps);
+    out0[b] = (mode == 0 && frozen) ? 0.f : v;
     if (mode == 1) {
       float bn = bnorm2[b];
       bn = bn > 0.f ? bn : 1.f;
       if (!(num[b] < bn * tol2)) not_done = 1;
     }
   }
-  if (mode == 1 && not_done && all_done) atomicExch(all_done, 0);
+  if (mode == 1 && not_done) atomicExch(&s_not_done, 1);
+  __syncthreads();
+  if (mode == 1 && threadIdx.x == 0 && done && s_not_done == 0) *done = 1;
 }
 
 // DDRM update, see header.  init != 0: first draw (diffusion.py:177-190); y_bar is normalised in place.

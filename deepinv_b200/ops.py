@@ -1,0 +1,240 @@
+"""Thin torch-tensor front end of the C ABI (pointers + sizes go down, nothing else).
+
+Every function here requires CUDA tensors and enqueues on torch's current stream.  Workspaces are
+torch tensors cached per (device, size) so that calls are allocation-free after warm-up and can be
+captured in CUDA graphs.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _ffi
+from ._lib import DinvkError, check, get_lib
+
+_ws_cache: dict[tuple, torch.Tensor] = {}
+
+
+def _require_cuda(*ts: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise DinvkError(
+                "deepinv_b200 operators run on CUDA tensors only (no CPU fallback); got a tensor on " f"{t.device}"
+            )
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise DinvkError(f"tensors on different devices: {dev} vs {t.device}")
+    if dev is None:
+        raise DinvkError("no tensor given")
+    return dev
+
+
+def _stream(dev: torch.device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[ctypes.c_void_p]:
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """fp32 + contiguous (inputs may be arbitrary views: the reference itself hands out transposed views)"""
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def workspace(dev: torch.device, nbytes: int, tag: str = "") -> torch.Tensor:
+    key = (dev, tag)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        _ws_cache[key] = ws
+    return ws
+
+
+# --------------------------------------------------------------------------------------------
+# spectral family
+# --------------------------------------------------------------------------------------------
+class MaskSpec:
+    """Device-side description of a spectral multiplier (see `dinvk_spectral_args`)."""
+
+    __slots__ = ("tensor", "sb", "sc", "sh", "complex")
+
+    def __init__(self, tensor: torch.Tensor, sb: int, sc: int, sh: int, complex_: bool = False):
+        self.tensor, self.sb, self.sc, self.sh, self.complex = tensor, sb, sc, sh, complex_
+
+
+def mask_spec_from_real(mask: torch.Tensor, H: int, W: int, compress: bool = True) -> MaskSpec:
+    """mask: (1|B, 2, H, W) fp32 as stored by the reference's MRI (`check_mask`, mixins.py:125-146).
+
+    With compress=True a mask that is constant along H and identical on both planes (the reference's
+    Cartesian line masks, physics/generator/mri.py:170-196) is stored as (B,1,1,W): the kernels then
+    skip the H-direction transforms in A^T A / prox (see dinvk.h)."""
+    m = _f32c(mask)
+    assert m.dim() == 4 and m.shape[1] == 2 and m.shape[2] == H and m.shape[3] == W, f"mask shape {tuple(m.shape)}"
+    B = m.shape[0]
+    if compress and H > 1:
+        row = m[:, :1, :1, :]
+        if bool((m == row).all()):
+            mc = row.contiguous()
+            return MaskSpec(mc, W if B > 1 else 0, 0, 0)
+    return MaskSpec(m, 2 * H * W if B > 1 else 0, H * W, W)
+
+
+def spectral(
+    p0: torch.Tensor,
+    H: int,
+    W: int,
+    *,
+    fwd: bool,
+    inv: bool,
+    centered: bool = True,
+    gmode: int = _ffi.G_NONE,
+    mask: Optional[MaskSpec] = None,
+    a0: float = 1.0,
+    p1: Optional[torch.Tensor] = None,
+    a1: float = 0.0,
+    c: float = 0.0,
+    c_batch: Optional[torch.Tensor] = None,
+    q0: Optional[torch.Tensor] = None,
+    e1: float = 0.0,
+    q1: Optional[torch.Tensor] = None,
+    e2: float = 0.0,
+    e0: float = 1.0,
+    ncoil: int = 0,
+    coil_mode: int = 0,
+    coil_maps: Optional[torch.Tensor] = None,
+    out: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """out = e0 * F^-1( g(mask) . F( a0*p0 + a1*p1 ) ) + e1*q0 + e2*q1 on planar (B,2,H,W) tensors."""
+    dev = _require_cuda(p0, p1, q0, q1, c_batch, coil_maps, None if mask is None else mask.tensor)
+    p0 = _f32c(p0)
+    p1, q0, q1, c_batch = _f32c(p1), _f32c(q0), _f32c(q1), _f32c(c_batch)
+    nc = ncoil if ncoil > 1 else 1
+    if nc > 1 and coil_mode == 1:
+        batch = p0.shape[0]
+        nimg = batch * nc
+        out_shape = (batch, 2, nc, H, W)
+    elif nc > 1:
+        batch = p0.shape[0]
+        nimg = batch * nc
+        out_shape = (batch, 2, H, W) if coil_mode == 2 else (batch, 1, H, W)
+    else:
+        nimg = p0.numel() // (2 * H * W)
+        out_shape = tuple(p0.shape)
+    if out is None:
+        out = torch.empty(out_shape, dtype=torch.float32, device=dev)
+    else:
+        assert out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == tuple(out_shape)
+    a = _ffi.SpectralArgs()
+    a.B, a.H, a.W = nimg, H, W
+    a.fwd, a.inv, a.centered, a.gmode = int(fwd), int(inv), int(centered), gmode
+    a.p0, a.p1, a.a0, a.a1 = p0.data_ptr(), (p1.data_ptr() if p1 is not None else None), a0, a1
+    if gmode != _ffi.G_NONE:
+        if mask is None:
+            raise DinvkError("spectral: gmode needs a mask")
+        a.mask, a.mask_sb, a.mask_sc, a.mask_sh = mask.tensor.data_ptr(), mask.sb, mask.sc, mask.sh
+    a.c = c
+    a.c_batch = c_batch.data_ptr() if c_batch is not None else None
+    a.q0, a.q1 = (q0.data_ptr() if q0 is not None else None), (q1.data_ptr() if q1 is not None else None)
+    a.e0, a.e1, a.e2 = e0, e1, e2
+    a.out = out.data_ptr()
+    a.ncoil, a.coil_mode = (nc if nc > 1 else 0), coil_mode
+    if coil_maps is not None:
+        cm = coil_maps if coil_maps.is_contiguous() else coil_maps.contiguous()
+        assert cm.dtype == torch.complex64
+        a.coil_maps = cm.data_ptr()
+        a.coil_sb = nc * H * W if cm.shape[0] > 1 else 0
+    lib = get_lib()
+    nbytes = lib.dinvk_spectral_workspace_bytes(nimg, H, W)
+    ws = workspace(dev, nbytes, "spectral")
+    check(lib.dinvk_spectral(ctypes.byref(a), _p(ws), ws.numel(), _stream(dev)))
+    return out
+
+
+def fft_prepare(n: int, centered: bool = True) -> None:
+    check(get_lib().dinvk_fft_prepare(n, int(centered)))
+
+
+# --------------------------------------------------------------------------------------------
+# elementwise / reductions
+# --------------------------------------------------------------------------------------------
+def axpbypcz(x, a: float, y=None, b: float = 0.0, z=None, c: float = 0.0, out=None) -> torch.Tensor:
+    dev = _require_cuda(x, y, z)
+    x, y, z = _f32c(x), _f32c(y), _f32c(z)
+    if out is None:
+        out = torch.empty_like(x)
+    check(get_lib().dinvk_axpbypcz(_p(out), _p(x), a, _p(y), b, _p(z), c, x.numel(), _stream(dev)))
+    return out
+
+
+def batched_dot(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """(B,) fp32: sum over all non-batch dims of x*y"""
+    dev = _require_cuda(x, y)
+    x, y = _f32c(x), _f32c(y)
+    B = x.shape[0]
+    n_per = x.numel() // max(B, 1)
+    out = torch.empty(B, dtype=torch.float32, device=dev)
+    lib = get_lib()
+    nb = lib.dinvk_batched_dot_workspace_bytes(B, n_per)
+    ws = workspace(dev, nb, "dot")
+    check(lib.dinvk_batched_dot(_p(out), _p(x), _p(y), B, n_per, _p(ws), ws.numel(), _stream(dev)))
+    return out
+
+
+def batched_axpy(x: torch.Tensor, y: torch.Tensor, s: torch.Tensor, sa: float = 1.0, out=None) -> torch.Tensor:
+    """out[b] = x[b] + sa * s[b] * y[b]"""
+    dev = _require_cuda(x, y, s)
+    x, y, s = _f32c(x), _f32c(y), _f32c(s)
+    B = x.shape[0]
+    if out is None:
+        out = torch.empty_like(x)
+    check(get_lib().dinvk_batched_axpy(_p(out), _p(x), _p(y), _p(s), sa, B, x.numel() // max(B, 1), _stream(dev)))
+    return out
+
+
+def cg_scalars(mode: int, num, den, eps: float, bnorm2=None, tol2: float = 0.0, done_flag=None) -> torch.Tensor:
+    dev = _require_cuda(num, den)
+    out = torch.empty_like(num)
+    check(get_lib().dinvk_cg_scalars(mode, _p(out), _p(num), _p(den), eps, _p(bnorm2), tol2, _p(done_flag), num.numel(),
+                                     _stream(dev)))
+    return out
+
+
+def ddrm_update(x_bar, x_bar_prev, y_bar, mask, noise, sigma_t, sigma_prev, sigma_noise, eta, etab, c_sig, eps, init):
+    dev = _require_cuda(y_bar, mask, noise)
+    out = torch.empty_like(y_bar)
+    check(get_lib().dinvk_ddrm_update(_p(out), _p(x_bar), _p(x_bar_prev), _p(y_bar), _p(mask), _p(noise), y_bar.numel(),
+                                      mask.numel(), sigma_t, sigma_prev, sigma_noise, eta, etab, c_sig, eps, int(init),
+                                      _stream(dev)))
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# denoiser convolutions, fp32 path
+# --------------------------------------------------------------------------------------------
+def conv_f32(x, weight, *, kind: int = 0, bias=None, xadd=None, res=None, relu: bool = False) -> torch.Tensor:
+    dev = _require_cuda(x, weight, bias, xadd, res)
+    x, weight, bias, xadd, res = _f32c(x), _f32c(weight), _f32c(bias), _f32c(xadd), _f32c(res)
+    B, Cin, H, W = x.shape
+    if kind == 2:
+        Cout = weight.shape[1]
+        out = torch.empty(B, Cout, 2 * H, 2 * W, dtype=torch.float32, device=dev)
+    elif kind == 1:
+        Cout = weight.shape[0]
+        out = torch.empty(B, Cout, H // 2, W // 2, dtype=torch.float32, device=dev)
+    else:
+        Cout = weight.shape[0]
+        out = torch.empty(B, Cout, H, W, dtype=torch.float32, device=dev)
+    check(get_lib().dinvk_conv_f32(_p(x), _p(xadd), _p(weight), _p(bias), _p(res), _p(out), B, Cin, Cout, H, W, kind,
+                                   int(relu), _stream(dev)))
+    return out

@@ -1,0 +1,225 @@
+"""Loop driver and named algorithms (deepinv/optim/optimizers.py:94-881, 1065-1734; fixed_point.py:262-406).
+
+Same constructor keywords, parameter handling (`sigma_denoiser`->`g_param`, `lambda_reg`->`lambda`,
+scalars or per-iteration lists, `unfold=True` turning them into nn.Parameters), initialisation
+x0 = z0 = A^T y (computed ONCE here and carried in the iterate as "aty"; the reference evaluates it
+twice at init and again inside every L2.grad), convergence criterion (batch-mean relative residual,
+optimizers.py:703-739) and metrics dictionary as the reference.
+"""
+from __future__ import annotations
+
+import warnings
+from collections.abc import Iterable
+from contextlib import nullcontext
+
+import torch
+import torch.nn as nn
+
+from .data_fidelity import ZeroFidelity
+from .optim_iterators import ADMMIteration, FISTAIteration, HQSIteration, OptimIterator, PGDIteration
+from .prior import ZeroPrior
+
+
+def objective_function(x, data_fidelity, prior, cur_params, y, physics):
+    return data_fidelity(x, y, physics) + cur_params["lambda"] * prior(x, cur_params["g_param"])
+
+
+class BaseOptim(nn.Module):
+    def __init__(self, iterator: OptimIterator, params_algo=None, data_fidelity=None, prior=None, max_iter: int = 100,
+                 crit_conv: str = "residual", thres_conv: float = 1e-5, early_stop: bool = False, has_cost: bool = False,
+                 custom_metrics=None, custom_init=None, get_output=lambda X: X["est"][0], unfold: bool = False,
+                 trainable_params=None, verbose: bool = False, show_progress_bar: bool = False, **kwargs):
+        super().__init__()
+        self.early_stop, self.crit_conv, self.verbose = early_stop, crit_conv, verbose
+        self.max_iter, self.thres_conv = max_iter, thres_conv
+        self.custom_metrics, self.custom_init, self.get_output = custom_metrics, custom_init, get_output
+        self.unfold = unfold
+        self.has_converged = False
+        self.iterator = iterator
+        self.prior = [ZeroPrior()] if prior is None else (list(prior) if isinstance(prior, Iterable) else [prior])
+        self.data_fidelity = [ZeroFidelity()] if data_fidelity is None else (
+            list(data_fidelity) if isinstance(data_fidelity, Iterable) else [data_fidelity])
+        self.has_cost = self.prior[0].explicit_prior
+        iterator.has_cost = self.has_cost
+        if self.has_cost and iterator.cost_fn is None:
+            iterator.cost_fn = objective_function
+
+        params_algo = dict({"lambda": 1.0, "stepsize": 1.0} if params_algo is None else params_algo)
+        if "g_param" not in params_algo:
+            params_algo["g_param"] = params_algo.pop("sigma_denoiser", None)
+        if "lambda" not in params_algo:
+            params_algo["lambda"] = params_algo.pop("lambda_reg", 1.0)
+        params_algo.setdefault("beta", 1.0)
+        for key, value in params_algo.items():
+            if not isinstance(value, Iterable) or (isinstance(value, torch.Tensor) and value.dim() == 0):
+                params_algo[key] = [value]
+            elif 1 < len(value) < self.max_iter:
+                raise ValueError(f"The number of elements in the parameter {key} is inferior to max_iter.")
+        self.init_params_algo = params_algo
+
+        if self.unfold:
+            if trainable_params is not None:
+                trainable_params = ["lambda" if p == "lambda_reg" else "g_param" if p == "sigma_denoiser" else p
+                                    for p in trainable_params]
+            else:
+                trainable_params = list(params_algo.keys())
+            for k in trainable_params:
+                if k in self.init_params_algo and self.init_params_algo[k][0] is not None:
+                    self.init_params_algo[k] = nn.ParameterList([
+                        nn.Parameter(torch.tensor(el).float() if not isinstance(el, torch.Tensor) else el.float())
+                        for el in self.init_params_algo[k]])
+            self.params_algo = nn.ParameterDict(
+                {k: v for k, v in self.init_params_algo.items() if isinstance(v, nn.ParameterList)})
+            self.prior = nn.ModuleList(self.prior)
+            self.data_fidelity = nn.ModuleList(self.data_fidelity)
+
+    # ---- per-iteration lookups (optimizers.py:464-502) --------------------------------------------
+    def update_params_fn(self, it: int) -> dict:
+        return {k: (v[it] if len(v) > 1 else v[0]) for k, v in self.init_params_algo.items()}
+
+    def update_prior_fn(self, it: int):
+        return self.prior[it] if len(self.prior) > 1 else self.prior[0]
+
+    def update_data_fidelity_fn(self, it: int):
+        return self.data_fidelity[it] if len(self.data_fidelity) > 1 else self.data_fidelity[0]
+
+    def init_iterate_fn(self, y, physics, init=None):
+        init = init if init is not None else self.custom_init
+        if init is not None:
+            if callable(init):
+                init = init(y, physics)
+            if isinstance(init, torch.Tensor):
+                X = {"est": (init,)}
+            elif isinstance(init, tuple):
+                X = {"est": init}
+            elif isinstance(init, dict):
+                X = dict(init)
+            else:
+                raise ValueError(f"Custom initial iterate must be a torch.Tensor, a tuple, or a dict. Got {type(init)}.")
+            if len(X["est"]) == 1:
+                X["est"] = (X["est"][0], X["est"][0])
+            X.setdefault("aty", None)
+        else:
+            aty = physics.A_adjoint(y)
+            X = {"est": (aty, aty.clone()), "aty": aty}
+        X["cost"] = None
+        return X
+
+    def check_conv_fn(self, it, X_prev, X) -> bool:
+        if self.crit_conv == "residual":
+            x_prev = self.get_output(X_prev).reshape(self.get_output(X_prev).shape[0], -1)
+            x = self.get_output(X).reshape(x_prev.shape[0], -1)
+            crit_cur = ((x_prev - x).norm(p=2, dim=-1) / (x.norm(p=2, dim=-1) + 1e-06)).mean()
+        elif self.crit_conv == "cost":
+            F_prev, F = X_prev["cost"], X["cost"]
+            crit_cur = ((F_prev - F).norm(dim=-1) / (F.norm(dim=-1) + 1e-06)).mean()
+        else:
+            raise ValueError("convergence criteria not implemented")
+        if crit_cur < self.thres_conv:
+            self.has_converged = True
+            if self.verbose:
+                print(f"Iteration {it}, current converge crit. = {crit_cur:.2E}, objective = {self.thres_conv:.2E}")
+            return True
+        return False
+
+    def _metrics_init(self, X, x_gt):
+        x0 = self.get_output(X)
+        self.batch_size = x0.shape[0]
+        m = {"psnr": [[] for _ in range(self.batch_size)], "residual": [[] for _ in range(self.batch_size)]}
+        if x_gt is not None:
+            for i in range(self.batch_size):
+                m["psnr"][i].append(_psnr(x0[i:i + 1], x_gt[i:i + 1]))
+        if self.has_cost:
+            m["cost"] = [[] for _ in range(self.batch_size)]
+        if self.custom_metrics is not None:
+            for name in self.custom_metrics:
+                m[name] = [[] for _ in range(self.batch_size)]
+        return m
+
+    def _metrics_update(self, m, X_prev, X, x_gt):
+        x_prev, x = self.get_output(X_prev), self.get_output(X)
+        for i in range(self.batch_size):
+            m["residual"][i].append(((x_prev[i] - x[i]).norm() / (x[i].norm() + 1e-06)).detach().cpu().item())
+            if x_gt is not None:
+                m["psnr"][i].append(_psnr(x[i:i + 1], x_gt[i:i + 1]))
+            if self.has_cost:
+                m["cost"][i].append(X["cost"][i].detach().cpu().item())
+            if self.custom_metrics is not None:
+                for name, fn in self.custom_metrics.items():
+                    m[name][i].append(fn(m[name], x_prev[i], x[i]))
+        return m
+
+    def single_iteration(self, X, it, y, physics, **kwargs):
+        return self.iterator(X, self.update_data_fidelity_fn(it), self.update_prior_fn(it), self.update_params_fn(it),
+                             y, physics, **kwargs)
+
+    def forward(self, y, physics, init=None, x_gt=None, compute_metrics: bool = False, **kwargs):
+        ctx = torch.no_grad() if not self.unfold else nullcontext()
+        with ctx:
+            X = self.init_iterate_fn(y, physics, init=init)
+            metrics = self._metrics_init(X, x_gt) if compute_metrics else None
+            self.has_converged = False
+            for it in range(self.max_iter):
+                X_prev = X
+                X = self.single_iteration(X, it, y, physics, **kwargs)
+                if compute_metrics:
+                    metrics = self._metrics_update(metrics, X_prev, X, x_gt)
+                if self.early_stop and it > 1 and self.check_conv_fn(it, X_prev, X):
+                    break
+        x = self.get_output(X)
+        return (x, metrics) if compute_metrics else x
+
+
+def _psnr(x, y, max_pixel=1.0):
+    mse = ((x - y) ** 2).mean()
+    return float(10 * torch.log10(max_pixel ** 2 / mse))
+
+
+def _named(iteration_cls):
+    class _Algo(BaseOptim):
+        def __init__(self, data_fidelity=None, prior=None, lambda_reg: float = 1.0, stepsize: float = 1.0,
+                     g_param=None, sigma_denoiser=None, beta: float = 1.0, max_iter: int = 100,
+                     crit_conv: str = "residual", thres_conv: float = 1e-5, early_stop: bool = False,
+                     custom_metrics=None, custom_init=None, g_first: bool = False, unfold: bool = False,
+                     trainable_params=None, cost_fn=None, params_algo=None, **kwargs):
+            if g_param is None and sigma_denoiser is not None:
+                g_param = sigma_denoiser
+            if params_algo is None:
+                params_algo = {"lambda": lambda_reg, "stepsize": stepsize, "g_param": g_param, "beta": beta}
+            super().__init__(iteration_cls(g_first=g_first, cost_fn=cost_fn), data_fidelity=data_fidelity, prior=prior,
+                             params_algo=params_algo, max_iter=max_iter, crit_conv=crit_conv, thres_conv=thres_conv,
+                             early_stop=early_stop, custom_metrics=custom_metrics, custom_init=custom_init,
+                             unfold=unfold, trainable_params=trainable_params, **kwargs)
+
+    return _Algo
+
+
+class PGD(_named(PGDIteration)):
+    """Proximal gradient descent (optimizers.py:1596-1734)"""
+
+
+class FISTA(_named(FISTAIteration)):
+    """FISTA (optimizers.py:1737-1880)"""
+
+    def __init__(self, *args, a: int = 3, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.init_params_algo.setdefault("a", [a])
+
+
+class ADMM(_named(ADMMIteration)):
+    """ADMM (optimizers.py:1065-1191)"""
+
+
+class HQS(_named(HQSIteration)):
+    """Half-quadratic splitting (optimizers.py:1194-1317)"""
+
+
+def optim_builder(iteration, max_iter=100, params_algo=None, data_fidelity=None, prior=None, g_first=False, **kwargs):
+    """legacy builder (optimizers.py:2560-2679): iteration given by name or as an OptimIterator"""
+    table = {"PGD": PGDIteration, "FISTA": FISTAIteration, "ADMM": ADMMIteration, "HQS": HQSIteration}
+    if isinstance(iteration, str):
+        if iteration not in table:
+            raise NotImplementedError(f"iteration {iteration!r} is outside the accelerated path")
+        iteration = table[iteration](g_first=g_first)
+    return BaseOptim(iteration, max_iter=max_iter, params_algo=params_algo, data_fidelity=data_fidelity, prior=prior,
+                     **kwargs)

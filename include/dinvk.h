@@ -140,9 +140,12 @@ int dinvk_batched_axpy(float* out, const float* x, const float* y, const float* 
 int dinvk_batched_dot(float* out, const float* x, const float* y, int B, int64_t n_per,
                       void* workspace, size_t workspace_bytes, void* stream);
 size_t dinvk_batched_dot_workspace_bytes(int B, int64_t n_per);
-/* CG scalar update on device, one thread per sample (conjugate_gradient.py:55-66):
- *   mode 0: alpha = rsold / (pAp + eps)        -> out0
- *   mode 1: beta  = rsnew / (rsold + eps)      -> out0, and done_flag &= all(rsnew < tol2*bnorm2) */
+/* CG scalar update on device, one thread per sample (conjugate_gradient.py:55-66).  `done_flag` is a
+ * sticky int32 the caller zeroes once per solve:
+ *   mode 0: alpha = rsold / (pAp + eps) -> out0, forced to 0 once done_flag is set (iterations issued
+ *           after convergence leave x and r untouched, so the host may poll the flag lazily)
+ *   mode 1: beta  = rsnew / (rsold + eps) -> out0, and done_flag <- 1 when all(rsnew < tol2*bnorm2)
+ *           (bnorm2 entries <= 0 are replaced by 1, conjugate_gradient.py:51) */
 int dinvk_cg_scalars(int mode, float* out0, const float* num, const float* den, float eps,
                      const float* bnorm2, float tol2, int32_t* all_done_flag, int B, void* stream);
 

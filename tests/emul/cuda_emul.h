@@ -27,7 +27,7 @@
 #define __restrict__
 #define __shared__ static
 #define __launch_bounds__(...)
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 
 struct uint3 { unsigned x, y, z; };
 struct dim3 {

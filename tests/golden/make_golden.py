@@ -1,0 +1,236 @@
+"""Generate the golden vectors under tests/golden/ by running the REAL reference.
+
+Run in the authoring container only (the reference tree is not available on the GPU box):
+
+    PYTHONPATH=oracle/_shim:/root/reference python tests/golden/make_golden.py
+
+`oracle/_shim` provides the three import shims the reference needs offline (package metadata,
+`natsort`, `h5py`).  Every fixture stores the inputs next to the reference's
+outputs, all produced on CPU in float32 by deepinv v0.4.1 through its public API.  The fixtures pin
+(1) the oracle restatement (tests/test_oracle_golden.py, CPU) and (2) the CUDA kernels
+(tests/test_gpu_golden.py, `-m gpu`).
+"""
+from __future__ import annotations
+
+import sys
+import warnings
+from pathlib import Path
+
+import numpy as np
+import torch
+
+warnings.filterwarnings("ignore")
+import deepinv as dinv  # noqa: E402  (the real reference)
+from deepinv.optim import ADMM, HQS, PGD, FISTA  # noqa: E402
+from deepinv.optim.data_fidelity import L2  # noqa: E402
+from deepinv.optim.prior import PnP  # noqa: E402
+from deepinv.physics import MRI, Blur, BlurFFT, MultiCoilMRI, Tomography  # noqa: E402
+from deepinv.physics.generator import RandomMaskGenerator  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+assert dinv.__version__ == "0.4.1", dinv.__version__
+
+
+def save(name, **arrays):
+    conv = {}
+    for k, v in arrays.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        conv[k] = np.asarray(v)
+    np.savez_compressed(OUT / f"{name}.npz", **conv)
+    print(f"{name}: {len(conv)} arrays, {sum(v.nbytes for v in conv.values()) / 1024:.0f} KiB")
+
+
+def g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def mri_fixtures():
+    for tag, (B, H, W), kind in [("mri_16x12_full", (2, 16, 12), "full"), ("mri_32x32_lines", (3, 32, 32), "lines"),
+                                 ("mri_17x11_odd", (2, 17, 11), "full"), ("mri_20x24_shared", (2, 20, 24), "shared")]:
+        x = torch.randn(B, 2, H, W, generator=g(1))
+        if kind == "lines":
+            mask = RandomMaskGenerator((2, H, W), acceleration=4, rng=g(0)).step(B)["mask"]
+        elif kind == "shared":
+            mask = (torch.rand(1, 1, H, W, generator=g(2)) > 0.6).float()
+        else:
+            mask = (torch.rand(B, 2, H, W, generator=g(2)) > 0.5).float()
+        phys = MRI(mask=mask, img_size=(2, H, W))
+        y = phys.A(x)
+        z = torch.randn(B, 2, H, W, generator=g(3))
+        save(tag, x=x, mask=phys.mask, y=y, At=phys.A_adjoint(y), AtA=phys.A_adjoint_A(x), AAt=phys.A_A_adjoint(y),
+             z=z, prox=phys.prox_l2(z, y, 0.7), dagger=phys.A_dagger(y), Vt=phys.V_adjoint(x), V=phys.V(x),
+             At_mag=phys.A_adjoint(y, mag=True), gamma=np.float32(0.7))
+
+
+def multicoil_fixtures():
+    B, N, H, W = 2, 3, 16, 20
+    x = torch.randn(B, 2, H, W, generator=g(1))
+    maps = torch.randn(B, N, H, W, generator=g(4), dtype=torch.complex64)
+    maps = maps / maps.abs().pow(2).sum(1, keepdim=True).sqrt()
+    mask = RandomMaskGenerator((2, H, W), acceleration=4, rng=g(0)).step(B)["mask"]
+    phys = MultiCoilMRI(mask=mask, coil_maps=maps, img_size=(2, H, W))
+    y = phys.A(x)
+    save("mcmri_16x20", x=x, mask=phys.mask, maps_re=maps.real, maps_im=maps.imag, y=y, At=phys.A_adjoint(y),
+         At_rss=phys.A_adjoint(y, rss=True))
+    # shared (batch-1) maps, CG pseudo-inverse
+    maps1 = maps[:1]
+    phys = MultiCoilMRI(mask=torch.ones(H, W), coil_maps=maps1, img_size=(2, H, W))
+    y = phys.A(x)
+    save("mcmri_shared_dagger", x=x, mask=phys.mask, maps_re=maps1.real, maps_im=maps1.imag, y=y, At=phys.A_adjoint(y),
+         dagger=phys.A_dagger(y))
+
+
+def tomo_fixtures():
+    for tag, W, nang, circle in [("tomo_16_a8", 16, 8, False), ("tomo_24_a10_circle", 24, 10, True), ("tomo_32_a12", 32, 12, False)]:
+        x = torch.randn(2, 1, W, W, generator=g(5))
+        phys = Tomography(angles=nang, img_width=W, circle=circle, normalize=False)
+        y = phys.A(x)
+        v = torch.randn(*y.shape, generator=g(6))
+        physb = Tomography(angles=nang, img_width=W, circle=circle, normalize=False, adjoint_via_backprop=False)
+        save(tag, x=x, angles=phys.angles, y=y.contiguous(), v=v, At=phys.A_adjoint(v), fbp=phys.A_dagger(y, fbp=True),
+             At_irad=physb.A_adjoint(v), fbp_irad=physb.A_dagger(y, fbp=True), filt=phys.iradon.filter(y))
+    # normalised operator: operator_norm comes from a seeded power iteration + global RNG -> stored
+    torch.manual_seed(0)
+    W, nang = 16, 8
+    phys = Tomography(angles=nang, img_width=W, normalize=True)
+    x = torch.randn(1, 1, W, W, generator=g(7))
+    y = phys.A(x)
+    save("tomo_16_norm", x=x, angles=phys.angles, operator_norm=phys.operator_norm, y=y.contiguous(), At=phys.A_adjoint(y),
+         fbp=phys.A_dagger(y, fbp=True), dagger=phys.A_dagger(y))
+
+
+def blur_fixtures():
+    B, C, H, W = 2, 2, 17, 19
+    x = torch.rand(B, C, H, W, generator=g(8))
+    for hw in [(3, 3), (4, 4), (5, 3), (6, 5)]:
+        filt = torch.rand(1, 1, *hw, generator=g(9))
+        filt = filt / filt.sum()
+        for pad in ["valid", "circular", "replicate", "reflect", "constant"]:
+            phys = Blur(filter=filt, padding=pad)
+            y = phys.A(x)
+            v = torch.rand(*y.shape, generator=g(10))
+            if pad == "circular" and 2 in hw:
+                continue
+            save(f"blur_{hw[0]}x{hw[1]}_{pad}", x=x, filt=filt, y=y, v=v, At=phys.A_adjoint(v))
+    # per-sample, per-channel filters
+    filt = torch.rand(B, C, 5, 5, generator=g(11))
+    phys = Blur(filter=filt, padding="reflect")
+    y = phys.A(x)
+    save("blur_5x5_perbc_reflect", x=x, filt=filt, y=y, v=y, At=phys.A_adjoint(y))
+    # CG prox on a circular blur
+    filt = dinv.physics.functional.gaussian_blur(sigma=(1.0, 1.0))
+    phys = Blur(filter=filt, padding="circular")
+    y = phys.A(x)
+    z = torch.rand(B, C, H, W, generator=g(12))
+    save("blur_gauss_circular_prox", x=x, filt=filt, y=y, z=z, prox=phys.prox_l2(z, y, 2.0), gamma=np.float32(2.0),
+         dagger=phys.A_dagger(y))
+
+
+def blurfft_fixtures():
+    for tag, (B, C, H, W), sig in [("blurfft_64_cfg1", (1, 1, 64, 64), 2.0), ("blurfft_18x20", (2, 3, 18, 20), 1.0),
+                                   ("blurfft_15x16_odd", (2, 1, 15, 16), 1.0)]:
+        x = torch.randn(B, C, H, W, generator=g(13))
+        filt = dinv.physics.functional.gaussian_blur(sigma=(sig, sig))
+        phys = BlurFFT(img_size=(C, H, W), filter=filt)
+        y = phys.A(x)
+        z = torch.randn(B, C, H, W, generator=g(14))
+        save(tag, x=x, filt=filt, y=y, At=phys.A_adjoint(y), prox=phys.prox_l2(z, y, 1.5), z=z, gamma=np.float32(1.5),
+             dagger=phys.A_dagger(y), mask=phys.mask, angle_re=phys.angle.real, angle_im=phys.angle.imag,
+             Vt=phys.V_adjoint(x), Ut=phys.U_adjoint(x), AtA=phys.A_adjoint_A(x))
+
+
+def tiny_drunet(cin):
+    torch.manual_seed(0)
+    return dinv.models.DRUNet(in_channels=cin, out_channels=cin, nc=(8, 16, 32, 64), nb=2, pretrained=None).eval()
+
+
+def tiny_dncnn(cin):
+    torch.manual_seed(0)
+    return dinv.models.DnCNN(in_channels=cin, out_channels=cin, depth=5, nf=8, pretrained=None).eval()
+
+
+def sd_arrays(model, prefix):
+    return {f"{prefix}{k.replace('.', '__')}": v for k, v in model.state_dict().items()}
+
+
+def model_fixtures():
+    den = tiny_drunet(2)
+    x = torch.randn(2, 2, 32, 40, generator=g(15))
+    with torch.no_grad():
+        out = den(x, 0.05)
+        sig = torch.tensor([0.03, 0.1])
+        out_b = den(x, sig)
+        xs = torch.randn(1, 2, 20, 36, generator=g(16))  # needs the replicate-pad path
+        out_s = den(xs, 0.05)
+    save("drunet_tiny", x=x, out=out, sig=sig, out_b=out_b, xs=xs, out_s=out_s, **sd_arrays(den, "sd__"))
+    dn = tiny_dncnn(1)
+    x = torch.randn(2, 1, 24, 28, generator=g(17))
+    with torch.no_grad():
+        out = dn(x, 0.1)
+    save("dncnn_tiny", x=x, out=out, **sd_arrays(dn, "sd__"))
+
+
+def optim_fixtures():
+    # cfg2 in miniature: MRI 32x32, 4x line mask, PnP-PGD + DRUNet
+    B, H, W = 2, 32, 32
+    x = torch.randn(B, 2, H, W, generator=g(1))
+    mask = RandomMaskGenerator((2, H, W), acceleration=4, rng=g(0)).step(B)["mask"]
+    phys = MRI(mask=mask, img_size=(2, H, W))
+    y = phys(x)
+    den = tiny_drunet(2)
+    with torch.no_grad():
+        pgd = PGD(data_fidelity=L2(), prior=PnP(den), stepsize=1.0, sigma_denoiser=0.05, max_iter=4, early_stop=False)
+        out_pgd = pgd(y, phys)
+        pgd2 = PGD(data_fidelity=L2(), prior=PnP(den), max_iter=3, early_stop=False,
+                   params_algo={"stepsize": 0.8, "g_param": 0.05, "lambda": 1.0, "beta": 0.9})
+        out_pgd2 = pgd2(y, phys)
+        hqs = HQS(data_fidelity=L2(), prior=PnP(den), stepsize=1.0, sigma_denoiser=0.05, max_iter=3, early_stop=False)
+        out_hqs = hqs(y, phys)
+        admm = ADMM(data_fidelity=L2(), prior=PnP(den), stepsize=1.0, sigma_denoiser=0.05, max_iter=3, early_stop=False)
+        out_admm = admm(y, phys)
+        fista = FISTA(data_fidelity=L2(), prior=PnP(den), stepsize=1.0, sigma_denoiser=0.05, max_iter=3, early_stop=False)
+        out_fista = fista(y, phys)
+    save("optim_mri_tiny", x=x, mask=phys.mask, y=y, pgd=out_pgd, pgd_relax=out_pgd2, hqs=out_hqs, admm=out_admm,
+         fista=out_fista, **sd_arrays(den, "sd__"))
+    # cfg5 in miniature: circular Blur (CG prox) + DnCNN, PnP-ADMM
+    B, C, H, W = 2, 1, 24, 28
+    x = torch.rand(B, C, H, W, generator=g(18))
+    filt = dinv.physics.functional.gaussian_blur(sigma=(1.0, 1.0))
+    phys = Blur(filter=filt, padding="circular")
+    y = phys(x)
+    dn = tiny_dncnn(1)
+    with torch.no_grad():
+        admm = ADMM(data_fidelity=L2(), prior=PnP(dn), stepsize=1.0, sigma_denoiser=0.05, max_iter=3, early_stop=False)
+        out = admm(y, phys)
+    save("optim_blur_tiny", x=x, filt=filt, y=y, admm=out, **sd_arrays(dn, "sd__"))
+
+
+def ddrm_fixture():
+    B, H, W = 2, 32, 32
+    x = torch.randn(B, 2, H, W, generator=g(1)) * 0.3
+    mask = RandomMaskGenerator((2, H, W), acceleration=4, rng=g(0)).step(1)["mask"]  # batch-1 mask (diffusion.py:173)
+    phys = MRI(mask=mask, img_size=(2, H, W), noise_model=dinv.physics.GaussianNoise(sigma=0.02, rng=g(3)))
+    y = phys(x)
+    den = tiny_drunet(2)
+    sigmas = np.linspace(1, 0, 5)
+    noises = [torch.randn(B, 2, H, W, generator=g(100 + t)) for t in range(len(sigmas))]
+    it = iter(noises)
+    orig = torch.randn_like
+    torch.randn_like = lambda t, **kw: next(it).to(t)
+    try:
+        model = dinv.sampling.DDRM(denoiser=den, sigmas=sigmas)
+        out = model(y, phys)
+    finally:
+        torch.randn_like = orig
+    save("ddrm_mri_tiny", x=x, mask=phys.mask, y=y, sigmas=sigmas, noises=torch.stack(noises), out=out,
+         sigma_noise=np.float32(0.02), **sd_arrays(den, "sd__"))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm"]
+    table = {"mri": mri_fixtures, "multicoil": multicoil_fixtures, "tomo": tomo_fixtures, "blur": blur_fixtures,
+             "blurfft": blurfft_fixtures, "model": model_fixtures, "optim": optim_fixtures, "ddrm": ddrm_fixture}
+    for w in which:
+        table[w]()
