@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — PnP-PGD iterations/s on MRI 256x256, 4x Cartesian mask, DRUNet denoiser (BASELINE.json configs[1]).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                 # the B200 arm (default)
+    python bench.py --impl reference --steps 2 --warmup 1          # the reference's CPU path (oracle port)
+    torchrun --nproc-per-node N bench.py --gpus N ...              # one rank per GPU, batch sharded (weak scaling)
+
+One "step" = one PnP-PGD iteration over the whole batch: fused L2 data step
+z = x - gamma (A^T A x - A^T y) followed by x = DRUNet(z, sigma), through the package's public
+optimiser API (deepinv_b200.optim.PGD.single_iteration).  Prints ONE JSON line (contract in the task
+statement): `value` with inputs resident in HBM, `e2e` through host buffers, `roofline` for the
+dominant kernel family (the denoiser convolutions) plus per-operator HBM fractions under
+`operators`, `cpu_baseline` (oracle timed on the host cores), clocks sampled during the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+H = W = 256
+BATCH = 64
+ACCEL = 4
+SIGMA_DEN = 0.05
+STEPSIZE = 1.0
+DRUNET_GFLOP_PER_IMAGE = 277.40  # SURVEY Appendix A.12 (C=2, 256x256)
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def cartesian_mask(batch: int, h: int, w: int, accel: int, seed: int) -> torch.Tensor:
+    """random Cartesian line masks like RandomMaskGenerator (generator/mri.py:136-196): a fully sampled centre
+    band (8 % for 4x, 4 % for 8x) plus uniformly random columns up to 1/accel density, constant along H"""
+    g = torch.Generator().manual_seed(seed)
+    center = {4: 0.08, 8: 0.04}.get(accel, 0.32 / accel)
+    n_center = int(round(w * center))
+    n_total = int(round(w / accel))
+    m = torch.zeros(batch, 1, 1, w)
+    lo = (w - n_center) // 2
+    for b in range(batch):
+        m[b, 0, 0, lo: lo + n_center] = 1
+        rest = torch.tensor([i for i in range(w) if not (lo <= i < lo + n_center)])
+        pick = rest[torch.randperm(len(rest), generator=g)[: n_total - n_center]]
+        m[b, 0, 0, pick] = 1
+    return m.expand(batch, 2, h, w).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in Path(self.f.name).read_text().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if r[col].strip().lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "power_w_max": max(float(r[3]) for r in rows),
+                "samples": len(rows), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the reference's CPU path
+# ---------------------------------------------------------------------------------------------
+def cpu_pgd_iteration_seconds(sample_batch: int, repeats: int, threads: int):
+    """time ONE PnP-PGD iteration of the oracle (torch-CPU restatement of the reference path) on
+    `sample_batch` images; returns best-of-`repeats` seconds"""
+    from oracle import ref_ops as R
+
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    import deepinv_b200 as dinv
+
+    den = dinv.models.DRUNet(in_channels=2, out_channels=2, pretrained=None)  # parameter container only (random init, seed 0)
+    sd = {k: v.detach() for k, v in den.state_dict().items()}
+    x = torch.randn(sample_batch, 2, H, W)
+    mask = cartesian_mask(sample_batch, H, W, ACCEL, seed=0)
+    y = R.mri_A(x, mask)
+    best = float("inf")
+    with torch.no_grad():
+        xk = R.mri_At(y, mask)
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            grad = R.mri_AtA(xk, mask) - R.mri_At(y, mask)          # data_fidelity.py:335-336
+            z = xk - STEPSIZE * grad                                  # pgd.py:137-139
+            xk = R.drunet_forward(z, SIGMA_DEN, sd)                   # prior.py:99-109 -> drunet.py:212-263
+            best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = 2
+    # warm-up + K timed "steps", each a bounded sample (one iteration on `sample` images)
+    for _ in range(max(args.warmup, 0)):
+        cpu_pgd_iteration_seconds(sample, 1, threads)
+    ts = [cpu_pgd_iteration_seconds(sample, 1, threads) for _ in range(max(args.steps, 1))]
+    t = sum(ts) / len(ts)
+    per_img = t / sample
+    its = 1.0 / (per_img * BATCH * args.gpus)  # whole-job batch = 64 per GPU
+    value = its * args.gpus
+    line = {
+        "impl": "reference", "metric": "pnp_pgd_iterations_per_s", "value": value, "unit": "it/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "MRI 4x Cartesian-mask 256x256, PnP-PGD + DRUNet, batch=64 per GPU", "global_batch": BATCH * args.gpus,
+                   "parallelism": f"dp{args.gpus}"},
+        "cpu_baseline": {"value": value, "unit": "it/s", "cores": threads, "kind": "port",
+                         "sample": f"one PnP-PGD iteration on {sample} of the 64 images per step, scaled linearly per image"},
+        "e2e": {"value": value, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+def time_cuda(fn, iters: int, warmup: int = 3) -> float:
+    """average milliseconds per call, CUDA events on the current stream"""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def run_b200(args):
+    import torch.distributed as dist
+
+    import deepinv_b200 as dinv
+    from deepinv_b200.optim import L2, PGD, PnP
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (deepinv_b200 has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = measured_peaks()
+
+    # ---- synthetic inputs (per-rank shard of the global batch) -----------------------------------
+    torch.manual_seed(0)
+    den = dinv.models.DRUNet(in_channels=2, out_channels=2, pretrained=None, precision=args.precision).to(dev).eval()
+    gen = torch.Generator().manual_seed(1234 + rank)
+    x_true = torch.randn(BATCH, 2, H, W, generator=gen)
+    mask = cartesian_mask(BATCH, H, W, ACCEL, seed=rank)
+    physics = dinv.physics.MRI(mask=mask.to(dev), img_size=(2, H, W), device=dev)
+    x_pin = x_true.pin_memory()
+    with torch.no_grad():
+        y = physics.A(x_pin.to(dev, non_blocking=True))
+    y_pin = y.cpu().pin_memory()
+    algo = PGD(data_fidelity=L2(), prior=PnP(den), stepsize=STEPSIZE, sigma_denoiser=SIGMA_DEN, max_iter=args.steps,
+               early_stop=False)
+
+    lib = dinv.get_lib()
+
+    def iteration(X, it):
+        return algo.single_iteration(X, it, y, physics)
+
+    with torch.no_grad():
+        X = algo.init_iterate_fn(y, physics)
+        for it in range(args.warmup):
+            X = iteration(X, it)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        launches0 = lib.dinvk_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for it in range(args.steps):
+            X = iteration(X, it)
+        x_hat = X["est"][0]
+        if world > 1:  # the only collective of the path: gather the final reconstructions
+            gathered = torch.empty(world * BATCH, 2, H, W, device=dev)
+            dist.all_gather_into_tensor(gathered, x_hat.contiguous())
+        e1.record()
+        torch.cuda.synchronize()
+        ms_total = e0.elapsed_time(e1)
+        launches = lib.dinvk_launch_count() - launches0
+        clk = clocks.stop() if rank == 0 else None
+        if world > 1:
+            t = torch.tensor([ms_total], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_total = float(t.item())
+        ms_step = ms_total / args.steps
+        value = world * 1000.0 / ms_step
+
+        # ---- e2e: host buffers in, host buffer out, every step ------------------------------------
+        xh = x_hat.cpu().pin_memory()
+        out_pin = torch.empty_like(xh)
+
+        def e2e_step():
+            xd = xh.to(dev, non_blocking=True)
+            yd = y_pin.to(dev, non_blocking=True)
+            Xn = algo.single_iteration({"est": (xd, xd), "aty": None}, 0, yd, physics)
+            out_pin.copy_(Xn["est"][0], non_blocking=True)
+
+        ms_e2e = time_cuda(e2e_step, max(2, min(args.steps, 5)), warmup=1)
+        if world > 1:
+            t = torch.tensor([ms_e2e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t.item())
+        h2d = xh.numel() * 4 + y_pin.numel() * 4
+        d2h = out_pin.numel() * 4
+
+        # ---- roofline of the dominant kernel family + per-operator HBM fractions (rank 0) ----------
+        roof, ops_report = None, None
+        if rank == 0:
+            z = X["est"][0]
+            ms_den = time_cuda(lambda: den(z, SIGMA_DEN), max(2, min(args.steps, 5)), warmup=1)
+            tflops = DRUNET_GFLOP_PER_IMAGE * BATCH / ms_den  # GFLOP / ms = TFLOP/s
+            peak = peaks["bf16_tflops_sustained"]
+            roof = {"bound": "tensor", "kernel": "DRUNet convolutions (%s path, 64 launches per step)" % args.precision,
+                    "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak, "traffic": None,
+                    "peak_source": peaks["source"] + " bf16 sustained", "ms_per_step": ms_den,
+                    "algorithmic_gflop_per_step": DRUNET_GFLOP_PER_IMAGE * BATCH}
+            aty = physics.A_adjoint(y)
+            xx = X["est"][0]
+            img_mb = BATCH * 2 * H * W * 4 / 1e6
+            cases = [
+                ("MRI.A (2-D FFT + mask)", lambda: physics.A(xx), 2 * img_mb),
+                ("MRI.A_adjoint (mask + 2-D iFFT)", lambda: physics.A_adjoint(y), 2 * img_mb),
+                ("PGD data step x-g(AtAx-Aty), line mask (1 pass)", lambda: physics.normal_step(xx, aty, STEPSIZE), 3 * img_mb),
+                ("MRI.prox_l2, line mask (1 pass)", lambda: physics.prox_l2(xx, y, 1.0), 3 * img_mb),
+            ]
+            ops_report = []
+            for name, fn, mb in cases:
+                ms = time_cuda(fn, 20, warmup=3)
+                gbs = mb / ms  # MB/ms = GB/s
+                ops_report.append({"op": name, "ms": ms, "algorithmic_MB": mb, "GBps": gbs, "frac_hbm": gbs / peaks["hbm_gbs"]})
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            t = cpu_pgd_iteration_seconds(2, 2, threads)
+            cpu = {"value": 1.0 / (t / 2 * BATCH), "unit": "it/s", "cores": threads, "kind": "port",
+                   "sample": "one PnP-PGD iteration of the oracle on 2 of the 64 images (best of 2), scaled linearly per image"}
+        line = {
+            "metric": "pnp_pgd_iterations_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 denoiser GEMMs (fp32 accumulate) + f32 operators" if args.precision == "bf16" else "f32",
+            "data": "synthetic",
+            "config": {"workload": "MRI 4x Cartesian-mask 256x256, PnP-PGD + DRUNet, batch=64 per GPU",
+                       "global_batch": BATCH * world, "parallelism": f"dp{world}", "denoiser_precision": args.precision,
+                       "l2_policy": "per-step working set (>= 1 GB of activations) exceeds the 126 MB L2; no explicit flush"},
+            "e2e": {"value": world * 1000.0 / ms_e2e, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": roof,
+            "operators": ops_report,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("DINVK_BENCH_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
