@@ -36,8 +36,8 @@ _SIGNATURES = {
     "dinvk_spectral_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "dinvk_spectral": (c_int, [C.POINTER(SpectralArgs), c_void_p, c_size_t, c_void_p]),
     "dinvk_fft_prepare": (c_int, [c_int, c_int]),
-    "dinvk_ramp_filter_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "dinvk_ramp_filter": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "dinvk_ramp_filter_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "dinvk_ramp_filter": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "dinvk_axpbypcz": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_float, c_void_p, c_float, c_int64, c_void_p]),
     "dinvk_batched_axpy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int64, c_void_p]),
     "dinvk_batched_dot": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_size_t, c_void_p]),
@@ -49,7 +49,8 @@ _SIGNATURES = {
     "dinvk_radon_adj": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p]),
     "dinvk_iradon_bp": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p]),
     "dinvk_blur_fwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_void_p]),
-    "dinvk_blur_adj": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_void_p]),
+    "dinvk_blur_adj_workspace_bytes": (c_size_t, [c_int] * 7),
+    "dinvk_blur_adj": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_void_p, c_size_t, c_void_p]),
     "dinvk_conv_f32": (c_int, [c_void_p] * 6 + [c_int] * 7 + [c_void_p]),
     "dinvk_conv3x3_bf16": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
     "dinvk_nchw_f32_to_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p]),

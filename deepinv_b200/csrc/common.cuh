@@ -22,6 +22,15 @@
 #include <cuda_runtime.h>
 #endif
 
+// dynamic shared memory, usable from both build modes
+#ifdef DINVK_EMUL
+#define DINVK_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(::emul::dyn_smem())
+#else
+#define DINVK_DYN_SMEM(type, name)                                      \
+  extern __shared__ __align__(16) unsigned char dinvk_dyn_smem_raw[];   \
+  type* name = reinterpret_cast<type*>(dinvk_dyn_smem_raw)
+#endif
+
 namespace dinvk {
 
 // ---- error plumbing -------------------------------------------------------------------------

@@ -1,0 +1,237 @@
+// radon.cu — parallel-beam Radon transform, its exact transpose, and the IRadon back-projection.
+//
+// Replaces (reference, relative to the deepinv tree):
+//   Radon.forward: pad -> grid_sample over all angles -> sum over rows      physics/functional/radon.py:252-309
+//   the autograd adjoint of Tomography.A (exact transpose)                  physics/tomography.py:322-342
+//   IRadon.forward(filtering=False): sample the sinogram, sum over angles   physics/functional/radon.py:396-450
+//
+// The reference materialises a (B,C,P,P*A) rotated stack (378 MB per 512^2 image) and reduces it; here
+// every ray / pixel accumulates in a register and the only HBM traffic is the image and the sinogram
+// (50.3 MB per cfg3 call).  These kernels are bound by fp32 issue + L1 gathers, not by HBM.
+//
+// Geometry is evaluated in fp32 exactly like affine_grid/grid_sample(align_corners=True):
+//   lin[k] = linspace(-1,1,P)[k];  g = R_theta (lin[j], lin[i]);  pix = ((g + 1) / 2) * (P - 1);
+//   bilinear weights from floor(pix), zeros outside.  Sinograms are stored ANGLE-major (BC, A, P): this is
+//   the memory the reference returns as the transposed view (B,C,P,A) (radon.py:291-293).
+#include "common.cuh"
+
+namespace dinvk {
+
+struct RadonGeom {
+  int W, P, A, pb, circle;
+  float step;  // linspace step 2/(P-1) in fp32
+};
+
+// torch.linspace(-1, 1, P) in fp32 (symmetric evaluation, ATen RangeFactories)
+__device__ __forceinline__ float lin_at(int k, int P, float step) {
+  return (k < P / 2) ? (-1.0f + step * (float)k) : (1.0f - step * (float)(P - 1 - k));
+}
+
+__device__ __forceinline__ void sample_pos(float c, float s, float xj, float yi, float pm1, float& px, float& py) {
+  const float gx = fmaf(s, yi, c * xj);
+  const float gy = fmaf(c, yi, -s * xj);
+  px = ((gx + 1.0f) * 0.5f) * pm1;
+  py = ((gy + 1.0f) * 0.5f) * pm1;
+}
+
+// image value at padded coordinates (X,Y): zero padding outside the W x W support; optional inscribed disc
+__device__ __forceinline__ float img_at(const float* __restrict__ img, const RadonGeom& G, int X, int Y) {
+  const int x = X - G.pb, y = Y - G.pb;
+  if (x < 0 || x >= G.W || y < 0 || y >= G.W) return 0.f;
+  float v = __ldg(img + (long long)y * G.W + x);
+  if (G.circle) {
+    const float ax = 2.0f * (float)x / (float)(G.W - 1) - 1.0f, ay = 2.0f * (float)y / (float)(G.W - 1) - 1.0f;
+    if (!(ax * ax + ay * ay <= 1.0f)) v = 0.f;
+  }
+  return v;
+}
+
+// one thread per ray (bc, t, j): sino[bc, t, j] = scale * sum_i bilinear(x_pad, S_t(i, j))
+__global__ void __launch_bounds__(128) radon_fwd_kernel(const float* __restrict__ x, float* __restrict__ sino, RadonGeom G,
+                                                        const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                                                        float scale) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y, bc = blockIdx.z;
+  if (j >= G.P) return;
+  const float c = __ldg(cos_t + t), s = __ldg(sin_t + t);
+  const float pm1 = (float)(G.P - 1);
+  const float xj = lin_at(j, G.P, G.step);
+  const float* img = x + (long long)bc * G.W * G.W;
+  // conservative row range in which the sample can touch the image support [pb-1, pb+W] (both axes):
+  // pix_x ~ cx + c (j-cx) + s (i-cx),  pix_y ~ cx - s (j-cx) + c (i-cx)
+  const float cx = 0.5f * pm1;
+  const float lo = (float)G.pb - 1.0f, hi = (float)(G.pb + G.W);
+  float i_lo = 0.f, i_hi = pm1;
+  {
+    const float bx = cx + c * ((float)j - cx), by = cx - s * ((float)j - cx);
+    // lo < bx + s*(i-cx) < hi   and   lo < by + c*(i-cx) < hi
+    if (fabsf(s) > 1e-6f) {
+      float a = (lo - bx) / s + cx, b = (hi - bx) / s + cx;
+      if (a > b) { const float tmp = a; a = b; b = tmp; }
+      i_lo = fmaxf(i_lo, a); i_hi = fminf(i_hi, b);
+    } else if (!(bx > lo - 1.f && bx < hi + 1.f)) { i_hi = -1.f; }
+    if (fabsf(c) > 1e-6f) {
+      float a = (lo - by) / c + cx, b = (hi - by) / c + cx;
+      if (a > b) { const float tmp = a; a = b; b = tmp; }
+      i_lo = fmaxf(i_lo, a); i_hi = fminf(i_hi, b);
+    } else if (!(by > lo - 1.f && by < hi + 1.f)) { i_hi = -1.f; }
+  }
+  const int i0 = max(0, (int)floorf(i_lo) - 2), i1 = min(G.P - 1, (int)ceilf(i_hi) + 2);
+  float acc = 0.f;
+  for (int i = i0; i <= i1; ++i) {
+    const float yi = lin_at(i, G.P, G.step);
+    float px, py;
+    sample_pos(c, s, xj, yi, pm1, px, py);
+    const float fx = floorf(px), fy = floorf(py);
+    const int X0 = (int)fx, Y0 = (int)fy;
+    const float wx1 = px - fx, wy1 = py - fy, wx0 = (fx + 1.0f) - px, wy0 = (fy + 1.0f) - py;
+    if (X0 < G.pb - 1 || X0 >= G.pb + G.W || Y0 < G.pb - 1 || Y0 >= G.pb + G.W) continue;
+    const float v00 = img_at(img, G, X0, Y0), v01 = img_at(img, G, X0 + 1, Y0);
+    const float v10 = img_at(img, G, X0, Y0 + 1), v11 = img_at(img, G, X0 + 1, Y0 + 1);
+    acc += v00 * (wx0 * wy0) + v01 * (wx1 * wy0) + v10 * (wx0 * wy1) + v11 * (wx1 * wy1);
+  }
+  sino[((long long)bc * G.A + t) * G.P + j] = acc * scale;
+}
+
+// exact transpose, gather form: one thread per image pixel.  For each angle the sample lattice is the
+// unit grid rotated about the centre; the samples whose bilinear footprint covers pixel (X,Y) lie within
+// sqrt(2) of its lattice coordinates, i.e. among the 3x3 lattice points around the nearest one.
+__global__ void __launch_bounds__(256) radon_adj_kernel(const float* __restrict__ sino, float* __restrict__ x, RadonGeom G,
+                                                        const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                                                        float scale) {
+  DINVK_DYN_SMEM(float, s_cs);  // cos[A], sin[A]
+  for (int k = threadIdx.x; k < G.A; k += blockDim.x) { s_cs[k] = __ldg(cos_t + k); s_cs[G.A + k] = __ldg(sin_t + k); }
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int bc = blockIdx.y;
+  const bool active = p < G.W * G.W;
+  const int yy = active ? p / G.W : 0, xx = active ? p - yy * G.W : 0;
+  const int X = xx + G.pb, Y = yy + G.pb;
+  const float pm1 = (float)(G.P - 1), cx = 0.5f * pm1;
+  const float dx = (float)X - cx, dy = (float)Y - cx;
+  const float* sbase = sino + (long long)bc * G.A * G.P;
+  float acc = 0.f;
+  if (active) {
+    for (int t = 0; t < G.A; ++t) {
+      const float c = s_cs[t], s = s_cs[G.A + t];
+      const int jc = __float2int_rn(cx + c * dx - s * dy), ic = __float2int_rn(cx + s * dx + c * dy);
+      const float* srow = sbase + (long long)t * G.P;
+#pragma unroll
+      for (int dj = -1; dj <= 1; ++dj) {
+        const int j = jc + dj;
+        if (j < 0 || j >= G.P) continue;
+        const float xj = lin_at(j, G.P, G.step);
+        float wsum = 0.f;
+#pragma unroll
+        for (int di = -1; di <= 1; ++di) {
+          const int i = ic + di;
+          if (i < 0 || i >= G.P) continue;
+          float px, py;
+          sample_pos(c, s, xj, lin_at(i, G.P, G.step), pm1, px, py);
+          const float fx = floorf(px), fy = floorf(py);
+          const int X0 = (int)fx, Y0 = (int)fy;
+          const float wx = (X0 == X) ? ((fx + 1.0f) - px) : ((X0 + 1 == X) ? (px - fx) : 0.f);
+          const float wy = (Y0 == Y) ? ((fy + 1.0f) - py) : ((Y0 + 1 == Y) ? (py - fy) : 0.f);
+          wsum += wx * wy;
+        }
+        acc = fmaf(__ldg(srow + j), wsum, acc);
+      }
+    }
+    if (G.circle) {
+      const float ax = 2.0f * (float)xx / (float)(G.W - 1) - 1.0f, ay = 2.0f * (float)yy / (float)(G.W - 1) - 1.0f;
+      if (!(ax * ax + ay * ay <= 1.0f)) acc = 0.f;
+    }
+    x[(long long)bc * G.W * G.W + p] = acc * scale;
+  }
+}
+
+// IRadon back-projection: reco[y,x] = scale * sum_t bilinear(sino as a (P x A) image, col = f(t), row = T(x,y,t))
+__global__ void __launch_bounds__(256) iradon_bp_kernel(const float* __restrict__ sino, float* __restrict__ x, RadonGeom G,
+                                                        const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                                                        float scale) {
+  DINVK_DYN_SMEM(float, s_cs);
+  for (int k = threadIdx.x; k < G.A; k += blockDim.x) { s_cs[k] = __ldg(cos_t + k); s_cs[G.A + k] = __ldg(sin_t + k); }
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int bc = blockIdx.y;
+  if (p >= G.W * G.W) return;
+  const int yy = p / G.W, xx = p - yy * G.W;
+  const float xg = lin_at(xx + G.pb, G.P, G.step), yg = lin_at(yy + G.pb, G.P, G.step);
+  const float pm1 = (float)(G.P - 1), am1 = (float)(G.A - 1);
+  const float* sbase = sino + (long long)bc * G.A * G.P;
+  float acc = 0.f;
+  for (int t = 0; t < G.A; ++t) {
+    const float T = xg * s_cs[t] - yg * s_cs[G.A + t];
+    const float Xn = ((1.0f * (float)t) * 2.0f) / am1 - 1.0f;
+    const float pxs = ((Xn + 1.0f) * 0.5f) * am1;  // column (angle) coordinate
+    const float pys = ((T + 1.0f) * 0.5f) * pm1;   // row (detector) coordinate
+    const float fx = floorf(pxs), fy = floorf(pys);
+    const int c0 = (int)fx, r0 = (int)fy;
+    const float wx1 = pxs - fx, wy1 = pys - fy, wx0 = (fx + 1.0f) - pxs, wy0 = (fy + 1.0f) - pys;
+    float v = 0.f;
+#pragma unroll
+    for (int dc = 0; dc < 2; ++dc) {
+      const int cc = c0 + dc;
+      if (cc < 0 || cc >= G.A) continue;
+      const float wx = dc ? wx1 : wx0;
+      if (wx == 0.f) continue;
+      const float* col = sbase + (long long)cc * G.P;  // angle-major storage: column cc of the (P x A) image is contiguous
+      if (r0 >= 0 && r0 < G.P) v += __ldg(col + r0) * (wx * wy0);
+      if (r0 + 1 >= 0 && r0 + 1 < G.P) v += __ldg(col + r0 + 1) * (wx * wy1);
+    }
+    acc += v;
+  }
+  if (G.circle && !(xg * xg + yg * yg <= 1.0f)) acc = 0.f;
+  x[(long long)bc * G.W * G.W + p] = acc * scale;
+}
+
+static int make_geom(RadonGeom* G, int W, int P, int A, int circle) {
+  if (W < 1 || P < W || A < 1) return set_error(DINVK_EINVAL, "radon: bad geometry W=%d P=%d A=%d", W, P, A);
+  if (circle && P != W) return set_error(DINVK_EINVAL, "radon: circle=1 requires P == W");
+  G->W = W; G->P = P; G->A = A; G->circle = circle ? 1 : 0;
+  G->pb = circle ? 0 : (P / 2 - W / 2);  // (W + pad)//2 - W//2 with pad = P - W   (radon.py:262-266)
+  G->step = P > 1 ? (1.0f - (-1.0f)) / (float)(P - 1) : 0.f;
+  return 0;
+}
+
+}  // namespace dinvk
+
+using namespace dinvk;
+
+extern "C" int dinvk_radon_fwd(const float* x, float* sino, int BC, int W, int P, int A, int circle, const float* cos_t,
+                               const float* sin_t, float scale, void* stream) {
+  DINVK_CHECK_ARG(x && sino && cos_t && sin_t && BC >= 0, "dinvk_radon_fwd: bad arguments");
+  RadonGeom G;
+  int rc = make_geom(&G, W, P, A, circle);
+  if (rc) return rc;
+  if (BC == 0) return DINVK_OK;
+  DINVK_CHECK_ARG(A <= 65535 && BC <= 65535, "dinvk_radon_fwd: grid too large");
+  DINVK_LAUNCH(radon_fwd_kernel, dim3(ceil_div(P, 128), A, BC), dim3(128), 0, stream, x, sino, G, cos_t, sin_t, scale);
+  return DINVK_POST_LAUNCH();
+}
+
+extern "C" int dinvk_radon_adj(const float* sino, float* x, int BC, int W, int P, int A, int circle, const float* cos_t,
+                               const float* sin_t, float scale, void* stream) {
+  DINVK_CHECK_ARG(x && sino && cos_t && sin_t && BC >= 0, "dinvk_radon_adj: bad arguments");
+  RadonGeom G;
+  int rc = make_geom(&G, W, P, A, circle);
+  if (rc) return rc;
+  if (BC == 0) return DINVK_OK;
+  DINVK_CHECK_ARG(BC <= 65535 && A <= 4096, "dinvk_radon_adj: grid too large");
+  DINVK_LAUNCH(radon_adj_kernel, dim3(ceil_div((long long)W * W, 256), BC), dim3(256), 2 * A * sizeof(float), stream, sino, x, G,
+               cos_t, sin_t, scale);
+  return DINVK_POST_LAUNCH();
+}
+
+extern "C" int dinvk_iradon_bp(const float* sino, float* x, int BC, int W, int P, int A, int circle, const float* cos_t,
+                               const float* sin_t, float scale, void* stream) {
+  DINVK_CHECK_ARG(x && sino && cos_t && sin_t && BC >= 0, "dinvk_iradon_bp: bad arguments");
+  RadonGeom G;
+  int rc = make_geom(&G, W, P, A, circle);
+  if (rc) return rc;
+  if (BC == 0) return DINVK_OK;
+  DINVK_CHECK_ARG(BC <= 65535 && A <= 4096, "dinvk_iradon_bp: grid too large");
+  DINVK_LAUNCH(iradon_bp_kernel, dim3(ceil_div((long long)W * W, 256), BC), dim3(256), 2 * A * sizeof(float), stream, sino, x, G,
+               cos_t, sin_t, scale);
+  return DINVK_POST_LAUNCH();
+}

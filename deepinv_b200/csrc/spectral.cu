@@ -31,6 +31,7 @@ namespace dinvk {
 // ---------------------------------------------------------------------------------------------
 struct PassParams {
   int B, H, W;          // B = number of complex images handled by this pass
+  int wv;               // valid width of the planar global rows (== W except for zero-padded 1-D filtering)
   int lines;            // rows per CTA (ROW) or columns per CTA (COL)
   // source
   const float* p0; const float* p1; float a0, a1;
@@ -85,21 +86,14 @@ __device__ __forceinline__ long long planar_base(int img, int nc, long long HW, 
   return (long long)(img / nc) * 2 * cs + (long long)(img % nc) * HW;
 }
 
-#ifdef DINVK_EMUL
-#define DINVK_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(::emul::dyn_smem())
-#else
-#define DINVK_DYN_SMEM(type, name)                                      \
-  extern __shared__ __align__(16) unsigned char dinvk_dyn_smem_raw[];   \
-  type* name = reinterpret_cast<type*>(dinvk_dyn_smem_raw)
-#endif
-
 template <bool COLS, int NTHR>
 __global__ void __launch_bounds__(NTHR, 1024 / NTHR) spectral_pass_kernel(const PassParams P) {
   DINVK_DYN_SMEM(float2, buf);
   const int tid = threadIdx.x;
   constexpr int nthr = NTHR;
   const int N = COLS ? P.H : P.W;          // transform length of this pass
-  const long long HW = (long long)P.H * P.W;
+  const long long HW = (long long)P.H * P.W;    // interleaved workspaces and coil maps
+  const long long HWg = (long long)P.H * P.wv;  // planar global tensors
 
   // tile geometry
   int img0 = 0, c0 = 0;
@@ -129,9 +123,13 @@ __global__ void __launch_bounds__(NTHR, 1024 / NTHR) spectral_pass_kernel(const 
       v = P.tin[(long long)img * HW + (long long)h * P.W + w];
     } else {
       long long cs;
-      const long long o = planar_base(img / P.src_div, P.src_nc, HW, cs) + (long long)h * P.W + w;
-      v = make_float2(P.a0 * __ldg(P.p0 + o), P.a0 * __ldg(P.p0 + o + cs));
-      if (P.p1) { v.x += P.a1 * __ldg(P.p1 + o); v.y += P.a1 * __ldg(P.p1 + o + cs); }
+      const long long o = planar_base(img / P.src_div, P.src_nc, HWg, cs) + (long long)h * P.wv + w;
+      if (w < P.wv) {
+        v = make_float2(P.a0 * __ldg(P.p0 + o), P.a0 * __ldg(P.p0 + o + cs));
+        if (P.p1) { v.x += P.a1 * __ldg(P.p1 + o); v.y += P.a1 * __ldg(P.p1 + o + cs); }
+      } else {
+        v = make_float2(0.f, 0.f);
+      }
     }
     if (P.coil) {
       const float2 s = __ldg(P.coil + (long long)(img / P.ncoil) * P.coil_sb + (long long)(img % P.ncoil) * HW + (long long)h * P.W + w);
@@ -182,9 +180,9 @@ __global__ void __launch_bounds__(NTHR, 1024 / NTHR) spectral_pass_kernel(const 
     if (P.dir2 == 0 && P.g_after) v = apply_g(P, v, img, h, w);
     if (P.tout) {
       P.tout[(long long)img * HW + (long long)h * P.W + w] = v;
-    } else {
+    } else if (w < P.wv) {
       long long cs;
-      const long long o = planar_base(img, P.dst_nc, HW, cs) + (long long)h * P.W + w;
+      const long long o = planar_base(img, P.dst_nc, HWg, cs) + (long long)h * P.wv + w;
       float re = P.e0 * v.x, im = P.e0 * v.y;
       if (P.q0) { re += P.e1 * __ldg(P.q0 + o); im += P.e1 * __ldg(P.q0 + o + cs); }
       if (P.q1) { re += P.e2 * __ldg(P.q1 + o); im += P.e2 * __ldg(P.q1 + o + cs); }
@@ -366,7 +364,7 @@ static int launch_pass(bool cols, PassParams& P, const TileCfg& cfg, void* strea
 
 static void init_pass(PassParams& P, const dinvk_spectral_args& a) {
   P = PassParams();
-  P.B = a.B; P.H = a.H; P.W = a.W;
+  P.B = a.B; P.H = a.H; P.W = a.W; P.wv = a.W;
   P.src_nc = 1; P.src_div = 1; P.dst_nc = 1; P.ncoil = a.ncoil > 1 ? a.ncoil : 1;
   P.a0 = 1.f; P.a1 = 0.f; P.e0 = 1.f; P.e1 = 0.f; P.e2 = 0.f;
   P.gmode = DINVK_G_NONE;
@@ -435,13 +433,14 @@ extern "C" int dinvk_spectral(const dinvk_spectral_args* ap, void* workspace, si
   const bool coil_reduce = nc > 1 && a.coil_mode >= 2;
 
   Tables tH, tW;
-  FftPlan pH, pW;
+  FftPlan pH = FftPlan(), pW = FftPlan();
   int rc;
   const int cen = a.centered ? 1 : 0;
   if ((rc = get_tables(a.H, cen, &tH))) return rc;
   if ((rc = get_tables(a.W, cen, &tW))) return rc;
   TileCfg rcfg, ccfg;
-  const bool fast = make_fft_plan(a.H, &pH) && make_fft_plan(a.W, &pW) && row_cfg(pW, a.W, &rcfg) && col_cfg(pH, a.H, a.W, &ccfg);
+  const bool okH = make_fft_plan(a.H, &pH), okW = make_fft_plan(a.W, &pW);  // both always initialised
+  const bool fast = okH && okW && row_cfg(pW, a.W, &rcfg) && col_cfg(pH, a.H, a.W, &ccfg);
   PassParams P;
 
   if (!a.fwd && !a.inv) {  // pure elementwise
@@ -517,6 +516,95 @@ extern "C" int dinvk_spectral(const dinvk_spectral_args* ap, void* workspace, si
                  (const float2*)T2, reinterpret_cast<const float2*>(a.coil_maps), (long long)a.coil_sb, a.out, batch, nc, HW,
                  a.coil_mode, a.e0);
     return DINVK_POST_LAUNCH();
+  }
+  return DINVK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ramp filter (FBP): rows of length N zero-padded to L, multiplied by 2*rfft(f) in the Fourier domain.
+// Two real rows are packed as one complex signal (the filter is real and even, so real and imaginary
+// parts filter independently); the ROW pass runs load(+pad) -> FFT -> multiply -> iFFT -> store(crop).
+// ---------------------------------------------------------------------------------------------
+namespace dinvk {
+static std::mutex g_ramp_mu;
+static std::map<std::vector<int>, float*> g_ramp;
+
+static int ramp_padded_len(int N) {
+  int L = 64;
+  while (L < 2 * N) L *= 2;  // max(64, 2^ceil(log2(2N)))  (radon.py:96-98)
+  return L;
+}
+static int get_ramp_table(int L, float** out) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_ramp_mu);
+  std::vector<int> key = {dev, L};
+  auto it = g_ramp.find(key);
+  if (it != g_ramp.end()) { *out = it->second; return 0; }
+  // f[0] = 1/4, f[odd k] = -1/(pi n)^2 with n = 1,3,..,L/2-1,L/2-1,..,3,1  (radon.py:151-162); f is even,
+  // so its DFT is real: F[k] = sum_n f[n] cos(2 pi k n / L); the multiplier is 2 F, stored for all L bins.
+  std::vector<double> f(L, 0.0);
+  f[0] = 0.25;
+  {
+    std::vector<double> nn;
+    for (int v = 1; v < L / 2 + 1; v += 2) nn.push_back(v);
+    for (int v = L / 2 - 1; v > 0; v -= 2) nn.push_back(v);
+    size_t q = 0;
+    for (int k = 1; k < L; k += 2) { const double d = 3.14159265358979323846264338327950288 * nn[q++]; f[k] = -1.0 / (d * d); }
+  }
+  std::vector<float> mult(L);
+  for (int k = 0; k <= L / 2; ++k) {
+    double acc = 0.0;
+    for (int n = 0; n < L; ++n) {
+      double c, s;
+      unit_root((long long)k * n, L, &c, &s);
+      acc += f[n] * c;
+    }
+    mult[k] = (float)(2.0 * acc);
+    if (k > 0 && k < L - k) mult[L - k] = mult[k];
+  }
+  float* d = nullptr;
+  if (cudaMalloc((void**)&d, sizeof(float) * (size_t)L) != cudaSuccess) return set_error(DINVK_ECUDA, "cudaMalloc of ramp table failed");
+  cudaMemcpy(d, mult.data(), sizeof(float) * (size_t)L, cudaMemcpyHostToDevice);
+  g_ramp[key] = d;
+  *out = d;
+  return 0;
+}
+}  // namespace dinvk
+
+extern "C" size_t dinvk_ramp_filter_workspace_bytes(int rows, int N) { (void)rows; (void)N; return 256; }
+
+extern "C" int dinvk_ramp_filter(const float* sino, float* out, int rows, int N, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  DINVK_CHECK_ARG(sino && out && rows >= 0 && N >= 1, "dinvk_ramp_filter: bad arguments");
+  if (rows == 0) return DINVK_OK;
+  DINVK_CHECK_ARG(rows >= 2, "dinvk_ramp_filter: needs at least 2 rows (rows are filtered in pairs)");
+  const int L = ramp_padded_len(N);
+  FftPlan pl;
+  TileCfg cfg;
+  if (!make_fft_plan(L, &pl) || !row_cfg(pl, L, &cfg)) return set_error(DINVK_EUNSUPPORTED, "dinvk_ramp_filter: padded length %d too large", L);
+  Tables tb;
+  int rc;
+  if ((rc = get_tables(L, 0, &tb))) return rc;
+  float* mult = nullptr;
+  if ((rc = get_ramp_table(L, &mult))) return rc;
+  auto run = [&](const float* src, float* dst, int npairs) -> int {
+    PassParams P = PassParams();
+    P.B = npairs; P.H = 1; P.W = L; P.wv = N;
+    P.src_nc = 1; P.src_div = 1; P.dst_nc = 1; P.ncoil = 1;
+    P.p0 = src; P.a0 = 1.f; P.out = dst; P.e0 = 1.f;
+    P.dir1 = -1; P.dir2 = +1;
+    P.gmode = DINVK_G_MASK; P.g = mult; P.gsb = 0; P.gsc = 0; P.gsh = 0; P.g_after = 1;
+    P.tw = tb.tw; P.pre = tb.pre; P.post = tb.post; P.plan = pack_plan(pl);
+    return launch_pass(false, P, cfg, stream);
+  };
+  const int npairs = rows / 2;
+  if ((rc = run(sino, out, npairs))) return rc;
+  if (rows & 1) {
+    // odd count: re-filter the last two rows as a pair (row rows-2 is recomputed identically)
+    const long long off = (long long)(rows - 2) * N;
+    if ((rc = run(sino + off, out + off, 1))) return rc;
   }
   return DINVK_OK;
 }

@@ -211,7 +211,7 @@ def cg_scalars(mode: int, num, den, eps: float, bnorm2=None, tol2: float = 0.0, 
 
 
 def ddrm_update(x_bar, x_bar_prev, y_bar, mask, noise, sigma_t, sigma_prev, sigma_noise, eta, etab, c_sig, eps, init):
-    dev = _require_cuda(y_bar, mask, noise)
+    dev = _require_cuda(y_bar, mask, noise, x_bar, x_bar_prev)
     out = torch.empty_like(y_bar)
     check(get_lib().dinvk_ddrm_update(_p(out), _p(x_bar), _p(x_bar_prev), _p(y_bar), _p(mask), _p(noise), y_bar.numel(),
                                       mask.numel(), sigma_t, sigma_prev, sigma_noise, eta, etab, c_sig, eps, int(init),
@@ -238,3 +238,68 @@ def conv_f32(x, weight, *, kind: int = 0, bias=None, xadd=None, res=None, relu: 
     check(get_lib().dinvk_conv_f32(_p(x), _p(xadd), _p(weight), _p(bias), _p(res), _p(out), B, Cin, Cout, H, W, kind,
                                    int(relu), _stream(dev)))
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# Radon family (sinograms live in angle-major memory (B, C, A, P); see csrc/radon.cu)
+# --------------------------------------------------------------------------------------------
+def radon_fwd(x, P: int, cos_t, sin_t, circle: bool, scale: float) -> torch.Tensor:
+    dev = _require_cuda(x, cos_t, sin_t)
+    x = _f32c(x)
+    B, C, W, _ = x.shape
+    A = cos_t.numel()
+    sino = torch.empty(B, C, A, P, dtype=torch.float32, device=dev)
+    check(get_lib().dinvk_radon_fwd(_p(x), _p(sino), B * C, W, P, A, int(circle), _p(cos_t), _p(sin_t), scale, _stream(dev)))
+    return sino
+
+
+def radon_adj(sino_am, W: int, cos_t, sin_t, circle: bool, scale: float, iradon: bool = False) -> torch.Tensor:
+    """sino_am: (B, C, A, P) contiguous angle-major"""
+    dev = _require_cuda(sino_am, cos_t, sin_t)
+    sino_am = _f32c(sino_am)
+    B, C, A, P = sino_am.shape
+    x = torch.empty(B, C, W, W, dtype=torch.float32, device=dev)
+    fn = get_lib().dinvk_iradon_bp if iradon else get_lib().dinvk_radon_adj
+    check(fn(_p(sino_am), _p(x), B * C, W, P, A, int(circle), _p(cos_t), _p(sin_t), scale, _stream(dev)))
+    return x
+
+
+def ramp_filter(sino_am) -> torch.Tensor:
+    """ramp-filter every detector row of an angle-major sinogram (B, C, A, P)"""
+    dev = _require_cuda(sino_am)
+    sino_am = _f32c(sino_am)
+    P = sino_am.shape[-1]
+    rows = sino_am.numel() // P
+    if rows == 1:  # the kernel filters rows in pairs
+        two = torch.cat([sino_am.reshape(1, P), torch.zeros(1, P, device=dev)], 0)
+        return ramp_filter(two.reshape(1, 1, 2, P))[..., :1, :].reshape(sino_am.shape)
+    out = torch.empty_like(sino_am)
+    check(get_lib().dinvk_ramp_filter(_p(sino_am), _p(out), rows, P, None, 0, _stream(dev)))
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# Blur (direct convolution)
+# --------------------------------------------------------------------------------------------
+def blur_fwd(x, filt, padding: int) -> torch.Tensor:
+    dev = _require_cuda(x, filt)
+    x, filt = _f32c(x), _f32c(filt)
+    B, C, H, W = x.shape
+    FB, FC, h, w = filt.shape
+    shape = (B, C, H - h + 1, W - w + 1) if padding == _ffi.PAD_VALID else (B, C, H, W)
+    y = torch.empty(shape, dtype=torch.float32, device=dev)
+    check(get_lib().dinvk_blur_fwd(_p(x), _p(filt), _p(y), B, C, H, W, FB, FC, h, w, padding, _stream(dev)))
+    return y
+
+
+def blur_adj(y, filt, padding: int, H: int, W: int) -> torch.Tensor:
+    dev = _require_cuda(y, filt)
+    y, filt = _f32c(y), _f32c(filt)
+    B, C = y.shape[:2]
+    FB, FC, h, w = filt.shape
+    x = torch.empty(B, C, H, W, dtype=torch.float32, device=dev)
+    lib = get_lib()
+    nb = lib.dinvk_blur_adj_workspace_bytes(B, C, H, W, h, w, padding)
+    ws = workspace(dev, nb, "blur")
+    check(lib.dinvk_blur_adj(_p(y), _p(filt), _p(x), B, C, H, W, FB, FC, h, w, padding, _p(ws), ws.numel(), _stream(dev)))
+    return x

@@ -116,12 +116,12 @@ int dinvk_spectral(const dinvk_spectral_args* args, void* workspace, size_t work
 /* build + cache the per-size tables now (call once before graph capture) */
 int dinvk_fft_prepare(int n, int centered);
 
-/* Ramp filter of filtered back-projection (deepinv/physics/functional/radon.py:79-162):
- * sino (B*C, N, A) fp32 contiguous, filtered along N after zero-padding to
- * L = max(64, 2^ceil(log2(2N))).  `filt_host` is the real spectrum multiplier of length L/2+1
- * is NOT needed: the library builds 2*rfft(f) itself from the closed form. */
-size_t dinvk_ramp_filter_workspace_bytes(int BC, int N, int A);
-int dinvk_ramp_filter(const float* sino, float* out, int BC, int N, int A,
+/* Ramp filter of filtered back-projection (deepinv/physics/functional/radon.py:79-162): `rows` (>= 2)
+ * signals of length N (contiguous, one per row — the angle-major sinogram memory (B*C*A, P)), each
+ * zero-padded to L = max(64, 2^ceil(log2(2N))), multiplied by 2*rfft(f) with f the reference's spatial ramp
+ * kernel (built by the library in double from the closed form, :151-162), inverse-transformed, cropped to N. */
+size_t dinvk_ramp_filter_workspace_bytes(int rows, int N);
+int dinvk_ramp_filter(const float* sino, float* out, int rows, int N,
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -189,8 +189,11 @@ int dinvk_iradon_bp(const float* sino, float* x, int BC, int W, int P, int A, in
 enum { DINVK_PAD_VALID = 0, DINVK_PAD_CIRCULAR = 1, DINVK_PAD_REPLICATE = 2, DINVK_PAD_REFLECT = 3, DINVK_PAD_CONSTANT = 4 };
 int dinvk_blur_fwd(const float* x, const float* filt, float* y, int B, int C, int H, int W,
                    int FB, int FC, int h, int w, int padding, void* stream);
+/* transpose; replicate/reflect need a workspace for the zero-extended (H+h-1, W+w-1) image that is folded back */
+size_t dinvk_blur_adj_workspace_bytes(int B, int C, int H, int W, int h, int w, int padding);
 int dinvk_blur_adj(const float* y, const float* filt, float* x, int B, int C, int H, int W,
-                   int FB, int FC, int h, int w, int padding, void* stream);
+                   int FB, int FC, int h, int w, int padding,
+                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Denoiser convolutions (deepinv/models/drunet.py:200-210,323-433; dncnn.py:116-131)

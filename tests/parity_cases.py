@@ -1,0 +1,196 @@
+"""Parity cases shared by the CUDA tests (`-m gpu`, real kernels) and the host-logic tests (CPU: the same
+package code driving the emulated kernels).  Every case compares the package's public API with the golden
+vectors produced by the real reference (tests/golden)."""
+import math
+
+import torch
+
+from conftest import load_golden, rel_err
+
+TOL = 1e-5
+
+
+def to_dev(g, dev):
+    return {k: ({kk: vv.to(dev) for kk, vv in v.items()} if isinstance(v, dict) else v.to(dev)) for k, v in g.items()}
+
+
+def load_model(cls, g, dev, **kw):
+    m = cls(pretrained=None, device=dev, **kw)
+    m.load_state_dict(g["sd"], strict=True)
+    return m.eval()
+
+
+def case_mri(name, dev):
+    import deepinv_b200 as dinv
+
+    g = to_dev(load_golden(name), dev)
+    x, y, z, gam = g["x"], g["y"], g["z"], float(g["gamma"])
+    phys = dinv.physics.MRI(mask=g["mask"], img_size=tuple(x.shape[1:]), device=dev)
+    yk = phys.A(x)
+    assert rel_err(yk, y) < TOL
+    assert torch.equal(yk == 0, y == 0)
+    assert rel_err(phys.A_adjoint(y), g["At"]) < TOL
+    assert rel_err(phys.A_adjoint_A(x), g["AtA"]) < TOL
+    assert rel_err(phys.A_A_adjoint(y), g["AAt"]) < TOL
+    assert rel_err(phys.prox_l2(z, y, gam), g["prox"]) < TOL
+    assert rel_err(phys.A_dagger(y), g["dagger"]) < TOL
+    assert rel_err(phys.V_adjoint(x), g["Vt"]) < TOL
+    assert rel_err(phys.V(x), g["V"]) < TOL
+    assert rel_err(phys.A_adjoint(y, mag=True), g["At_mag"]) < TOL
+    assert rel_err(phys.normal_step(x, phys.A_adjoint(y), 0.8), x - 0.8 * (g["AtA"] - g["At"])) < TOL
+    phys2 = dinv.physics.MRI(img_size=tuple(x.shape[1:]), device=dev)  # mask= kwarg is stored (forward.py:249-276)
+    assert rel_err(phys2.A(x, mask=g["mask"]), y) < TOL
+    assert torch.equal(phys2.mask, g["mask"])
+    xr = x.clone().requires_grad_(True)  # autograd: backward of A is A^T
+    phys.A(xr).backward(y)
+    assert rel_err(xr.grad, phys.A_adjoint(y)) < TOL
+
+
+def case_multicoil(name, dev):
+    import deepinv_b200 as dinv
+
+    g = to_dev(load_golden(name), dev)
+    maps = torch.complex(g["maps_re"], g["maps_im"])
+    phys = dinv.physics.MultiCoilMRI(mask=g["mask"], coil_maps=maps, img_size=tuple(g["x"].shape[1:]), device=dev)
+    assert rel_err(phys.A(g["x"]), g["y"]) < TOL
+    assert rel_err(phys.A_adjoint(g["y"]), g["At"]) < TOL
+    if "At_rss" in g:
+        assert rel_err(phys.A_adjoint(g["y"], rss=True), g["At_rss"]) < TOL
+    if "dagger" in g:
+        assert rel_err(phys.A_dagger(g["y"]), g["dagger"]) < 1e-4
+
+
+def case_tomography(name, dev):
+    import deepinv_b200 as dinv
+
+    g = to_dev(load_golden(name), dev)
+    circle = "circle" in name
+    W = g["x"].shape[-1]
+    phys = dinv.physics.Tomography(angles=g["angles"], img_width=W, circle=circle, normalize=False, device=dev)
+    y = phys.A(g["x"])
+    assert y.shape == g["y"].shape and not y.is_contiguous()  # the reference returns the transposed view
+    assert rel_err(y, g["y"]) < TOL
+    assert rel_err(phys.A_adjoint(g["v"]), g["At"]) < TOL
+    assert rel_err(phys.A_dagger(g["y"], fbp=True), g["fbp"]) < TOL
+    physb = dinv.physics.Tomography(angles=g["angles"], img_width=W, circle=circle, normalize=False,
+                                    adjoint_via_backprop=False, device=dev)
+    assert rel_err(physb.A_adjoint(g["v"]), g["At_irad"]) < TOL
+    assert rel_err(physb.A_dagger(g["y"], fbp=True), g["fbp_irad"]) < TOL
+    u, v = torch.randn_like(g["x"]), torch.randn_like(g["y"])
+    lhs, rhs = (phys.A(u) * v).sum().double(), (u * phys.A_adjoint(v)).sum().double()
+    assert abs(float(lhs - rhs)) < 1e-4 * max(1.0, abs(float(lhs)))  # exact transpose (reference asserts 1e-3)
+
+
+def case_tomography_normalised(dev):
+    import deepinv_b200 as dinv
+
+    g = to_dev(load_golden("tomo_16_norm"), dev)
+    phys = dinv.physics.Tomography(angles=g["angles"], img_width=16, normalize=True, device=dev)
+    # the reference's norm depends on the global RNG state at construction: compare ours loosely, then adopt theirs
+    assert abs(float(phys.operator_norm) / float(g["operator_norm"]) - 1) < 2e-2
+    phys.operator_norm = g["operator_norm"].clone()
+    assert rel_err(phys.A(g["x"]), g["y"]) < TOL
+    assert rel_err(phys.A_adjoint(g["y"]), g["At"]) < TOL
+    assert rel_err(phys.A_dagger(g["y"], fbp=True), g["fbp"]) < TOL
+    assert rel_err(phys.A_dagger(g["y"]), g["dagger"]) < 5e-3  # unregularised CG, see tests/test_oracle_golden.py
+
+
+def case_blur(name, dev):
+    import deepinv_b200 as dinv
+
+    g = to_dev(load_golden(name), dev)
+    pad = name.split("_")[-1]
+    phys = dinv.physics.Blur(filter=g["filt"], padding=pad, device=dev)
+    assert rel_err(phys.A(g["x"]), g["y"]) < TOL
+    assert rel_err(phys.A_adjoint(g["v"]), g["At"]) < TOL
+
+
+def case_blur_cg(dev):
+    import deepinv_b200 as dinv
+
+    g = to_dev(load_golden("blur_gauss_circular_prox"), dev)
+    phys = dinv.physics.Blur(filter=g["filt"], padding="circular", device=dev)
+    assert rel_err(phys.prox_l2(g["z"], g["y"], float(g["gamma"])), g["prox"]) < 1e-4
+    assert rel_err(phys.A_dagger(g["y"]), g["dagger"]) < 5e-3
+
+
+def case_blurfft(name, dev):
+    import deepinv_b200 as dinv
+
+    g = to_dev(load_golden(name), dev)
+    x = g["x"]
+    phys = dinv.physics.BlurFFT(img_size=tuple(x.shape[1:]), filter=g["filt"], device=dev)
+    assert rel_err(phys.mask, g["mask"]) < TOL
+    assert rel_err(phys.A(x), g["y"]) < TOL
+    assert rel_err(phys.A_adjoint(g["y"]), g["At"]) < TOL
+    assert rel_err(phys.A_adjoint_A(x), g["AtA"]) < TOL
+    assert rel_err(phys.prox_l2(g["z"], g["y"], float(g["gamma"])), g["prox"]) < TOL
+    assert rel_err(phys.A_dagger(g["y"]), g["dagger"]) < 1e-4
+    assert rel_err(phys.V_adjoint(x), g["Vt"]) < TOL
+    assert rel_err(phys.U_adjoint(x), g["Ut"]) < TOL
+    assert rel_err(phys.V(phys.V_adjoint(x)), x) < TOL
+    assert rel_err(phys.U(phys.mask * phys.V_adjoint(x)), g["y"]) < TOL
+    blur = dinv.physics.Blur(filter=g["filt"], padding="circular", device=dev)  # reference test_blur: Blur == BlurFFT
+    assert rel_err(blur.A(x), g["y"]) < TOL
+
+
+def case_drunet(dev):
+    import deepinv_b200 as dinv
+
+    g = to_dev(load_golden("drunet_tiny"), dev)
+    den = load_model(dinv.models.DRUNet, g, dev, in_channels=2, out_channels=2, nc=(8, 16, 32, 64), nb=2)
+    with torch.no_grad():
+        assert rel_err(den(g["x"], 0.05), g["out"]) < TOL
+        assert rel_err(den(g["x"], g["sig"]), g["out_b"]) < TOL
+        assert rel_err(den(g["xs"], 0.05), g["out_s"]) < TOL
+
+
+def case_dncnn(dev):
+    import deepinv_b200 as dinv
+
+    g = to_dev(load_golden("dncnn_tiny"), dev)
+    den = load_model(dinv.models.DnCNN, g, dev, in_channels=1, out_channels=1, depth=5, nf=8)
+    with torch.no_grad():
+        assert rel_err(den(g["x"], 0.1), g["out"]) < TOL
+
+
+def case_pnp_mri(dev):
+    import deepinv_b200 as dinv
+    from deepinv_b200.optim import ADMM, FISTA, HQS, L2, PGD, PnP
+
+    g = to_dev(load_golden("optim_mri_tiny"), dev)
+    den = load_model(dinv.models.DRUNet, g, dev, in_channels=2, out_channels=2, nc=(8, 16, 32, 64), nb=2)
+    phys = dinv.physics.MRI(mask=g["mask"], img_size=(2, 32, 32), device=dev)
+    y = g["y"]
+    kw = dict(data_fidelity=L2(), prior=PnP(den), early_stop=False)
+    assert rel_err(PGD(stepsize=1.0, sigma_denoiser=0.05, max_iter=4, **kw)(y, phys), g["pgd"]) < TOL
+    relax = PGD(max_iter=3, params_algo={"stepsize": 0.8, "g_param": 0.05, "lambda": 1.0, "beta": 0.9}, **kw)
+    assert rel_err(relax(y, phys), g["pgd_relax"]) < TOL
+    assert rel_err(HQS(stepsize=1.0, sigma_denoiser=0.05, max_iter=3, **kw)(y, phys), g["hqs"]) < TOL
+    assert rel_err(ADMM(stepsize=1.0, sigma_denoiser=0.05, max_iter=3, **kw)(y, phys), g["admm"]) < TOL
+    assert rel_err(FISTA(stepsize=1.0, sigma_denoiser=0.05, max_iter=3, **kw)(y, phys), g["fista"]) < TOL
+    x, m = PGD(stepsize=1.0, sigma_denoiser=0.05, max_iter=2, **kw)(y, phys, compute_metrics=True, x_gt=g["x"])
+    assert len(m["residual"]) == y.shape[0] and len(m["residual"][0]) == 2 and len(m["psnr"][0]) == 3
+
+
+def case_pnp_blur_admm(dev):
+    import deepinv_b200 as dinv
+    from deepinv_b200.optim import ADMM, L2, PnP
+
+    g = to_dev(load_golden("optim_blur_tiny"), dev)
+    den = load_model(dinv.models.DnCNN, g, dev, in_channels=1, out_channels=1, depth=5, nf=8)
+    phys = dinv.physics.Blur(filter=g["filt"], padding="circular", device=dev)
+    out = ADMM(data_fidelity=L2(), prior=PnP(den), stepsize=1.0, sigma_denoiser=0.05, max_iter=3, early_stop=False)(g["y"], phys)
+    assert rel_err(out, g["admm"]) < 1e-4  # three CG solves inside
+
+
+def case_ddrm(dev):
+    import deepinv_b200 as dinv
+
+    g = to_dev(load_golden("ddrm_mri_tiny"), dev)
+    den = load_model(dinv.models.DRUNet, g, dev, in_channels=2, out_channels=2, nc=(8, 16, 32, 64), nb=2)
+    phys = dinv.physics.MRI(mask=g["mask"], img_size=(2, 32, 32), device=dev,
+                            noise_model=dinv.physics.GaussianNoise(sigma=float(g["sigma_noise"])))
+    model = dinv.sampling.DDRM(denoiser=den, sigmas=[float(s) for s in g["sigmas"]])
+    out = model(g["y"], phys, noises=list(g["noises"]))
+    assert rel_err(out, g["out"]) < TOL
