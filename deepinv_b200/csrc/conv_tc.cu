@@ -1,0 +1,499 @@
+// conv_tc.cu — bf16 tensor-core convolutions for the denoisers: tcgen05 implicit GEMM fed by TMA.
+//
+// Replaces the cuDNN/ATen calls behind deepinv/models/drunet.py:200-210 and dncnn.py:116-131 on the
+// throughput path (fp32 parity path: conv_simt.cu).  Activations are NHWC bf16, weights (Cout, taps*Cin)
+// bf16 K-major.  The GEMM view of a 3x3 convolution: M = output pixels, N = output channels,
+// K = 9 taps x Cin; there is no im2col buffer — for each tap the A operand is the same NHWC tensor read
+// through a 4-D TMA box shifted by (dx, dy); out-of-range coordinates are zero-filled by TMA, which IS the
+// zero padding of the convolution.
+//
+// Kernel structure (one persistent CTA per SM, 192 threads):
+//   warp 0   : TMA producer — per (tap, 64-channel block): one 4-D box (64 ch x 16 x x 8 y) of activations
+//              = 128 pixels x 128 B, and one 2-D box (64 k x BN rows) of weights, 128-byte swizzled,
+//              into an mbarrier-guarded ring of shared-memory stages.
+//   warp 1   : MMA issuer — one elected thread issues 4 x tcgen05.mma (M=128, N=BN, K=16) per stage into a
+//              TMEM accumulator (fp32), commits the stage back to the producer; two accumulator buffers
+//              in TMEM so that the epilogue of tile i overlaps the main loop of tile i+1.
+//   warps 2-5: epilogue — tcgen05.ld (32 lanes x 32 columns per warp), + residual(s), ReLU, bf16 pack,
+//              128-bit stores (NHWC), or fp32 NCHW stores for the network tail.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+#include <mutex>
+
+namespace dinvk {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int TC_TX = 16, TC_TY = 8;            // pixel tile: 16 x 8 = 128 GEMM rows
+constexpr int TC_KB = 64;                        // K block: 64 bf16 = 128 B = one swizzle row
+constexpr int TC_A_BYTES = 128 * TC_KB * 2;      // 16 KB
+constexpr int TC_THREADS = 192;
+
+struct ConvTcParams {
+  int B, H, W, Cin, Cout;       // Cout = number of GEMM columns actually stored (real channels)
+  int ntaps, kc_per_tap;
+  int dx[9], dy[9];
+  int tiles_x, tiles_y, n_tiles;
+  int relu;
+  const bf16* res;
+  const bf16* res2;
+  bf16* out;        // NHWC bf16 (B,H,W,Cout) or null
+  float* out_f32;   // NCHW fp32 (B,Cout,H,W) or null (tail)
+  const float* add_f32;  // optional NCHW fp32 term added in tail mode (DnCNN's "+ x")
+  const float* bias;     // optional fp32 bias per output channel (DnCNN), added before the activation
+};
+
+template <int BN>
+struct TcCfg {
+  static constexpr int B_BYTES = BN * TC_KB * 2;
+  static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024;  // + alignment slack
+  static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams P) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  __shared__ __align__(8) uint64_t full_bar[Cfg::STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[Cfg::STAGES];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pixel_tiles = P.B * P.tiles_y * P.tiles_x;
+  const int total_tiles = pixel_tiles * P.n_tiles;
+  const int nk = P.ntaps * P.kc_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull_bar[a], 1); tc::mbar_init(&tempty_bar[a], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_smem);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t / pixel_tiles, pt = t - nt * pixel_tiles;
+        const int b = pt / (P.tiles_y * P.tiles_x), r = pt - b * (P.tiles_y * P.tiles_x);
+        const int y0 = (r / P.tiles_x) * TC_TY, x0 = (r % P.tiles_x) * TC_TX;
+        for (int kb = 0; kb < nk; ++kb) {
+          const int tap = kb / P.kc_per_tap, kc = kb - tap * P.kc_per_tap;
+          tc::mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + TC_A_BYTES;
+          tc::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          tc::tma_load_4d(sa, &tmA, &full_bar[s], kc * TC_KB, x0 + P.dx[tap], y0 + P.dy[tap], b);
+          tc::tma_load_2d(sb, &tmB, &full_bar[s], tap * P.Cin + kc * TC_KB, nt * BN);
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN);
+      int s = 0; uint32_t ph = 0;
+      int acc = 0; uint32_t pa = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        tc::mbar_wait(&tempty_bar[acc], pa ^ 1);
+        tc::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < nk; ++kb) {
+          tc::mbar_wait(&full_bar[s], ph);
+          tc::tc_fence_after();
+          const uint32_t a_addr = tc::smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + TC_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_KB / 16; ++k) {
+            const uint64_t da = tc::make_desc_sw128(a_addr + k * 32, 1024);
+            const uint64_t db = tc::make_desc_sw128(b_addr + k * 32, 1024);
+            tc::umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc::umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
+        tc::umma_commit(&tfull_bar[acc]);  // accumulator complete
+        if (++acc == 2) { acc = 0; pa ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
+    const int q = warp & 3;
+    int acc = 0; uint32_t pa = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nt = t / pixel_tiles, pt = t - nt * pixel_tiles;
+      const int b = pt / (P.tiles_y * P.tiles_x), r = pt - b * (P.tiles_y * P.tiles_x);
+      const int y0 = (r / P.tiles_x) * TC_TY, x0 = (r % P.tiles_x) * TC_TX;
+      const int m = q * 32 + lane;
+      const int y = y0 + m / TC_TX, x = x0 + m % TC_TX;
+      const bool inside = (y < P.H) && (x < P.W);
+      tc::mbar_wait(&tfull_bar[acc], pa);
+      tc::tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      constexpr int CH = (BN >= 32) ? 32 : 16;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += CH) {
+        float v[CH];
+        if constexpr (CH == 32) {
+          uint32_t rr[32];
+          tc::tmem_ld_32x32b_x32(t_addr + c0, rr);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
+        } else {
+          uint32_t rr[16];
+          tc::tmem_ld_32x32b_x16(t_addr + c0, rr);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]);
+        }
+        const int n0 = nt * BN + c0;
+        if (P.bias) {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) v[i] += (n0 + i < P.Cout) ? __ldg(P.bias + n0 + i) : 0.f;
+        }
+        if (inside && n0 < P.Cout) {
+          const long long pix = ((long long)b * P.H + y) * P.W + x;
+          if (P.out_f32) {
+            // network tail: fp32 NCHW, only the real channels
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+              const int c = n0 + i;
+              if (c < P.Cout) {
+                const long long o = (((long long)b * P.Cout + c) * P.H + y) * P.W + x;
+                float val = v[i];
+                if (P.relu) val = fmaxf(val, 0.f);
+                if (P.add_f32) val += __ldg(P.add_f32 + o);
+                P.out_f32[o] = val;
+              }
+            }
+          } else {
+            if (P.relu) {
+#pragma unroll
+              for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            const long long o = pix * P.Cout + n0;
+            if (P.res) {
+              const uint4* rp = reinterpret_cast<const uint4*>(P.res + o);
+#pragma unroll
+              for (int j = 0; j < CH / 8; ++j) {
+                const uint4 u = __ldg(rp + j);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[j * 8 + 2 * e] += f.x; v[j * 8 + 2 * e + 1] += f.y; }
+              }
+            }
+            if (P.res2) {
+              const uint4* rp = reinterpret_cast<const uint4*>(P.res2 + o);
+#pragma unroll
+              for (int j = 0; j < CH / 8; ++j) {
+                const uint4 u = __ldg(rp + j);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[j * 8 + 2 * e] += f.x; v[j * 8 + 2 * e + 1] += f.y; }
+              }
+            }
+            uint4* op = reinterpret_cast<uint4*>(P.out + o);
+#pragma unroll
+            for (int j = 0; j < CH / 8; ++j) {
+              uint4 u;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
+              op[j] = u;
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; pa ^= 1; }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ---- layout converters ---------------------------------------------------------------------------------
+// NCHW fp32 -> NHWC bf16 with channel padding; channel C is filled with the noise level (DRUNet's sigma map)
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, bf16* __restrict__ out, int C, int H, int W,
+                                                           int Cpad, float fill_scalar, const float* __restrict__ fill_batch,
+                                                           int has_fill, long long npix) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long HW = (long long)H * W;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += stride) {
+    const long long b = p / HW, hw = p - b * HW;
+    bf16* o = out + p * Cpad;
+    for (int c0 = 0; c0 < Cpad; c0 += 8) {
+      uint4 u;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float f[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int c = c0 + 2 * e + k;
+          float val = 0.f;
+          if (c < C) val = __ldg(in + (b * C + c) * HW + hw);
+          else if (c == C && has_fill) val = fill_batch ? __ldg(fill_batch + b) : fill_scalar;
+          f[k] = val;
+        }
+        h[e] = __floats2bfloat162_rn(f[0], f[1]);
+      }
+      *reinterpret_cast<uint4*>(o + c0) = u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const bf16* __restrict__ in, const float* __restrict__ add,
+                                                           float* __restrict__ out, int C, int H, int W, int Cpad, long long npix) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long HW = (long long)H * W;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += stride) {
+    const long long b = p / HW, hw = p - b * HW;
+    for (int c = 0; c < C; ++c) {
+      const long long o = (b * C + c) * HW + hw;
+      float v = __bfloat162float(in[p * Cpad + c]);
+      if (add) v += __ldg(add + o);
+      out[o] = v;
+    }
+  }
+}
+
+// ---- 2x2 stride-2 down / transposed up (bf16 NHWC, CUDA cores; < 3 % of DRUNet's FLOPs) -----------------
+// down: out[b,yo,xo,co] = sum_{dy,dx,c} w[co, (dy*2+dx)*Cin + c] * (x + xadd)[b, 2yo+dy, 2xo+dx, c]
+// up  : out[b,2y+dy,2x+dx,co] = sum_c w[(dy*2+dx)*Cout + co, c] * (x + xadd)[b, y, x, c]
+// one CTA: 32 GEMM rows x 64 GEMM columns, K staged through shared memory in chunks of 64
+template <bool UP>
+__global__ void __launch_bounds__(256) conv2x2_bf16_kernel(const bf16* __restrict__ x, const bf16* __restrict__ xadd,
+                                                           const bf16* __restrict__ w, bf16* __restrict__ out, int B, int H, int W,
+                                                           int Cin, int Cout) {
+  constexpr int TM = 32, TN = 64, TK = 64;
+  __shared__ float sA[TK][TM + 1];
+  __shared__ float sW[TK][TN + 1];
+  const int Ho = H / 2, Wo = W / 2;
+  const long long M = UP ? (long long)B * H * W : (long long)B * Ho * Wo;
+  const int N = UP ? 4 * Cout : Cout;
+  const int K = UP ? Cin : 4 * Cin;
+  const long long m0 = (long long)blockIdx.x * TM;
+  const int n0 = blockIdx.y * TN;
+  const int tid = threadIdx.x;
+  const int tm = tid & 31, tn = tid >> 5;  // thread: row tm, columns tn*8 .. tn*8+7
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += TK) {
+    for (int idx = tid; idx < TM * TK; idx += 256) {
+      const int mm = idx / TK, kk = idx - mm * TK;  // k fastest: contiguous channels
+      const long long m = m0 + mm;
+      const int k = k0 + kk;
+      float v = 0.f;
+      if (m < M && k < K) {
+        long long o;
+        if (UP) {
+          o = m * Cin + k;
+        } else {
+          const int xo = (int)(m % Wo), yo = (int)((m / Wo) % Ho);
+          const long long bb = m / ((long long)Wo * Ho);
+          const int tap = k / Cin, c = k - tap * Cin;
+          o = ((bb * H + 2 * yo + (tap >> 1)) * W + 2 * xo + (tap & 1)) * Cin + c;
+        }
+        v = __bfloat162float(x[o]);
+        if (xadd) v += __bfloat162float(xadd[o]);
+      }
+      sA[kk][mm] = v;
+    }
+    for (int idx = tid; idx < TN * TK; idx += 256) {
+      const int nn = idx / TK, kk = idx - nn * TK;
+      const int n = n0 + nn, k = k0 + kk;
+      sW[kk][nn] = (n < N && k < K) ? __bfloat162float(w[(long long)n * K + k]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < TK; ++kk) {
+      const float a = sA[kk][tm];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(a, sW[kk][tn * 8 + i], acc[i]);
+    }
+    __syncthreads();
+  }
+  const long long m = m0 + tm;
+  if (m < M) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = n0 + tn * 8 + i;
+      if (n >= N) continue;
+      long long o;
+      if (UP) {
+        const long long HWl = (long long)H * W;
+        const long long bb = m / HWl, p = m - bb * HWl;
+        const int y = (int)(p / W), xx = (int)(p - (long long)y * W);
+        const int tap = n / Cout, co = n - tap * Cout;
+        o = ((bb * (2 * H) + 2 * y + (tap >> 1)) * (2LL * W) + 2 * xx + (tap & 1)) * Cout + co;
+      } else {
+        o = m * Cout + n;
+      }
+      out[o] = __float2bfloat16(acc[i]);
+    }
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(DINVK_ECUDA, "cuTensorMapEncodeTiled is unavailable");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {TC_KB, TC_TX, TC_TY, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(DINVK_ECUDA, "cuTensorMapEncodeTiled(activations) failed: %d", (int)r);
+  return 0;
+}
+static int make_w_map(CUtensorMap* m, const void* ptr, int K, int rows, int bn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(DINVK_ECUDA, "cuTensorMapEncodeTiled is unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {TC_KB, (cuuint32_t)bn};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(DINVK_ECUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+  return 0;
+}
+
+template <int BN>
+static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParams& P, void* stream) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return set_error(DINVK_ECUDA, "cudaFuncSetAttribute(conv_tc<%d>): %s", BN, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const long long tiles = (long long)P.B * P.tiles_y * P.tiles_x * P.n_tiles;
+  const int grid = (int)std::min<long long>(tiles, sm_count());
+  count_launch();
+  conv_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, (cudaStream_t)stream>>>(tmA, tmB, P);
+  return DINVK_POST_LAUNCH();
+}
+
+static int conv3x3_tc(const void* x, const void* weight, const float* bias, const void* res, const void* res2, void* out,
+                      float* out_f32, const float* add_f32, int B, int H, int W, int Cin, int Cout_real, int rows, int act, void* stream) {
+  DINVK_CHECK_ARG(x && weight && (out || out_f32), "conv3x3_bf16: null pointer");
+  DINVK_CHECK_ARG(B >= 0 && H >= 1 && W >= 1, "conv3x3_bf16: bad shape");
+  DINVK_CHECK_ARG(Cin % 64 == 0 && Cin >= 64, "conv3x3_bf16: Cin=%d must be a multiple of 64", Cin);
+  DINVK_CHECK_ARG(out_f32 || (Cout_real % 64 == 0), "conv3x3_bf16: Cout=%d must be a multiple of 64", Cout_real);
+  if (B == 0) return DINVK_OK;
+  int bn;
+  if (out_f32) bn = 16;
+  else if (rows % 256 == 0) bn = 256;
+  else if (rows % 128 == 0) bn = 128;
+  else bn = 64;
+  DINVK_CHECK_ARG(rows % bn == 0, "conv3x3_bf16: weight rows %d not a multiple of the N tile %d", rows, bn);
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_act_map(&tmA, x, B, H, W, Cin))) return rc;
+  if ((rc = make_w_map(&tmB, weight, 9 * Cin, rows, bn))) return rc;
+  ConvTcParams P;
+  P.B = B; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout_real;
+  P.ntaps = 9; P.kc_per_tap = Cin / TC_KB;
+  for (int t = 0; t < 9; ++t) { P.dx[t] = t % 3 - 1; P.dy[t] = t / 3 - 1; }
+  P.tiles_x = ceil_div(W, TC_TX); P.tiles_y = ceil_div(H, TC_TY); P.n_tiles = rows / bn;
+  P.relu = act; P.res = (const bf16*)res; P.res2 = (const bf16*)res2; P.out = (bf16*)out; P.out_f32 = out_f32; P.add_f32 = add_f32; P.bias = bias;
+  switch (bn) {
+    case 16: return launch_conv_tc<16>(tmA, tmB, P, stream);
+    case 64: return launch_conv_tc<64>(tmA, tmB, P, stream);
+    case 128: return launch_conv_tc<128>(tmA, tmB, P, stream);
+    default: return launch_conv_tc<256>(tmA, tmB, P, stream);
+  }
+}
+
+}  // namespace dinvk
+
+using namespace dinvk;
+
+extern "C" int dinvk_conv3x3_bf16(const void* x, const void* weight, const float* bias, const void* res, const void* res2, void* out,
+                                  int B, int H, int W, int Cin, int Cout, int act, void* stream) {
+  return conv3x3_tc(x, weight, bias, res, res2, out, nullptr, nullptr, B, H, W, Cin, Cout, Cout, act, stream);
+}
+
+extern "C" int dinvk_conv3x3_bf16_tail(const void* x, const void* weight16, const float* bias, const float* add_nchw,
+                                       float* out_nchw, int B, int H, int W, int Cin, int Cout, void* stream) {
+  DINVK_CHECK_ARG(Cout >= 1 && Cout <= 16, "conv3x3_bf16_tail: Cout=%d must be <= 16", Cout);
+  return conv3x3_tc(x, weight16, bias, nullptr, nullptr, nullptr, out_nchw, add_nchw, B, H, W, Cin, Cout, 16, 0, stream);
+}
+
+extern "C" int dinvk_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, int Cpad, float fill_scalar,
+                                           const float* fill_batch, int has_fill, void* stream) {
+  DINVK_CHECK_ARG(in && out && B >= 0 && C >= 1 && Cpad >= C + (has_fill ? 1 : 0) && Cpad % 8 == 0, "nchw_to_nhwc: bad arguments");
+  if (B == 0) return DINVK_OK;
+  const long long npix = (long long)B * H * W;
+  const int grid = (int)std::min<long long>((npix + 255) / 256, (long long)sm_count() * 16);
+  DINVK_LAUNCH(nchw_to_nhwc_kernel, dim3(grid), dim3(256), 0, stream, in, (bf16*)out, C, H, W, Cpad, fill_scalar, fill_batch, has_fill, npix);
+  return DINVK_POST_LAUNCH();
+}
+
+extern "C" int dinvk_nhwc_bf16_to_nchw_f32(const void* in, const float* add, float* out, int B, int C, int H, int W, int Cpad,
+                                           void* stream) {
+  DINVK_CHECK_ARG(in && out && B >= 0 && C >= 1 && Cpad >= C, "nhwc_to_nchw: bad arguments");
+  if (B == 0) return DINVK_OK;
+  const long long npix = (long long)B * H * W;
+  const int grid = (int)std::min<long long>((npix + 255) / 256, (long long)sm_count() * 16);
+  DINVK_LAUNCH(nhwc_to_nchw_kernel, dim3(grid), dim3(256), 0, stream, (const bf16*)in, add, out, C, H, W, Cpad, npix);
+  return DINVK_POST_LAUNCH();
+}
+
+extern "C" int dinvk_conv2x2_down_bf16(const void* x, const void* xadd, const void* weight, void* out, int B, int H, int W, int Cin,
+                                       int Cout, void* stream) {
+  DINVK_CHECK_ARG(x && weight && out && B >= 0 && H % 2 == 0 && W % 2 == 0, "conv2x2_down_bf16: bad arguments");
+  if (B == 0) return DINVK_OK;
+  const long long M = (long long)B * (H / 2) * (W / 2);
+  DINVK_LAUNCH(conv2x2_bf16_kernel<false>, dim3((unsigned)ceil_div(M, 32), ceil_div(Cout, 64)), dim3(256), 0, stream, (const bf16*)x,
+               (const bf16*)xadd, (const bf16*)weight, (bf16*)out, B, H, W, Cin, Cout);
+  return DINVK_POST_LAUNCH();
+}
+
+extern "C" int dinvk_conv2x2_up_bf16(const void* x, const void* xadd, const void* weight, void* out, int B, int H, int W, int Cin,
+                                     int Cout, void* stream) {
+  DINVK_CHECK_ARG(x && weight && out && B >= 0, "conv2x2_up_bf16: bad arguments");
+  if (B == 0) return DINVK_OK;
+  const long long M = (long long)B * H * W;
+  DINVK_LAUNCH(conv2x2_bf16_kernel<true>, dim3((unsigned)ceil_div(M, 32), ceil_div(4 * Cout, 64)), dim3(256), 0, stream, (const bf16*)x,
+               (const bf16*)xadd, (const bf16*)weight, (bf16*)out, B, H, W, Cin, Cout);
+  return DINVK_POST_LAUNCH();
+}

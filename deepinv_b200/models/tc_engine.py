@@ -1,0 +1,118 @@
+"""bf16 tensor-core execution of DRUNet / DnCNN (precision="bf16").
+
+Activations stay NHWC bf16 in HBM between layers; every 3x3 convolution is one launch of the tcgen05
+implicit-GEMM kernel (csrc/conv_tc.cu) with ReLU / residual / U-Net-skip additions fused into its
+epilogue; the network tail writes fp32 NCHW directly.  Weights are repacked once per parameter version
+into the K-major (Cout, taps*Cin) bf16 layout the kernel's TMA descriptors expect.
+
+Numerics: bf16 operands, fp32 accumulation — the same class as PyTorch's default GPU autocast; the fp32
+path (precision="fp32") is the one that matches the reference to 1e-5.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+
+
+def _pack3x3(w: torch.Tensor, cin_pad: int | None = None, rows_pad: int | None = None) -> torch.Tensor:
+    """(Cout, Cin, 3, 3) -> (rows, 9*Cin_pad) bf16 with k = (ky*3+kx)*Cin_pad + c"""
+    co, ci = w.shape[:2]
+    cp = ci if cin_pad is None else cin_pad
+    rp = co if rows_pad is None else rows_pad
+    out = torch.zeros(rp, 3, 3, cp, dtype=torch.float32, device=w.device)
+    out[:co, :, :, :ci] = w.detach().float().permute(0, 2, 3, 1)
+    return out.reshape(rp, 9 * cp).to(torch.bfloat16).contiguous()
+
+
+def _pack_down(w: torch.Tensor) -> torch.Tensor:
+    """(Cout, Cin, 2, 2) -> (Cout, 4*Cin), k = (dy*2+dx)*Cin + c"""
+    return w.detach().float().permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
+
+
+def _pack_up(w: torch.Tensor) -> torch.Tensor:
+    """(Cin, Cout, 2, 2) -> (4*Cout, Cin), row = (dy*2+dx)*Cout + co"""
+    return w.detach().float().permute(2, 3, 1, 0).reshape(-1, w.shape[0]).to(torch.bfloat16).contiguous()
+
+
+def _version_key(model) -> tuple:
+    return tuple((p.data_ptr(), p._version) for p in model.parameters())
+
+
+def _pad64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+class _DrunetPack:
+    def __init__(self, m):
+        nb = m.nb
+        for conv in [m.m_head, m.m_tail]:
+            pass
+        self.key = _version_key(m)
+        self.nc = [m.m_head.weight.shape[0], m.m_down1[nb].weight.shape[0], m.m_down2[nb].weight.shape[0],
+                   m.m_down3[nb].weight.shape[0]]
+        if any(c % 64 for c in self.nc):
+            raise NotImplementedError("precision='bf16' needs channel counts that are multiples of 64 (tensor-core N/K tiles); "
+                                      f"got nc={self.nc}; use precision='fp32'")
+        self.cin0 = m.m_head.weight.shape[1]
+        self.head = _pack3x3(m.m_head.weight, cin_pad=_pad64(self.cin0))
+        self.tail = _pack3x3(m.m_tail.weight, rows_pad=16)
+        self.cout = m.m_tail.weight.shape[0]
+        rb = lambda blocks: [(_pack3x3(b.res[0].weight), _pack3x3(b.res[2].weight)) for b in blocks]
+        self.down = [(rb(list(st)[:nb]), _pack_down(st[nb].weight)) for st in (m.m_down1, m.m_down2, m.m_down3)]
+        self.body = rb(list(m.m_body))
+        self.up = [(_pack_up(st[0].weight), rb(list(st)[1:])) for st in (m.m_up3, m.m_up2, m.m_up1)]
+
+
+def _resblocks(t, blocks, skip=None):
+    """x + conv(relu(conv(x))) chain; `skip` is added to the LAST block's output (the consumer's `x + x_k`)"""
+    for i, (w0, w1) in enumerate(blocks):
+        u = ops.conv3x3_bf16(t, w0, relu=True)
+        t = ops.conv3x3_bf16(u, w1, res=t, res2=skip if i == len(blocks) - 1 else None)
+    return t
+
+
+def drunet_forward_bf16(model, x0: torch.Tensor) -> torch.Tensor:
+    """x0: (B, C+1, H, W) fp32 (noise map already concatenated) -> (B, C_out, H, W) fp32"""
+    pk = model._tc
+    if pk is None or pk.key != _version_key(model):
+        pk = model._tc = _DrunetPack(model)
+    a = ops.nchw_to_nhwc_bf16(x0, _pad64(pk.cin0))
+    x1 = ops.conv3x3_bf16(a, pk.head)
+    skips = [x1]
+    t = x1
+    for blocks, wd in pk.down:
+        t = _resblocks(t, blocks)
+        t = ops.conv2x2_bf16(t, wd, wd.shape[0], up=False)
+        skips.append(t)
+    # skips = [x1, x2, x3, x4]; body output gets + x4, each up stage's output gets the next skip
+    t = _resblocks(t, pk.body, skip=skips[3])
+    for i, (wu, blocks) in enumerate(pk.up):
+        t = ops.conv2x2_bf16(t, wu, wu.shape[0] // 4, up=True)
+        t = _resblocks(t, blocks, skip=skips[2 - i])
+    return ops.conv3x3_bf16_tail(t, pk.tail, pk.cout)
+
+
+class _DncnnPack:
+    def __init__(self, m):
+        self.key = _version_key(m)
+        nf = m.in_conv.weight.shape[0]
+        if nf % 64:
+            raise NotImplementedError("precision='bf16' needs nf to be a multiple of 64; use precision='fp32'")
+        self.cin = m.in_conv.weight.shape[1]
+        self.cout = m.out_conv.weight.shape[0]
+        f32 = lambda b: None if b is None else b.detach().float().contiguous()
+        self.first = (_pack3x3(m.in_conv.weight, cin_pad=_pad64(self.cin)), f32(m.in_conv.bias))
+        self.mid = [(_pack3x3(c.weight), f32(c.bias)) for c in m.conv_list]
+        self.last = (_pack3x3(m.out_conv.weight, rows_pad=16), f32(m.out_conv.bias))
+
+
+def dncnn_forward_bf16(model, x: torch.Tensor) -> torch.Tensor:
+    pk = model._tc
+    if pk is None or pk.key != _version_key(model):
+        pk = model._tc = _DncnnPack(model)
+    t = ops.nchw_to_nhwc_bf16(x, _pad64(pk.cin))
+    t = ops.conv3x3_bf16(t, pk.first[0], bias=pk.first[1], relu=True)
+    for w, b in pk.mid:
+        t = ops.conv3x3_bf16(t, w, bias=b, relu=True)
+    return ops.conv3x3_bf16_tail(t, pk.last[0], pk.cout, bias=pk.last[1], add=x)

@@ -303,3 +303,56 @@ def blur_adj(y, filt, padding: int, H: int, W: int) -> torch.Tensor:
     ws = workspace(dev, nb, "blur")
     check(lib.dinvk_blur_adj(_p(y), _p(filt), _p(x), B, C, H, W, FB, FC, h, w, padding, _p(ws), ws.numel(), _stream(dev)))
     return x
+
+
+# --------------------------------------------------------------------------------------------
+# denoiser convolutions, bf16 tensor-core path (NHWC bf16 activations)
+# --------------------------------------------------------------------------------------------
+def nchw_to_nhwc_bf16(x, cpad: int, fill=None) -> torch.Tensor:
+    """(B,C,H,W) fp32 -> (B,H,W,cpad) bf16; `fill` (float or (B,) tensor) goes to channel C (DRUNet's noise map)"""
+    dev = _require_cuda(x)
+    x = _f32c(x)
+    B, C, H, W = x.shape
+    out = torch.empty(B, H, W, cpad, dtype=torch.bfloat16, device=dev)
+    fb = _f32c(fill) if isinstance(fill, torch.Tensor) else None
+    fs = float(fill) if (fill is not None and fb is None) else 0.0
+    check(get_lib().dinvk_nchw_f32_to_nhwc_bf16(_p(x), _p(out), B, C, H, W, cpad, fs, _p(fb), int(fill is not None), _stream(dev)))
+    return out
+
+
+def nhwc_bf16_to_nchw(x, C: int, add=None) -> torch.Tensor:
+    dev = _require_cuda(x)
+    B, H, W, cpad = x.shape
+    out = torch.empty(B, C, H, W, dtype=torch.float32, device=dev)
+    check(get_lib().dinvk_nhwc_bf16_to_nchw_f32(_p(x), _p(_f32c(add)), _p(out), B, C, H, W, cpad, _stream(dev)))
+    return out
+
+
+def conv3x3_bf16(x, w2d, *, bias=None, res=None, res2=None, relu: bool = False) -> torch.Tensor:
+    """x (B,H,W,Cin) bf16, w2d (Cout, 9*Cin) bf16 -> (B,H,W,Cout) bf16 = act(conv + bias) + res + res2"""
+    dev = _require_cuda(x, w2d)
+    B, H, W, Cin = x.shape
+    Cout = w2d.shape[0]
+    out = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=dev)
+    check(get_lib().dinvk_conv3x3_bf16(_p(x), _p(w2d), _p(bias), _p(res), _p(res2), _p(out), B, H, W, Cin, Cout, int(relu),
+                                       _stream(dev)))
+    return out
+
+
+def conv3x3_bf16_tail(x, w16, cout: int, *, bias=None, add=None) -> torch.Tensor:
+    """network tail: (B,H,W,Cin) bf16 -> (B,cout,H,W) fp32 NCHW (+ bias + add)"""
+    dev = _require_cuda(x, w16)
+    B, H, W, Cin = x.shape
+    out = torch.empty(B, cout, H, W, dtype=torch.float32, device=dev)
+    check(get_lib().dinvk_conv3x3_bf16_tail(_p(x), _p(w16), _p(bias), _p(_f32c(add)), _p(out), B, H, W, Cin, cout, _stream(dev)))
+    return out
+
+
+def conv2x2_bf16(x, w2d, cout: int, *, up: bool, xadd=None) -> torch.Tensor:
+    dev = _require_cuda(x, w2d)
+    B, H, W, Cin = x.shape
+    shape = (B, 2 * H, 2 * W, cout) if up else (B, H // 2, W // 2, cout)
+    out = torch.empty(shape, dtype=torch.bfloat16, device=dev)
+    fn = get_lib().dinvk_conv2x2_up_bf16 if up else get_lib().dinvk_conv2x2_down_bf16
+    check(fn(_p(x), _p(xadd), _p(w2d), _p(out), B, H, W, Cin, cout, _stream(dev)))
+    return out

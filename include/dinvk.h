@@ -209,10 +209,15 @@ int dinvk_conv_f32(const float* x, const float* xadd, const float* weight, const
 
 /* bf16 tensor-core path (tcgen05 implicit GEMM, TMA-fed), NHWC bf16 activations:
  *   x (B,H,W,Cin) bf16, weight (Cout, 9*Cin) bf16 K-major with k = (ky*3+kx)*Cin + c,
- *   out (B,H,W,Cout) bf16;  out = act(conv3x3(x)) + res   (res optional, bf16 NHWC)
- *   Cin, Cout multiples of 64 (host pads the head/tail layers). */
-int dinvk_conv3x3_bf16(const void* x, const void* weight, const void* res, void* out,
-                       int B, int H, int W, int Cin, int Cout, int act, void* stream);
+ *   out (B,H,W,Cout) bf16;  out = act(conv3x3(x) + bias) + res + res2   (bias fp32 (Cout) optional;
+ *   res/res2 optional, bf16 NHWC; res2 carries the U-Net skip that the reference adds before the next
+ *   stage, drunet.py:206-209).  Cin, Cout multiples of 64 (the host pads the head layer's input channels). */
+int dinvk_conv3x3_bf16(const void* x, const void* weight, const float* bias, const void* res, const void* res2,
+                       void* out, int B, int H, int W, int Cin, int Cout, int act, void* stream);
+/* network tail: Cout <= 16 real output channels (weight padded to 16 rows), result written as fp32 NCHW
+ *   out_nchw = conv3x3(x) + bias + add_nchw   (add_nchw optional: DnCNN's "+ x", dncnn.py:138) */
+int dinvk_conv3x3_bf16_tail(const void* x, const void* weight16, const float* bias, const float* add_nchw,
+                            float* out_nchw, int B, int H, int W, int Cin, int Cout, void* stream);
 /* layout converters between the reference's NCHW fp32 and the tensor-core NHWC bf16 layout
  *   nchw_to_nhwc: out[b,h,w,c] = c < C ? in[b,c,h,w] : (c == C ? fill[b] or fill_scalar : 0), c < Cpad
  *   nhwc_to_nchw: out[b,c,h,w] = in[b,h,w,c] (+ add[b,c,h,w] if add), c < C */
