@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace dinvk {
@@ -30,10 +31,17 @@ constexpr int TC_KB = 64;                        // K block: 64 bf16 = 128 B = o
 constexpr int TC_A_BYTES = 128 * TC_KB * 2;      // 16 KB
 constexpr int TC_THREADS = 192;
 
+struct TcMaps {
+  CUtensorMap a[4];  // activation views (3x3 and transposed-up: one; strided 2x2 down: one per tap)
+  CUtensorMap b;     // weights
+};
+
 struct ConvTcParams {
-  int B, H, W, Cin, Cout;       // Cout = number of GEMM columns actually stored (real channels)
+  int B, H, W, Cin, Cout;       // H, W: pixel grid the GEMM rows tile (3x3: image; down: OUTPUT grid; up: INPUT grid)
+                                // Cout = number of output channels actually stored
   int ntaps, kc_per_tap;
-  int dx[9], dy[9];
+  int dx[9], dy[9], amap[9];    // per tap: box shift and which activation view to read
+  int mode;                     // 0: NHWC bf16 same grid; 1: fp32 NCHW tail; 2: 2x up-scatter (GEMM column = tap*Cout + co)
   int tiles_x, tiles_y, n_tiles;
   int relu;
   const bf16* res;
@@ -55,7 +63,7 @@ struct TcCfg {
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams P) {
+conv_tc_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -71,8 +79,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int nk = P.ntaps * P.kc_per_tap;
 
   if (warp == 0 && lane == 0) {
-    tc::prefetch_tmap(&tmA);
-    tc::prefetch_tmap(&tmB);
+    tc::prefetch_tmap(&M.a[0]);
+    tc::prefetch_tmap(&M.b);
     for (int s = 0; s < Cfg::STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull_bar[a], 1); tc::mbar_init(&tempty_bar[a], 4); }
     tc::fence_barrier_init();
@@ -97,8 +105,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + TC_A_BYTES;
           tc::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-          tc::tma_load_4d(sa, &tmA, &full_bar[s], kc * TC_KB, x0 + P.dx[tap], y0 + P.dy[tap], b);
-          tc::tma_load_2d(sb, &tmB, &full_bar[s], tap * P.Cin + kc * TC_KB, nt * BN);
+          tc::tma_load_4d(sa, &M.a[P.amap[tap]], &full_bar[s], kc * TC_KB, x0 + P.dx[tap], y0 + P.dy[tap], b);
+          tc::tma_load_2d(sb, &M.b, &full_bar[s], tap * P.Cin + kc * TC_KB, nt * BN);
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -163,11 +171,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]);
         }
         const int n0 = nt * BN + c0;
+        const int ncols = P.mode == 2 ? 4 * P.Cout : P.Cout;
         if (P.bias) {
 #pragma unroll
           for (int i = 0; i < CH; ++i) v[i] += (n0 + i < P.Cout) ? __ldg(P.bias + n0 + i) : 0.f;
         }
-        if (inside && n0 < P.Cout) {
+        if (inside && n0 < ncols) {
           const long long pix = ((long long)b * P.H + y) * P.W + x;
           if (P.out_f32) {
             // network tail: fp32 NCHW, only the real channels
@@ -187,7 +196,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
             }
-            const long long o = pix * P.Cout + n0;
+            long long o = pix * P.Cout + n0;
+            if (P.mode == 2) {  // transposed 2x2 stride-2: this N tile belongs to one (dy,dx) tap
+              const int tap = n0 / P.Cout;
+              o = (((long long)b * (2 * P.H) + 2 * y + (tap >> 1)) * (2LL * P.W) + 2 * x + (tap & 1)) * P.Cout + (n0 - tap * P.Cout);
+            }
             if (P.res) {
               const uint4* rp = reinterpret_cast<const uint4*>(P.res + o);
 #pragma unroll
@@ -371,11 +384,13 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C) {
+// 4-D activation view (C, X, Y, B) with arbitrary element strides (bytes) — plain NHWC for 3x3 / up, a stride-2
+// sub-lattice of the input for each tap of the 2x2 down-conv
+static int make_act_map(CUtensorMap* m, const void* ptr, int B, int Y, int X, int C, long long sx, long long sy, long long sb) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_error(DINVK_ECUDA, "cuTensorMapEncodeTiled is unavailable");
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)sx, (cuuint64_t)sy, (cuuint64_t)sb};
   cuuint32_t box[4] = {TC_KB, TC_TX, TC_TY, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -397,7 +412,7 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int K, int rows, int bn) 
 }
 
 template <int BN>
-static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParams& P, void* stream) {
+static int launch_conv_tc(const TcMaps& M, const ConvTcParams& P, void* stream) {
   using Cfg = TcCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -408,8 +423,19 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   const long long tiles = (long long)P.B * P.tiles_y * P.tiles_x * P.n_tiles;
   const int grid = (int)std::min<long long>(tiles, sm_count());
   count_launch();
-  conv_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, (cudaStream_t)stream>>>(tmA, tmB, P);
+  conv_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, (cudaStream_t)stream>>>(M, P);
   return DINVK_POST_LAUNCH();
+}
+
+static int pick_bn(int rows) { return rows % 256 == 0 ? 256 : (rows % 128 == 0 ? 128 : 64); }
+
+static int dispatch_conv_tc(int bn, const TcMaps& M, const ConvTcParams& P, void* stream) {
+  switch (bn) {
+    case 16: return launch_conv_tc<16>(M, P, stream);
+    case 64: return launch_conv_tc<64>(M, P, stream);
+    case 128: return launch_conv_tc<128>(M, P, stream);
+    default: return launch_conv_tc<256>(M, P, stream);
+  }
 }
 
 static int conv3x3_tc(const void* x, const void* weight, const float* bias, const void* res, const void* res2, void* out,
@@ -419,28 +445,61 @@ static int conv3x3_tc(const void* x, const void* weight, const float* bias, cons
   DINVK_CHECK_ARG(Cin % 64 == 0 && Cin >= 64, "conv3x3_bf16: Cin=%d must be a multiple of 64", Cin);
   DINVK_CHECK_ARG(out_f32 || (Cout_real % 64 == 0), "conv3x3_bf16: Cout=%d must be a multiple of 64", Cout_real);
   if (B == 0) return DINVK_OK;
-  int bn;
-  if (out_f32) bn = 16;
-  else if (rows % 256 == 0) bn = 256;
-  else if (rows % 128 == 0) bn = 128;
-  else bn = 64;
+  const int bn = out_f32 ? 16 : pick_bn(rows);
   DINVK_CHECK_ARG(rows % bn == 0, "conv3x3_bf16: weight rows %d not a multiple of the N tile %d", rows, bn);
-  CUtensorMap tmA, tmB;
+  TcMaps M;
   int rc;
-  if ((rc = make_act_map(&tmA, x, B, H, W, Cin))) return rc;
-  if ((rc = make_w_map(&tmB, weight, 9 * Cin, rows, bn))) return rc;
+  if ((rc = make_act_map(&M.a[0], x, B, H, W, Cin, (long long)Cin * 2, (long long)W * Cin * 2, (long long)H * W * Cin * 2))) return rc;
+  M.a[1] = M.a[0]; M.a[2] = M.a[0]; M.a[3] = M.a[0];
+  if ((rc = make_w_map(&M.b, weight, 9 * Cin, rows, bn))) return rc;
   ConvTcParams P;
   P.B = B; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout_real;
   P.ntaps = 9; P.kc_per_tap = Cin / TC_KB;
-  for (int t = 0; t < 9; ++t) { P.dx[t] = t % 3 - 1; P.dy[t] = t / 3 - 1; }
+  for (int t = 0; t < 9; ++t) { P.dx[t] = t % 3 - 1; P.dy[t] = t / 3 - 1; P.amap[t] = 0; }
+  P.mode = out_f32 ? 1 : 0;
   P.tiles_x = ceil_div(W, TC_TX); P.tiles_y = ceil_div(H, TC_TY); P.n_tiles = rows / bn;
   P.relu = act; P.res = (const bf16*)res; P.res2 = (const bf16*)res2; P.out = (bf16*)out; P.out_f32 = out_f32; P.add_f32 = add_f32; P.bias = bias;
-  switch (bn) {
-    case 16: return launch_conv_tc<16>(tmA, tmB, P, stream);
-    case 64: return launch_conv_tc<64>(tmA, tmB, P, stream);
-    case 128: return launch_conv_tc<128>(tmA, tmB, P, stream);
-    default: return launch_conv_tc<256>(tmA, tmB, P, stream);
+  return dispatch_conv_tc(bn, M, P, stream);
+}
+
+// 2x2 stride-2 convolution as a 4-tap implicit GEMM: tap (dy,dx) reads the stride-2 sub-lattice of the input that
+// starts at (dy,dx) through its own tensor map; GEMM rows tile the OUTPUT grid
+static int conv2x2_down_tc(const void* x, const void* weight, void* out, int B, int H, int W, int Cin, int Cout, void* stream) {
+  const int Ho = H / 2, Wo = W / 2;
+  const int bn = pick_bn(Cout);
+  TcMaps M;
+  int rc;
+  for (int t = 0; t < 4; ++t) {
+    const char* base = static_cast<const char*>(x) + ((long long)(t >> 1) * W + (t & 1)) * Cin * 2;
+    if ((rc = make_act_map(&M.a[t], base, B, Ho, Wo, Cin, 2LL * Cin * 2, 2LL * W * Cin * 2, (long long)H * W * Cin * 2))) return rc;
   }
+  if ((rc = make_w_map(&M.b, weight, 4 * Cin, Cout, bn))) return rc;
+  ConvTcParams P;
+  P.B = B; P.H = Ho; P.W = Wo; P.Cin = Cin; P.Cout = Cout;
+  P.ntaps = 4; P.kc_per_tap = Cin / TC_KB;
+  for (int t = 0; t < 9; ++t) { P.dx[t] = 0; P.dy[t] = 0; P.amap[t] = t < 4 ? t : 0; }
+  P.mode = 0;
+  P.tiles_x = ceil_div(Wo, TC_TX); P.tiles_y = ceil_div(Ho, TC_TY); P.n_tiles = Cout / bn;
+  P.relu = 0; P.res = nullptr; P.res2 = nullptr; P.out = (bf16*)out; P.out_f32 = nullptr; P.add_f32 = nullptr; P.bias = nullptr;
+  return dispatch_conv_tc(bn, M, P, stream);
+}
+
+// transposed 2x2 stride-2 convolution as a 1-tap GEMM with N = 4*Cout (column = tap*Cout + co) and a scatter epilogue
+static int conv2x2_up_tc(const void* x, const void* weight, void* out, int B, int H, int W, int Cin, int Cout, void* stream) {
+  const int bn = pick_bn(Cout);  // an N tile never spans two taps
+  TcMaps M;
+  int rc;
+  if ((rc = make_act_map(&M.a[0], x, B, H, W, Cin, (long long)Cin * 2, (long long)W * Cin * 2, (long long)H * W * Cin * 2))) return rc;
+  M.a[1] = M.a[0]; M.a[2] = M.a[0]; M.a[3] = M.a[0];
+  if ((rc = make_w_map(&M.b, weight, Cin, 4 * Cout, bn))) return rc;
+  ConvTcParams P;
+  P.B = B; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout;
+  P.ntaps = 1; P.kc_per_tap = Cin / TC_KB;
+  for (int t = 0; t < 9; ++t) { P.dx[t] = 0; P.dy[t] = 0; P.amap[t] = 0; }
+  P.mode = 2;
+  P.tiles_x = ceil_div(W, TC_TX); P.tiles_y = ceil_div(H, TC_TY); P.n_tiles = 4 * Cout / bn;
+  P.relu = 0; P.res = nullptr; P.res2 = nullptr; P.out = (bf16*)out; P.out_f32 = nullptr; P.add_f32 = nullptr; P.bias = nullptr;
+  return dispatch_conv_tc(bn, M, P, stream);
 }
 
 }  // namespace dinvk
@@ -482,6 +541,8 @@ extern "C" int dinvk_conv2x2_down_bf16(const void* x, const void* xadd, const vo
                                        int Cout, void* stream) {
   DINVK_CHECK_ARG(x && weight && out && B >= 0 && H % 2 == 0 && W % 2 == 0, "conv2x2_down_bf16: bad arguments");
   if (B == 0) return DINVK_OK;
+  if (!xadd && Cin % 64 == 0 && Cout % 64 == 0 && !getenv("DINVK_NO_TC_2X2"))
+    return conv2x2_down_tc(x, weight, out, B, H, W, Cin, Cout, stream);
   const long long M = (long long)B * (H / 2) * (W / 2);
   DINVK_LAUNCH(conv2x2_bf16_kernel<false>, dim3((unsigned)ceil_div(M, 32), ceil_div(Cout, 64)), dim3(256), 0, stream, (const bf16*)x,
                (const bf16*)xadd, (const bf16*)weight, (bf16*)out, B, H, W, Cin, Cout);
@@ -492,6 +553,8 @@ extern "C" int dinvk_conv2x2_up_bf16(const void* x, const void* xadd, const void
                                      int Cout, void* stream) {
   DINVK_CHECK_ARG(x && weight && out && B >= 0, "conv2x2_up_bf16: bad arguments");
   if (B == 0) return DINVK_OK;
+  if (!xadd && Cin % 64 == 0 && Cout % 64 == 0 && !getenv("DINVK_NO_TC_2X2"))
+    return conv2x2_up_tc(x, weight, out, B, H, W, Cin, Cout, stream);
   const long long M = (long long)B * H * W;
   DINVK_LAUNCH(conv2x2_bf16_kernel<true>, dim3((unsigned)ceil_div(M, 32), ceil_div(4 * Cout, 64)), dim3(256), 0, stream, (const bf16*)x,
                (const bf16*)xadd, (const bf16*)weight, (bf16*)out, B, H, W, Cin, Cout);

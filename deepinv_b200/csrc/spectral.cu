@@ -20,6 +20,7 @@
 #include "fft_core.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -42,6 +43,7 @@ struct PassParams {
   long long coil_sb; int ncoil;
   // transforms along this pass's axis
   int dir1, dir2;       // 0 none, -1 forward, +1 inverse
+  int centered;         // centred transform (fast path computes the +-1 phases itself; the generic path uses pre/post)
   // pointwise multiplier
   int gmode; int g_at_load; int g_after;
   const float* g; long long gsb, gsc, gsh; float gc; const float* gcb;
@@ -191,6 +193,10 @@ __global__ void __launch_bounds__(NTHR, 1024 / NTHR) spectral_pass_kernel(const 
     }
   }
 }
+
+}  // namespace dinvk
+#include "spectral_fast.cuh"
+namespace dinvk {
 
 // O(N^2) DFT along one axis of an interleaved (B,H,W) tensor — sizes with prime factors > 5.
 // out[k] = N^-1/2 * sum_n in[n] * w^{(k-c)(n-c)}  (c = N/2 when centred, else 0); dir = -1 fwd / +1 inv
@@ -346,7 +352,59 @@ static int launch_pass_t(PassParams& P, const TileCfg& cfg, void* stream) {
   DINVK_LAUNCH(kern, dim3(grid), dim3(NTHR), cfg.smem, stream, P);
   return DINVK_POST_LAUNCH();
 }
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int LOGN, bool COLS, int NTHR, int LINES>
+static int launch_fast_t(PassParams& P, void* stream) {
+  constexpr int N = 1 << LOGN;
+  const size_t smem = COLS ? (size_t)16 * N * sizeof(float2) : (size_t)LINES * (N + (N >> 4) + 1) * sizeof(float2);
+  auto kern = spectral_fast_kernel<LOGN, COLS, NTHR, LINES>;
+  int rc;
+  if ((rc = allow_smem(kern, smem))) return rc;
+  const unsigned grid = COLS ? (unsigned)P.B * (unsigned)(P.W >> 4) : (unsigned)P.B * (unsigned)(P.H / LINES);
+  P.lines = LINES;
+  DINVK_LAUNCH(kern, dim3(grid), dim3(NTHR), smem, stream, P);
+  return DINVK_POST_LAUNCH();
+}
+
+// power-of-two fast path; returns -1 when the pass does not qualify (caller falls back to the generic kernel)
+static int try_launch_fast(bool cols, PassParams& P, void* stream) {
+  static const bool disabled = getenv("DINVK_NO_FAST_FFT") != nullptr;
+  if (disabled) return -1;
+  const int N = cols ? P.H : P.W;
+  if (N < 64 || N > 1024 || (N & (N - 1))) return -1;
+  if (P.wv != P.W || (P.W & 3)) return -1;
+  if (!al16(P.p0) || !al16(P.p1) || !al16(P.q0) || !al16(P.q1) || !al16(P.out) || !al16(P.tin) || !al16(P.tout) || !al16(P.coil) || !al16(P.g)) return -1;
+  if (P.gmode != DINVK_G_NONE && ((P.gsb & 3) || (P.gsc & 3) || (P.gsh & 3))) return -1;
+  if (P.gmode == DINVK_G_CMUL || P.gmode == DINVK_G_CMUL_CONJ) { if ((P.gsb & 1) || (P.gsh & 1)) return -1; }
+  if (((long long)P.H * P.W) & 3) return -1;
+  if (cols) {
+    if (P.W & 15) return -1;
+    switch (N) {
+      case 128: return launch_fast_t<7, true, 128, 16>(P, stream);
+      case 256: return launch_fast_t<8, true, 256, 16>(P, stream);
+      case 512: return launch_fast_t<9, true, 512, 16>(P, stream);
+      case 1024: return launch_fast_t<10, true, 1024, 16>(P, stream);
+      default: return -1;
+    }
+  }
+  const int lines = 4096 / N;
+  if (P.H % lines) return -1;
+  switch (N) {
+    case 64: return launch_fast_t<6, false, 256, 64>(P, stream);
+    case 128: return launch_fast_t<7, false, 256, 32>(P, stream);
+    case 256: return launch_fast_t<8, false, 256, 16>(P, stream);
+    case 512: return launch_fast_t<9, false, 256, 8>(P, stream);
+    case 1024: return launch_fast_t<10, false, 256, 4>(P, stream);
+    default: return -1;
+  }
+}
+
 static int launch_pass(bool cols, PassParams& P, const TileCfg& cfg, void* stream) {
+  if (P.dir1 != 0) {
+    const int rc = try_launch_fast(cols, P, stream);
+    if (rc >= 0) return rc;
+  }
   P.lines = cfg.lines;
   if (cols) {
     switch (cfg.nthr) {
@@ -364,7 +422,7 @@ static int launch_pass(bool cols, PassParams& P, const TileCfg& cfg, void* strea
 
 static void init_pass(PassParams& P, const dinvk_spectral_args& a) {
   P = PassParams();
-  P.B = a.B; P.H = a.H; P.W = a.W; P.wv = a.W;
+  P.B = a.B; P.H = a.H; P.W = a.W; P.wv = a.W; P.centered = a.centered ? 1 : 0;
   P.src_nc = 1; P.src_div = 1; P.dst_nc = 1; P.ncoil = a.ncoil > 1 ? a.ncoil : 1;
   P.a0 = 1.f; P.a1 = 0.f; P.e0 = 1.f; P.e1 = 0.f; P.e2 = 0.f;
   P.gmode = DINVK_G_NONE;

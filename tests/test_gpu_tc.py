@@ -86,8 +86,18 @@ def test_conv2x2_bf16(dev):
     out = ops.conv2x2_bf16(_nhwc(x).to(dev), _pack_down(w.to(dev)), 128, up=False)
     assert rel_err(out.float().permute(0, 3, 1, 2), F.conv2d(x.float(), w.float(), stride=2)) < 4e-3
     wt = (torch.randn(64, 32, 2, 2, generator=gen) / 8).to(torch.bfloat16)
-    out = ops.conv2x2_bf16(_nhwc(x).to(dev), _pack_up(wt.to(dev)), 32, up=True, xadd=_nhwc(xa).to(dev))
+    out = ops.conv2x2_bf16(_nhwc(x).to(dev), _pack_up(wt.to(dev)), 32, up=True, xadd=_nhwc(xa).to(dev))  # CUDA-core variant
     assert rel_err(out.float().permute(0, 3, 1, 2), F.conv_transpose2d(x.float() + xa.float(), wt.float(), stride=2)) < 4e-3
+    # tensor-core variants (channel counts multiples of 64, no fused input add)
+    for (B, Cin, Cout, H, W) in [(2, 64, 128, 16, 32), (1, 128, 256, 32, 16), (2, 256, 512, 8, 16), (1, 64, 64, 18, 34)]:
+        x = torch.randn(B, Cin, H, W, generator=gen).to(torch.bfloat16)
+        w = (torch.randn(Cout, Cin, 2, 2, generator=gen) / (2 * Cin ** 0.5)).to(torch.bfloat16)
+        out = ops.conv2x2_bf16(_nhwc(x).to(dev), _pack_down(w.to(dev)), Cout, up=False)
+        assert rel_err(out.float().permute(0, 3, 1, 2), F.conv2d(x.float(), w.float(), stride=2)) < 4e-3
+        wt = (torch.randn(Cout, Cin, 2, 2, generator=gen) / (Cout ** 0.5)).to(torch.bfloat16)  # (in=Cout, out=Cin)
+        xx = torch.randn(B, Cout, H, W, generator=gen).to(torch.bfloat16)
+        out = ops.conv2x2_bf16(_nhwc(xx).to(dev), _pack_up(wt.to(dev)), Cin, up=True)
+        assert rel_err(out.float().permute(0, 3, 1, 2), F.conv_transpose2d(xx.float(), wt.float(), stride=2)) < 4e-3
 
 
 def test_drunet_bf16_vs_fp32(dev):
