@@ -244,6 +244,217 @@ conv_tc_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P) {
   if (warp == 2) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// 3x3 convolution with HALO REUSE (64- and 128-channel layers).
+//
+// The per-tap kernel above re-reads every activation tile 9 times from L2; ncu shows the 64/128-channel layers are
+// L2-bandwidth bound because of it (lts ~55-58 %, 11-14 TB/s of L2->SM traffic, tensor pipe 24 % / 47 % active).
+// Here one TMA box brings an (18 y) x (16 x) x 64-channel slab (the 16x8 output tile plus its halo; 16 pixels per
+// slab row keeps every 8-row group 1024-byte periodic) into shared memory ONCE per 64-channel block, and the nine
+// taps are nine UMMA descriptors into that same slab: start address shifted by (ky*16 + kx) rows of 128 B,
+// stride between 8-row groups = one slab row (2048 B), descriptor base_offset = kx to re-phase the 128-byte swizzle.
+// L2->SM activation traffic drops 4x (36 KB instead of 144 KB per tile and channel block).  For 64->64 layers the
+// whole weight tensor (9 x 64 x 64 bf16 = 72 KB) stays resident in shared memory for the lifetime of the CTA.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int HL_TX = 8, HL_TY = 16;                 // output tile: 8 x by 16 y (GEMM row m = ty*8 + tx)
+constexpr int HL_SLAB_X = 16, HL_SLAB_Y = HL_TY + 2; // slab box in pixels
+constexpr int HL_SLAB_BYTES = HL_SLAB_X * HL_SLAB_Y * 128;  // 36864
+
+template <int BN, bool RESIDENT>
+struct HaloCfg {
+  static constexpr int B_TILE = BN * 128;
+  static constexpr int A_STAGES = RESIDENT ? 4 : 2;
+  static constexpr int B_STAGES = RESIDENT ? 9 : 8;   // resident: all nine taps; streamed: ring
+  static constexpr int SMEM = A_STAGES * HL_SLAB_BYTES + B_STAGES * B_TILE + 1024;
+  static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+};
+
+template <int BN, bool RESIDENT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, const int use_base_offset) {
+  using Cfg = HaloCfg<BN, RESIDENT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_b = smem + Cfg::A_STAGES * HL_SLAB_BYTES;
+  __shared__ __align__(8) uint64_t afull[Cfg::A_STAGES];
+  __shared__ __align__(8) uint64_t aempty[Cfg::A_STAGES];
+  __shared__ __align__(8) uint64_t bfull[Cfg::B_STAGES];
+  __shared__ __align__(8) uint64_t bempty[Cfg::B_STAGES];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pixel_tiles = P.B * P.tiles_y * P.tiles_x;
+  const int total_tiles = pixel_tiles * P.n_tiles;
+  const int nkc = P.kc_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&M.a[0]);
+    tc::prefetch_tmap(&M.b);
+    for (int s = 0; s < Cfg::A_STAGES; ++s) { tc::mbar_init(&afull[s], 1); tc::mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < Cfg::B_STAGES; ++s) { tc::mbar_init(&bfull[s], 1); tc::mbar_init(&bempty[s], 1); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull_bar[a], 1); tc::mbar_init(&tempty_bar[a], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_smem);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      if (RESIDENT) {  // the whole 3x3 weight tensor, once
+        for (int tap = 0; tap < 9; ++tap) {
+          tc::mbar_arrive_expect_tx(&bfull[tap], Cfg::B_TILE);
+          tc::tma_load_2d(smem_b + tap * Cfg::B_TILE, &M.b, &bfull[tap], tap * P.Cin, 0);
+        }
+      }
+      int sa = 0; uint32_t pha = 0;
+      int sb = 0; uint32_t phb = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t / pixel_tiles, pt = t - nt * pixel_tiles;
+        const int b = pt / (P.tiles_y * P.tiles_x), r = pt - b * (P.tiles_y * P.tiles_x);
+        const int y0 = (r / P.tiles_x) * HL_TY, x0 = (r % P.tiles_x) * HL_TX;
+        for (int kc = 0; kc < nkc; ++kc) {
+          tc::mbar_wait(&aempty[sa], pha ^ 1);
+          tc::mbar_arrive_expect_tx(&afull[sa], HL_SLAB_BYTES);
+          tc::tma_load_4d(smem + sa * HL_SLAB_BYTES, &M.a[0], &afull[sa], kc * TC_KB, x0 - 1, y0 - 1, b);
+          if (++sa == Cfg::A_STAGES) { sa = 0; pha ^= 1; }
+          if (!RESIDENT) {
+            for (int tap = 0; tap < 9; ++tap) {
+              tc::mbar_wait(&bempty[sb], phb ^ 1);
+              tc::mbar_arrive_expect_tx(&bfull[sb], Cfg::B_TILE);
+              tc::tma_load_2d(smem_b + sb * Cfg::B_TILE, &M.b, &bfull[sb], tap * P.Cin + kc * TC_KB, nt * BN);
+              if (++sb == Cfg::B_STAGES) { sb = 0; phb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN);
+      int sa = 0; uint32_t pha = 0;
+      int sb = 0; uint32_t phb = 0;
+      int acc = 0; uint32_t pa = 0;
+      if (RESIDENT) {
+        for (int tap = 0; tap < 9; ++tap) tc::mbar_wait(&bfull[tap], 0);
+      }
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        tc::mbar_wait(&tempty_bar[acc], pa ^ 1);
+        tc::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kc = 0; kc < nkc; ++kc) {
+          tc::mbar_wait(&afull[sa], pha);
+          tc::tc_fence_after();
+          const uint32_t slab = tc::smem_u32(smem + sa * HL_SLAB_BYTES);
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const int ky = tap / 3, kx = tap - ky * 3;
+            uint32_t b_addr;
+            if (RESIDENT) {
+              b_addr = tc::smem_u32(smem_b + tap * Cfg::B_TILE);
+            } else {
+              tc::mbar_wait(&bfull[sb], phb);
+              tc::tc_fence_after();
+              b_addr = tc::smem_u32(smem_b + sb * Cfg::B_TILE);
+            }
+            const uint32_t a_addr = slab + static_cast<uint32_t>((ky * HL_SLAB_X + kx) * 128);
+            const uint32_t boff = use_base_offset ? static_cast<uint32_t>(kx) : 0u;
+#pragma unroll
+            for (int k = 0; k < TC_KB / 16; ++k) {
+              const uint64_t da = tc::make_desc_sw128(a_addr + k * 32, HL_SLAB_X * 128, boff);
+              const uint64_t db = tc::make_desc_sw128(b_addr + k * 32, 1024);
+              tc::umma_bf16(d_tmem, da, db, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+            }
+            if (!RESIDENT) {
+              tc::umma_commit(&bempty[sb]);
+              if (++sb == Cfg::B_STAGES) { sb = 0; phb ^= 1; }
+            }
+          }
+          tc::umma_commit(&aempty[sa]);
+          if (++sa == Cfg::A_STAGES) { sa = 0; pha ^= 1; }
+        }
+        tc::umma_commit(&tfull_bar[acc]);
+        if (++acc == 2) { acc = 0; pa ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int acc = 0; uint32_t pa = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nt = t / pixel_tiles, pt = t - nt * pixel_tiles;
+      const int b = pt / (P.tiles_y * P.tiles_x), r = pt - b * (P.tiles_y * P.tiles_x);
+      const int y0 = (r / P.tiles_x) * HL_TY, x0 = (r % P.tiles_x) * HL_TX;
+      const int m = q * 32 + lane;
+      const int y = y0 + (m >> 3), x = x0 + (m & 7);
+      const bool inside = (y < P.H) && (x < P.W);
+      tc::mbar_wait(&tfull_bar[acc], pa);
+      tc::tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        uint32_t rr[32];
+        tc::tmem_ld_32x32b_x32(t_addr + c0, rr);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
+        const int n0 = nt * BN + c0;
+        if (P.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += __ldg(P.bias + n0 + i);
+        }
+        if (inside) {
+          if (P.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          const long long o = (((long long)b * P.H + y) * P.W + x) * P.Cout + n0;
+          if (P.res) {
+            const uint4* rp = reinterpret_cast<const uint4*>(P.res + o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = __ldg(rp + j);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[j * 8 + 2 * e] += f.x; v[j * 8 + 2 * e + 1] += f.y; }
+            }
+          }
+          if (P.res2) {
+            const uint4* rp = reinterpret_cast<const uint4*>(P.res2 + o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = __ldg(rp + j);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[j * 8 + 2 * e] += f.x; v[j * 8 + 2 * e + 1] += f.y; }
+            }
+          }
+          uint4* op = reinterpret_cast<uint4*>(P.out + o);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
+            op[j] = u;
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; pa ^= 1; }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
 // ---- layout converters ---------------------------------------------------------------------------------
 // NCHW fp32 -> NHWC bf16 with channel padding; channel C is filled with the noise level (DRUNet's sigma map)
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, bf16* __restrict__ out, int C, int H, int W,
@@ -427,6 +638,46 @@ static int launch_conv_tc(const TcMaps& M, const ConvTcParams& P, void* stream) 
   return DINVK_POST_LAUNCH();
 }
 
+static int make_slab_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(DINVK_ECUDA, "cuTensorMapEncodeTiled is unavailable");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {TC_KB, HL_SLAB_X, HL_SLAB_Y, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(DINVK_ECUDA, "cuTensorMapEncodeTiled(slab) failed: %d", (int)r);
+  return 0;
+}
+
+template <int BN, bool RESIDENT>
+static int launch_conv_halo(const TcMaps& M, const ConvTcParams& P, int use_base_offset, void* stream) {
+  using Cfg = HaloCfg<BN, RESIDENT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BN, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return set_error(DINVK_ECUDA, "cudaFuncSetAttribute(conv_tc_halo<%d>): %s", BN, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const long long tiles = (long long)P.B * P.tiles_y * P.tiles_x * P.n_tiles;
+  const int grid = (int)std::min<long long>(tiles, sm_count());
+  count_launch();
+  conv_tc_halo_kernel<BN, RESIDENT><<<grid, TC_THREADS, Cfg::SMEM, (cudaStream_t)stream>>>(M, P, use_base_offset);
+  return DINVK_POST_LAUNCH();
+}
+
+// halo mode: 0 off, 1 on with descriptor base_offset = kx (PTX ISA rule for starts that are not 1024-byte aligned),
+// 2 on with base_offset = 0 (pure address-based swizzle); selectable for validation via DINVK_CONV_HALO
+static int halo_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("DINVK_CONV_HALO");
+    mode = e ? atoi(e) : 1;
+  }
+  return mode;
+}
+
 static int pick_bn(int rows) { return rows % 256 == 0 ? 256 : (rows % 128 == 0 ? 128 : 64); }
 
 static int dispatch_conv_tc(int bn, const TcMaps& M, const ConvTcParams& P, void* stream) {
@@ -449,6 +700,22 @@ static int conv3x3_tc(const void* x, const void* weight, const float* bias, cons
   DINVK_CHECK_ARG(rows % bn == 0, "conv3x3_bf16: weight rows %d not a multiple of the N tile %d", rows, bn);
   TcMaps M;
   int rc;
+  if (!out_f32 && halo_mode() != 0 && ((rows == 64 && Cin == 64) || bn == 128)) {
+    // 64- and 128-channel layers: slab + halo kernel (activations read once per channel block, not once per tap)
+    if ((rc = make_slab_map(&M.a[0], x, B, H, W, Cin))) return rc;
+    M.a[1] = M.a[0]; M.a[2] = M.a[0]; M.a[3] = M.a[0];
+    if ((rc = make_w_map(&M.b, weight, 9 * Cin, rows, bn))) return rc;
+    ConvTcParams P;
+    P.B = B; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout_real;
+    P.ntaps = 9; P.kc_per_tap = Cin / TC_KB;
+    for (int t = 0; t < 9; ++t) { P.dx[t] = t % 3 - 1; P.dy[t] = t / 3 - 1; P.amap[t] = 0; }
+    P.mode = 0;
+    P.tiles_x = ceil_div(W, HL_TX); P.tiles_y = ceil_div(H, HL_TY); P.n_tiles = rows / bn;
+    P.relu = act; P.res = (const bf16*)res; P.res2 = (const bf16*)res2; P.out = (bf16*)out; P.out_f32 = nullptr; P.add_f32 = nullptr; P.bias = bias;
+    const int ubo = halo_mode() == 1 ? 1 : 0;
+    if (bn == 64) return launch_conv_halo<64, true>(M, P, ubo, stream);
+    return launch_conv_halo<128, false>(M, P, ubo, stream);
+  }
   if ((rc = make_act_map(&M.a[0], x, B, H, W, Cin, (long long)Cin * 2, (long long)W * Cin * 2, (long long)H * W * Cin * 2))) return rc;
   M.a[1] = M.a[0]; M.a[2] = M.a[0]; M.a[3] = M.a[0];
   if ((rc = make_w_map(&M.b, weight, 9 * Cin, rows, bn))) return rc;
