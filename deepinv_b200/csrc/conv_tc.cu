@@ -252,7 +252,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P) {
 // Here one TMA box brings an (18 y) x (16 x) x 64-channel slab (the 16x8 output tile plus its halo; 16 pixels per
 // slab row keeps every 8-row group 1024-byte periodic) into shared memory ONCE per 64-channel block, and the nine
 // taps are nine UMMA descriptors into that same slab: start address shifted by (ky*16 + kx) rows of 128 B,
-// stride between 8-row groups = one slab row (2048 B), descriptor base_offset = kx to re-phase the 128-byte swizzle.
+// stride between 8-row groups = one slab row (2048 B).  The 128-byte swizzle is a function of the shared-memory
+// ADDRESS bits [7:9] on both the TMA write and the UMMA read, so a start address that is not 1024-byte aligned needs
+// no descriptor base_offset (measured on B200: base_offset = 0 is bit-correct, base_offset = kx is wrong).
 // L2->SM activation traffic drops 4x (36 KB instead of 144 KB per tile and channel block).  For 64->64 layers the
 // whole weight tensor (9 x 64 x 64 bf16 = 72 KB) stays resident in shared memory for the lifetime of the CTA.
 // ---------------------------------------------------------------------------------------------------------------
@@ -667,8 +669,8 @@ static int launch_conv_halo(const TcMaps& M, const ConvTcParams& P, int use_base
   return DINVK_POST_LAUNCH();
 }
 
-// halo mode: 0 off, 1 on with descriptor base_offset = kx (PTX ISA rule for starts that are not 1024-byte aligned),
-// 2 on with base_offset = 0 (pure address-based swizzle); selectable for validation via DINVK_CONV_HALO
+// halo mode (DINVK_CONV_HALO): 0 = off (per-tap kernel), 1 = on (default; descriptor base_offset 0),
+// 3 = on with base_offset = kx (kept only to document the hardware behaviour: it produces wrong results)
 static int halo_mode() {
   static int mode = -1;
   if (mode < 0) {
@@ -712,7 +714,7 @@ static int conv3x3_tc(const void* x, const void* weight, const float* bias, cons
     P.mode = 0;
     P.tiles_x = ceil_div(W, HL_TX); P.tiles_y = ceil_div(H, HL_TY); P.n_tiles = rows / bn;
     P.relu = act; P.res = (const bf16*)res; P.res2 = (const bf16*)res2; P.out = (bf16*)out; P.out_f32 = nullptr; P.add_f32 = nullptr; P.bias = bias;
-    const int ubo = halo_mode() == 1 ? 1 : 0;
+    const int ubo = halo_mode() == 3 ? 1 : 0;
     if (bn == 64) return launch_conv_halo<64, true>(M, P, ubo, stream);
     return launch_conv_halo<128, false>(M, P, ubo, stream);
   }
