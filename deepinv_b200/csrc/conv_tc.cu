@@ -393,6 +393,23 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
       const int m = q * 32 + lane;
       const int y = y0 + (m >> 3), x = x0 + (m & 7);
       const bool inside = (y < P.H) && (x < P.W);
+      // residual operands are fetched one 32-channel chunk AHEAD of the accumulator reads, starting before the
+      // accumulator is even complete: their HBM latency overlaps the MMA main loop instead of serialising the epilogue
+      const long long obase = (((long long)b * P.H + y) * P.W + x) * P.Cout + (long long)nt * BN;
+      uint4 ra[4], rb[4];
+      auto fetch = [&](int c0, uint4 (&a)[4], uint4 (&bb)[4]) {
+        if (inside && P.res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(P.res + obase + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a[j] = __ldg(rp + j);
+        }
+        if (inside && P.res2) {
+          const uint4* rp = reinterpret_cast<const uint4*>(P.res2 + obase + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bb[j] = __ldg(rp + j);
+        }
+      };
+      fetch(0, ra, rb);
       tc::mbar_wait(&tfull_bar[acc], pa);
       tc::tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
@@ -401,6 +418,8 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
         float v[32];
         uint32_t rr[32];
         tc::tmem_ld_32x32b_x32(t_addr + c0, rr);
+        uint4 na[4], nb[4];
+        if (c0 + 32 < BN) fetch(c0 + 32, na, nb);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
@@ -414,28 +433,23 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
           }
-          const long long o = (((long long)b * P.H + y) * P.W + x) * P.Cout + n0;
           if (P.res) {
-            const uint4* rp = reinterpret_cast<const uint4*>(P.res + o);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 u = __ldg(rp + j);
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&ra[j]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[j * 8 + 2 * e] += f.x; v[j * 8 + 2 * e + 1] += f.y; }
             }
           }
           if (P.res2) {
-            const uint4* rp = reinterpret_cast<const uint4*>(P.res2 + o);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 u = __ldg(rp + j);
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rb[j]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[j * 8 + 2 * e] += f.x; v[j * 8 + 2 * e + 1] += f.y; }
             }
           }
-          uint4* op = reinterpret_cast<uint4*>(P.out + o);
+          uint4* op = reinterpret_cast<uint4*>(P.out + obase + c0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 u;
@@ -444,6 +458,10 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
             for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
             op[j] = u;
           }
+        }
+        if (c0 + 32 < BN) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { ra[j] = na[j]; rb[j] = nb[j]; }
         }
       }
       tc::tc_fence_before();

@@ -16,10 +16,25 @@ dev = torch.device("cuda:0")
 PEAK = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
 
 
+USE_GRAPH = "--graph" in sys.argv
+
+
 def t(fn, iters=10, warmup=3):
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
+    if USE_GRAPH:  # replay a captured call: device time without the Python / ctypes launch path
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            fn()
+        torch.cuda.current_stream().wait_stream(s)
+        with torch.cuda.graph(g):
+            fn()
+        fn = g.replay
+        fn()
+        torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
@@ -38,7 +53,7 @@ def report(name, ms, mb=None, gflop=None):
     print(json.dumps(d), flush=True)
 
 
-which = sys.argv[1:] or ["mri", "tomo", "blur", "mcmri"]
+which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["mri", "tomo", "blur", "mcmri"]
 g = torch.Generator(device=dev).manual_seed(0)
 with torch.no_grad():
     if "mri" in which:
