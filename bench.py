@@ -133,29 +133,43 @@ def cpu_pgd_iteration_seconds(sample_batch: int, repeats: int, threads: int):
     return best
 
 
+def best_cpu_threads(sample: int):
+    """the reference user would run torch's default (= all cores); MKL-DNN convolutions on a handful of images do not
+    scale to 100+ threads, so the CPU arm reports the BEST of a few thread counts (the count used is reported)"""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({ncpu, max(1, ncpu // 2), max(1, ncpu // 4), min(ncpu, 32), min(ncpu, 16)}, reverse=True)
+    best = (float("inf"), ncpu)
+    for th in cands:
+        t = cpu_pgd_iteration_seconds(sample, 1, th)
+        if t < best[0]:
+            best = (t, th)
+    return best[1]
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    sample = 2
+    sample = 4
+    threads = best_cpu_threads(sample)
     # warm-up + K timed "steps", each a bounded sample (one iteration on `sample` images)
     for _ in range(max(args.warmup, 0)):
         cpu_pgd_iteration_seconds(sample, 1, threads)
     ts = [cpu_pgd_iteration_seconds(sample, 1, threads) for _ in range(max(args.steps, 1))]
     t = sum(ts) / len(ts)
     per_img = t / sample
-    its = 1.0 / (per_img * BATCH * args.gpus)  # whole-job batch = 64 per GPU
-    value = its * args.gpus
+    value = 1.0 / (per_img * BATCH)  # every rank's shard is 64 images; the CPU arm runs them one shard after another
+    value_job = value  # whole job at N GPUs = N shards on the same host: N x the work, N x the time
     line = {
-        "impl": "reference", "metric": "pnp_pgd_iterations_per_s", "value": value, "unit": "it/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True,
+        "impl": "reference", "metric": "pnp_pgd_iterations_per_s", "value": value_job, "unit": "it/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value_job, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "MRI 4x Cartesian-mask 256x256, PnP-PGD + DRUNet, batch=64 per GPU", "global_batch": BATCH * args.gpus,
                    "parallelism": f"dp{args.gpus}"},
-        "cpu_baseline": {"value": value, "unit": "it/s", "cores": threads, "kind": "port",
-                         "sample": f"one PnP-PGD iteration on {sample} of the 64 images per step, scaled linearly per image"},
-        "e2e": {"value": value, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {"value": value_job, "unit": "it/s", "cores": threads, "kind": "port",
+                         "sample": f"one PnP-PGD iteration of the oracle (torch-CPU restatement of the reference path) on {sample} "
+                                   f"of the 64 images per step, scaled linearly per image; best of thread counts, {threads} used"},
+        "e2e": {"value": value_job, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
@@ -292,10 +306,11 @@ def run_b200(args):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            t = cpu_pgd_iteration_seconds(2, 2, threads)
-            cpu = {"value": 1.0 / (t / 2 * BATCH), "unit": "it/s", "cores": threads, "kind": "port",
-                   "sample": "one PnP-PGD iteration of the oracle on 2 of the 64 images (best of 2), scaled linearly per image"}
+            threads = best_cpu_threads(4)
+            t = cpu_pgd_iteration_seconds(4, 2, threads)
+            cpu = {"value": 1.0 / (t / 4 * BATCH), "unit": "it/s", "cores": threads, "kind": "port",
+                   "sample": "one PnP-PGD iteration of the oracle on 4 of the 64 images (best of 2, best of thread counts), "
+                             "scaled linearly per image"}
         line = {
             "metric": "pnp_pgd_iterations_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
