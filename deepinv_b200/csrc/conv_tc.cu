@@ -265,9 +265,10 @@ constexpr int HL_SLAB_BYTES = HL_SLAB_X * HL_SLAB_Y * 128;  // 36864
 template <int BN, bool RESIDENT>
 struct HaloCfg {
   static constexpr int B_TILE = BN * 128;
-  static constexpr int A_STAGES = RESIDENT ? 4 : 2;
-  static constexpr int B_STAGES = RESIDENT ? 9 : 8;   // resident: all nine taps; streamed: ring
-  static constexpr int SMEM = A_STAGES * HL_SLAB_BYTES + B_STAGES * B_TILE + 1024;
+  static constexpr int A_STAGES = 2;
+  static constexpr int B_STAGES = RESIDENT ? 9 : 5;   // resident: all nine taps; streamed: ring
+  static constexpr int SCRATCH = 4 * 3 * 4096;        // per epilogue warp: 32 rows x 128 B for out, res, res2
+  static constexpr int SMEM = A_STAGES * HL_SLAB_BYTES + B_STAGES * B_TILE + SCRATCH + 1024;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
 };
 
@@ -393,76 +394,92 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
       const int m = q * 32 + lane;
       const int y = y0 + (m >> 3), x = x0 + (m & 7);
       const bool inside = (y < P.H) && (x < P.W);
-      // residual operands are fetched one 32-channel chunk AHEAD of the accumulator reads, starting before the
-      // accumulator is even complete: their HBM latency overlaps the MMA main loop instead of serialising the epilogue
-      const long long obase = (((long long)b * P.H + y) * P.W + x) * P.Cout + (long long)nt * BN;
-      uint4 ra[4], rb[4];
-      auto fetch = [&](int c0, uint4 (&a)[4], uint4 (&bb)[4]) {
-        if (inside && P.res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(P.res + obase + c0);
+      // Warp-local transpose through shared memory: a lane owns one pixel ROW of the accumulator (TMEM lane), but a
+      // coalesced global access needs 8 consecutive lanes on one pixel's 128 bytes (64 channels).  Each warp owns 32
+      // pixels = 4 image rows x 8 x, i.e. four 1 KB contiguous runs in the NHWC tensor; residuals are loaded and the
+      // result stored with 512-byte-contiguous warp instructions, the row<->chunk exchange happens in a 4 KB
+      // per-warp scratch with the usual 16-byte XOR swizzle.  Residual loads are issued BEFORE the accumulator is
+      // complete, so their HBM latency overlaps the MMA main loop.
+      uint8_t* scr = smem_b + Cfg::B_STAGES * Cfg::B_TILE + q * (3 * 4096);
+      uint4* s_out = reinterpret_cast<uint4*>(scr);
+      uint4* s_r1 = reinterpret_cast<uint4*>(scr + 4096);
+      uint4* s_r2 = reinterpret_cast<uint4*>(scr + 8192);
+      const int cch = lane & 7;            // 16-byte chunk (8 channels) this lane moves in the coalesced phases
+      long long goff[8];                   // global element offset of (row r = i*4 + lane/8, chunk cch), -1 if outside
 #pragma unroll
-          for (int j = 0; j < 4; ++j) a[j] = __ldg(rp + j);
-        }
-        if (inside && P.res2) {
-          const uint4* rp = reinterpret_cast<const uint4*>(P.res2 + obase + c0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) bb[j] = __ldg(rp + j);
-        }
-      };
-      fetch(0, ra, rb);
-      tc::mbar_wait(&tfull_bar[acc], pa);
-      tc::tc_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + (lane >> 3);
+        const int mm = q * 32 + r;
+        const int yy = y0 + (mm >> 3), xx = x0 + (mm & 7);
+        goff[i] = (yy < P.H && xx < P.W) ? ((((long long)b * P.H + yy) * P.W + xx) * P.Cout + (long long)nt * BN + cch * 8) : -1;
+      }
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        float v[32];
-        uint32_t rr[32];
-        tc::tmem_ld_32x32b_x32(t_addr + c0, rr);
-        uint4 na[4], nb[4];
-        if (c0 + 32 < BN) fetch(c0 + 32, na, nb);
-        tc::tmem_ld_wait();
+      for (int nb = 0; nb < BN; nb += 64) {
+        if (P.res) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
-        const int n0 = nt * BN + c0;
-        if (P.bias) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += __ldg(P.bias + n0 + i);
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + (lane >> 3);
+            if (goff[i] >= 0) s_r1[r * 8 + (cch ^ (r & 7))] = __ldg(reinterpret_cast<const uint4*>(P.res + goff[i] + nb));
+          }
         }
-        if (inside) {
+        if (P.res2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + (lane >> 3);
+            if (goff[i] >= 0) s_r2[r * 8 + (cch ^ (r & 7))] = __ldg(reinterpret_cast<const uint4*>(P.res2 + goff[i] + nb));
+          }
+        }
+        if (nb == 0) {
+          tc::mbar_wait(&tfull_bar[acc], pa);
+          tc::tc_fence_after();
+        }
+        __syncwarp();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + nb);
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          float v[32];
+          uint32_t rr[32];
+          tc::tmem_ld_32x32b_x32(t_addr + c0, rr);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
+          if (P.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += __ldg(P.bias + nt * BN + nb + c0 + i);
+          }
           if (P.relu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
           }
-          if (P.res) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&ra[j]);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[j * 8 + 2 * e] += f.x; v[j * 8 + 2 * e + 1] += f.y; }
-            }
-          }
-          if (P.res2) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rb[j]);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[j * 8 + 2 * e] += f.x; v[j * 8 + 2 * e + 1] += f.y; }
-            }
-          }
-          uint4* op = reinterpret_cast<uint4*>(P.out + obase + c0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            uint4 u;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+            const int ch = (c0 >> 3) + j;  // logical 16-byte chunk of this lane's own row
+            if (P.res) {
+              const uint4 u = s_r1[lane * 8 + (ch ^ (lane & 7))];
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
-            op[j] = u;
+              for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[j * 8 + 2 * e] += f.x; v[j * 8 + 2 * e + 1] += f.y; }
+            }
+            if (P.res2) {
+              const uint4 u = s_r2[lane * 8 + (ch ^ (lane & 7))];
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[j * 8 + 2 * e] += f.x; v[j * 8 + 2 * e + 1] += f.y; }
+            }
+            uint4 o4;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
+            s_out[lane * 8 + (ch ^ (lane & 7))] = o4;
           }
         }
-        if (c0 + 32 < BN) {
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 4; ++j) { ra[j] = na[j]; rb[j] = nb[j]; }
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + (lane >> 3);
+          if (goff[i] >= 0) *reinterpret_cast<uint4*>(P.out + goff[i] + nb) = s_out[r * 8 + (cch ^ (r & 7))];
         }
+        __syncwarp();
       }
       tc::tc_fence_before();
       __syncwarp();
