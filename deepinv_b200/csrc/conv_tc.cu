@@ -262,20 +262,23 @@ constexpr int HL_TX = 8, HL_TY = 16;                 // output tile: 8 x by 16 y
 constexpr int HL_SLAB_X = 16, HL_SLAB_Y = HL_TY + 2; // slab box in pixels
 constexpr int HL_SLAB_BYTES = HL_SLAB_X * HL_SLAB_Y * 128;  // 36864
 
-template <int BN, bool RESIDENT>
+// AST: activation slabs in flight; BST: weight tiles in the ring (streamed mode); EPI: 0 = direct per-row epilogue with
+// register prefetch of the residuals, 1 = coalesced epilogue through a per-warp swizzled transpose scratch
+template <int BN, bool RESIDENT, int AST, int BST, int EPI>
 struct HaloCfg {
   static constexpr int B_TILE = BN * 128;
-  static constexpr int A_STAGES = 2;
-  static constexpr int B_STAGES = RESIDENT ? 9 : 5;   // resident: all nine taps; streamed: ring
-  static constexpr int SCRATCH = 4 * 3 * 4096;        // per epilogue warp: 32 rows x 128 B for out, res, res2
+  static constexpr int A_STAGES = AST;
+  static constexpr int B_STAGES = RESIDENT ? 9 : BST;
+  static constexpr int SCRATCH = EPI ? 4 * 2 * 4096 : 0;  // per epilogue warp: 32 rows x 128 B for out and res
   static constexpr int SMEM = A_STAGES * HL_SLAB_BYTES + B_STAGES * B_TILE + SCRATCH + 1024;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
 };
 
-template <int BN, bool RESIDENT>
+template <int BN, bool RESIDENT, int AST, int BST, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, const int use_base_offset) {
-  using Cfg = HaloCfg<BN, RESIDENT>;
+  using Cfg = HaloCfg<BN, RESIDENT, AST, BST, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_b = smem + Cfg::A_STAGES * HL_SLAB_BYTES;
@@ -394,16 +397,16 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
       const int m = q * 32 + lane;
       const int y = y0 + (m >> 3), x = x0 + (m & 7);
       const bool inside = (y < P.H) && (x < P.W);
+      if constexpr (EPI == 1) {
       // Warp-local transpose through shared memory: a lane owns one pixel ROW of the accumulator (TMEM lane), but a
       // coalesced global access needs 8 consecutive lanes on one pixel's 128 bytes (64 channels).  Each warp owns 32
       // pixels = 4 image rows x 8 x, i.e. four 1 KB contiguous runs in the NHWC tensor; residuals are loaded and the
       // result stored with 512-byte-contiguous warp instructions, the row<->chunk exchange happens in a 4 KB
       // per-warp scratch with the usual 16-byte XOR swizzle.  Residual loads are issued BEFORE the accumulator is
       // complete, so their HBM latency overlaps the MMA main loop.
-      uint8_t* scr = smem_b + Cfg::B_STAGES * Cfg::B_TILE + q * (3 * 4096);
+      uint8_t* scr = smem_b + Cfg::B_STAGES * Cfg::B_TILE + q * (2 * 4096);
       uint4* s_out = reinterpret_cast<uint4*>(scr);
       uint4* s_r1 = reinterpret_cast<uint4*>(scr + 4096);
-      uint4* s_r2 = reinterpret_cast<uint4*>(scr + 8192);
       const int cch = lane & 7;            // 16-byte chunk (8 channels) this lane moves in the coalesced phases
       long long goff[8];                   // global element offset of (row r = i*4 + lane/8, chunk cch), -1 if outside
 #pragma unroll
@@ -420,13 +423,6 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
           for (int i = 0; i < 8; ++i) {
             const int r = i * 4 + (lane >> 3);
             if (goff[i] >= 0) s_r1[r * 8 + (cch ^ (r & 7))] = __ldg(reinterpret_cast<const uint4*>(P.res + goff[i] + nb));
-          }
-        }
-        if (P.res2) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = i * 4 + (lane >> 3);
-            if (goff[i] >= 0) s_r2[r * 8 + (cch ^ (r & 7))] = __ldg(reinterpret_cast<const uint4*>(P.res2 + goff[i] + nb));
           }
         }
         if (nb == 0) {
@@ -460,8 +456,8 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
 #pragma unroll
               for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[j * 8 + 2 * e] += f.x; v[j * 8 + 2 * e + 1] += f.y; }
             }
-            if (P.res2) {
-              const uint4 u = s_r2[lane * 8 + (ch ^ (lane & 7))];
+            if (P.res2 && inside) {  // the U-Net skip (6 of 58 layers): read directly from global memory
+              const uint4 u = __ldg(reinterpret_cast<const uint4*>(P.res2 + (((long long)b * P.H + y) * P.W + x) * P.Cout + (long long)nt * BN + nb + c0) + j);
               const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
               for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[j * 8 + 2 * e] += f.x; v[j * 8 + 2 * e + 1] += f.y; }
@@ -480,6 +476,79 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
           if (goff[i] >= 0) *reinterpret_cast<uint4*>(P.out + goff[i] + nb) = s_out[r * 8 + (cch ^ (r & 7))];
         }
         __syncwarp();
+      }
+      } else {
+      // residual operands are fetched one 32-channel chunk AHEAD of the accumulator reads, starting before the
+      // accumulator is even complete: their HBM latency overlaps the MMA main loop instead of serialising the epilogue
+      const long long obase = (((long long)b * P.H + y) * P.W + x) * P.Cout + (long long)nt * BN;
+      uint4 ra[4], rb[4];
+      auto fetch = [&](int c0, uint4 (&a)[4], uint4 (&bb)[4]) {
+        if (inside && P.res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(P.res + obase + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a[j] = __ldg(rp + j);
+        }
+        if (inside && P.res2) {
+          const uint4* rp = reinterpret_cast<const uint4*>(P.res2 + obase + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bb[j] = __ldg(rp + j);
+        }
+      };
+      fetch(0, ra, rb);
+      tc::mbar_wait(&tfull_bar[acc], pa);
+      tc::tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        uint32_t rr[32];
+        tc::tmem_ld_32x32b_x32(t_addr + c0, rr);
+        uint4 na[4], nb[4];
+        if (c0 + 32 < BN) fetch(c0 + 32, na, nb);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
+        const int n0 = nt * BN + c0;
+        if (P.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += __ldg(P.bias + n0 + i);
+        }
+        if (inside) {
+          if (P.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (P.res) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&ra[j]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[j * 8 + 2 * e] += f.x; v[j * 8 + 2 * e + 1] += f.y; }
+            }
+          }
+          if (P.res2) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rb[j]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[j * 8 + 2 * e] += f.x; v[j * 8 + 2 * e + 1] += f.y; }
+            }
+          }
+          uint4* op = reinterpret_cast<uint4*>(P.out + obase + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
+            op[j] = u;
+          }
+        }
+        if (c0 + 32 < BN) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { ra[j] = na[j]; rb[j] = nb[j]; }
+        }
+      }
       }
       tc::tc_fence_before();
       __syncwarp();
@@ -688,19 +757,19 @@ static int make_slab_map(CUtensorMap* m, const void* ptr, int B, int H, int W, i
   return 0;
 }
 
-template <int BN, bool RESIDENT>
+template <int BN, bool RESIDENT, int AST, int BST, int EPI>
 static int launch_conv_halo(const TcMaps& M, const ConvTcParams& P, int use_base_offset, void* stream) {
-  using Cfg = HaloCfg<BN, RESIDENT>;
+  using Cfg = HaloCfg<BN, RESIDENT, AST, BST, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BN, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BN, RESIDENT, AST, BST, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return set_error(DINVK_ECUDA, "cudaFuncSetAttribute(conv_tc_halo<%d>): %s", BN, cudaGetErrorString(e));
     attr_set = true;
   }
   const long long tiles = (long long)P.B * P.tiles_y * P.tiles_x * P.n_tiles;
   const int grid = (int)std::min<long long>(tiles, sm_count());
   count_launch();
-  conv_tc_halo_kernel<BN, RESIDENT><<<grid, TC_THREADS, Cfg::SMEM, (cudaStream_t)stream>>>(M, P, use_base_offset);
+  conv_tc_halo_kernel<BN, RESIDENT, AST, BST, EPI><<<grid, TC_THREADS, Cfg::SMEM, (cudaStream_t)stream>>>(M, P, use_base_offset);
   return DINVK_POST_LAUNCH();
 }
 
@@ -750,8 +819,19 @@ static int conv3x3_tc(const void* x, const void* weight, const float* bias, cons
     P.tiles_x = ceil_div(W, HL_TX); P.tiles_y = ceil_div(H, HL_TY); P.n_tiles = rows / bn;
     P.relu = act; P.res = (const bf16*)res; P.res2 = (const bf16*)res2; P.out = (bf16*)out; P.out_f32 = nullptr; P.add_f32 = nullptr; P.bias = bias;
     const int ubo = halo_mode() == 3 ? 1 : 0;
-    if (bn == 64) return launch_conv_halo<64, true>(M, P, ubo, stream);
-    return launch_conv_halo<128, false>(M, P, ubo, stream);
+    static const int variant = getenv("DINVK_HALO_VARIANT") ? atoi(getenv("DINVK_HALO_VARIANT")) : 0;
+    if (bn == 64) {
+      switch (variant) {
+        case 1: return launch_conv_halo<64, true, 2, 0, 0>(M, P, ubo, stream);
+        case 2: return launch_conv_halo<64, true, 3, 0, 1>(M, P, ubo, stream);
+        default: return launch_conv_halo<64, true, 4, 0, 0>(M, P, ubo, stream);
+      }
+    }
+    switch (variant) {
+      case 1: return launch_conv_halo<128, false, 2, 5, 0>(M, P, ubo, stream);
+      case 2: return launch_conv_halo<128, false, 2, 6, 1>(M, P, ubo, stream);
+      default: return launch_conv_halo<128, false, 2, 8, 0>(M, P, ubo, stream);
+    }
   }
   if ((rc = make_act_map(&M.a[0], x, B, H, W, Cin, (long long)Cin * 2, (long long)W * Cin * 2, (long long)H * W * Cin * 2))) return rc;
   M.a[1] = M.a[0]; M.a[2] = M.a[0]; M.a[3] = M.a[0];
