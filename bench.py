@@ -227,10 +227,20 @@ def run_b200(args):
     def iteration(X, it):
         return algo.single_iteration(X, it, y, physics)
 
+    graphed = None
     with torch.no_grad():
         X = algo.init_iterate_fn(y, physics)
         for it in range(args.warmup):
             X = iteration(X, it)
+        if not args.no_graph:
+            try:  # replay the same public-API iteration from a CUDA graph (no Python / ctypes launch path in the loop)
+                from deepinv_b200.optim import GraphedIteration
+
+                graphed = GraphedIteration(algo, y, physics, X=X)
+                graphed.run(args.warmup)
+            except Exception as exc:  # noqa: BLE001
+                print(f"bench.py: CUDA-graph capture unavailable ({exc}); timing the eager loop", file=sys.stderr)
+                graphed = None
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -241,9 +251,12 @@ def run_b200(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        for it in range(args.steps):
-            X = iteration(X, it)
-        x_hat = X["est"][0]
+        if graphed is not None:
+            x_hat = graphed.run(args.steps)
+        else:
+            for it in range(args.steps):
+                X = iteration(X, it)
+            x_hat = X["est"][0]
         if world > 1:  # the only collective of the path: gather the final reconstructions
             gathered = torch.empty(world * BATCH, 2, H, W, device=dev)
             dist.all_gather_into_tensor(gathered, x_hat.contiguous())
@@ -251,6 +264,8 @@ def run_b200(args):
         torch.cuda.synchronize()
         ms_total = e0.elapsed_time(e1)
         launches = lib.dinvk_launch_count() - launches0
+        if graphed is not None:
+            launches = graphed.launches_per_step * args.steps
         clk = clocks.stop() if rank == 0 else None
         if world > 1:
             t = torch.tensor([ms_total], device=dev)
@@ -280,7 +295,7 @@ def run_b200(args):
         # ---- roofline of the dominant kernel family + per-operator HBM fractions (rank 0) ----------
         roof, ops_report = None, None
         if rank == 0:
-            z = X["est"][0]
+            z = x_hat
             ms_den = time_cuda(lambda: den(z, SIGMA_DEN), max(2, min(args.steps, 5)), warmup=1)
             tflops = DRUNET_GFLOP_PER_IMAGE * BATCH / ms_den  # GFLOP / ms = TFLOP/s
             peak = peaks["bf16_tflops_sustained"]
@@ -289,7 +304,7 @@ def run_b200(args):
                     "peak_source": peaks["source"] + " bf16 sustained", "ms_per_step": ms_den,
                     "algorithmic_gflop_per_step": DRUNET_GFLOP_PER_IMAGE * BATCH}
             aty = physics.A_adjoint(y)
-            xx = X["est"][0]
+            xx = x_hat
             img_mb = BATCH * 2 * H * W * 4 / 1e6
             cases = [
                 ("MRI.A (2-D FFT + mask)", lambda: physics.A(xx), 2 * img_mb),
@@ -317,7 +332,7 @@ def run_b200(args):
             "dtype": "bf16 denoiser GEMMs (fp32 accumulate) + f32 operators" if args.precision == "bf16" else "f32",
             "data": "synthetic",
             "config": {"workload": "MRI 4x Cartesian-mask 256x256, PnP-PGD + DRUNet, batch=64 per GPU",
-                       "global_batch": BATCH * world, "parallelism": f"dp{world}", "denoiser_precision": args.precision,
+                       "global_batch": BATCH * world, "parallelism": f"dp{world}", "denoiser_precision": args.precision, "cuda_graph": graphed is not None,
                        "l2_policy": "per-step working set (>= 1 GB of activations) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": world * 1000.0 / ms_e2e, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
@@ -339,6 +354,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("DINVK_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager Python loop instead of CUDA-graph replays")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
