@@ -113,31 +113,37 @@ conv_tc_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN);
-      int s = 0; uint32_t ph = 0;
-      int acc = 0; uint32_t pa = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        tc::mbar_wait(&tempty_bar[acc], pa ^ 1);
+    // The whole warp runs this loop converged so that every operand stays in uniform registers; one elected lane
+    // issues the tcgen05 instructions.  Per MMA the issue cost is one 32-bit add on the descriptor's low word (the
+    // first version rebuilt 64-bit descriptors in a divergent single-lane branch: ~40 instructions and several
+    // R2UR moves per MMA, which capped the tensor pipe at 24 % / 47 % / 75 % for N = 64 / 128 / 256).
+    constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN);
+    constexpr uint32_t HI = tc::desc_hi_sw128(1024);
+    const uint32_t smem_lo = tc::smem_u32(smem) >> 4;
+    int s = 0; uint32_t ph = 0;
+    int acc = 0; uint32_t pa = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      tc::mbar_wait(&tempty_bar[acc], pa ^ 1);
+      tc::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      for (int kb = 0; kb < nk; ++kb) {
+        tc::mbar_wait(&full_bar[s], ph);
         tc::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int kb = 0; kb < nk; ++kb) {
-          tc::mbar_wait(&full_bar[s], ph);
-          tc::tc_fence_after();
-          const uint32_t a_addr = tc::smem_u32(smem + s * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + TC_A_BYTES;
-#pragma unroll
-          for (int k = 0; k < TC_KB / 16; ++k) {
-            const uint64_t da = tc::make_desc_sw128(a_addr + k * 32, 1024);
-            const uint64_t db = tc::make_desc_sw128(b_addr + k * 32, 1024);
-            tc::umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+        const uint32_t a_lo = smem_lo + static_cast<uint32_t>(s) * (Cfg::STAGE_BYTES >> 4);
+        const uint32_t b_lo = a_lo + (TC_A_BYTES >> 4);
+        if (tc::elect_one()) {
+          tc::umma_bf16_lohi(d_tmem, a_lo, HI, b_lo, HI, idesc, kb != 0 ? 1u : 0u);
+          tc::umma_bf16_lohi(d_tmem, a_lo + 2, HI, b_lo + 2, HI, idesc, 1u);
+          tc::umma_bf16_lohi(d_tmem, a_lo + 4, HI, b_lo + 4, HI, idesc, 1u);
+          tc::umma_bf16_lohi(d_tmem, a_lo + 6, HI, b_lo + 6, HI, idesc, 1u);
           tc::umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
-          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
-        tc::umma_commit(&tfull_bar[acc]);  // accumulator complete
-        if (++acc == 2) { acc = 0; pa ^= 1; }
+        __syncwarp();
+        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
       }
+      if (tc::elect_one()) tc::umma_commit(&tfull_bar[acc]);  // accumulator complete
+      __syncwarp();
+      if (++acc == 2) { acc = 0; pa ^= 1; }
     }
   } else {
     // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
@@ -340,52 +346,64 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN);
-      int sa = 0; uint32_t pha = 0;
-      int sb = 0; uint32_t phb = 0;
-      int acc = 0; uint32_t pa = 0;
-      if (RESIDENT) {
-        for (int tap = 0; tap < 9; ++tap) tc::mbar_wait(&bfull[tap], 0);
-      }
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        tc::mbar_wait(&tempty_bar[acc], pa ^ 1);
+    // converged warp, uniform operands, one elected issuer (see conv_tc_kernel)
+    constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN);
+    constexpr uint32_t HI_A = tc::desc_hi_sw128(HL_SLAB_X * 128);
+    constexpr uint32_t HI_B = tc::desc_hi_sw128(1024);
+    const uint32_t slab_lo0 = tc::smem_u32(smem) >> 4;
+    const uint32_t bt_lo0 = tc::smem_u32(smem_b) >> 4;
+    int sa = 0; uint32_t pha = 0;
+    int sb = 0; uint32_t phb = 0;
+    int acc = 0; uint32_t pa = 0;
+    if (RESIDENT) {
+      for (int tap = 0; tap < 9; ++tap) tc::mbar_wait(&bfull[tap], 0);
+    }
+    (void)use_base_offset;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      tc::mbar_wait(&tempty_bar[acc], pa ^ 1);
+      tc::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      for (int kc = 0; kc < nkc; ++kc) {
+        tc::mbar_wait(&afull[sa], pha);
         tc::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int kc = 0; kc < nkc; ++kc) {
-          tc::mbar_wait(&afull[sa], pha);
-          tc::tc_fence_after();
-          const uint32_t slab = tc::smem_u32(smem + sa * HL_SLAB_BYTES);
+        const uint32_t slab_lo = slab_lo0 + static_cast<uint32_t>(sa) * (HL_SLAB_BYTES >> 4);
+        if (RESIDENT) {
+          if (tc::elect_one()) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t a_lo = slab_lo + static_cast<uint32_t>(((tap / 3) * HL_SLAB_X + (tap % 3)) * 8);
+              const uint32_t b_lo = bt_lo0 + static_cast<uint32_t>(tap * (Cfg::B_TILE >> 4));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                tc::umma_bf16_lohi(d_tmem, a_lo + 2 * k, HI_A, b_lo + 2 * k, HI_B, idesc, (tap | k) != 0 ? 1u : (kc != 0 ? 1u : 0u));
+            }
+            tc::umma_commit(&aempty[sa]);
+          }
+          __syncwarp();
+        } else {
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
-            const int ky = tap / 3, kx = tap - ky * 3;
-            uint32_t b_addr;
-            if (RESIDENT) {
-              b_addr = tc::smem_u32(smem_b + tap * Cfg::B_TILE);
-            } else {
-              tc::mbar_wait(&bfull[sb], phb);
-              tc::tc_fence_after();
-              b_addr = tc::smem_u32(smem_b + sb * Cfg::B_TILE);
-            }
-            const uint32_t a_addr = slab + static_cast<uint32_t>((ky * HL_SLAB_X + kx) * 128);
-            const uint32_t boff = use_base_offset ? static_cast<uint32_t>(kx) : 0u;
-#pragma unroll
-            for (int k = 0; k < TC_KB / 16; ++k) {
-              const uint64_t da = tc::make_desc_sw128(a_addr + k * 32, HL_SLAB_X * 128, boff);
-              const uint64_t db = tc::make_desc_sw128(b_addr + k * 32, 1024);
-              tc::umma_bf16(d_tmem, da, db, idesc, (kc | tap | k) != 0 ? 1u : 0u);
-            }
-            if (!RESIDENT) {
+            tc::mbar_wait(&bfull[sb], phb);
+            tc::tc_fence_after();
+            const uint32_t a_lo = slab_lo + static_cast<uint32_t>(((tap / 3) * HL_SLAB_X + (tap % 3)) * 8);
+            const uint32_t b_lo = bt_lo0 + static_cast<uint32_t>(sb) * (Cfg::B_TILE >> 4);
+            if (tc::elect_one()) {
+              tc::umma_bf16_lohi(d_tmem, a_lo, HI_A, b_lo, HI_B, idesc, (kc | tap) != 0 ? 1u : 0u);
+              tc::umma_bf16_lohi(d_tmem, a_lo + 2, HI_A, b_lo + 2, HI_B, idesc, 1u);
+              tc::umma_bf16_lohi(d_tmem, a_lo + 4, HI_A, b_lo + 4, HI_B, idesc, 1u);
+              tc::umma_bf16_lohi(d_tmem, a_lo + 6, HI_A, b_lo + 6, HI_B, idesc, 1u);
               tc::umma_commit(&bempty[sb]);
-              if (++sb == Cfg::B_STAGES) { sb = 0; phb ^= 1; }
+              if (tap == 8) tc::umma_commit(&aempty[sa]);
             }
+            __syncwarp();
+            if (++sb == Cfg::B_STAGES) { sb = 0; phb ^= 1; }
           }
-          tc::umma_commit(&aempty[sa]);
-          if (++sa == Cfg::A_STAGES) { sa = 0; pha ^= 1; }
         }
-        tc::umma_commit(&tfull_bar[acc]);
-        if (++acc == 2) { acc = 0; pa ^= 1; }
+        if (++sa == Cfg::A_STAGES) { sa = 0; pha ^= 1; }
       }
+      if (tc::elect_one()) tc::umma_commit(&tfull_bar[acc]);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; pa ^= 1; }
     }
   } else {
     const int q = warp & 3;
