@@ -207,34 +207,34 @@ conv_tc_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P) {
               const int tap = n0 / P.Cout;
               o = (((long long)b * (2 * P.H) + 2 * y + (tap >> 1)) * (2LL * P.W) + 2 * x + (tap & 1)) * P.Cout + (n0 - tap * P.Cout);
             }
+            // 256-bit accesses (CH is 32 here: bf16 outputs use N tiles >= 64): one full 32-byte sector per lane
             if (P.res) {
-              const uint4* rp = reinterpret_cast<const uint4*>(P.res + o);
 #pragma unroll
-              for (int j = 0; j < CH / 8; ++j) {
-                const uint4 u = __ldg(rp + j);
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+              for (int j = 0; j < CH / 16; ++j) {
+                uint32_t u[8];
+                tc::ldg256(P.res + o + j * 16, u);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[j * 8 + 2 * e] += f.x; v[j * 8 + 2 * e + 1] += f.y; }
+                for (int e = 0; e < 8; ++e) { const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[e])); v[j * 16 + 2 * e] += f.x; v[j * 16 + 2 * e + 1] += f.y; }
               }
             }
             if (P.res2) {
-              const uint4* rp = reinterpret_cast<const uint4*>(P.res2 + o);
 #pragma unroll
-              for (int j = 0; j < CH / 8; ++j) {
-                const uint4 u = __ldg(rp + j);
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+              for (int j = 0; j < CH / 16; ++j) {
+                uint32_t u[8];
+                tc::ldg256(P.res2 + o + j * 16, u);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[j * 8 + 2 * e] += f.x; v[j * 8 + 2 * e + 1] += f.y; }
+                for (int e = 0; e < 8; ++e) { const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[e])); v[j * 16 + 2 * e] += f.x; v[j * 16 + 2 * e + 1] += f.y; }
               }
             }
-            uint4* op = reinterpret_cast<uint4*>(P.out + o);
 #pragma unroll
-            for (int j = 0; j < CH / 8; ++j) {
-              uint4 u;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+            for (int j = 0; j < CH / 16; ++j) {
+              uint32_t u[8];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
-              op[j] = u;
+              for (int e = 0; e < 8; ++e) {
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(v[j * 16 + 2 * e], v[j * 16 + 2 * e + 1]);
+                u[e] = *reinterpret_cast<const uint32_t*>(&hh);
+              }
+              tc::stg256(P.out + o + j * 16, u);
             }
           }
         }
@@ -500,16 +500,20 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
       // accumulator is even complete: their HBM latency overlaps the MMA main loop instead of serialising the epilogue
       const long long obase = (((long long)b * P.H + y) * P.W + x) * P.Cout + (long long)nt * BN;
       uint4 ra[4], rb[4];
-      auto fetch = [&](int c0, uint4 (&a)[4], uint4 (&bb)[4]) {
+      auto fetch = [&](int c0, uint4 (&a)[4], uint4 (&bb)[4]) {  // 2 x 256-bit loads per residual: a full sector per lane
         if (inside && P.res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(P.res + obase + c0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) a[j] = __ldg(rp + j);
+          uint32_t t0[8], t1[8];
+          tc::ldg256(P.res + obase + c0, t0);
+          tc::ldg256(P.res + obase + c0 + 16, t1);
+          a[0] = make_uint4(t0[0], t0[1], t0[2], t0[3]); a[1] = make_uint4(t0[4], t0[5], t0[6], t0[7]);
+          a[2] = make_uint4(t1[0], t1[1], t1[2], t1[3]); a[3] = make_uint4(t1[4], t1[5], t1[6], t1[7]);
         }
         if (inside && P.res2) {
-          const uint4* rp = reinterpret_cast<const uint4*>(P.res2 + obase + c0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) bb[j] = __ldg(rp + j);
+          uint32_t t0[8], t1[8];
+          tc::ldg256(P.res2 + obase + c0, t0);
+          tc::ldg256(P.res2 + obase + c0 + 16, t1);
+          bb[0] = make_uint4(t0[0], t0[1], t0[2], t0[3]); bb[1] = make_uint4(t0[4], t0[5], t0[6], t0[7]);
+          bb[2] = make_uint4(t1[0], t1[1], t1[2], t1[3]); bb[3] = make_uint4(t1[4], t1[5], t1[6], t1[7]);
         }
       };
       fetch(0, ra, rb);
@@ -552,14 +556,15 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
               for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[j * 8 + 2 * e] += f.x; v[j * 8 + 2 * e + 1] += f.y; }
             }
           }
-          uint4* op = reinterpret_cast<uint4*>(P.out + obase + c0);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 u;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+          for (int j = 0; j < 2; ++j) {  // 2 x 256-bit stores: 16 channels each
+            uint32_t u[8];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
-            op[j] = u;
+            for (int e = 0; e < 8; ++e) {
+              const __nv_bfloat162 hh = __floats2bfloat162_rn(v[j * 16 + 2 * e], v[j * 16 + 2 * e + 1]);
+              u[e] = *reinterpret_cast<const uint32_t*>(&hh);
+            }
+            tc::stg256(P.out + obase + c0 + j * 16, u);
           }
         }
         if (c0 + 32 < BN) {
