@@ -29,7 +29,7 @@ using bf16 = __nv_bfloat16;
 constexpr int TC_TX = 16, TC_TY = 8;            // pixel tile: 16 x 8 = 128 GEMM rows
 constexpr int TC_KB = 64;                        // K block: 64 bf16 = 128 B = one swizzle row
 constexpr int TC_A_BYTES = 128 * TC_KB * 2;      // 16 KB
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 and 6-9: two epilogue groups (one per TMEM accumulator)
 
 struct TcMaps {
   CUtensorMap a[4];  // activation views (3x3 and transposed-up: one; strided 2x2 down: one per tap)
@@ -147,9 +147,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P) {
     }
   } else {
     // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
+    // two epilogue groups of four warps: group g drains accumulator buffer g, i.e. every other tile, so two tiles'
+    // epilogues (TMEM reads, residual loads, stores) are in flight while the MMA warp fills the next buffer
     const int q = warp & 3;
-    int acc = 0; uint32_t pa = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int group = (warp - 2) >> 2;
+    const int acc = group;
+    uint32_t pa = 0;
+    int local = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+      if ((local & 1) != group) continue;
       const int nt = t / pixel_tiles, pt = t - nt * pixel_tiles;
       const int b = pt / (P.tiles_y * P.tiles_x), r = pt - b * (P.tiles_y * P.tiles_x);
       const int y0 = (r / P.tiles_x) * TC_TY, x0 = (r % P.tiles_x) * TC_TX;
@@ -242,7 +248,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P) {
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) { acc = 0; pa ^= 1; }
+      pa ^= 1;
     }
   }
   tc::tc_fence_before();
@@ -275,7 +281,7 @@ struct HaloCfg {
   static constexpr int B_TILE = BN * 128;
   static constexpr int A_STAGES = AST;
   static constexpr int B_STAGES = RESIDENT ? 9 : BST;
-  static constexpr int SCRATCH = EPI ? 4 * 2 * 4096 : 0;  // per epilogue warp: 32 rows x 128 B for out and res
+  static constexpr int SCRATCH = EPI ? 8 * 2 * 4096 : 0;  // per epilogue warp (8 of them): 32 rows x 128 B for out and res
   static constexpr int SMEM = A_STAGES * HL_SLAB_BYTES + B_STAGES * B_TILE + SCRATCH + 1024;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
@@ -407,8 +413,12 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
     }
   } else {
     const int q = warp & 3;
-    int acc = 0; uint32_t pa = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int group = (warp - 2) >> 2;  // two epilogue groups, one per accumulator buffer (see conv_tc_kernel)
+    const int acc = group;
+    uint32_t pa = 0;
+    int local = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+      if ((local & 1) != group) continue;
       const int nt = t / pixel_tiles, pt = t - nt * pixel_tiles;
       const int b = pt / (P.tiles_y * P.tiles_x), r = pt - b * (P.tiles_y * P.tiles_x);
       const int y0 = (r / P.tiles_x) * HL_TY, x0 = (r % P.tiles_x) * HL_TX;
@@ -422,7 +432,7 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
       // result stored with 512-byte-contiguous warp instructions, the row<->chunk exchange happens in a 4 KB
       // per-warp scratch with the usual 16-byte XOR swizzle.  Residual loads are issued BEFORE the accumulator is
       // complete, so their HBM latency overlaps the MMA main loop.
-      uint8_t* scr = smem_b + Cfg::B_STAGES * Cfg::B_TILE + q * (2 * 4096);
+      uint8_t* scr = smem_b + Cfg::B_STAGES * Cfg::B_TILE + (group * 4 + q) * (2 * 4096);
       uint4* s_out = reinterpret_cast<uint4*>(scr);
       uint4* s_r1 = reinterpret_cast<uint4*>(scr + 4096);
       const int cch = lane & 7;            // 16-byte chunk (8 channels) this lane moves in the coalesced phases
@@ -576,7 +586,7 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) { acc = 0; pa ^= 1; }
+      pa ^= 1;
     }
   }
   tc::tc_fence_before();
@@ -846,13 +856,11 @@ static int conv3x3_tc(const void* x, const void* weight, const float* bias, cons
     if (bn == 64) {
       switch (variant) {
         case 1: return launch_conv_halo<64, true, 2, 0, 0>(M, P, ubo, stream);
-        case 2: return launch_conv_halo<64, true, 3, 0, 1>(M, P, ubo, stream);
         default: return launch_conv_halo<64, true, 4, 0, 0>(M, P, ubo, stream);
       }
     }
     switch (variant) {
       case 1: return launch_conv_halo<128, false, 2, 5, 0>(M, P, ubo, stream);
-      case 2: return launch_conv_halo<128, false, 2, 6, 1>(M, P, ubo, stream);
       default: return launch_conv_halo<128, false, 2, 8, 0>(M, P, ubo, stream);
     }
   }
