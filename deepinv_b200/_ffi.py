@@ -54,6 +54,7 @@ _SIGNATURES = {
     "dinvk_conv_f32": (c_int, [c_void_p] * 6 + [c_int] * 7 + [c_void_p]),
     "dinvk_conv3x3_bf16": (c_int, [c_void_p] * 6 + [c_int] * 6 + [c_void_p]),
     "dinvk_conv3x3_bf16_tail": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p]),
+    "dinvk_conv3x3_head_bf16": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_void_p, c_int, c_int, c_void_p]),
     "dinvk_nchw_f32_to_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p]),
     "dinvk_nhwc_bf16_to_nchw_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dinvk_conv2x2_down_bf16": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),

@@ -37,7 +37,7 @@ def get_lib() -> ctypes.CDLL:
                         "(deepinv_b200 has no CPU or PyTorch fallback)."
                     )
                 lib = ctypes.CDLL(str(_LIB_PATH))
-                _ffi.bind(lib, required=False)  # TODO(round 1): required=True once every entry point exists
+                _ffi.bind(lib, required=True)  # every symbol of include/dinvk.h must be exported
                 if lib.dinvk_version() < 100:
                     raise DinvkError("libdinvk.so is older than this package")
                 _lib = lib

@@ -274,15 +274,15 @@ constexpr int HL_TX = 8, HL_TY = 16;                 // output tile: 8 x by 16 y
 constexpr int HL_SLAB_X = 16, HL_SLAB_Y = HL_TY + 2; // slab box in pixels
 constexpr int HL_SLAB_BYTES = HL_SLAB_X * HL_SLAB_Y * 128;  // 36864
 
-// AST: activation slabs in flight; BST: weight tiles in the ring (streamed mode); EPI: 0 = direct per-row epilogue with
-// register prefetch of the residuals, 1 = coalesced epilogue through a per-warp swizzled transpose scratch
+// AST: activation slabs in flight; BST: weight tiles in the ring (streamed mode); EPI: reserved (a coalesced epilogue
+// through a shared-memory transpose was measured slower than the direct per-row one and removed).  BN = 16 is the
+// network tail (64 -> Cout <= 16, fp32 NCHW output).
 template <int BN, bool RESIDENT, int AST, int BST, int EPI>
 struct HaloCfg {
   static constexpr int B_TILE = BN * 128;
   static constexpr int A_STAGES = AST;
   static constexpr int B_STAGES = RESIDENT ? 9 : BST;
-  static constexpr int SCRATCH = EPI ? 8 * 2 * 4096 : 0;  // per epilogue warp (8 of them): 32 rows x 128 B for out and res
-  static constexpr int SMEM = A_STAGES * HL_SLAB_BYTES + B_STAGES * B_TILE + SCRATCH + 1024;
+  static constexpr int SMEM = A_STAGES * HL_SLAB_BYTES + B_STAGES * B_TILE + 1024;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
 };
@@ -425,85 +425,25 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
       const int m = q * 32 + lane;
       const int y = y0 + (m >> 3), x = x0 + (m & 7);
       const bool inside = (y < P.H) && (x < P.W);
-      if constexpr (EPI == 1) {
-      // Warp-local transpose through shared memory: a lane owns one pixel ROW of the accumulator (TMEM lane), but a
-      // coalesced global access needs 8 consecutive lanes on one pixel's 128 bytes (64 channels).  Each warp owns 32
-      // pixels = 4 image rows x 8 x, i.e. four 1 KB contiguous runs in the NHWC tensor; residuals are loaded and the
-      // result stored with 512-byte-contiguous warp instructions, the row<->chunk exchange happens in a 4 KB
-      // per-warp scratch with the usual 16-byte XOR swizzle.  Residual loads are issued BEFORE the accumulator is
-      // complete, so their HBM latency overlaps the MMA main loop.
-      uint8_t* scr = smem_b + Cfg::B_STAGES * Cfg::B_TILE + (group * 4 + q) * (2 * 4096);
-      uint4* s_out = reinterpret_cast<uint4*>(scr);
-      uint4* s_r1 = reinterpret_cast<uint4*>(scr + 4096);
-      const int cch = lane & 7;            // 16-byte chunk (8 channels) this lane moves in the coalesced phases
-      long long goff[8];                   // global element offset of (row r = i*4 + lane/8, chunk cch), -1 if outside
+      if constexpr (BN == 16) {
+      // network tail (Cout <= 16): fp32 NCHW stores of the real channels, optional "+ x" term
+      tc::mbar_wait(&tfull_bar[acc], pa);
+      tc::tc_fence_after();
+      uint32_t rr[16];
+      tc::tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN), rr);
+      tc::tmem_ld_wait();
+      if (inside) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = i * 4 + (lane >> 3);
-        const int mm = q * 32 + r;
-        const int yy = y0 + (mm >> 3), xx = x0 + (mm & 7);
-        goff[i] = (yy < P.H && xx < P.W) ? ((((long long)b * P.H + yy) * P.W + xx) * P.Cout + (long long)nt * BN + cch * 8) : -1;
-      }
-#pragma unroll 1
-      for (int nb = 0; nb < BN; nb += 64) {
-        if (P.res) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = i * 4 + (lane >> 3);
-            if (goff[i] >= 0) s_r1[r * 8 + (cch ^ (r & 7))] = __ldg(reinterpret_cast<const uint4*>(P.res + goff[i] + nb));
+        for (int c = 0; c < 16; ++c) {
+          if (c < P.Cout) {
+            const long long o = (((long long)b * P.Cout + c) * P.H + y) * P.W + x;
+            float val = __uint_as_float(rr[c]);
+            if (P.bias) val += __ldg(P.bias + c);
+            if (P.relu) val = fmaxf(val, 0.f);
+            if (P.add_f32) val += __ldg(P.add_f32 + o);
+            P.out_f32[o] = val;
           }
         }
-        if (nb == 0) {
-          tc::mbar_wait(&tfull_bar[acc], pa);
-          tc::tc_fence_after();
-        }
-        __syncwarp();
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + nb);
-#pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 32) {
-          float v[32];
-          uint32_t rr[32];
-          tc::tmem_ld_32x32b_x32(t_addr + c0, rr);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
-          if (P.bias) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += __ldg(P.bias + nt * BN + nb + c0 + i);
-          }
-          if (P.relu) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int ch = (c0 >> 3) + j;  // logical 16-byte chunk of this lane's own row
-            if (P.res) {
-              const uint4 u = s_r1[lane * 8 + (ch ^ (lane & 7))];
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[j * 8 + 2 * e] += f.x; v[j * 8 + 2 * e + 1] += f.y; }
-            }
-            if (P.res2 && inside) {  // the U-Net skip (6 of 58 layers): read directly from global memory
-              const uint4 u = __ldg(reinterpret_cast<const uint4*>(P.res2 + (((long long)b * P.H + y) * P.W + x) * P.Cout + (long long)nt * BN + nb + c0) + j);
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[j * 8 + 2 * e] += f.x; v[j * 8 + 2 * e + 1] += f.y; }
-            }
-            uint4 o4;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o4);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
-            s_out[lane * 8 + (ch ^ (lane & 7))] = o4;
-          }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + (lane >> 3);
-          if (goff[i] >= 0) *reinterpret_cast<uint4*>(P.out + goff[i] + nb) = s_out[r * 8 + (cch ^ (r & 7))];
-        }
-        __syncwarp();
       }
       } else {
       // residual operands are fetched one 32-channel chunk AHEAD of the accumulator reads, starting before the
@@ -592,6 +532,190 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 2) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Network HEAD: 3x3 convolution from a few-channel NCHW fp32 image (+ optional constant noise-level channel, DRUNet's
+// sigma map) to 64 NHWC bf16 channels.  Going through the generic kernel means padding 3 channels to 64 (a 537 MB
+// converter write and 9 taps x 64 channels of zeros through L2 and the tensor pipe): 640 us per DRUNet forward.
+// Here the im2col row of a pixel (K = 9 taps x CT channels <= 64, k = tap*CT + c) is BUILT IN SHARED MEMORY by CUDA
+// threads straight from the fp32 input (33 MB), in the 128-byte-swizzled K-major layout the UMMA descriptor expects
+// (16-byte chunk j of row m lives at chunk j ^ (m & 7)), so the whole layer is one K=64 GEMM step per 128-pixel tile
+// and the only real traffic is the 537 MB output write.
+//   warps 0-7 : two builder groups (tile parity g -> A stage g), 128 threads each, one pixel per thread
+//   warp  8   : MMA issuer (4 x tcgen05.mma M128 N64 K16 per tile)
+//   warps 9-16: two epilogue groups (accumulator g), TMEM lane quarter = warp % 4
+// ---------------------------------------------------------------------------------------------------------------
+struct HeadParams {
+  const float* x;          // (B, C, H, W) fp32
+  const bf16* w;           // (64, 64) bf16, k = tap*CT + c, zero padded
+  const float* bias;       // optional (64)
+  bf16* out;               // (B, H, W, 64)
+  int B, C, H, W;
+  float fill_scalar;
+  const float* fill_batch;
+  int has_fill;
+  int relu;
+  int tiles_x, tiles_y;
+};
+constexpr int HD_TX = 32, HD_TY = 4;
+constexpr int HD_THREADS = 17 * 32;
+constexpr int HD_SMEM = 2 * TC_A_BYTES + 64 * 128 + 1024;
+
+template <int CT>
+__global__ void __launch_bounds__(HD_THREADS, 1) conv_head_kernel(const HeadParams P) {
+  constexpr int KREAL = 9 * CT;
+  constexpr int NCH = (KREAL + 7) / 8;  // 16-byte chunks rewritten for every tile
+  static_assert(KREAL <= 64, "head: 9 * channels must fit one 64-wide K block");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_b = smem + 2 * TC_A_BYTES;
+  __shared__ __align__(8) uint64_t afull[2];
+  __shared__ __align__(8) uint64_t aempty[2];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = P.B * P.tiles_y * P.tiles_x;
+
+  if (threadIdx.x == 0) {
+    for (int a = 0; a < 2; ++a) {
+      tc::mbar_init(&afull[a], 128); tc::mbar_init(&aempty[a], 1);
+      tc::mbar_init(&tfull_bar[a], 1); tc::mbar_init(&tempty_bar[a], 4);
+    }
+    tc::fence_barrier_init();
+  }
+  // zero both A stages once (chunks >= NCH are never written again), stage the weights with the same swizzle
+  for (int i = threadIdx.x; i < 2 * TC_A_BYTES / 16; i += HD_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 64 * 8; i += HD_THREADS) {
+    const int n = i >> 3, j = i & 7;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.w) + i);
+    *reinterpret_cast<uint4*>(smem_b + n * 128 + ((j ^ (n & 7)) << 4)) = v;
+  }
+  tc::fence_proxy_async();
+  if (warp == 8) tc::tmem_alloc<128>(&tmem_base_smem);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp < 8) {
+    // ===================== builders =====================
+    const int group = warp >> 2;
+    const int m = (warp & 3) * 32 + lane;  // GEMM row = (warp&3) tile row, lane = x
+    uint8_t* row = smem + group * TC_A_BYTES + m * 128;
+    uint32_t ph = 0;
+    int local = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+      if ((local & 1) != group) continue;
+      const int b = t / (P.tiles_y * P.tiles_x), r = t - b * (P.tiles_y * P.tiles_x);
+      const int y = (r / P.tiles_x) * HD_TY + (warp & 3), x = (r % P.tiles_x) * HD_TX + lane;
+      const float fillv = P.has_fill ? (P.fill_batch ? __ldg(P.fill_batch + b) : P.fill_scalar) : 0.f;
+      float v[NCH * 8];
+#pragma unroll
+      for (int k = KREAL; k < NCH * 8; ++k) v[k] = 0.f;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        const bool inb = (yy >= 0) && (yy < P.H) && (xx >= 0) && (xx < P.W);
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+          float val = 0.f;
+          if (inb) val = (c < P.C) ? __ldg(P.x + (((long long)b * P.C + c) * P.H + yy) * P.W + xx) : fillv;
+          v[tap * CT + c] = val;
+        }
+      }
+      tc::mbar_wait(&aempty[group], ph ^ 1);
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        uint4 u;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
+        *reinterpret_cast<uint4*>(row + ((j ^ (m & 7)) << 4)) = u;
+      }
+      tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      tc::mbar_arrive(&afull[group]);
+      ph ^= 1;
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = tc::make_idesc_bf16(128, 64);
+    constexpr uint32_t HI = tc::desc_hi_sw128(1024);
+    const uint32_t a_lo0 = tc::smem_u32(smem) >> 4;
+    const uint32_t b_lo = tc::smem_u32(smem_b) >> 4;
+    uint32_t ph[2] = {0, 0};
+    int local = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+      const int g = local & 1;
+      tc::mbar_wait(&tempty_bar[g], ph[g] ^ 1);
+      tc::mbar_wait(&afull[g], ph[g]);
+      tc::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(g * 64);
+      const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(g) * (TC_A_BYTES >> 4);
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc::umma_bf16_lohi(d_tmem, a_lo + 2 * k, HI, b_lo + 2 * k, HI, idesc, k != 0 ? 1u : 0u);
+        tc::umma_commit(&aempty[g]);
+        tc::umma_commit(&tfull_bar[g]);
+      }
+      __syncwarp();
+      ph[g] ^= 1;
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int group = (warp - 9) >> 2;
+    uint32_t pa = 0;
+    int local = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+      if ((local & 1) != group) continue;
+      const int b = t / (P.tiles_y * P.tiles_x), r = t - b * (P.tiles_y * P.tiles_x);
+      const int y = (r / P.tiles_x) * HD_TY + q, x = (r % P.tiles_x) * HD_TX + lane;
+      const bool inside = (y < P.H) && (x < P.W);
+      bf16* o = P.out + (((long long)b * P.H + y) * P.W + x) * 64;
+      tc::mbar_wait(&tfull_bar[group], pa);
+      tc::tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(group * 64);
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t rr[32];
+        tc::tmem_ld_32x32b_x32(t_addr + c0, rr);
+        tc::tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
+        if (P.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += __ldg(P.bias + c0 + i);
+        }
+        if (P.relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (inside) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            uint32_t u[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const __nv_bfloat162 hh = __floats2bfloat162_rn(v[j * 16 + 2 * e], v[j * 16 + 2 * e + 1]);
+              u[e] = *reinterpret_cast<const uint32_t*>(&hh);
+            }
+            tc::stg256(o + c0 + j * 16, u);
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty_bar[group]);
+      pa ^= 1;
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc<128>(tmem_base);
 }
 
 // ---- layout converters ---------------------------------------------------------------------------------
@@ -839,7 +963,8 @@ static int conv3x3_tc(const void* x, const void* weight, const float* bias, cons
   DINVK_CHECK_ARG(rows % bn == 0, "conv3x3_bf16: weight rows %d not a multiple of the N tile %d", rows, bn);
   TcMaps M;
   int rc;
-  if (!out_f32 && halo_mode() != 0 && ((rows == 64 && Cin == 64) || bn == 128)) {
+  const bool halo_tail = out_f32 && Cin == 64 && rows == 16 && !getenv("DINVK_NO_HALO_TAIL");
+  if (halo_mode() != 0 && (halo_tail || (!out_f32 && ((rows == 64 && Cin == 64) || bn == 128)))) {
     // 64- and 128-channel layers: slab + halo kernel (activations read once per channel block, not once per tap)
     if ((rc = make_slab_map(&M.a[0], x, B, H, W, Cin))) return rc;
     M.a[1] = M.a[0]; M.a[2] = M.a[0]; M.a[3] = M.a[0];
@@ -848,10 +973,11 @@ static int conv3x3_tc(const void* x, const void* weight, const float* bias, cons
     P.B = B; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout_real;
     P.ntaps = 9; P.kc_per_tap = Cin / TC_KB;
     for (int t = 0; t < 9; ++t) { P.dx[t] = t % 3 - 1; P.dy[t] = t / 3 - 1; P.amap[t] = 0; }
-    P.mode = 0;
+    P.mode = out_f32 ? 1 : 0;
     P.tiles_x = ceil_div(W, HL_TX); P.tiles_y = ceil_div(H, HL_TY); P.n_tiles = rows / bn;
-    P.relu = act; P.res = (const bf16*)res; P.res2 = (const bf16*)res2; P.out = (bf16*)out; P.out_f32 = nullptr; P.add_f32 = nullptr; P.bias = bias;
+    P.relu = act; P.res = (const bf16*)res; P.res2 = (const bf16*)res2; P.out = (bf16*)out; P.out_f32 = out_f32; P.add_f32 = add_f32; P.bias = bias;
     const int ubo = halo_mode() == 3 ? 1 : 0;
+    if (halo_tail) return launch_conv_halo<16, true, 4, 0, 0>(M, P, ubo, stream);
     static const int variant = getenv("DINVK_HALO_VARIANT") ? atoi(getenv("DINVK_HALO_VARIANT")) : 0;
     if (bn == 64) {
       switch (variant) {
@@ -930,6 +1056,40 @@ extern "C" int dinvk_conv3x3_bf16_tail(const void* x, const void* weight16, cons
                                        float* out_nchw, int B, int H, int W, int Cin, int Cout, void* stream) {
   DINVK_CHECK_ARG(Cout >= 1 && Cout <= 16, "conv3x3_bf16_tail: Cout=%d must be <= 16", Cout);
   return conv3x3_tc(x, weight16, bias, nullptr, nullptr, nullptr, out_nchw, add_nchw, B, H, W, Cin, Cout, 16, 0, stream);
+}
+
+template <int CT>
+static int launch_head(const HeadParams& P, void* stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_head_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, HD_SMEM);
+    if (e != cudaSuccess) return set_error(DINVK_ECUDA, "cudaFuncSetAttribute(conv_head<%d>): %s", CT, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const long long tiles = (long long)P.B * P.tiles_y * P.tiles_x;
+  const int grid = (int)std::min<long long>(tiles, sm_count());
+  count_launch();
+  conv_head_kernel<CT><<<grid, HD_THREADS, HD_SMEM, (cudaStream_t)stream>>>(P);
+  return DINVK_POST_LAUNCH();
+}
+
+extern "C" int dinvk_conv3x3_head_bf16(const float* x_nchw, const void* weight64, const float* bias, void* out_nhwc, int B, int C, int H,
+                                       int W, float fill_scalar, const float* fill_batch, int has_fill, int act, void* stream) {
+  DINVK_CHECK_ARG(x_nchw && weight64 && out_nhwc && B >= 0 && C >= 1 && H >= 1 && W >= 1, "conv3x3_head_bf16: bad arguments");
+  const int CT = C + (has_fill ? 1 : 0);
+  DINVK_CHECK_ARG(CT >= 1 && CT <= 4, "conv3x3_head_bf16: %d input channels (incl. noise map) not in 1..4", CT);
+  if (B == 0) return DINVK_OK;
+  HeadParams P;
+  P.x = x_nchw; P.w = (const bf16*)weight64; P.bias = bias; P.out = (bf16*)out_nhwc;
+  P.B = B; P.C = C; P.H = H; P.W = W;
+  P.fill_scalar = fill_scalar; P.fill_batch = fill_batch; P.has_fill = has_fill; P.relu = act;
+  P.tiles_x = ceil_div(W, HD_TX); P.tiles_y = ceil_div(H, HD_TY);
+  switch (CT) {
+    case 1: return launch_head<1>(P, stream);
+    case 2: return launch_head<2>(P, stream);
+    case 3: return launch_head<3>(P, stream);
+    default: return launch_head<4>(P, stream);
+  }
 }
 
 extern "C" int dinvk_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, int Cpad, float fill_scalar,

@@ -142,8 +142,12 @@ struct Dft<16> {
       Dft<4>::run(t);
 #pragma unroll
       for (int k1 = 0; k1 < 4; ++k1) {
-        const int m = n2 * k1;
-        y[n2][k1] = (m == 0) ? t[k1] : cmul(t[k1], make_float2(wr[m], wi[m]));
+        const int m = n2 * k1;  // compile-time after unrolling: the trivial and the 45-degree twiddles are special-cased
+        if (m == 0) y[n2][k1] = t[k1];
+        else if (m == 4) y[n2][k1] = make_float2(t[k1].y, -t[k1].x);
+        else if (m == 2) y[n2][k1] = make_float2(h * (t[k1].x + t[k1].y), h * (t[k1].y - t[k1].x));
+        else if (m == 6) y[n2][k1] = make_float2(h * (t[k1].y - t[k1].x), -h * (t[k1].x + t[k1].y));
+        else y[n2][k1] = cmul(t[k1], make_float2(wr[m], wi[m]));
       }
     }
 #pragma unroll

@@ -43,6 +43,17 @@ def _pad64(c: int) -> int:
     return (c + 63) // 64 * 64
 
 
+def _pack_head(w: torch.Tensor) -> torch.Tensor | None:
+    """(64, Cin<=4, 3, 3) -> (64, 64) bf16 with k = (ky*3+kx)*Cin + c (zero padded): operand of the dedicated head
+    kernel, which builds the im2col rows in shared memory from the NCHW fp32 input; None if the shape does not fit"""
+    co, ci = w.shape[:2]
+    if co != 64 or ci > 4:
+        return None
+    out = torch.zeros(64, 64, dtype=torch.float32, device=w.device)
+    out[:, : 9 * ci] = w.detach().float().permute(0, 2, 3, 1).reshape(64, 9 * ci)
+    return out.to(torch.bfloat16).contiguous()
+
+
 class _DrunetPack:
     def __init__(self, m):
         nb = m.nb
@@ -55,7 +66,8 @@ class _DrunetPack:
             raise NotImplementedError("precision='bf16' needs channel counts that are multiples of 64 (tensor-core N/K tiles); "
                                       f"got nc={self.nc}; use precision='fp32'")
         self.cin0 = m.m_head.weight.shape[1]
-        self.head = _pack3x3(m.m_head.weight, cin_pad=_pad64(self.cin0))
+        self.head64 = _pack_head(m.m_head.weight)
+        self.head = None if self.head64 is not None else _pack3x3(m.m_head.weight, cin_pad=_pad64(self.cin0))
         self.tail = _pack3x3(m.m_tail.weight, rows_pad=16)
         self.cout = m.m_tail.weight.shape[0]
         rb = lambda blocks: [(_pack3x3(b.res[0].weight), _pack3x3(b.res[2].weight)) for b in blocks]
@@ -77,8 +89,10 @@ def drunet_forward_bf16(model, x0: torch.Tensor) -> torch.Tensor:
     pk = model._tc
     if pk is None or pk.key != _version_key(model):
         pk = model._tc = _DrunetPack(model)
-    a = ops.nchw_to_nhwc_bf16(x0, _pad64(pk.cin0))
-    x1 = ops.conv3x3_bf16(a, pk.head)
+    if pk.head64 is not None:
+        x1 = ops.conv3x3_head_bf16(x0, pk.head64)
+    else:
+        x1 = ops.conv3x3_bf16(ops.nchw_to_nhwc_bf16(x0, _pad64(pk.cin0)), pk.head)
     skips = [x1]
     t = x1
     for blocks, wd in pk.down:
@@ -102,7 +116,8 @@ class _DncnnPack:
         self.cin = m.in_conv.weight.shape[1]
         self.cout = m.out_conv.weight.shape[0]
         f32 = lambda b: None if b is None else b.detach().float().contiguous()
-        self.first = (_pack3x3(m.in_conv.weight, cin_pad=_pad64(self.cin)), f32(m.in_conv.bias))
+        self.first64 = _pack_head(m.in_conv.weight)
+        self.first = (None if self.first64 is not None else _pack3x3(m.in_conv.weight, cin_pad=_pad64(self.cin)), f32(m.in_conv.bias))
         self.mid = [(_pack3x3(c.weight), f32(c.bias)) for c in m.conv_list]
         self.last = (_pack3x3(m.out_conv.weight, rows_pad=16), f32(m.out_conv.bias))
 
@@ -111,8 +126,10 @@ def dncnn_forward_bf16(model, x: torch.Tensor) -> torch.Tensor:
     pk = model._tc
     if pk is None or pk.key != _version_key(model):
         pk = model._tc = _DncnnPack(model)
-    t = ops.nchw_to_nhwc_bf16(x, _pad64(pk.cin))
-    t = ops.conv3x3_bf16(t, pk.first[0], bias=pk.first[1], relu=True)
+    if pk.first64 is not None:
+        t = ops.conv3x3_head_bf16(x, pk.first64, bias=pk.first[1], relu=True)
+    else:
+        t = ops.conv3x3_bf16(ops.nchw_to_nhwc_bf16(x, _pad64(pk.cin)), pk.first[0], bias=pk.first[1], relu=True)
     for w, b in pk.mid:
         t = ops.conv3x3_bf16(t, w, bias=b, relu=True)
     return ops.conv3x3_bf16_tail(t, pk.last[0], pk.cout, bias=pk.last[1], add=x)

@@ -339,6 +339,21 @@ def conv3x3_bf16(x, w2d, *, bias=None, res=None, res2=None, relu: bool = False) 
     return out
 
 
+def conv3x3_head_bf16(x, w64, *, bias=None, fill=None, relu: bool = False) -> torch.Tensor:
+    """network head: (B,C,H,W) fp32 NCHW (+ constant channel `fill`: float or (B,) tensor) -> (B,H,W,64) bf16"""
+    dev = _require_cuda(x, w64)
+    x = _f32c(x)
+    B, C, H, W = x.shape
+    out = torch.empty(B, H, W, 64, dtype=torch.bfloat16, device=dev)
+    fill_t = _f32c(fill.reshape(-1)) if torch.is_tensor(fill) else None
+    if fill_t is not None and fill_t.numel() == 1:
+        fill_t = fill_t.expand(B).contiguous()
+    check(get_lib().dinvk_conv3x3_head_bf16(_p(x), _p(w64), _p(bias), _p(out), B, C, H, W,
+                                            float(fill) if (fill is not None and fill_t is None) else 0.0,
+                                            _p(fill_t), int(fill is not None), int(relu), _stream(dev)))
+    return out
+
+
 def conv3x3_bf16_tail(x, w16, cout: int, *, bias=None, add=None) -> torch.Tensor:
     """network tail: (B,H,W,Cin) bf16 -> (B,cout,H,W) fp32 NCHW (+ bias + add)"""
     dev = _require_cuda(x, w16)

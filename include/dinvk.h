@@ -218,6 +218,13 @@ int dinvk_conv3x3_bf16(const void* x, const void* weight, const float* bias, con
  *   out_nchw = conv3x3(x) + bias + add_nchw   (add_nchw optional: DnCNN's "+ x", dncnn.py:138) */
 int dinvk_conv3x3_bf16_tail(const void* x, const void* weight16, const float* bias, const float* add_nchw,
                             float* out_nchw, int B, int H, int W, int Cin, int Cout, void* stream);
+/* network head: 3x3 convolution straight from the reference's NCHW fp32 image to 64 NHWC bf16 channels
+ *   x_nchw (B,C,H,W) fp32; has_fill appends one constant channel (DRUNet's noise-level map, drunet.py:190-200:
+ *   fill_batch[b] if non-null else fill_scalar); CT = C + has_fill in 1..4;
+ *   weight64 (64, 64) bf16 with k = (ky*3+kx)*CT + c, zero padded to 64;  out = act(conv3x3(x) + bias)  */
+int dinvk_conv3x3_head_bf16(const float* x_nchw, const void* weight64, const float* bias, void* out_nhwc, int B,
+                            int C, int H, int W, float fill_scalar, const float* fill_batch, int has_fill,
+                            int act, void* stream);
 /* layout converters between the reference's NCHW fp32 and the tensor-core NHWC bf16 layout
  *   nchw_to_nhwc: out[b,h,w,c] = c < C ? in[b,c,h,w] : (c == C ? fill[b] or fill_scalar : 0), c < Cpad
  *   nhwc_to_nchw: out[b,c,h,w] = in[b,h,w,c] (+ add[b,c,h,w] if add), c < C */

@@ -75,6 +75,58 @@ def test_conv3x3_tail_and_layout(dev):
     assert rel_err(back, tb.float()) < 1e-6
 
 
+@pytest.mark.parametrize("C,fill", [(2, "batch"), (3, "scalar"), (1, None), (3, None), (4, None)])
+@pytest.mark.parametrize("hw", [(24, 40), (37, 61), (128, 128)])
+def test_conv3x3_head(C, fill, hw, dev):
+    """dedicated head kernel (im2col rows built in shared memory, one K=64 MMA block per tile) against the fp32
+    convolution of the bf16-rounded operands; covers ragged tiles (H % 4, W % 32 != 0) and the constant channel"""
+    from deepinv_b200 import ops
+    from deepinv_b200.models.tc_engine import _pack_head
+
+    H, W = hw
+    B = 3
+    gen = torch.Generator().manual_seed(C * 100 + H)
+    x = torch.randn(B, C, H, W, generator=gen)
+    ct = C + (fill is not None)
+    w = torch.randn(64, ct, 3, 3, generator=gen) / (3 * ct ** 0.5)
+    bias = torch.randn(64, generator=gen)
+    if fill == "batch":
+        fv = torch.tensor([0.1, 0.45, 0.8])
+        xin = torch.cat([x, fv.view(B, 1, 1, 1).expand(B, 1, H, W)], 1)
+        kw = dict(fill=fv.to(dev))
+    elif fill == "scalar":
+        xin = torch.cat([x, torch.full((B, 1, H, W), 0.3)], 1)
+        kw = dict(fill=0.3)
+    else:
+        xin, kw = x, {}
+    w64 = _pack_head(w.to(dev))
+    assert w64 is not None and w64.shape == (64, 64)
+    ref = _ref_conv(xin.to(torch.bfloat16), w.to(torch.bfloat16))
+    out = ops.conv3x3_head_bf16(x.to(dev), w64, **kw)
+    assert out.shape == (B, H, W, 64) and out.dtype == torch.bfloat16
+    assert rel_err(out.float().permute(0, 3, 1, 2), ref) < 4e-3
+    out = ops.conv3x3_head_bf16(x.to(dev), w64, bias=bias.to(dev), relu=True, **kw)
+    assert rel_err(out.float().permute(0, 3, 1, 2), F.relu(ref + bias.view(1, -1, 1, 1))) < 4e-3
+
+
+@pytest.mark.parametrize("cout,hw", [(1, (16, 8)), (3, (37, 61)), (2, (128, 96))])
+def test_conv3x3_tail_halo(cout, hw, dev):
+    """64 -> Cout <= 16 tail through the slab/halo kernel (N = 16 tile), ragged sizes"""
+    from deepinv_b200 import ops
+    from deepinv_b200.models.tc_engine import _pack3x3
+
+    H, W = hw
+    gen = torch.Generator().manual_seed(cout)
+    t = torch.randn(2, 64, H, W, generator=gen)
+    w = torch.randn(cout, 64, 3, 3, generator=gen) / 24
+    add = torch.randn(2, cout, H, W, generator=gen)
+    tb, wb = t.to(torch.bfloat16), w.to(torch.bfloat16)
+    out = ops.conv3x3_bf16_tail(_nhwc(tb).to(dev), _pack3x3(w.to(dev), rows_pad=16), cout, add=add.to(dev))
+    assert rel_err(out, _ref_conv(tb, wb) + add) < 1e-4
+    out = ops.conv3x3_bf16_tail(_nhwc(tb).to(dev), _pack3x3(w.to(dev), rows_pad=16), cout)
+    assert rel_err(out, _ref_conv(tb, wb)) < 1e-4
+
+
 def test_conv2x2_bf16(dev):
     from deepinv_b200 import ops
     from deepinv_b200.models.tc_engine import _pack_down, _pack_up
