@@ -270,30 +270,43 @@ conv_tc_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P) {
 // L2->SM activation traffic drops 4x (36 KB instead of 144 KB per tile and channel block).  For 64->64 layers the
 // whole weight tensor (9 x 64 x 64 bf16 = 72 KB) stays resident in shared memory for the lifetime of the CTA.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int HL_TX = 8, HL_TY = 16;                 // output tile: 8 x by 16 y (GEMM row m = ty*8 + tx)
-constexpr int HL_SLAB_X = 16, HL_SLAB_Y = HL_TY + 2; // slab box in pixels
-constexpr int HL_SLAB_BYTES = HL_SLAB_X * HL_SLAB_Y * 128;  // 36864
+// MH x-halves per CTA tile: the tile is 8*MH x by 16 y output pixels, half h (x in [8h, 8h+8)) is one M=128 accumulator.
+// MH = 2 shares every weight tile between two MMAs groups (256 pixels per B stage): the streamed-weight layers
+// (>= 128 channels) were bound by the L2->SM weight traffic (TMA round trips), not by the tensor pipe.
+constexpr int HL_TY = 16;
+template <int MH> struct HaloGeom {
+  static constexpr int TX = 8 * MH;
+  static constexpr int SLAB_X = TX + 8;              // >= TX + 2, multiple of 8 so that every slab row is 1024-byte periodic
+  static constexpr int SLAB_Y = HL_TY + 2;
+  static constexpr int SLAB_BYTES = SLAB_X * SLAB_Y * 128;
+};
 
-// AST: activation slabs in flight; BST: weight tiles in the ring (streamed mode); EPI: reserved (a coalesced epilogue
-// through a shared-memory transpose was measured slower than the direct per-row one and removed).  BN = 16 is the
-// network tail (64 -> Cout <= 16, fp32 NCHW output).
-template <int BN, bool RESIDENT, int AST, int BST, int EPI>
+// AST: activation slabs in flight; BST: weight tiles in the ring (streamed mode).  BN = 16 is the network tail
+// (64 -> Cout <= 16, fp32 NCHW output).
+template <int BN, bool RESIDENT, int AST, int BST, int MH>
 struct HaloCfg {
+  using G = HaloGeom<MH>;
   static constexpr int B_TILE = BN * 128;
   static constexpr int A_STAGES = AST;
   static constexpr int B_STAGES = RESIDENT ? 9 : BST;
-  static constexpr int SMEM = A_STAGES * HL_SLAB_BYTES + B_STAGES * B_TILE + 1024;
+  static constexpr int SMEM = A_STAGES * G::SLAB_BYTES + B_STAGES * B_TILE + 1024;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
-  static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static_assert(G::SLAB_BYTES % 1024 == 0, "slab stages must stay 1024-byte aligned");
+  static constexpr int NSETS = (2 * MH * BN <= 512) ? 2 : 1;   // accumulator sets (one set = MH accumulators of BN columns)
+  static_assert(MH * BN <= 512, "tensor memory budget");
+  static_assert(MH == 2 || NSETS == 2, "one-half tiles need two accumulator sets (one per epilogue group)");
+  static constexpr int ACC_COLS = NSETS * MH * BN;
+  static constexpr uint32_t TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
 };
 
-template <int BN, bool RESIDENT, int AST, int BST, int EPI>
+template <int BN, bool RESIDENT, int AST, int BST, int MH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, const int use_base_offset) {
-  using Cfg = HaloCfg<BN, RESIDENT, AST, BST, EPI>;
+conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P) {
+  using Cfg = HaloCfg<BN, RESIDENT, AST, BST, MH>;
+  using G = HaloGeom<MH>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* smem_b = smem + Cfg::A_STAGES * HL_SLAB_BYTES;
+  uint8_t* smem_b = smem + Cfg::A_STAGES * G::SLAB_BYTES;
   __shared__ __align__(8) uint64_t afull[Cfg::A_STAGES];
   __shared__ __align__(8) uint64_t aempty[Cfg::A_STAGES];
   __shared__ __align__(8) uint64_t bfull[Cfg::B_STAGES];
@@ -312,7 +325,7 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
     tc::prefetch_tmap(&M.b);
     for (int s = 0; s < Cfg::A_STAGES; ++s) { tc::mbar_init(&afull[s], 1); tc::mbar_init(&aempty[s], 1); }
     for (int s = 0; s < Cfg::B_STAGES; ++s) { tc::mbar_init(&bfull[s], 1); tc::mbar_init(&bempty[s], 1); }
-    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull_bar[a], 1); tc::mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull_bar[a], 1); tc::mbar_init(&tempty_bar[a], 4 * MH); }
     tc::fence_barrier_init();
   }
   if (warp == 2) tc::tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_smem);
@@ -334,11 +347,11 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int nt = t / pixel_tiles, pt = t - nt * pixel_tiles;
         const int b = pt / (P.tiles_y * P.tiles_x), r = pt - b * (P.tiles_y * P.tiles_x);
-        const int y0 = (r / P.tiles_x) * HL_TY, x0 = (r % P.tiles_x) * HL_TX;
+        const int y0 = (r / P.tiles_x) * HL_TY, x0 = (r % P.tiles_x) * G::TX;
         for (int kc = 0; kc < nkc; ++kc) {
           tc::mbar_wait(&aempty[sa], pha ^ 1);
-          tc::mbar_arrive_expect_tx(&afull[sa], HL_SLAB_BYTES);
-          tc::tma_load_4d(smem + sa * HL_SLAB_BYTES, &M.a[0], &afull[sa], kc * TC_KB, x0 - 1, y0 - 1, b);
+          tc::mbar_arrive_expect_tx(&afull[sa], G::SLAB_BYTES);
+          tc::tma_load_4d(smem + sa * G::SLAB_BYTES, &M.a[0], &afull[sa], kc * TC_KB, x0 - 1, y0 - 1, b);
           if (++sa == Cfg::A_STAGES) { sa = 0; pha ^= 1; }
           if (!RESIDENT) {
             for (int tap = 0; tap < 9; ++tap) {
@@ -354,34 +367,36 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
   } else if (warp == 1) {
     // converged warp, uniform operands, one elected issuer (see conv_tc_kernel)
     constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN);
-    constexpr uint32_t HI_A = tc::desc_hi_sw128(HL_SLAB_X * 128);
+    constexpr uint32_t HI_A = tc::desc_hi_sw128(G::SLAB_X * 128);
     constexpr uint32_t HI_B = tc::desc_hi_sw128(1024);
     const uint32_t slab_lo0 = tc::smem_u32(smem) >> 4;
     const uint32_t bt_lo0 = tc::smem_u32(smem_b) >> 4;
     int sa = 0; uint32_t pha = 0;
     int sb = 0; uint32_t phb = 0;
-    int acc = 0; uint32_t pa = 0;
+    int set = 0; uint32_t pset = 0;  // bit s of pset: phase of accumulator set s
     if (RESIDENT) {
       for (int tap = 0; tap < 9; ++tap) tc::mbar_wait(&bfull[tap], 0);
     }
-    (void)use_base_offset;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      tc::mbar_wait(&tempty_bar[acc], pa ^ 1);
+      tc::mbar_wait(&tempty_bar[set], ((pset >> set) & 1u) ^ 1u);
       tc::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(set * MH * BN);
       for (int kc = 0; kc < nkc; ++kc) {
         tc::mbar_wait(&afull[sa], pha);
         tc::tc_fence_after();
-        const uint32_t slab_lo = slab_lo0 + static_cast<uint32_t>(sa) * (HL_SLAB_BYTES >> 4);
+        const uint32_t slab_lo = slab_lo0 + static_cast<uint32_t>(sa) * (G::SLAB_BYTES >> 4);
         if (RESIDENT) {
           if (tc::elect_one()) {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-              const uint32_t a_lo = slab_lo + static_cast<uint32_t>(((tap / 3) * HL_SLAB_X + (tap % 3)) * 8);
               const uint32_t b_lo = bt_lo0 + static_cast<uint32_t>(tap * (Cfg::B_TILE >> 4));
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                tc::umma_bf16_lohi(d_tmem, a_lo + 2 * k, HI_A, b_lo + 2 * k, HI_B, idesc, (tap | k) != 0 ? 1u : (kc != 0 ? 1u : 0u));
+              for (int h = 0; h < MH; ++h) {
+                const uint32_t a_lo = slab_lo + static_cast<uint32_t>(((tap / 3) * G::SLAB_X + (tap % 3) + 8 * h) * 8);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  tc::umma_bf16_lohi(d_tmem + h * BN, a_lo + 2 * k, HI_A, b_lo + 2 * k, HI_B, idesc, (tap | k) != 0 ? 1u : (kc != 0 ? 1u : 0u));
+              }
             }
             tc::umma_commit(&aempty[sa]);
           }
@@ -391,13 +406,16 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
           for (int tap = 0; tap < 9; ++tap) {
             tc::mbar_wait(&bfull[sb], phb);
             tc::tc_fence_after();
-            const uint32_t a_lo = slab_lo + static_cast<uint32_t>(((tap / 3) * HL_SLAB_X + (tap % 3)) * 8);
+            const uint32_t a_lo = slab_lo + static_cast<uint32_t>(((tap / 3) * G::SLAB_X + (tap % 3)) * 8);
             const uint32_t b_lo = bt_lo0 + static_cast<uint32_t>(sb) * (Cfg::B_TILE >> 4);
             if (tc::elect_one()) {
-              tc::umma_bf16_lohi(d_tmem, a_lo, HI_A, b_lo, HI_B, idesc, (kc | tap) != 0 ? 1u : 0u);
-              tc::umma_bf16_lohi(d_tmem, a_lo + 2, HI_A, b_lo + 2, HI_B, idesc, 1u);
-              tc::umma_bf16_lohi(d_tmem, a_lo + 4, HI_A, b_lo + 4, HI_B, idesc, 1u);
-              tc::umma_bf16_lohi(d_tmem, a_lo + 6, HI_A, b_lo + 6, HI_B, idesc, 1u);
+#pragma unroll
+              for (int h = 0; h < MH; ++h) {
+                tc::umma_bf16_lohi(d_tmem + h * BN, a_lo + 64 * h, HI_A, b_lo, HI_B, idesc, (kc | tap) != 0 ? 1u : 0u);
+                tc::umma_bf16_lohi(d_tmem + h * BN, a_lo + 64 * h + 2, HI_A, b_lo + 2, HI_B, idesc, 1u);
+                tc::umma_bf16_lohi(d_tmem + h * BN, a_lo + 64 * h + 4, HI_A, b_lo + 4, HI_B, idesc, 1u);
+                tc::umma_bf16_lohi(d_tmem + h * BN, a_lo + 64 * h + 6, HI_A, b_lo + 6, HI_B, idesc, 1u);
+              }
               tc::umma_commit(&bempty[sb]);
               if (tap == 8) tc::umma_commit(&aempty[sa]);
             }
@@ -407,30 +425,37 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
         }
         if (++sa == Cfg::A_STAGES) { sa = 0; pha ^= 1; }
       }
-      if (tc::elect_one()) tc::umma_commit(&tfull_bar[acc]);
+      if (tc::elect_one()) tc::umma_commit(&tfull_bar[set]);
       __syncwarp();
-      if (++acc == 2) { acc = 0; pa ^= 1; }
+      pset ^= 1u << set;
+      if (++set == Cfg::NSETS) set = 0;
     }
   } else {
+    // two epilogue groups of four warps (TMEM lane quarter = warp % 4).  MH == 1: group g drains accumulator set g,
+    // i.e. every other tile.  MH == 2: both groups work on every tile, group g drains x-half g of the current set.
     const int q = warp & 3;
-    const int group = (warp - 2) >> 2;  // two epilogue groups, one per accumulator buffer (see conv_tc_kernel)
-    const int acc = group;
-    uint32_t pa = 0;
+    const int group = (warp - 2) >> 2;
+    const int half = (MH == 2) ? group : 0;
+    uint32_t pset = 0;
     int local = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
-      if ((local & 1) != group) continue;
+      if (MH == 1 && (local & 1) != group) continue;
+      const int set = (MH == 1) ? group : (local % Cfg::NSETS);
+      const uint32_t pa = (pset >> set) & 1u;
+      pset ^= 1u << set;
       const int nt = t / pixel_tiles, pt = t - nt * pixel_tiles;
       const int b = pt / (P.tiles_y * P.tiles_x), r = pt - b * (P.tiles_y * P.tiles_x);
-      const int y0 = (r / P.tiles_x) * HL_TY, x0 = (r % P.tiles_x) * HL_TX;
+      const int y0 = (r / P.tiles_x) * HL_TY, x0 = (r % P.tiles_x) * G::TX;
       const int m = q * 32 + lane;
-      const int y = y0 + (m >> 3), x = x0 + (m & 7);
+      const int y = y0 + (m >> 3), x = x0 + 8 * half + (m & 7);
       const bool inside = (y < P.H) && (x < P.W);
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((set * MH + half) * BN);
       if constexpr (BN == 16) {
       // network tail (Cout <= 16): fp32 NCHW stores of the real channels, optional "+ x" term
-      tc::mbar_wait(&tfull_bar[acc], pa);
+      tc::mbar_wait(&tfull_bar[set], pa);
       tc::tc_fence_after();
       uint32_t rr[16];
-      tc::tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN), rr);
+      tc::tmem_ld_32x32b_x16(t_addr, rr);
       tc::tmem_ld_wait();
       if (inside) {
 #pragma unroll
@@ -467,9 +492,8 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
         }
       };
       fetch(0, ra, rb);
-      tc::mbar_wait(&tfull_bar[acc], pa);
+      tc::mbar_wait(&tfull_bar[set], pa);
       tc::tc_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
@@ -525,8 +549,7 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps M, const ConvTcParams P, cons
       }
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
-      pa ^= 1;
+      if (lane == 0) tc::mbar_arrive(&tempty_bar[set]);
     }
   }
   tc::tc_fence_before();
@@ -602,42 +625,60 @@ __global__ void __launch_bounds__(HD_THREADS, 1) conv_head_kernel(const HeadPara
 
   if (warp < 8) {
     // ===================== builders =====================
+    // The 9*CT input values of a pixel are fetched with UNCONDITIONAL loads from clamped coordinates (then masked), one
+    // tile ahead of their use: all loads of a tile are independent and in flight while the previous tile is converted,
+    // stored and handed to the MMA warp (the first version interleaved predicated loads with their uses and spent
+    // ~3400 cycles per tile waiting on them, ncu: 73 % long-scoreboard stalls).
     const int group = warp >> 2;
     const int m = (warp & 3) * 32 + lane;  // GEMM row = (warp&3) tile row, lane = x
     uint8_t* row = smem + group * TC_A_BYTES + m * 128;
-    uint32_t ph = 0;
-    int local = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
-      if ((local & 1) != group) continue;
-      const int b = t / (P.tiles_y * P.tiles_x), r = t - b * (P.tiles_y * P.tiles_x);
+    const int tiles_per_img = P.tiles_y * P.tiles_x;
+    auto gather = [&](int t, float (&v)[9 * CT]) {
+      const int b = t / tiles_per_img, r = t - b * tiles_per_img;
       const int y = (r / P.tiles_x) * HD_TY + (warp & 3), x = (r % P.tiles_x) * HD_TX + lane;
       const float fillv = P.has_fill ? (P.fill_batch ? __ldg(P.fill_batch + b) : P.fill_scalar) : 0.f;
-      float v[NCH * 8];
-#pragma unroll
-      for (int k = KREAL; k < NCH * 8; ++k) v[k] = 0.f;
+      const float* img = P.x + (long long)b * P.C * P.H * P.W;
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
         const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
         const bool inb = (yy >= 0) && (yy < P.H) && (xx >= 0) && (xx < P.W);
+        const int yc = min(max(yy, 0), P.H - 1), xc = min(max(xx, 0), P.W - 1);
 #pragma unroll
         for (int c = 0; c < CT; ++c) {
-          float val = 0.f;
-          if (inb) val = (c < P.C) ? __ldg(P.x + (((long long)b * P.C + c) * P.H + yy) * P.W + xx) : fillv;
-          v[tap * CT + c] = val;
+          const int cc = min(c, P.C - 1);
+          const float val = __ldg(img + ((long long)cc * P.H + yc) * P.W + xc);
+          v[tap * CT + c] = inb ? ((c < P.C) ? val : fillv) : 0.f;  // a select, not a branch: the load above is unconditional
         }
       }
+    };
+    uint32_t ph = 0;
+    const int stride2 = 2 * gridDim.x;
+    int t = blockIdx.x + group * gridDim.x;
+    float cur[9 * CT];
+    if (t < total_tiles) gather(t, cur);
+    for (; t < total_tiles; t += stride2) {
+      float nxt[9 * CT];
+      const bool more = t + stride2 < total_tiles;
+      if (more) gather(t + stride2, nxt);
       tc::mbar_wait(&aempty[group], ph ^ 1);
 #pragma unroll
       for (int j = 0; j < NCH; ++j) {
         uint4 u;
         __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
+        for (int e = 0; e < 4; ++e) {
+          const int k0 = j * 8 + 2 * e;
+          h[e] = __floats2bfloat162_rn(k0 < KREAL ? cur[k0] : 0.f, k0 + 1 < KREAL ? cur[k0 + 1] : 0.f);
+        }
         *reinterpret_cast<uint4*>(row + ((j ^ (m & 7)) << 4)) = u;
       }
       tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
       tc::mbar_arrive(&afull[group]);
       ph ^= 1;
+      if (more) {
+#pragma unroll
+        for (int k = 0; k < 9 * CT; ++k) cur[k] = nxt[k];
+      }
     }
   } else if (warp == 8) {
     // ===================== MMA issuer =====================
@@ -901,12 +942,12 @@ static int launch_conv_tc(const TcMaps& M, const ConvTcParams& P, void* stream) 
   return DINVK_POST_LAUNCH();
 }
 
-static int make_slab_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C) {
+static int make_slab_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int slab_x) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_error(DINVK_ECUDA, "cuTensorMapEncodeTiled is unavailable");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {TC_KB, HL_SLAB_X, HL_SLAB_Y, 1};
+  cuuint32_t box[4] = {TC_KB, (cuuint32_t)slab_x, HL_TY + 2, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -914,24 +955,30 @@ static int make_slab_map(CUtensorMap* m, const void* ptr, int B, int H, int W, i
   return 0;
 }
 
-template <int BN, bool RESIDENT, int AST, int BST, int EPI>
-static int launch_conv_halo(const TcMaps& M, const ConvTcParams& P, int use_base_offset, void* stream) {
-  using Cfg = HaloCfg<BN, RESIDENT, AST, BST, EPI>;
+template <int BN, bool RESIDENT, int AST, int BST, int MH>
+static int launch_conv_halo(TcMaps& M, ConvTcParams& P, const void* x, void* stream) {
+  using Cfg = HaloCfg<BN, RESIDENT, AST, BST, MH>;
+  using G = HaloGeom<MH>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BN, RESIDENT, AST, BST, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BN, RESIDENT, AST, BST, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return set_error(DINVK_ECUDA, "cudaFuncSetAttribute(conv_tc_halo<%d>): %s", BN, cudaGetErrorString(e));
     attr_set = true;
   }
+  int rc;
+  if ((rc = make_slab_map(&M.a[0], x, P.B, P.H, P.W, P.Cin, G::SLAB_X))) return rc;
+  M.a[1] = M.a[0]; M.a[2] = M.a[0]; M.a[3] = M.a[0];
+  P.tiles_x = ceil_div(P.W, G::TX); P.tiles_y = ceil_div(P.H, HL_TY);
   const long long tiles = (long long)P.B * P.tiles_y * P.tiles_x * P.n_tiles;
   const int grid = (int)std::min<long long>(tiles, sm_count());
   count_launch();
-  conv_tc_halo_kernel<BN, RESIDENT, AST, BST, EPI><<<grid, TC_THREADS, Cfg::SMEM, (cudaStream_t)stream>>>(M, P, use_base_offset);
+  conv_tc_halo_kernel<BN, RESIDENT, AST, BST, MH><<<grid, TC_THREADS, Cfg::SMEM, (cudaStream_t)stream>>>(M, P);
   return DINVK_POST_LAUNCH();
 }
 
-// halo mode (DINVK_CONV_HALO): 0 = off (per-tap kernel), 1 = on (default; descriptor base_offset 0),
-// 3 = on with base_offset = kx (kept only to document the hardware behaviour: it produces wrong results)
+// halo mode (DINVK_CONV_HALO): 0 = off (per-tap kernel), 1 = on (default).  The UMMA descriptors into the slab use
+// base_offset 0: the 128-byte swizzle is a function of the shared-memory address, so a start address that is not
+// 1024-byte aligned needs no correction (base_offset = kx was tried on B200 and produces wrong results).
 static int halo_mode() {
   static int mode = -1;
   if (mode < 0) {
@@ -963,32 +1010,38 @@ static int conv3x3_tc(const void* x, const void* weight, const float* bias, cons
   DINVK_CHECK_ARG(rows % bn == 0, "conv3x3_bf16: weight rows %d not a multiple of the N tile %d", rows, bn);
   TcMaps M;
   int rc;
+  // slab + halo kernel (activations read once per 64-channel block instead of once per tap):
+  //   64 -> 64 and the 64 -> (<=16) tail with the weights resident in shared memory; >= 128 output channels with streamed
+  //   weights.  Body layers use 16x16-pixel CTA tiles = TWO M=128 accumulators per weight tile (measured on B200 at the
+  //   DRUNet shapes, one vs two accumulators: 64 ch 309 -> 285 us, 128 ch 280 -> 238 us, 256 ch 219 -> 203 us).
+  // DINVK_HALO_VARIANT selects the measured alternatives (1: previous one-accumulator kernels / per-tap kernel for N=256).
+  static const int variant = getenv("DINVK_HALO_VARIANT") ? atoi(getenv("DINVK_HALO_VARIANT")) : 0;
   const bool halo_tail = out_f32 && Cin == 64 && rows == 16 && !getenv("DINVK_NO_HALO_TAIL");
-  if (halo_mode() != 0 && (halo_tail || (!out_f32 && ((rows == 64 && Cin == 64) || bn == 128)))) {
-    // 64- and 128-channel layers: slab + halo kernel (activations read once per channel block, not once per tap)
-    if ((rc = make_slab_map(&M.a[0], x, B, H, W, Cin))) return rc;
-    M.a[1] = M.a[0]; M.a[2] = M.a[0]; M.a[3] = M.a[0];
+  // (Cin >= 512 at 32x32 pixels: 512 tile jobs over 148 CTAs quantise badly with 256-pixel tiles; the per-tap kernel is faster)
+  const bool halo_body = !out_f32 && ((rows == 64 && Cin == 64) || bn == 128 || (bn == 256 && Cin < 512 && variant != 1));
+  if (halo_mode() != 0 && (halo_tail || halo_body)) {
     if ((rc = make_w_map(&M.b, weight, 9 * Cin, rows, bn))) return rc;
     ConvTcParams P;
     P.B = B; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout_real;
     P.ntaps = 9; P.kc_per_tap = Cin / TC_KB;
     for (int t = 0; t < 9; ++t) { P.dx[t] = t % 3 - 1; P.dy[t] = t / 3 - 1; P.amap[t] = 0; }
     P.mode = out_f32 ? 1 : 0;
-    P.tiles_x = ceil_div(W, HL_TX); P.tiles_y = ceil_div(H, HL_TY); P.n_tiles = rows / bn;
+    P.tiles_x = 0; P.tiles_y = 0; P.n_tiles = rows / bn;  // tiles_x/y: set by the launcher from the kernel's tile geometry
     P.relu = act; P.res = (const bf16*)res; P.res2 = (const bf16*)res2; P.out = (bf16*)out; P.out_f32 = out_f32; P.add_f32 = add_f32; P.bias = bias;
-    const int ubo = halo_mode() == 3 ? 1 : 0;
-    if (halo_tail) return launch_conv_halo<16, true, 4, 0, 0>(M, P, ubo, stream);
-    static const int variant = getenv("DINVK_HALO_VARIANT") ? atoi(getenv("DINVK_HALO_VARIANT")) : 0;
+    if (halo_tail) return launch_conv_halo<16, true, 4, 0, 1>(M, P, x, stream);
     if (bn == 64) {
       switch (variant) {
-        case 1: return launch_conv_halo<64, true, 2, 0, 0>(M, P, ubo, stream);
-        default: return launch_conv_halo<64, true, 4, 0, 0>(M, P, ubo, stream);
+        case 1: return launch_conv_halo<64, true, 4, 0, 1>(M, P, x, stream);
+        default: return launch_conv_halo<64, true, 2, 0, 2>(M, P, x, stream);
       }
     }
-    switch (variant) {
-      case 1: return launch_conv_halo<128, false, 2, 5, 0>(M, P, ubo, stream);
-      default: return launch_conv_halo<128, false, 2, 8, 0>(M, P, ubo, stream);
+    if (bn == 128) {
+      switch (variant) {
+        case 1: return launch_conv_halo<128, false, 2, 8, 1>(M, P, x, stream);
+        default: return launch_conv_halo<128, false, 2, 7, 2>(M, P, x, stream);
+      }
     }
+    return launch_conv_halo<256, false, 2, 3, 2>(M, P, x, stream);
   }
   if ((rc = make_act_map(&M.a[0], x, B, H, W, Cin, (long long)Cin * 2, (long long)W * Cin * 2, (long long)H * W * Cin * 2))) return rc;
   M.a[1] = M.a[0]; M.a[2] = M.a[0]; M.a[3] = M.a[0];

@@ -1,5 +1,5 @@
 from .data_fidelity import L2, DataFidelity, ZeroFidelity  # noqa: F401
-from .graphed import GraphedIteration  # noqa: F401
+from .graphed import GraphedIteration, HostStreamedIteration  # noqa: F401
 from .linear import conjugate_gradient, least_squares  # noqa: F401
 from .optim_iterators import (ADMMIteration, FISTAIteration, HQSIteration, OptimIterator,  # noqa: F401
                               PGDIteration)

@@ -55,3 +55,70 @@ class GraphedIteration:
         for _ in range(n):
             self.graph.replay()
         return self.x
+
+
+class HostStreamedIteration:
+    """A stream of independent single-iteration requests whose inputs AND outputs live in pinned host memory.
+
+    Request k uploads its iterate x_k and measurement y_k (host -> device), runs one iteration of `algo`
+    (`A^T y_k` included — nothing is cached across requests) and downloads the new iterate.  Uploads, compute and
+    downloads run on three CUDA streams over two device slots, so the PCIe traffic of request k+1 / k-1 overlaps the
+    compute of request k; every request still moves all of its bytes over PCIe.  Compute is a CUDA-graph replay of the
+    public `single_iteration` (one graph per slot, bound to that slot's buffers).
+    """
+
+    def __init__(self, algo, physics, x_host: torch.Tensor, y_host: torch.Tensor, device, slots: int = 2, it: int = 0):
+        if any(len(v) > 1 for v in algo.init_params_algo.values()):
+            raise ValueError("per-iteration parameter schedules cannot be captured in a single graph")
+        self.device = device
+        self.n = 0
+        self.up, self.down = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+        self.slots = []
+        with torch.no_grad():
+            for _ in range(slots):
+                s = {
+                    "x": torch.empty(x_host.shape, dtype=x_host.dtype, device=device),
+                    "y": torch.empty(y_host.shape, dtype=y_host.dtype, device=device),
+                    "uploaded": torch.cuda.Event(), "computed": torch.cuda.Event(), "downloaded": torch.cuda.Event(),
+                }
+                s["x"].copy_(x_host)
+                s["y"].copy_(y_host)
+                body = lambda s=s: algo.single_iteration({"est": (s["x"], s["x"]), "aty": None}, it, s["y"], physics)["est"][0]
+                side = torch.cuda.Stream(device=device)
+                side.wait_stream(torch.cuda.current_stream(device))
+                with torch.cuda.stream(side):
+                    s["out"] = torch.empty_like(body())
+                torch.cuda.current_stream(device).wait_stream(side)
+                torch.cuda.synchronize(device)
+                s["graph"] = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(s["graph"]):
+                    s["out"].copy_(body())
+                self.slots.append(s)
+
+    def submit(self, x_host: torch.Tensor, y_host: torch.Tensor, out_host: torch.Tensor) -> None:
+        """enqueue one request (asynchronous; `out_host` is valid after `drain()`)"""
+        s = self.slots[self.n % len(self.slots)]
+        first_use = self.n < len(self.slots)
+        self.n += 1
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.up):
+            if not first_use:
+                self.up.wait_event(s["computed"])  # the slot's previous request no longer reads x / y
+            s["x"].copy_(x_host, non_blocking=True)
+            s["y"].copy_(y_host, non_blocking=True)
+            s["uploaded"].record(self.up)
+        cur.wait_event(s["uploaded"])
+        if not first_use:
+            cur.wait_event(s["downloaded"])  # the slot's previous result has left the device
+        s["graph"].replay()
+        s["computed"].record(cur)
+        with torch.cuda.stream(self.down):
+            self.down.wait_event(s["computed"])
+            out_host.copy_(s["out"], non_blocking=True)
+            s["downloaded"].record(self.down)
+
+    def drain(self) -> None:
+        """make the current stream wait for every enqueued upload / download"""
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self.up)
+        cur.wait_stream(self.down)
