@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(NTHR, 1024 / NTHR) spectral_pass_kernel(const 
 
 }  // namespace dinvk
 #include "spectral_fast.cuh"
+#include "spectral_pipe.cuh"
 namespace dinvk {
 
 // O(N^2) DFT along one axis of an interleaved (B,H,W) tensor — sizes with prime factors > 5.
@@ -305,6 +306,54 @@ static int get_tables(int n, int centered, Tables* out) {
   *out = t;
   return 0;
 }
+
+
+#ifndef DINVK_EMUL
+static inline bool al16(const void* p);
+// 256x256 single-coil fast path (spectral_pipe.cuh).  Returns -1 when the call does not qualify.
+static int try_pipe(const dinvk_spectral_args& a, float2* T1, const Tables& tW, void* stream) {
+  if (a.H != 256 || a.W != 256 || a.ncoil > 1) return -1;
+  if (getenv("DINVK_NO_PIPE_FFT")) return -1;
+  if (!(a.fwd || a.inv)) return -1;
+  if (a.gmode == DINVK_G_CMUL || a.gmode == DINVK_G_CMUL_CONJ) return -1;
+  if (!al16(a.p0) || !al16(a.p1) || !al16(a.q0) || !al16(a.q1) || !al16(a.out) || !al16(a.mask)) return -1;
+  if (a.gmode != DINVK_G_NONE && ((a.mask_sb & 1) || (a.mask_sc & 1) || (a.mask_sh & 1))) return -1;
+  const bool fused = a.fwd && a.inv;
+  if (fused && a.gmode != DINVK_G_NONE && (a.mask_sh != 0 || a.mask_sc != 0)) return -1;  // full masks: 3 tile passes
+  sp::PipeParams P = sp::PipeParams();
+  P.B = a.B;
+  P.p0 = a.p0; P.p1 = a.p1; P.a0 = a.a0; P.a1 = a.p1 ? a.a1 : 0.f;
+  P.gmode = a.gmode; P.g = a.mask; P.gsb = a.mask_sb; P.gsc = a.mask_sc; P.gsh = a.mask_sh; P.gc = a.c; P.gcb = a.c_batch;
+  P.q0 = a.q0; P.q1 = a.q1; P.e0 = a.e0; P.e1 = a.q0 ? a.e1 : 0.f; P.e2 = a.q1 ? a.e2 : 0.f;
+  P.out = a.out; P.ws = T1; P.tw = tW.tw; P.centered = a.centered ? 1 : 0;
+  const int ntiles = a.B * 16;
+  const unsigned grid = (unsigned)std::min(ntiles, 2 * sm_count());
+  int rc;
+  if (fused) {
+    if (a.p1) {
+      if ((rc = allow_smem(sp::sp_row_fused<true>, sp::ROW_SMEM))) return rc;
+      DINVK_LAUNCH(sp::sp_row_fused<true>, dim3(grid), dim3(sp::NT), sp::ROW_SMEM, stream, P);
+    } else {
+      if ((rc = allow_smem(sp::sp_row_fused<false>, sp::ROW_SMEM))) return rc;
+      DINVK_LAUNCH(sp::sp_row_fused<false>, dim3(grid), dim3(sp::NT), sp::ROW_SMEM, stream, P);
+    }
+    return DINVK_POST_LAUNCH();
+  }
+  P.inverse = a.inv ? 1 : 0;
+  P.g_at_load = a.inv ? 1 : 0;  // A^T: multiplier on the k-space source; A: multiplier on the k-space result
+  if (a.p1) {
+    if ((rc = allow_smem(sp::sp_pass1<true>, sp::ROW_SMEM))) return rc;
+    DINVK_LAUNCH(sp::sp_pass1<true>, dim3(grid), dim3(sp::NT), sp::ROW_SMEM, stream, P);
+  } else {
+    if ((rc = allow_smem(sp::sp_pass1<false>, sp::ROW_SMEM))) return rc;
+    DINVK_LAUNCH(sp::sp_pass1<false>, dim3(grid), dim3(sp::NT), sp::ROW_SMEM, stream, P);
+  }
+  if ((rc = DINVK_POST_LAUNCH())) return rc;
+  if ((rc = allow_smem(sp::sp_pass2, sp::P2_SMEM))) return rc;
+  DINVK_LAUNCH(sp::sp_pass2, dim3(grid), dim3(sp::P2_NT), sp::P2_SMEM, stream, P);
+  return DINVK_POST_LAUNCH();
+}
+#endif
 
 static int pow2floor(int x) { int p = 1; while (2 * p <= x) p *= 2; return p; }
 
@@ -508,6 +557,12 @@ extern "C" int dinvk_spectral(const dinvk_spectral_args* ap, void* workspace, si
     return launch_pass(false, P, ecfg, stream);
   }
 
+#ifndef DINVK_EMUL
+  if (fast) {
+    const int prc = try_pipe(a, T1, tW, stream);
+    if (prc >= 0) return prc;
+  }
+#endif
   if (fast) {
     if (a.fwd && !a.inv) {
       // A: COL(fwd) planar -> T1 ; ROW(fwd, multiplier) T1 -> out

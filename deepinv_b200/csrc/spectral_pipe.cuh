@@ -1,0 +1,483 @@
+// spectral_pipe.cuh — persistent, bulk-copy-pipelined spectral kernels for 256x256 images (included by spectral.cu).
+//
+// Same arithmetic as the tile passes in spectral.cu / spectral_fast.cuh (radix-16 Stockham stages, fp64-generated
+// twiddles), restructured around what bounds the operator on B200:
+//
+//   * HBM latency: the old passes kept < 40 KB per SM in flight (load -> barrier -> transform -> store inside each
+//     CTA).  Here every kernel is persistent (2 CTAs per SM, static round-robin over tiles) and its tiles arrive by
+//     `cp.async.bulk` (TMA 1-D bulk copies completing on an mbarrier) into a shared-memory ring filled one tile ahead,
+//     so the loads of tile i+1 are in flight while tile i is transformed and stored.
+//   * issue slots: a 256x256 fp32 FFT on B200 needs about as many issue cycles as HBM cycles.  Signs of the centred
+//     transform, the orthonormal scale and the conjugations of the inverse are folded into per-thread constants or
+//     the twiddle tables; all indexing is compile-time; the forward -> multiplier -> inverse row pass keeps the
+//     spectrum in registers between the two transforms (the bins a thread owns after the last forward stage,
+//     {j + 16 r}, are exactly the inputs of its first inverse butterfly).
+//   * no narrow column strips: the H-direction transform is split 256 = 16 x 16.  Pass 1 owns the 16 rows
+//     {b + 16 a} of an image (1 KB contiguous segments), transforms them along W, does the a-butterfly of the
+//     H-transform per column in registers, and writes the intermediate as [k_lo][b][w]; pass 2 reads 16 contiguous
+//     intermediate rows (one 32 KB bulk copy), does the b-butterfly per column and stores 16 output rows.
+//     Every global access is a >= 1 KB contiguous segment.
+//
+// Kernels:  sp_row_fused   out = e0 * F_W^-1( g(mask[w]) * F_W(a0 p0 + a1 p1) ) + e1 q0 + e2 q1     (line masks)
+//           sp_pass1       planar rows -> W transform -> H stage 1 (+ twiddle) -> interleaved workspace
+//           sp_pass2       workspace -> H stage 2 -> multiplier / epilogue -> planar rows
+// Restricted to H = W = 256, single-coil planar (B,2,H,W) tensors; everything else takes the tile passes.
+#pragma once
+#ifndef DINVK_EMUL
+#include "fft_core.cuh"
+
+namespace dinvk {
+namespace sp {
+
+constexpr int N = 256;
+constexpr int NT = 256;                 // threads per CTA (row kernels)
+constexpr int LS = 272;                 // staged line stride, floats (272 % 32 == 16: two lines per warp, no conflicts)
+constexpr int PLANE_F = 16 * LS;        // floats per staged plane
+constexpr int STAGE_F = 2 * PLANE_F;    // floats per staged tile (re plane, im plane)
+constexpr int RLS = 273;                // work-buffer line stride, float2 (pad16 layout)
+constexpr int WORK_F2 = 16 * RLS;
+constexpr size_t ROW_SMEM = (size_t)2 * STAGE_F * 4 + (size_t)WORK_F2 * 8 + 2 * 256 * 8 + 64;
+constexpr int P2_NT = 128;
+constexpr int P2_STAGES = 3;
+constexpr int P2_TILE_F = 16 * 256 * 2;  // floats per workspace tile (16 rows of 256 interleaved complex)
+constexpr size_t P2_SMEM = (size_t)P2_STAGES * P2_TILE_F * 4 + 64;
+
+struct PipeParams {
+  int B;
+  const float* p0; const float* p1; float a0, a1;
+  int gmode; const float* g; long long gsb, gsc, gsh; float gc; const float* gcb;
+  const float* q0; const float* q1; float e0, e1, e2;
+  float* out;
+  float2* ws;
+  const float2* tw;   // exp(-2 pi i k / 256), k = 0..255
+  int inverse;        // pass1 / pass2: 0 forward, 1 inverse (by conjugation)
+  int centered;
+  int g_at_load;      // pass1 applies the multiplier to the source (A^T); pass2 applies it to the result (A)
+};
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok) : "r"(s_u32(bar)), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// 1-D bulk copy global -> shared, completion counted in bytes on `bar` (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(dst)),
+               "l"(src), "r"(bytes), "r"(s_u32(bar))
+               : "memory");
+}
+
+// multiplier transform applied to K raw mask values at once: the mode switch sits outside the element loop
+template <int K>
+__device__ __forceinline__ void gmap(int gmode, float (&m)[K], float c) {
+  if (gmode == DINVK_G_SQ) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) m[i] = m[i] * m[i];
+  } else if (gmode == DINVK_G_INV_SQ_PLUS_C) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) m[i] = 1.0f / (m[i] * m[i] + c);
+  } else if (gmode == DINVK_G_PINV) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) m[i] = m[i] > 1e-5f ? 1.0f / m[i] : 0.0f;
+  }
+}
+
+// ---- W-direction transform of one 16-line tile, thread = (line, j) ------------------------------------------------
+// stage 1: inputs x[j + 16 r] from the staged planes, butterfly, autosort store work[line][16 j + r]
+__device__ __forceinline__ void w_stage1_store(float2 (&v)[16], float2* work, int line, int j) {
+  Dft<16>::run(v);
+  float2* w = work + line * RLS + 17 * j;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) w[r] = v[r];
+}
+// stage 2: inputs work[line][j + 16 r] (pad16 -> j + 17 r) times tws[r][j], butterfly -> v[r] = X[j + 16 r]
+__device__ __forceinline__ void w_stage2(float2 (&v)[16], const float2* work, const float2* tws, int line, int j) {
+  const float2* w = work + line * RLS + j;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) v[r] = w[17 * r];
+#pragma unroll
+  for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], tws[r * 16 + j]);
+  Dft<16>::run(v);
+}
+
+// shared-memory carve-up of the row kernels
+struct RowSmem {
+  float* in0;
+  float2* work;
+  float2* tws;   // [r][j]: sign(r) * w256^(r j)   (sign = (-1)^r for centred transforms: the (-1)^n pre-phase)
+  float2* twf;   // w256^k, k = 0..255
+  uint64_t* full;
+};
+__device__ __forceinline__ RowSmem carve_row(unsigned char* raw) {
+  RowSmem s;
+  s.in0 = reinterpret_cast<float*>(raw);
+  s.work = reinterpret_cast<float2*>(s.in0 + 2 * STAGE_F);
+  s.tws = s.work + WORK_F2;
+  s.twf = s.tws + 256;
+  s.full = reinterpret_cast<uint64_t*>(s.twf + 256);
+  return s;
+}
+__device__ __forceinline__ void fill_tables(const RowSmem& s, const float2* __restrict__ tw, int centered, int tid) {
+  const int r = tid >> 4, j = tid & 15;
+  float2 t = __ldg(tw + ((r * j) & 255));
+  if (centered && (r & 1)) { t.x = -t.x; t.y = -t.y; }
+  s.tws[tid] = t;
+  s.twf[tid] = __ldg(tw + tid);
+}
+
+// issue the 32 row copies (16 rows x 2 planes, 1 KB each) of one tile; called by warp 0 (all lanes)
+__device__ __forceinline__ void issue_rows(float* dst, const float* src_img, long long plane_stride, int row0, int row_step,
+                                           uint64_t* bar, int lane) {
+  if (lane == 0) mb_expect_tx(bar, 32 * 1024);
+  __syncwarp();
+  const int plane = lane >> 4, row = lane & 15;
+  bulk_g2s(dst + plane * PLANE_F + row * LS, src_img + plane * plane_stride + (long long)(row0 + row * row_step) * N, 1024, bar);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// fused row pass (line masks): one tile = 16 consecutive rows of one image
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool HAS_P1>
+__global__ void __launch_bounds__(NT, 2) sp_row_fused(const PipeParams P) {
+  extern __shared__ __align__(128) unsigned char sp_raw[];
+  const RowSmem S = carve_row(sp_raw);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int line = tid >> 4, j = tid & 15;
+  const int ntiles = P.B * 16;
+  constexpr long long HW = (long long)N * N;
+
+  fill_tables(S, P.tw, P.centered, tid);
+  if (tid == 0) { mb_init(&S.full[0], 1); mb_init(&S.full[1], 1); fence_mbar_init(); }
+  __syncthreads();
+  int t0 = blockIdx.x;
+  if (tid < 32 && t0 < ntiles) issue_rows(S.in0, P.p0 + (long long)(t0 >> 4) * 2 * HW, HW, (t0 & 15) * 16, 1, &S.full[0], lane);
+
+  const float scale = 0.0625f;                                   // 1/sqrt(256)
+  const float sj = (P.centered && (j & 1)) ? -1.0f : 1.0f;      // (-1)^k post-phase, k = j + 16 r
+  const float fmid = sj * scale;                                 // after the forward transform
+  const float fend = sj * scale * P.e0;                          // after the inverse transform (and the epilogue weight)
+  const bool q0_smem = (P.q0 != nullptr) && (P.q0 == P.p0) && !HAS_P1 && P.a0 == 1.0f;
+
+  int it = 0;
+  for (int t = t0; t < ntiles; t += gridDim.x, ++it) {
+    const int s = it & 1;
+    const int img = t >> 4, h0 = (t & 15) * 16;
+    // prefetch the next tile into the other buffer (its previous contents were consumed before the barrier that ended
+    // the previous iteration)
+    const int tn = t + gridDim.x;
+    if (tid < 32 && tn < ntiles) {
+      fence_async_smem();
+      issue_rows((S.in0 + (s ^ 1) * STAGE_F), P.p0 + (long long)(tn >> 4) * 2 * HW, HW, (tn & 15) * 16, 1, &S.full[s ^ 1], lane);
+    }
+    mb_wait(&S.full[s], (it >> 1) & 1);
+    float* sre = (S.in0 + s * STAGE_F);
+    float* sim = sre + PLANE_F;
+
+    float2 v[16];
+    {
+      const float* pr = sre + line * LS + j;
+      const float* pi = sim + line * LS + j;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r] = make_float2(pr[16 * r], pi[16 * r]);
+    }
+    if (HAS_P1) {
+      const float* g1 = P.p1 + (long long)img * 2 * HW + (long long)(h0 + line) * N + j;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        v[r].x = P.a0 * v[r].x + P.a1 * __ldg(g1 + 16 * r);
+        v[r].y = P.a0 * v[r].y + P.a1 * __ldg(g1 + HW + 16 * r);
+      }
+    } else if (P.a0 != 1.0f) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) { v[r].x *= P.a0; v[r].y *= P.a0; }
+    }
+    w_stage1_store(v, S.work, line, j);
+    __syncthreads();
+    w_stage2(v, S.work, S.tws, line, j);
+    // multiplier g(mask[img, w = j + 16 r]), forward post-phase and scale, conjugation for the inverse-by-conjugation
+    if (P.gmode != DINVK_G_NONE) {
+      const float* gp = P.g + (long long)img * P.gsb + j;
+      const float c = P.gcb ? __ldg(P.gcb + img) : P.gc;
+      float m[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) m[r] = __ldg(gp + 16 * r);
+      gmap<16>(P.gmode, m, c);
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const float mf = m[r] * fmid;
+        v[r].x *= mf; v[r].y *= -mf;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) { v[r].x *= fmid; v[r].y *= -fmid; }
+    }
+    __syncthreads();  // every thread has read its stage-2 inputs: the work buffer may be overwritten
+    w_stage1_store(v, S.work, line, j);
+    __syncthreads();
+    // epilogue operands that are not already staged: 8 x 128-bit per thread per operand, issued before the last butterfly
+    float4 qb[8];
+    const bool ldq0 = (P.q0 != nullptr) && !q0_smem;  // rare: loaded inline in the final pass
+    const bool ldq1 = P.q1 != nullptr;
+    const long long gbase = (long long)img * 2 * HW + (long long)h0 * N;
+    if (ldq1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int f = tid + i * NT, plane = f >> 10, row = (f >> 6) & 15, c4 = f & 63;
+        qb[i] = __ldg(reinterpret_cast<const float4*>(P.q1 + gbase + plane * HW + row * N + 4 * c4));
+      }
+    }
+    w_stage2(v, S.work, S.tws, line, j);
+    {  // conj, post-phase, scale, e0; + e1 * x when q0 is the staged source; in place into the staging planes
+      float* pr = sre + line * LS + j;
+      float* pi = sim + line * LS + j;
+      if (q0_smem) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          pr[16 * r] = fend * v[r].x + P.e1 * pr[16 * r];
+          pi[16 * r] = -fend * v[r].y + P.e1 * pi[16 * r];
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) { pr[16 * r] = fend * v[r].x; pi[16 * r] = -fend * v[r].y; }
+      }
+    }
+    __syncthreads();
+    {
+      float* ob = P.out + gbase;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int f = tid + i * NT, plane = f >> 10, row = (f >> 6) & 15, c4 = f & 63;
+        float4 o = *reinterpret_cast<const float4*>(sre + plane * PLANE_F + row * LS + 4 * c4);
+        if (ldq0) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(P.q0 + gbase + plane * HW + row * N + 4 * c4));
+          o.x += P.e1 * a.x; o.y += P.e1 * a.y; o.z += P.e1 * a.z; o.w += P.e1 * a.w;
+        }
+        if (ldq1) { o.x += P.e2 * qb[i].x; o.y += P.e2 * qb[i].y; o.z += P.e2 * qb[i].z; o.w += P.e2 * qb[i].w; }
+        *reinterpret_cast<float4*>(ob + plane * HW + row * N + 4 * c4) = o;
+      }
+    }
+    __syncthreads();  // staging buffer s fully consumed: the next iteration may refill it
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pass 1: tile = rows {b + 16 a} of one image.  W transform, then the a-butterfly of the H transform per column,
+// twiddle w256^(b k_lo), store to ws[img][k_lo][b][w] (interleaved)
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool HAS_P1>
+__global__ void __launch_bounds__(NT, 2) sp_pass1(const PipeParams P) {
+  extern __shared__ __align__(128) unsigned char sp_raw[];
+  const RowSmem S = carve_row(sp_raw);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int line = tid >> 4, j = tid & 15;
+  const int ntiles = P.B * 16;
+  constexpr long long HW = (long long)N * N;
+
+  fill_tables(S, P.tw, P.centered, tid);
+  if (tid == 0) { mb_init(&S.full[0], 1); mb_init(&S.full[1], 1); fence_mbar_init(); }
+  __syncthreads();
+  int t0 = blockIdx.x;
+  if (tid < 32 && t0 < ntiles) issue_rows(S.in0, P.p0 + (long long)(t0 >> 4) * 2 * HW, HW, t0 & 15, 16, &S.full[0], lane);
+
+  const float sgn_im = P.inverse ? -1.0f : 1.0f;                  // conj of the source for the inverse-by-conjugation
+  const float sw = (P.centered && (tid & 1)) ? -1.0f : 1.0f;      // (-1)^k_w post-phase of the W transform, column = tid
+
+  int it = 0;
+  for (int t = t0; t < ntiles; t += gridDim.x, ++it) {
+    const int s = it & 1;
+    const int img = t >> 4, b = t & 15;
+    const int tn = t + gridDim.x;
+    if (tid < 32 && tn < ntiles) {
+      fence_async_smem();
+      issue_rows((S.in0 + (s ^ 1) * STAGE_F), P.p0 + (long long)(tn >> 4) * 2 * HW, HW, tn & 15, 16, &S.full[s ^ 1], lane);
+    }
+    mb_wait(&S.full[s], (it >> 1) & 1);
+    const float* sre = (S.in0 + s * STAGE_F);
+    const float* sim = sre + PLANE_F;
+    const int h = b + 16 * line;
+
+    float2 v[16];
+    {
+      const float* pr = sre + line * LS + j;
+      const float* pi = sim + line * LS + j;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r] = make_float2(pr[16 * r], pi[16 * r]);
+    }
+    if (HAS_P1) {
+      const float* g1 = P.p1 + (long long)img * 2 * HW + (long long)h * N + j;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        v[r].x = P.a0 * v[r].x + P.a1 * __ldg(g1 + 16 * r);
+        v[r].y = P.a0 * v[r].y + P.a1 * __ldg(g1 + HW + 16 * r);
+      }
+    } else if (P.a0 != 1.0f) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) { v[r].x *= P.a0; v[r].y *= P.a0; }
+    }
+    if (P.g_at_load && P.gmode != DINVK_G_NONE) {
+      const float* gp = P.g + (long long)img * P.gsb + (long long)h * P.gsh + j;
+      const float c = P.gcb ? __ldg(P.gcb + img) : P.gc;
+      float m0[16], m1[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) { m0[r] = __ldg(gp + 16 * r); m1[r] = __ldg(gp + P.gsc + 16 * r); }
+      gmap<16>(P.gmode, m0, c);
+      gmap<16>(P.gmode, m1, c);
+#pragma unroll
+      for (int r = 0; r < 16; ++r) { v[r].x *= m0[r]; v[r].y *= sgn_im * m1[r]; }
+    } else if (P.inverse) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r].y = -v[r].y;
+    }
+    w_stage1_store(v, S.work, line, j);
+    __syncthreads();
+    w_stage2(v, S.work, S.tws, line, j);
+    __syncthreads();  // stage-2 inputs consumed
+    {
+      float2* w = S.work + line * RLS + j;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) w[17 * r] = v[r];  // bin j + 16 r -> pad16 index j + 17 r
+    }
+    __syncthreads();
+    // column stage: thread = column w = tid, butterfly over a (the tile's lines)
+    {
+      const float2* w = S.work + tid + (tid >> 4);
+#pragma unroll
+      for (int a = 0; a < 16; ++a) v[a] = w[a * RLS];
+    }
+    Dft<16>::run(v);
+    {
+      // twiddle w256^(b k_lo), H pre-phase (-1)^h = (-1)^b and W post-phase (-1)^w folded into one complex factor
+      const float sb = ((P.centered && (b & 1)) ? -1.0f : 1.0f) * sw;
+      float2* o = P.ws + ((long long)img * 256 + b) * N + tid;
+      o[0] = make_float2(sb * v[0].x, sb * v[0].y);
+#pragma unroll
+      for (int k = 1; k < 16; ++k) {
+        float2 tw = S.twf[(b * k) & 255];
+        tw.x *= sb; tw.y *= sb;
+        o[(long long)k * 16 * N] = cmul(v[k], tw);
+      }
+    }
+    __syncthreads();  // staging buffer s and the work buffer are free again
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pass 2: tile = ws[img][k_lo][0..15][*] (32 KB contiguous).  b-butterfly per column -> rows h = k_lo + 16 k_hi,
+// multiplier (A), scale, conjugation (inverse), epilogue, planar store.  128 threads, 2 columns per thread.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(P2_NT, 2) sp_pass2(const PipeParams P) {
+  extern __shared__ __align__(128) unsigned char sp_raw[];
+  float* ring = reinterpret_cast<float*>(sp_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + P2_STAGES * P2_TILE_F);
+  const int tid = threadIdx.x;
+  const int ntiles = P.B * 16;
+  constexpr long long HW = (long long)N * N;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < P2_STAGES; ++i) mb_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < P2_STAGES - 1; ++i) {
+      const int t = blockIdx.x + i * gridDim.x;
+      if (t < ntiles) {
+        mb_expect_tx(&full[i], P2_TILE_F * 4);
+        bulk_g2s(ring + i * P2_TILE_F, P.ws + (long long)t * 16 * N, P2_TILE_F * 4, &full[i]);
+      }
+    }
+  }
+  const float s2 = 1.0f / 256.0f;
+  const float sgn_im = P.inverse ? -1.0f : 1.0f;
+  const int w = 2 * tid;
+
+  int it = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    const int s = it % P2_STAGES;
+    const int img = t >> 4, klo = t & 15;
+    {
+      const int ahead = it + P2_STAGES - 1;
+      const int tn = blockIdx.x + ahead * gridDim.x;
+      if (tid == 0 && tn < ntiles) {
+        const int sn = ahead % P2_STAGES;  // consumed during iteration it-1 (barrier at its end)
+        fence_async_smem();
+        mb_expect_tx(&full[sn], P2_TILE_F * 4);
+        bulk_g2s(ring + sn * P2_TILE_F, P.ws + (long long)tn * 16 * N, P2_TILE_F * 4, &full[sn]);
+      }
+    }
+    mb_wait(&full[s], (it / P2_STAGES) & 1);
+    const float4* src = reinterpret_cast<const float4*>(ring + s * P2_TILE_F) + tid;
+    float2 u[16], z[16];
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+      const float4 q = src[b * 128];
+      u[b] = make_float2(q.x, q.y);
+      z[b] = make_float2(q.z, q.w);
+    }
+    Dft<16>::run(u);
+    Dft<16>::run(z);
+    // (-1)^h post-phase = (-1)^k_lo; scale 1/256; e0
+    const float f = ((P.centered && (klo & 1)) ? -1.0f : 1.0f) * s2 * P.e0;
+    const long long obase = (long long)img * 2 * HW + (long long)klo * N + w;
+    const bool mult = (P.gmode != DINVK_G_NONE) && !P.g_at_load;
+    const float c = (mult && P.gcb) ? __ldg(P.gcb + img) : P.gc;
+    if (mult) {  // A: multiplier on the k-space result, rows h = k_lo + 16 k
+      const float* gp = P.g + (long long)img * P.gsb + (long long)klo * P.gsh + w;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float m0[16], m1[16];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float* gk = gp + (long long)(16 * (k + 8 * half)) * P.gsh;
+          const float2 a = __ldg(reinterpret_cast<const float2*>(gk));
+          const float2 bq = __ldg(reinterpret_cast<const float2*>(gk + P.gsc));
+          m0[2 * k] = a.x; m0[2 * k + 1] = a.y; m1[2 * k] = bq.x; m1[2 * k + 1] = bq.y;
+        }
+        gmap<16>(P.gmode, m0, c);
+        gmap<16>(P.gmode, m1, c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int kk = k + 8 * half;
+          u[kk].x *= m0[2 * k]; z[kk].x *= m0[2 * k + 1];
+          u[kk].y *= m1[2 * k]; z[kk].y *= m1[2 * k + 1];
+        }
+      }
+    }
+    const float fi = sgn_im * f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const long long o = obase + (long long)k * 16 * N;
+      float2 re = make_float2(f * u[k].x, f * z[k].x);
+      float2 im = make_float2(fi * u[k].y, fi * z[k].y);
+      if (P.q0) {
+        const float2 a = __ldg(reinterpret_cast<const float2*>(P.q0 + o)), bq = __ldg(reinterpret_cast<const float2*>(P.q0 + o + HW));
+        re.x += P.e1 * a.x; re.y += P.e1 * a.y; im.x += P.e1 * bq.x; im.y += P.e1 * bq.y;
+      }
+      if (P.q1) {
+        const float2 a = __ldg(reinterpret_cast<const float2*>(P.q1 + o)), bq = __ldg(reinterpret_cast<const float2*>(P.q1 + o + HW));
+        re.x += P.e2 * a.x; re.y += P.e2 * a.y; im.x += P.e2 * bq.x; im.y += P.e2 * bq.y;
+      }
+      *reinterpret_cast<float2*>(P.out + o) = re;
+      *reinterpret_cast<float2*>(P.out + o + HW) = im;
+    }
+    __syncthreads();  // ring stage s consumed
+  }
+}
+
+}  // namespace sp
+}  // namespace dinvk
+#endif  // DINVK_EMUL
