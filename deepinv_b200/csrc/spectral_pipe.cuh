@@ -30,10 +30,11 @@ namespace dinvk {
 namespace sp {
 
 constexpr int N = 256;
-constexpr int NT = 256;                 // threads per CTA (row kernels)
-constexpr int LS = 272;                 // staged line stride, floats (272 % 32 == 16: two lines per warp, no conflicts)
-constexpr int PLANE_F = 16 * LS;        // floats per staged plane
-constexpr int STAGE_F = 2 * PLANE_F;    // floats per staged tile (re plane, im plane)
+constexpr int NT = 256;                 // threads per CTA (row kernels): thread = (line, j), a warp owns two lines
+constexpr int IMO = 272;                // offset of the imaginary row inside a staged line, floats
+constexpr int LSTR = 560;               // staged line stride, floats: [re 256 | pad 16 | im 256 | pad 32]; 560 % 32 == 16, so
+                                        // the two lines of a warp hit disjoint banks; reused as 280 float2 for the transpose
+constexpr int STAGE_F = 16 * LSTR;      // floats per staged tile
 constexpr int RLS = 273;                // work-buffer line stride, float2 (pad16 layout)
 constexpr int WORK_F2 = 16 * RLS;
 constexpr size_t ROW_SMEM = (size_t)2 * STAGE_F * 4 + (size_t)WORK_F2 * 8 + 2 * 256 * 8 + 64;
@@ -61,6 +62,9 @@ __device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
@@ -94,31 +98,34 @@ __device__ __forceinline__ void gmap(int gmode, float (&m)[K], float c) {
   }
 }
 
-// ---- W-direction transform of one 16-line tile, thread = (line, j) ------------------------------------------------
-// stage 1: inputs x[j + 16 r] from the staged planes, butterfly, autosort store work[line][16 j + r]
-__device__ __forceinline__ void w_stage1_store(float2 (&v)[16], float2* work, int line, int j) {
+// ---- W-direction transform of one line, thread = (line, j); the 16 threads of a line sit in one warp, so the exchange
+// between the two radix-16 stages only needs __syncwarp -------------------------------------------------------------
+// stage 1: butterfly of x[j + 16 r], autosort store wk[16 j + r] (pad16 -> 17 j + r)
+__device__ __forceinline__ void w_stage1_store(float2 (&v)[16], float2* wk, int j) {
   Dft<16>::run(v);
-  float2* w = work + line * RLS + 17 * j;
+  float2* w = wk + 17 * j;
 #pragma unroll
   for (int r = 0; r < 16; ++r) w[r] = v[r];
 }
-// stage 2: inputs work[line][j + 16 r] (pad16 -> j + 17 r) times tws[r][j], butterfly -> v[r] = X[j + 16 r]
-__device__ __forceinline__ void w_stage2(float2 (&v)[16], const float2* work, const float2* tws, int line, int j) {
-  const float2* w = work + line * RLS + j;
+// stage 2: inputs wk[j + 16 r] (pad16 -> j + 17 r) times tw[r], butterfly -> v[r] = X[j + 16 r]
+template <class TW>
+__device__ __forceinline__ void w_stage2(float2 (&v)[16], const float2* wk, int j, TW tw) {
+  const float2* w = wk + j;
 #pragma unroll
   for (int r = 0; r < 16; ++r) v[r] = w[17 * r];
 #pragma unroll
-  for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], tws[r * 16 + j]);
+  for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], tw(r));
   Dft<16>::run(v);
 }
 
 // shared-memory carve-up of the row kernels
 struct RowSmem {
-  float* in0;
-  float2* work;
+  float* in0;    // two staged tiles
+  float2* work;  // 16 lines x RLS, rows private to the warp that owns the line
   float2* tws;   // [r][j]: sign(r) * w256^(r j)   (sign = (-1)^r for centred transforms: the (-1)^n pre-phase)
   float2* twf;   // w256^k, k = 0..255
-  uint64_t* full;
+  uint64_t* full;   // [2] bulk copies landed
+  uint64_t* empty;  // [2] all 8 warps released the stage
 };
 __device__ __forceinline__ RowSmem carve_row(unsigned char* raw) {
   RowSmem s;
@@ -127,6 +134,7 @@ __device__ __forceinline__ RowSmem carve_row(unsigned char* raw) {
   s.tws = s.work + WORK_F2;
   s.twf = s.tws + 256;
   s.full = reinterpret_cast<uint64_t*>(s.twf + 256);
+  s.empty = s.full + 2;
   return s;
 }
 __device__ __forceinline__ void fill_tables(const RowSmem& s, const float2* __restrict__ tw, int centered, int tid) {
@@ -136,6 +144,11 @@ __device__ __forceinline__ void fill_tables(const RowSmem& s, const float2* __re
   s.tws[tid] = t;
   s.twf[tid] = __ldg(tw + tid);
 }
+__device__ __forceinline__ void init_row_barriers(const RowSmem& s) {
+  mb_init(&s.full[0], 1); mb_init(&s.full[1], 1);
+  mb_init(&s.empty[0], NT / 32); mb_init(&s.empty[1], NT / 32);
+  fence_mbar_init();
+}
 
 // issue the 32 row copies (16 rows x 2 planes, 1 KB each) of one tile; called by warp 0 (all lanes)
 __device__ __forceinline__ void issue_rows(float* dst, const float* src_img, long long plane_stride, int row0, int row_step,
@@ -143,55 +156,58 @@ __device__ __forceinline__ void issue_rows(float* dst, const float* src_img, lon
   if (lane == 0) mb_expect_tx(bar, 32 * 1024);
   __syncwarp();
   const int plane = lane >> 4, row = lane & 15;
-  bulk_g2s(dst + plane * PLANE_F + row * LS, src_img + plane * plane_stride + (long long)(row0 + row * row_step) * N, 1024, bar);
+  bulk_g2s(dst + row * LSTR + plane * IMO, src_img + plane * plane_stride + (long long)(row0 + row * row_step) * N, 1024, bar);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// fused row pass (line masks): one tile = 16 consecutive rows of one image
+// fused row pass (line masks): one tile = 16 consecutive rows of one image.  No CTA-wide barrier in the tile loop: a warp
+// carries its two lines through both transforms; stages are recycled through full / empty mbarriers.
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool HAS_P1>
 __global__ void __launch_bounds__(NT, 2) sp_row_fused(const PipeParams P) {
   extern __shared__ __align__(128) unsigned char sp_raw[];
   const RowSmem S = carve_row(sp_raw);
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int line = tid >> 4, j = tid & 15;
   const int ntiles = P.B * 16;
   constexpr long long HW = (long long)N * N;
 
+  const int t0 = blockIdx.x;
+  if (tid < 32) {  // first tile on its way before anything else
+    if (tid == 0) init_row_barriers(S);
+    __syncwarp();
+    if (t0 < ntiles) issue_rows(S.in0, P.p0 + (long long)(t0 >> 4) * 2 * HW, HW, (t0 & 15) * 16, 1, &S.full[0], lane);
+  }
   fill_tables(S, P.tw, P.centered, tid);
-  if (tid == 0) { mb_init(&S.full[0], 1); mb_init(&S.full[1], 1); fence_mbar_init(); }
   __syncthreads();
-  int t0 = blockIdx.x;
-  if (tid < 32 && t0 < ntiles) issue_rows(S.in0, P.p0 + (long long)(t0 >> 4) * 2 * HW, HW, (t0 & 15) * 16, 1, &S.full[0], lane);
 
   const float scale = 0.0625f;                                   // 1/sqrt(256)
   const float sj = (P.centered && (j & 1)) ? -1.0f : 1.0f;      // (-1)^k post-phase, k = j + 16 r
   const float fmid = sj * scale;                                 // after the forward transform
   const float fend = sj * scale * P.e0;                          // after the inverse transform (and the epilogue weight)
   const bool q0_smem = (P.q0 != nullptr) && (P.q0 == P.p0) && !HAS_P1 && P.a0 == 1.0f;
+  const bool ldq0 = (P.q0 != nullptr) && !q0_smem;  // rare: loaded inline in the final pass
+  const bool ldq1 = P.q1 != nullptr;
+  float2* wk = S.work + line * RLS;
+  const float2* twj = S.tws + j;
+  auto tw = [&](int r) { return twj[16 * r]; };
 
   int it = 0;
   for (int t = t0; t < ntiles; t += gridDim.x, ++it) {
     const int s = it & 1;
     const int img = t >> 4, h0 = (t & 15) * 16;
-    // prefetch the next tile into the other buffer (its previous contents were consumed before the barrier that ended
-    // the previous iteration)
     const int tn = t + gridDim.x;
-    if (tid < 32 && tn < ntiles) {
+    if (tid < 32 && tn < ntiles) {  // refill the other stage once every warp has released it (its use in iteration it-1)
+      if (it >= 1) mb_wait(&S.empty[s ^ 1], ((it - 1) >> 1) & 1);
       fence_async_smem();
-      issue_rows((S.in0 + (s ^ 1) * STAGE_F), P.p0 + (long long)(tn >> 4) * 2 * HW, HW, (tn & 15) * 16, 1, &S.full[s ^ 1], lane);
+      issue_rows(S.in0 + (s ^ 1) * STAGE_F, P.p0 + (long long)(tn >> 4) * 2 * HW, HW, (tn & 15) * 16, 1, &S.full[s ^ 1], lane);
     }
     mb_wait(&S.full[s], (it >> 1) & 1);
-    float* sre = (S.in0 + s * STAGE_F);
-    float* sim = sre + PLANE_F;
+    float* sl = S.in0 + s * STAGE_F + line * LSTR;
 
     float2 v[16];
-    {
-      const float* pr = sre + line * LS + j;
-      const float* pi = sim + line * LS + j;
 #pragma unroll
-      for (int r = 0; r < 16; ++r) v[r] = make_float2(pr[16 * r], pi[16 * r]);
-    }
+    for (int r = 0; r < 16; ++r) v[r] = make_float2(sl[j + 16 * r], sl[IMO + j + 16 * r]);
     if (HAS_P1) {
       const float* g1 = P.p1 + (long long)img * 2 * HW + (long long)(h0 + line) * N + j;
 #pragma unroll
@@ -203,9 +219,9 @@ __global__ void __launch_bounds__(NT, 2) sp_row_fused(const PipeParams P) {
 #pragma unroll
       for (int r = 0; r < 16; ++r) { v[r].x *= P.a0; v[r].y *= P.a0; }
     }
-    w_stage1_store(v, S.work, line, j);
-    __syncthreads();
-    w_stage2(v, S.work, S.tws, line, j);
+    w_stage1_store(v, wk, j);
+    __syncwarp();
+    w_stage2(v, wk, j, tw);
     // multiplier g(mask[img, w = j + 16 r]), forward post-phase and scale, conjugation for the inverse-by-conjugation
     if (P.gmode != DINVK_G_NONE) {
       const float* gp = P.g + (long long)img * P.gsb + j;
@@ -223,58 +239,56 @@ __global__ void __launch_bounds__(NT, 2) sp_row_fused(const PipeParams P) {
 #pragma unroll
       for (int r = 0; r < 16; ++r) { v[r].x *= fmid; v[r].y *= -fmid; }
     }
-    __syncthreads();  // every thread has read its stage-2 inputs: the work buffer may be overwritten
-    w_stage1_store(v, S.work, line, j);
-    __syncthreads();
-    // epilogue operands that are not already staged: 8 x 128-bit per thread per operand, issued before the last butterfly
+    __syncwarp();  // every lane has read its stage-2 inputs: the warp's work rows may be overwritten
+    w_stage1_store(v, wk, j);
+    __syncwarp();
+    // the warp writes its own two lines: lane handles 8 x 128 bits, f = lane + 32 i -> (line of the pair, plane, column group)
+    const long long gbase = (long long)img * 2 * HW + (long long)(h0 + 2 * warp) * N;
     float4 qb[8];
-    const bool ldq0 = (P.q0 != nullptr) && !q0_smem;  // rare: loaded inline in the final pass
-    const bool ldq1 = P.q1 != nullptr;
-    const long long gbase = (long long)img * 2 * HW + (long long)h0 * N;
     if (ldq1) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int f = tid + i * NT, plane = f >> 10, row = (f >> 6) & 15, c4 = f & 63;
-        qb[i] = __ldg(reinterpret_cast<const float4*>(P.q1 + gbase + plane * HW + row * N + 4 * c4));
+        const int f = lane + 32 * i, lp = f >> 7, plane = (f >> 6) & 1, c4 = f & 63;
+        qb[i] = __ldg(reinterpret_cast<const float4*>(P.q1 + gbase + plane * HW + lp * N + 4 * c4));
       }
     }
-    w_stage2(v, S.work, S.tws, line, j);
-    {  // conj, post-phase, scale, e0; + e1 * x when q0 is the staged source; in place into the staging planes
-      float* pr = sre + line * LS + j;
-      float* pi = sim + line * LS + j;
-      if (q0_smem) {
+    w_stage2(v, wk, j, tw);
+    // conj, post-phase, scale, e0; + e1 * x when q0 is the staged source; in place into the staged line
+    if (q0_smem) {
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          pr[16 * r] = fend * v[r].x + P.e1 * pr[16 * r];
-          pi[16 * r] = -fend * v[r].y + P.e1 * pi[16 * r];
-        }
-      } else {
-#pragma unroll
-        for (int r = 0; r < 16; ++r) { pr[16 * r] = fend * v[r].x; pi[16 * r] = -fend * v[r].y; }
+      for (int r = 0; r < 16; ++r) {
+        sl[j + 16 * r] = fend * v[r].x + P.e1 * sl[j + 16 * r];
+        sl[IMO + j + 16 * r] = -fend * v[r].y + P.e1 * sl[IMO + j + 16 * r];
       }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) { sl[j + 16 * r] = fend * v[r].x; sl[IMO + j + 16 * r] = -fend * v[r].y; }
     }
-    __syncthreads();
+    __syncwarp();
     {
+      const float* sw2 = S.in0 + s * STAGE_F + (2 * warp) * LSTR;
       float* ob = P.out + gbase;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int f = tid + i * NT, plane = f >> 10, row = (f >> 6) & 15, c4 = f & 63;
-        float4 o = *reinterpret_cast<const float4*>(sre + plane * PLANE_F + row * LS + 4 * c4);
+        const int f = lane + 32 * i, lp = f >> 7, plane = (f >> 6) & 1, c4 = f & 63;
+        float4 o = *reinterpret_cast<const float4*>(sw2 + lp * LSTR + plane * IMO + 4 * c4);
         if (ldq0) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(P.q0 + gbase + plane * HW + row * N + 4 * c4));
+          const float4 a = __ldg(reinterpret_cast<const float4*>(P.q0 + gbase + plane * HW + lp * N + 4 * c4));
           o.x += P.e1 * a.x; o.y += P.e1 * a.y; o.z += P.e1 * a.z; o.w += P.e1 * a.w;
         }
         if (ldq1) { o.x += P.e2 * qb[i].x; o.y += P.e2 * qb[i].y; o.z += P.e2 * qb[i].z; o.w += P.e2 * qb[i].w; }
-        *reinterpret_cast<float4*>(ob + plane * HW + row * N + 4 * c4) = o;
+        *reinterpret_cast<float4*>(ob + plane * HW + lp * N + 4 * c4) = o;
       }
     }
-    __syncthreads();  // staging buffer s fully consumed: the next iteration may refill it
+    __syncwarp();
+    if (lane == 0) mb_arrive(&S.empty[s]);  // this warp is done with stage s
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// pass 1: tile = rows {b + 16 a} of one image.  W transform, then the a-butterfly of the H transform per column,
-// twiddle w256^(b k_lo), store to ws[img][k_lo][b][w] (interleaved)
+// pass 1: tile = rows {b + 16 a} of one image.  W transform (warp-local), transpose through the warp's own staged lines,
+// one CTA barrier, then the a-butterfly of the H transform per column, twiddle w256^(b k_lo), store to
+// ws[img][k_lo][b][w] (interleaved)
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool HAS_P1>
 __global__ void __launch_bounds__(NT, 2) sp_pass1(const PipeParams P) {
@@ -285,14 +299,22 @@ __global__ void __launch_bounds__(NT, 2) sp_pass1(const PipeParams P) {
   const int ntiles = P.B * 16;
   constexpr long long HW = (long long)N * N;
 
+  const int t0 = blockIdx.x;
+  if (tid < 32) {
+    if (tid == 0) init_row_barriers(S);
+    __syncwarp();
+    if (t0 < ntiles) issue_rows(S.in0, P.p0 + (long long)(t0 >> 4) * 2 * HW, HW, t0 & 15, 16, &S.full[0], lane);
+  }
   fill_tables(S, P.tw, P.centered, tid);
-  if (tid == 0) { mb_init(&S.full[0], 1); mb_init(&S.full[1], 1); fence_mbar_init(); }
   __syncthreads();
-  int t0 = blockIdx.x;
-  if (tid < 32 && t0 < ntiles) issue_rows(S.in0, P.p0 + (long long)(t0 >> 4) * 2 * HW, HW, t0 & 15, 16, &S.full[0], lane);
 
   const float sgn_im = P.inverse ? -1.0f : 1.0f;                  // conj of the source for the inverse-by-conjugation
   const float sw = (P.centered && (tid & 1)) ? -1.0f : 1.0f;      // (-1)^k_w post-phase of the W transform, column = tid
+  float2* wk = S.work + line * RLS;
+  float2 twr[16];  // stage-2 twiddles of this thread, kept in registers across tiles
+#pragma unroll
+  for (int r = 0; r < 16; ++r) twr[r] = S.tws[r * 16 + j];
+  auto tw = [&](int r) { return twr[r]; };
 
   int it = 0;
   for (int t = t0; t < ntiles; t += gridDim.x, ++it) {
@@ -300,21 +322,18 @@ __global__ void __launch_bounds__(NT, 2) sp_pass1(const PipeParams P) {
     const int img = t >> 4, b = t & 15;
     const int tn = t + gridDim.x;
     if (tid < 32 && tn < ntiles) {
+      if (it >= 1) mb_wait(&S.empty[s ^ 1], ((it - 1) >> 1) & 1);
       fence_async_smem();
-      issue_rows((S.in0 + (s ^ 1) * STAGE_F), P.p0 + (long long)(tn >> 4) * 2 * HW, HW, tn & 15, 16, &S.full[s ^ 1], lane);
+      issue_rows(S.in0 + (s ^ 1) * STAGE_F, P.p0 + (long long)(tn >> 4) * 2 * HW, HW, tn & 15, 16, &S.full[s ^ 1], lane);
     }
     mb_wait(&S.full[s], (it >> 1) & 1);
-    const float* sre = (S.in0 + s * STAGE_F);
-    const float* sim = sre + PLANE_F;
+    float* stage = S.in0 + s * STAGE_F;
+    float* sl = stage + line * LSTR;
     const int h = b + 16 * line;
 
     float2 v[16];
-    {
-      const float* pr = sre + line * LS + j;
-      const float* pi = sim + line * LS + j;
 #pragma unroll
-      for (int r = 0; r < 16; ++r) v[r] = make_float2(pr[16 * r], pi[16 * r]);
-    }
+    for (int r = 0; r < 16; ++r) v[r] = make_float2(sl[j + 16 * r], sl[IMO + j + 16 * r]);
     if (HAS_P1) {
       const float* g1 = P.p1 + (long long)img * 2 * HW + (long long)h * N + j;
 #pragma unroll
@@ -340,22 +359,23 @@ __global__ void __launch_bounds__(NT, 2) sp_pass1(const PipeParams P) {
 #pragma unroll
       for (int r = 0; r < 16; ++r) v[r].y = -v[r].y;
     }
-    w_stage1_store(v, S.work, line, j);
-    __syncthreads();
-    w_stage2(v, S.work, S.tws, line, j);
-    __syncthreads();  // stage-2 inputs consumed
+    w_stage1_store(v, wk, j);
+    __syncwarp();  // also: every lane of the warp has consumed its staged line
+    w_stage2(v, wk, j, tw);
     {
-      float2* w = S.work + line * RLS + j;
+      float2* tl = reinterpret_cast<float2*>(sl) + j;  // transpose through the warp's own staged line (280 float2)
 #pragma unroll
-      for (int r = 0; r < 16; ++r) w[17 * r] = v[r];  // bin j + 16 r -> pad16 index j + 17 r
+      for (int r = 0; r < 16; ++r) tl[17 * r] = v[r];  // bin j + 16 r -> pad16 index j + 17 r
     }
     __syncthreads();
     // column stage: thread = column w = tid, butterfly over a (the tile's lines)
     {
-      const float2* w = S.work + tid + (tid >> 4);
+      const float2* cl = reinterpret_cast<const float2*>(stage) + tid + (tid >> 4);
 #pragma unroll
-      for (int a = 0; a < 16; ++a) v[a] = w[a * RLS];
+      for (int a = 0; a < 16; ++a) v[a] = cl[a * (LSTR / 2)];
     }
+    __syncwarp();
+    if (lane == 0) mb_arrive(&S.empty[s]);  // stage s consumed by this warp
     Dft<16>::run(v);
     {
       // twiddle w256^(b k_lo), H pre-phase (-1)^h = (-1)^b and W post-phase (-1)^w folded into one complex factor
@@ -364,12 +384,11 @@ __global__ void __launch_bounds__(NT, 2) sp_pass1(const PipeParams P) {
       o[0] = make_float2(sb * v[0].x, sb * v[0].y);
 #pragma unroll
       for (int k = 1; k < 16; ++k) {
-        float2 tw = S.twf[(b * k) & 255];
-        tw.x *= sb; tw.y *= sb;
-        o[(long long)k * 16 * N] = cmul(v[k], tw);
+        float2 tk = S.twf[(b * k) & 255];
+        tk.x *= sb; tk.y *= sb;
+        o[(long long)k * 16 * N] = cmul(v[k], tk);
       }
     }
-    __syncthreads();  // staging buffer s and the work buffer are free again
   }
 }
 
