@@ -310,6 +310,19 @@ static int get_tables(int n, int centered, Tables* out) {
 
 #ifndef DINVK_EMUL
 static inline bool al16(const void* p);
+// launch with programmatic stream serialization (PDL): the kernel may begin its prologue while the previous kernel in the
+// stream drains; it executes griddepcontrol.wait before touching memory (see spectral_pipe.cuh)
+template <typename K, typename... Args>
+static void launch_pdl(K kern, unsigned grid, unsigned block, size_t smem, void* stream, const Args&... args) {
+  count_launch();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = getenv("DINVK_NO_PDL") ? 0 : 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  (void)cudaLaunchKernelEx(&cfg, kern, args...);
+}
 // 256x256 single-coil fast path (spectral_pipe.cuh).  Returns -1 when the call does not qualify.
 static int try_pipe(const dinvk_spectral_args& a, float2* T1, const Tables& tW, void* stream) {
   if (a.H != 256 || a.W != 256 || a.ncoil > 1) return -1;
@@ -332,10 +345,10 @@ static int try_pipe(const dinvk_spectral_args& a, float2* T1, const Tables& tW, 
   if (fused) {
     if (a.p1) {
       if ((rc = allow_smem(sp::sp_row_fused<true>, sp::ROW_SMEM))) return rc;
-      DINVK_LAUNCH(sp::sp_row_fused<true>, dim3(grid), dim3(sp::NT), sp::ROW_SMEM, stream, P);
+      launch_pdl(sp::sp_row_fused<true>, grid, sp::NT, sp::ROW_SMEM, stream, P);
     } else {
       if ((rc = allow_smem(sp::sp_row_fused<false>, sp::ROW_SMEM))) return rc;
-      DINVK_LAUNCH(sp::sp_row_fused<false>, dim3(grid), dim3(sp::NT), sp::ROW_SMEM, stream, P);
+      launch_pdl(sp::sp_row_fused<false>, grid, sp::NT, sp::ROW_SMEM, stream, P);
     }
     return DINVK_POST_LAUNCH();
   }
@@ -343,14 +356,14 @@ static int try_pipe(const dinvk_spectral_args& a, float2* T1, const Tables& tW, 
   P.g_at_load = a.inv ? 1 : 0;  // A^T: multiplier on the k-space source; A: multiplier on the k-space result
   if (a.p1) {
     if ((rc = allow_smem(sp::sp_pass1<true>, sp::ROW_SMEM))) return rc;
-    DINVK_LAUNCH(sp::sp_pass1<true>, dim3(grid), dim3(sp::NT), sp::ROW_SMEM, stream, P);
+    launch_pdl(sp::sp_pass1<true>, grid, sp::NT, sp::ROW_SMEM, stream, P);
   } else {
     if ((rc = allow_smem(sp::sp_pass1<false>, sp::ROW_SMEM))) return rc;
-    DINVK_LAUNCH(sp::sp_pass1<false>, dim3(grid), dim3(sp::NT), sp::ROW_SMEM, stream, P);
+    launch_pdl(sp::sp_pass1<false>, grid, sp::NT, sp::ROW_SMEM, stream, P);
   }
   if ((rc = DINVK_POST_LAUNCH())) return rc;
   if ((rc = allow_smem(sp::sp_pass2, sp::P2_SMEM))) return rc;
-  DINVK_LAUNCH(sp::sp_pass2, dim3(grid), dim3(sp::P2_NT), sp::P2_SMEM, stream, P);
+  launch_pdl(sp::sp_pass2, grid, sp::P2_NT, sp::P2_SMEM, stream, P);
   return DINVK_POST_LAUNCH();
 }
 #endif

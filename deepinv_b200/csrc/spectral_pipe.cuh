@@ -38,10 +38,10 @@ constexpr int STAGE_F = 16 * LSTR;      // floats per staged tile
 constexpr int RLS = 273;                // work-buffer line stride, float2 (pad16 layout)
 constexpr int WORK_F2 = 16 * RLS;
 constexpr size_t ROW_SMEM = (size_t)2 * STAGE_F * 4 + (size_t)WORK_F2 * 8 + 2 * 256 * 8 + 64;
-constexpr int P2_NT = 128;
+constexpr int P2_NT = 256;
 constexpr int P2_STAGES = 3;
 constexpr int P2_TILE_F = 16 * 256 * 2;  // floats per workspace tile (16 rows of 256 interleaved complex)
-constexpr size_t P2_SMEM = (size_t)P2_STAGES * P2_TILE_F * 4 + 64;
+constexpr size_t P2_SMEM = (size_t)P2_STAGES * P2_TILE_F * 4 + 128;
 
 struct PipeParams {
   int B;
@@ -74,6 +74,11 @@ __device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(s_u32(bar)), "r"(parity) : "memory");
   }
 }
+// programmatic dependent launch: the kernels are launched with programmatic stream serialization, so their prologue
+// (barrier init, twiddle tables) overlaps the tail of the previous kernel; nothing that depends on earlier kernels is
+// touched before griddep_wait() returns (= previous grids complete and visible)
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // 1-D bulk copy global -> shared, completion counted in bytes on `bar` (SASS: UBLKCP)
@@ -175,6 +180,8 @@ __global__ void __launch_bounds__(NT, 2) sp_row_fused(const PipeParams P) {
   const int t0 = blockIdx.x;
   if (tid < 32) {  // first tile on its way before anything else
     if (tid == 0) init_row_barriers(S);
+    griddep_wait();
+    if (tid == 0) griddep_launch();
     __syncwarp();
     if (t0 < ntiles) issue_rows(S.in0, P.p0 + (long long)(t0 >> 4) * 2 * HW, HW, (t0 & 15) * 16, 1, &S.full[0], lane);
   }
@@ -302,6 +309,8 @@ __global__ void __launch_bounds__(NT, 2) sp_pass1(const PipeParams P) {
   const int t0 = blockIdx.x;
   if (tid < 32) {
     if (tid == 0) init_row_barriers(S);
+    griddep_wait();
+    if (tid == 0) griddep_launch();
     __syncwarp();
     if (t0 < ntiles) issue_rows(S.in0, P.p0 + (long long)(t0 >> 4) * 2 * HW, HW, t0 & 15, 16, &S.full[0], lane);
   }
@@ -393,24 +402,25 @@ __global__ void __launch_bounds__(NT, 2) sp_pass1(const PipeParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// pass 2: tile = ws[img][k_lo][0..15][*] (32 KB contiguous).  b-butterfly per column -> rows h = k_lo + 16 k_hi,
-// multiplier (A), scale, conjugation (inverse), epilogue, planar store.  128 threads, 2 columns per thread.
+// pass 2: tile = ws[img][k_lo][0..15][*] (32 KB contiguous, one bulk copy).  b-butterfly per column -> rows
+// h = k_lo + 16 k_hi, multiplier (A), scale, conjugation (inverse), epilogue, planar store.  256 threads, thread = column;
+// 3-stage ring recycled through full / empty mbarriers (no CTA barrier in the loop).
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(P2_NT, 2) sp_pass2(const PipeParams P) {
   extern __shared__ __align__(128) unsigned char sp_raw[];
   float* ring = reinterpret_cast<float*>(sp_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + P2_STAGES * P2_TILE_F);
-  const int tid = threadIdx.x;
+  uint64_t* empty = full + P2_STAGES;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int ntiles = P.B * 16;
   constexpr long long HW = (long long)N * N;
 
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < P2_STAGES; ++i) mb_init(&full[i], 1);
+    for (int i = 0; i < P2_STAGES; ++i) { mb_init(&full[i], 1); mb_init(&empty[i], P2_NT / 32); }
     fence_mbar_init();
-  }
-  __syncthreads();
-  if (tid == 0) {
+    griddep_wait();
+    griddep_launch();
 #pragma unroll
     for (int i = 0; i < P2_STAGES - 1; ++i) {
       const int t = blockIdx.x + i * gridDim.x;
@@ -420,9 +430,10 @@ __global__ void __launch_bounds__(P2_NT, 2) sp_pass2(const PipeParams P) {
       }
     }
   }
+  __syncthreads();
   const float s2 = 1.0f / 256.0f;
   const float sgn_im = P.inverse ? -1.0f : 1.0f;
-  const int w = 2 * tid;
+  const bool mult = (P.gmode != DINVK_G_NONE) && !P.g_at_load;
 
   int it = 0;
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
@@ -431,69 +442,55 @@ __global__ void __launch_bounds__(P2_NT, 2) sp_pass2(const PipeParams P) {
     {
       const int ahead = it + P2_STAGES - 1;
       const int tn = blockIdx.x + ahead * gridDim.x;
-      if (tid == 0 && tn < ntiles) {
-        const int sn = ahead % P2_STAGES;  // consumed during iteration it-1 (barrier at its end)
-        fence_async_smem();
-        mb_expect_tx(&full[sn], P2_TILE_F * 4);
-        bulk_g2s(ring + sn * P2_TILE_F, P.ws + (long long)tn * 16 * N, P2_TILE_F * 4, &full[sn]);
+      if (tid < 32 && tn < ntiles) {
+        const int sn = ahead % P2_STAGES;  // == (it - 1) % STAGES: last used in iteration it-1
+        if (it >= 1) mb_wait(&empty[sn], ((it - 1) / P2_STAGES) & 1);
+        if (lane == 0) {
+          fence_async_smem();
+          mb_expect_tx(&full[sn], P2_TILE_F * 4);
+          bulk_g2s(ring + sn * P2_TILE_F, P.ws + (long long)tn * 16 * N, P2_TILE_F * 4, &full[sn]);
+        }
+        __syncwarp();
       }
     }
     mb_wait(&full[s], (it / P2_STAGES) & 1);
-    const float4* src = reinterpret_cast<const float4*>(ring + s * P2_TILE_F) + tid;
-    float2 u[16], z[16];
+    float2 u[16];
+    {
+      const float2* src = reinterpret_cast<const float2*>(ring + s * P2_TILE_F) + tid;
 #pragma unroll
-    for (int b = 0; b < 16; ++b) {
-      const float4 q = src[b * 128];
-      u[b] = make_float2(q.x, q.y);
-      z[b] = make_float2(q.z, q.w);
+      for (int b = 0; b < 16; ++b) u[b] = src[b * N];
     }
+    __syncwarp();
+    if (lane == 0) mb_arrive(&empty[s]);
     Dft<16>::run(u);
-    Dft<16>::run(z);
     // (-1)^h post-phase = (-1)^k_lo; scale 1/256; e0
     const float f = ((P.centered && (klo & 1)) ? -1.0f : 1.0f) * s2 * P.e0;
-    const long long obase = (long long)img * 2 * HW + (long long)klo * N + w;
-    const bool mult = (P.gmode != DINVK_G_NONE) && !P.g_at_load;
-    const float c = (mult && P.gcb) ? __ldg(P.gcb + img) : P.gc;
-    if (mult) {  // A: multiplier on the k-space result, rows h = k_lo + 16 k
-      const float* gp = P.g + (long long)img * P.gsb + (long long)klo * P.gsh + w;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float m0[16], m1[16];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float* gk = gp + (long long)(16 * (k + 8 * half)) * P.gsh;
-          const float2 a = __ldg(reinterpret_cast<const float2*>(gk));
-          const float2 bq = __ldg(reinterpret_cast<const float2*>(gk + P.gsc));
-          m0[2 * k] = a.x; m0[2 * k + 1] = a.y; m1[2 * k] = bq.x; m1[2 * k + 1] = bq.y;
-        }
-        gmap<16>(P.gmode, m0, c);
-        gmap<16>(P.gmode, m1, c);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int kk = k + 8 * half;
-          u[kk].x *= m0[2 * k]; z[kk].x *= m0[2 * k + 1];
-          u[kk].y *= m1[2 * k]; z[kk].y *= m1[2 * k + 1];
-        }
-      }
-    }
     const float fi = sgn_im * f;
+    const long long obase = (long long)img * 2 * HW + (long long)klo * N + tid;
+    if (mult) {  // A: multiplier on the k-space result, rows h = k_lo + 16 k
+      const float c = P.gcb ? __ldg(P.gcb + img) : P.gc;
+      const float* gp = P.g + (long long)img * P.gsb + (long long)klo * P.gsh + tid;
+      float m0[16], m1[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float* gk = gp + (long long)(16 * k) * P.gsh;
+        m0[k] = __ldg(gk);
+        m1[k] = __ldg(gk + P.gsc);
+      }
+      gmap<16>(P.gmode, m0, c);
+      gmap<16>(P.gmode, m1, c);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { u[k].x *= m0[k]; u[k].y *= m1[k]; }
+    }
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const long long o = obase + (long long)k * 16 * N;
-      float2 re = make_float2(f * u[k].x, f * z[k].x);
-      float2 im = make_float2(fi * u[k].y, fi * z[k].y);
-      if (P.q0) {
-        const float2 a = __ldg(reinterpret_cast<const float2*>(P.q0 + o)), bq = __ldg(reinterpret_cast<const float2*>(P.q0 + o + HW));
-        re.x += P.e1 * a.x; re.y += P.e1 * a.y; im.x += P.e1 * bq.x; im.y += P.e1 * bq.y;
-      }
-      if (P.q1) {
-        const float2 a = __ldg(reinterpret_cast<const float2*>(P.q1 + o)), bq = __ldg(reinterpret_cast<const float2*>(P.q1 + o + HW));
-        re.x += P.e2 * a.x; re.y += P.e2 * a.y; im.x += P.e2 * bq.x; im.y += P.e2 * bq.y;
-      }
-      *reinterpret_cast<float2*>(P.out + o) = re;
-      *reinterpret_cast<float2*>(P.out + o + HW) = im;
+      float re = f * u[k].x, im = fi * u[k].y;
+      if (P.q0) { re += P.e1 * __ldg(P.q0 + o); im += P.e1 * __ldg(P.q0 + o + HW); }
+      if (P.q1) { re += P.e2 * __ldg(P.q1 + o); im += P.e2 * __ldg(P.q1 + o + HW); }
+      P.out[o] = re;
+      P.out[o + HW] = im;
     }
-    __syncthreads();  // ring stage s consumed
   }
 }
 
