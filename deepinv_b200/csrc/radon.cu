@@ -14,6 +14,9 @@
 //   bilinear weights from floor(pix), zeros outside.  Sinograms are stored ANGLE-major (BC, A, P): this is
 //   the memory the reference returns as the transposed view (B,C,P,A) (radon.py:291-293).
 #include "common.cuh"
+#ifndef DINVK_EMUL
+#include <cstdlib>
+#endif
 
 namespace dinvk {
 
@@ -185,6 +188,162 @@ __global__ void __launch_bounds__(256) iradon_bp_kernel(const float* __restrict_
   x[(long long)bc * G.W * G.W + p] = acc * scale;
 }
 
+
+#ifndef DINVK_EMUL
+// ---------------------------------------------------------------------------------------------------------------------
+// Tiled forward projection and exact transpose (the default path on the GPU).
+//
+// A CTA owns one 64 x 64-pixel tile of one image for ALL angles: the tile (+1 pixel halo, 66 x 68) is staged once in
+// shared memory with explicit zeros outside the image — the reference's zero padding (radon.py:262-266), so the sqrt(2)
+// padded image never exists — and every bilinear tap of the 47 M samples per image that fall in the image support is a
+// shared-memory access instead of an L1 gather (the ray-per-thread kernel above is bound by L1 tag lookups: a warp of
+// adjacent rays touches up to 32 cache lines per tap).  Each sample (i, j) of the rotated lattice is owned by exactly
+// one tile (the one that contains floor(px), floor(py)); a warp takes one angle at a time, its lanes adjacent rays,
+// each lane walks the clipped range of steps i of its ray and accumulates in a register.
+//   forward:   lane partial sums -> one fp32 atomicAdd per (tile, angle, ray) into the zeroed sinogram
+//   transpose: lane reads sino[t, j] once, scatters w * y into the zeroed shared tile (shared-memory atomics, same
+//              fp32 weights as the forward => <Ax, y> = <x, A^T y> up to summation order), tile added to the image at the end
+// Sample geometry is evaluated with the same fp32 formulas as above.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int RT = 64;    // tile edge (pixels)
+constexpr int RTW = 68;   // staged row pitch / box width (floats; 272 B rows keep the TMA box a multiple of 16 B)
+constexpr int RTH = 66;   // staged rows
+constexpr int RT_THREADS = 128;
+
+template <bool ADJ>
+__global__ void __launch_bounds__(RT_THREADS) radon_tiled_kernel(const float* __restrict__ src,
+                                                                 float* __restrict__ out, RadonGeom G, const float* __restrict__ cos_t,
+                                                                 const float* __restrict__ sin_t, float scale, int tps) {
+  extern __shared__ __align__(128) unsigned char rt_raw[];
+  float* T = reinterpret_cast<float*>(rt_raw);                 // [RTH][RTW]
+  float* s_cs = T + RTH * RTW;                                  // cos[A], sin[A]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ty = blockIdx.x / tps, tx = blockIdx.x - ty * tps;
+  const int bc = blockIdx.y;
+  // tile origin in image coordinates (first staged pixel) and in padded coordinates
+  const int ox = RT * tx - 1, oy = RT * ty - 1;
+  const int xl = G.pb + ox, yl = G.pb + oy;
+  // owned floor coordinates: offsets 0 .. xr (the last tile also owns the floor W-1, whose right tap is the zero padding)
+  const int xr = (tx == tps - 1) ? (G.W - 1 - ox) : (RT - 1);
+  const int yr = (ty == tps - 1) ? (G.W - 1 - oy) : (RT - 1);
+
+  if (!ADJ) {
+    // stage the tile once (coalesced rows; explicit zeros outside the image = the reference's zero padding)
+    const float* img = src + (long long)bc * G.W * G.W;
+    for (int e = tid; e < RTH * RTW; e += RT_THREADS) {
+      const int uy = e / RTW, ux = e - uy * RTW;
+      const int x = ox + ux, y = oy + uy;
+      T[e] = (x >= 0 && x < G.W && y >= 0 && y < G.W) ? __ldg(img + (long long)y * G.W + x) : 0.f;
+    }
+  } else {
+    for (int e = tid; e < RTH * RTW; e += RT_THREADS) T[e] = 0.f;
+  }
+  for (int k = tid; k < G.A; k += RT_THREADS) { s_cs[k] = __ldg(cos_t + k); s_cs[G.A + k] = __ldg(sin_t + k); }
+  __syncthreads();
+  if (!ADJ) {
+    if (G.circle) {  // inscribed-disc mask of the image (radon.py:268-279), applied once to the staged tile
+      for (int e = tid; e < RTH * RTW; e += RT_THREADS) {
+        const int uy = e / RTW, ux = e - uy * RTW;
+        const int x = ox + ux, y = oy + uy;
+        const float ax = 2.0f * (float)x / (float)(G.W - 1) - 1.0f, ay = 2.0f * (float)y / (float)(G.W - 1) - 1.0f;
+        if (!(ax * ax + ay * ay <= 1.0f)) T[e] = 0.f;
+      }
+      __syncthreads();
+    }
+  }
+
+  const float pm1 = (float)(G.P - 1), cx = 0.5f * pm1;
+  const float fxl = (float)xl, fxu = (float)(xl + xr + 1), fyl = (float)yl, fyu = (float)(yl + yr + 1);
+  const long long srow0 = (long long)bc * G.A * G.P;
+  for (int t = warp; t < G.A; t += RT_THREADS / 32) {
+    const float c = s_cs[t], s = s_cs[G.A + t];
+    // ray range of the tile: j ~ cx + c (X - cx) - s (Y - cx) over the corners of [xl, xu+1] x [yl, yu+1]
+    const float j00 = c * (fxl - cx) - s * (fyl - cx), j10 = c * (fxu - cx) - s * (fyl - cx);
+    const float j01 = c * (fxl - cx) - s * (fyu - cx), j11 = c * (fxu - cx) - s * (fyu - cx);
+    const int jmin = max(0, (int)floorf(cx + fminf(fminf(j00, j10), fminf(j01, j11))) - 1);
+    const int jmax = min(G.P - 1, (int)ceilf(cx + fmaxf(fmaxf(j00, j10), fmaxf(j01, j11))) + 1);
+    for (int j = jmin + lane; j <= jmax; j += 32) {
+      const float xj = lin_at(j, G.P, G.step);
+      // steps whose sample can fall in the tile: fxl <= bx + s (i - cx) < fxu and fyl <= by + c (i - cx) < fyu (+- 2 margin)
+      float i_lo = 0.f, i_hi = pm1;
+      const float bx = cx + c * ((float)j - cx), by = cx - s * ((float)j - cx);
+      if (fabsf(s) > 1e-6f) {
+        float a = (fxl - bx) / s + cx, b = (fxu - bx) / s + cx;
+        if (a > b) { const float tmp = a; a = b; b = tmp; }
+        i_lo = fmaxf(i_lo, a); i_hi = fminf(i_hi, b);
+      } else if (!(bx > fxl - 1.f && bx < fxu + 1.f)) { i_hi = -1.f; }
+      if (fabsf(c) > 1e-6f) {
+        float a = (fyl - by) / c + cx, b = (fyu - by) / c + cx;
+        if (a > b) { const float tmp = a; a = b; b = tmp; }
+        i_lo = fmaxf(i_lo, a); i_hi = fminf(i_hi, b);
+      } else if (!(by > fyl - 1.f && by < fyu + 1.f)) { i_hi = -1.f; }
+      const int i0 = max(0, (int)floorf(i_lo) - 2), i1 = min(G.P - 1, (int)ceilf(i_hi) + 2);
+      float acc = 0.f;
+      float yv = 0.f;
+      if (ADJ && i0 <= i1) yv = __ldg(src + srow0 + (long long)t * G.P + j) * scale;
+      bool any = false;
+      for (int i = i0; i <= i1; ++i) {
+        const float yi = lin_at(i, G.P, G.step);
+        float px, py;
+        sample_pos(c, s, xj, yi, pm1, px, py);
+        const float fx = floorf(px), fy = floorf(py);
+        const unsigned ux = (unsigned)((int)fx - xl), uy = (unsigned)((int)fy - yl);
+        if (ux > (unsigned)xr || uy > (unsigned)yr) continue;
+        const float wx1 = px - fx, wy1 = py - fy, wx0 = (fx + 1.0f) - px, wy0 = (fy + 1.0f) - py;
+        float* tp = T + uy * RTW + ux;
+        if (!ADJ) {
+          acc += tp[0] * (wx0 * wy0) + tp[1] * (wx1 * wy0) + tp[RTW] * (wx0 * wy1) + tp[RTW + 1] * (wx1 * wy1);
+          any = true;
+        } else {
+          atomicAdd(tp, yv * (wx0 * wy0));
+          atomicAdd(tp + 1, yv * (wx1 * wy0));
+          atomicAdd(tp + RTW, yv * (wx0 * wy1));
+          atomicAdd(tp + RTW + 1, yv * (wx1 * wy1));
+        }
+      }
+      if (!ADJ && any) atomicAdd(out + srow0 + (long long)t * G.P + j, acc * scale);
+    }
+  }
+  if (ADJ) {
+    __syncthreads();
+    float* img = out + (long long)bc * G.W * G.W;
+    for (int e = tid; e < RTH * RTH; e += RT_THREADS) {
+      const int uy = e / RTH, ux = e - uy * RTH;
+      const int x = ox + ux, y = oy + uy;
+      if (x < 0 || x >= G.W || y < 0 || y >= G.W) continue;
+      float v = T[uy * RTW + ux];
+      if (G.circle) {
+        const float ax = 2.0f * (float)x / (float)(G.W - 1) - 1.0f, ay = 2.0f * (float)y / (float)(G.W - 1) - 1.0f;
+        if (!(ax * ax + ay * ay <= 1.0f)) v = 0.f;
+      }
+      if (v != 0.f) atomicAdd(img + (long long)y * G.W + x, v);
+    }
+  }
+}
+
+static bool tiled_ok(const void* img, int W, int A) {
+  if (getenv("DINVK_NO_TILED_RADON")) return false;
+  return W >= RT && (W % 4) == 0 && A <= 2048 && (reinterpret_cast<uintptr_t>(img) & 15) == 0;
+}
+// returns -1 when the tiled path does not apply
+static int launch_tiled(bool adj, const float* x_img, const float* sino_in, float* out, int BC, const RadonGeom& G, const float* cos_t,
+                        const float* sin_t, float scale, void* stream) {
+  const int tps = (G.W + RT - 1) / RT;
+  const size_t smem = (size_t)RTH * RTW * 4 + (size_t)(2 * G.A + 2) * 4 + 16;
+  const size_t out_bytes = adj ? (size_t)BC * G.W * G.W * 4 : (size_t)BC * G.A * G.P * 4;
+  if (cudaMemsetAsync(out, 0, out_bytes, (cudaStream_t)stream) != cudaSuccess) return set_error(DINVK_ECUDA, "radon: memset failed");
+  int rc;
+  if (adj) {
+    if ((rc = allow_smem(radon_tiled_kernel<true>, smem))) return rc;
+    DINVK_LAUNCH(radon_tiled_kernel<true>, dim3(tps * tps, BC), dim3(RT_THREADS), smem, stream, sino_in, out, G, cos_t, sin_t, scale, tps);
+  } else {
+    if ((rc = allow_smem(radon_tiled_kernel<false>, smem))) return rc;
+    DINVK_LAUNCH(radon_tiled_kernel<false>, dim3(tps * tps, BC), dim3(RT_THREADS), smem, stream, x_img, out, G, cos_t, sin_t, scale, tps);
+  }
+  return DINVK_POST_LAUNCH();
+}
+#endif  // DINVK_EMUL
+
 static int make_geom(RadonGeom* G, int W, int P, int A, int circle) {
   if (W < 1 || P < W || A < 1) return set_error(DINVK_EINVAL, "radon: bad geometry W=%d P=%d A=%d", W, P, A);
   if (circle && P != W) return set_error(DINVK_EINVAL, "radon: circle=1 requires P == W");
@@ -206,6 +365,12 @@ extern "C" int dinvk_radon_fwd(const float* x, float* sino, int BC, int W, int P
   if (rc) return rc;
   if (BC == 0) return DINVK_OK;
   DINVK_CHECK_ARG(A <= 65535 && BC <= 65535, "dinvk_radon_fwd: grid too large");
+#ifndef DINVK_EMUL
+  if (tiled_ok(x, W, A)) {
+    rc = launch_tiled(false, x, nullptr, sino, BC, G, cos_t, sin_t, scale, stream);
+    if (rc >= 0) return rc;
+  }
+#endif
   DINVK_LAUNCH(radon_fwd_kernel, dim3(ceil_div(P, 128), A, BC), dim3(128), 0, stream, x, sino, G, cos_t, sin_t, scale);
   return DINVK_POST_LAUNCH();
 }
@@ -218,6 +383,12 @@ extern "C" int dinvk_radon_adj(const float* sino, float* x, int BC, int W, int P
   if (rc) return rc;
   if (BC == 0) return DINVK_OK;
   DINVK_CHECK_ARG(BC <= 65535 && A <= 4096, "dinvk_radon_adj: grid too large");
+#ifndef DINVK_EMUL
+  if (tiled_ok(x, W, A)) {
+    rc = launch_tiled(true, nullptr, sino, x, BC, G, cos_t, sin_t, scale, stream);
+    if (rc >= 0) return rc;
+  }
+#endif
   DINVK_LAUNCH(radon_adj_kernel, dim3(ceil_div((long long)W * W, 256), BC), dim3(256), 2 * A * sizeof(float), stream, sino, x, G,
                cos_t, sin_t, scale);
   return DINVK_POST_LAUNCH();

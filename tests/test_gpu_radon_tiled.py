@@ -1,0 +1,81 @@
+"""GPU parity of the TMA-staged tiled Radon kernels (csrc/radon.cu, radon_tiled_kernel): against the oracle
+(CPU restatement of Radon.forward / the autograd transpose, radon.py:252-309, tomography.py:322-342) at sizes that
+exercise partial tiles, several tiles per side and the inscribed-disc option, against the ray-per-thread kernels of the
+same library (`DINVK_NO_TILED_RADON=1`), and the adjoint identity at the cfg3 size.
+
+Tolerance: 1e-5 relative L2 (fp32) up to W = 128.  Beyond that the comparison with the CPU oracle is limited by fp32 rounding of
+the sampling coordinates, not by the kernels: a coordinate of magnitude ~W carries an ulp of ~W * 6e-8, one ulp moves a bilinear
+weight by that much, and the oracle evaluates linspace / affine_grid with ATen's CPU kernels (vectorised arange, sgemm) while the
+kernels use the scalar symmetric linspace formula of ATen's CUDA kernel.  Both kernel families (ray-per-thread, tiled) sit at
+1.1e-5 .. 1.2e-5 from the oracle at W = 192 (measured, also under CPU emulation of the ray-per-thread kernel) and agree with
+each other to 2e-6; the bound used for W > 128 is 1e-5 * W / 128."""
+import os
+
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+class per_ray_kernels:
+    def __enter__(self):
+        os.environ["DINVK_NO_TILED_RADON"] = "1"
+
+    def __exit__(self, *exc):
+        os.environ.pop("DINVK_NO_TILED_RADON", None)
+
+
+@pytest.mark.parametrize("W,nang,circle", [(64, 30, False), (100, 24, False), (128, 45, True), (192, 20, False), (64, 16, True)])
+def test_tiled_vs_oracle(W, nang, circle, dev):
+    import deepinv_b200 as dinv
+    from oracle import ref_ops as R
+
+    gen = torch.Generator().manual_seed(W + nang)
+    x = torch.randn(2, 1, W, W, generator=gen)
+    ang = R.default_angles(nang)
+    phys = dinv.physics.Tomography(angles=nang, img_width=W, circle=circle, normalize=False, device=dev)
+    y = R.radon_forward(x, ang, circle=circle)
+    tol = 1e-5 * max(1.0, W / 128)
+    assert rel_err(phys.A(x.to(dev)), y) < tol
+    v = torch.randn(*y.shape, generator=gen)
+    assert rel_err(phys.A_adjoint(v.to(dev)), R.radon_adjoint(v, ang, W, circle=circle)) < tol
+
+
+@pytest.mark.parametrize("W,nang,circle,B", [(256, 60, False, 3), (512, 36, False, 2), (320, 40, True, 2)])
+def test_tiled_vs_per_ray(W, nang, circle, B, dev):
+    import deepinv_b200 as dinv
+
+    gen = torch.Generator(device=dev).manual_seed(1)
+    phys = dinv.physics.Tomography(angles=nang, img_width=W, circle=circle, normalize=False, device=dev)
+    x = torch.randn(B, 2, W, W, device=dev, generator=gen)
+    y = phys.A(x)
+    v = torch.randn(*y.shape, device=dev, generator=gen)
+    xt = phys.A_adjoint(v)
+    with per_ray_kernels():
+        y0 = phys.A(x)
+        xt0 = phys.A_adjoint(v)
+    assert rel_err(y, y0) < 2e-6
+    assert rel_err(xt, xt0) < 2e-6
+    lhs, rhs = (y.double() * v.double()).sum(), (x.double() * xt.double()).sum()
+    assert abs(float(lhs - rhs)) / abs(float(lhs)) < 1e-5
+
+
+def test_tiled_adjointness_cfg3(dev):
+    import deepinv_b200 as dinv
+
+    phys = dinv.physics.Tomography(angles=180, img_width=512, normalize=False, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(4, 1, 512, 512, device=dev, generator=gen)
+    v = torch.randn(4, 1, 725, 180, device=dev, generator=gen)
+    y, xt = phys.A(x), phys.A_adjoint(v)
+    lhs, rhs = (y.double() * v.double()).sum(), (x.double() * xt.double()).sum()
+    assert abs(float(lhs - rhs)) / abs(float(lhs)) < 1e-5

@@ -19,11 +19,11 @@ PEAK = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROO
 USE_GRAPH = "--graph" in sys.argv
 
 
-def t(fn, iters=10, warmup=3):
+def t(fn, iters=10, warmup=3, graph=None):
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
-    if USE_GRAPH:  # replay a captured call: device time without the Python / ctypes launch path
+    if USE_GRAPH if graph is None else graph:  # replay a captured call: device time without the Python / ctypes launch path
         g = torch.cuda.CUDAGraph()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -89,7 +89,7 @@ with torch.no_grad():
         report("Tomography.__init__ (power iteration norm=%.2f)" % float(pn.operator_norm), (time.perf_counter() - t0) * 1e3)
         xs = x[:4]
         ys = p.A(xs)
-        report("Tomography.prox_l2 (CG<=50) batch 4", t(lambda: p.prox_l2(xs, ys, 1.0), 1, 1))
+        report("Tomography.prox_l2 (CG<=50) batch 4", t(lambda: p.prox_l2(xs, ys, 1.0), 1, 1, graph=False))
     if "blur" in which:
         B, H, W, k = 32, 1024, 1024, 31
         x = torch.rand(B, 1, H, W, device=dev, generator=g)
@@ -109,7 +109,7 @@ with torch.no_grad():
         report("BlurFFT.prox_l2", t(lambda: pf.prox_l2(x, y, 1.0), 10, 2), 5 * img)
         pc = dinv.physics.Blur(filter=f, padding="circular", device=dev)
         xs, ys = x[:4], pc.A(x[:4])
-        report("Blur.prox_l2 (CG<=50) batch 4", t(lambda: pc.prox_l2(xs, ys, 1.0), 1, 1))
+        report("Blur.prox_l2 (CG<=50) batch 4", t(lambda: pc.prox_l2(xs, ys, 1.0), 1, 1, graph=False))
     if "mcmri" in which:
         B, N, H, W = 32, 8, 320, 320
         x = torch.randn(B, 2, H, W, device=dev, generator=g)
@@ -121,4 +121,4 @@ with torch.no_grad():
         mb = (B * 2 * H * W + B * 2 * N * H * W + N * H * W * 2) * 4 / 1e6
         report("MultiCoilMRI.A 32x8x320^2", t(lambda: p.A(x), 10, 2), mb)
         report("MultiCoilMRI.A_adjoint", t(lambda: p.A_adjoint(y), 10, 2), mb)
-        report("MultiCoilMRI.A_dagger (CG)", t(lambda: p.A_dagger(y), 1, 1))
+        report("MultiCoilMRI.A_dagger (CG)", t(lambda: p.A_dagger(y), 1, 1, graph=False))
