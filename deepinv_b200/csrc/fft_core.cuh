@@ -160,6 +160,48 @@ struct Dft<16> {
   }
 };
 
+
+// 20-point DFT as 5 x 4 Cooley-Tukey: n = 4 n1 + n2, k = k1 + 5 k2
+//   X[k1 + 5 k2] = sum_n2 w4^(n2 k2) [ w20^(n2 k1) sum_n1 x[4 n1 + n2] w5^(n1 k1) ]
+template <>
+struct Dft<20> {
+  static __host__ __device__ __forceinline__ void run(float2* v) {
+    // w20^m = exp(-2 pi i m / 20) for the products n2 * k1 that occur (m = 1,2,3,4,6,8,9,12)
+    const float c1 = 0.95105651629515357212f, s1 = 0.30901699437494742410f;   // m = 1
+    const float c2 = 0.80901699437494742410f, s2 = 0.58778525229247312917f;   // m = 2
+    const float c3 = 0.58778525229247312917f, s3 = 0.80901699437494742410f;   // m = 3
+    const float c4 = 0.30901699437494742410f, s4 = 0.95105651629515357212f;   // m = 4
+    float2 T[4][5];
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) {
+      float2 t[5] = {v[n2], v[4 + n2], v[8 + n2], v[12 + n2], v[16 + n2]};
+      Dft<5>::run(t);
+#pragma unroll
+      for (int k1 = 0; k1 < 5; ++k1) T[n2][k1] = t[k1];
+    }
+    // twiddles (real, imag) of w20^m: (cos, -sin)
+    T[1][1] = cmul(T[1][1], make_float2(c1, -s1));
+    T[1][2] = cmul(T[1][2], make_float2(c2, -s2));
+    T[1][3] = cmul(T[1][3], make_float2(c3, -s3));
+    T[1][4] = cmul(T[1][4], make_float2(c4, -s4));
+    T[2][1] = cmul(T[2][1], make_float2(c2, -s2));
+    T[2][2] = cmul(T[2][2], make_float2(c4, -s4));
+    T[2][3] = cmul(T[2][3], make_float2(-c4, -s4));   // m = 6
+    T[2][4] = cmul(T[2][4], make_float2(-c2, -s2));   // m = 8
+    T[3][1] = cmul(T[3][1], make_float2(c3, -s3));
+    T[3][2] = cmul(T[3][2], make_float2(-c4, -s4));   // m = 6
+    T[3][3] = cmul(T[3][3], make_float2(-c1, -s1));   // m = 9
+    T[3][4] = cmul(T[3][4], make_float2(-c2, s2));    // m = 12
+#pragma unroll
+    for (int k1 = 0; k1 < 5; ++k1) {
+      float2 u[4] = {T[0][k1], T[1][k1], T[2][k1], T[3][k1]};
+      Dft<4>::run(u);
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) v[k1 + 5 * k2] = u[k2];
+    }
+  }
+};
+
 // ---- shared-memory tile layouts ---------------------------------------------------------------
 // ROW: each line is contiguous (padded by one float2 every 16 to break power-of-two strides);
 //      consecutive threads take consecutive butterflies of the same line.

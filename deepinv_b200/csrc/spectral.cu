@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(NTHR, 1024 / NTHR) spectral_pass_kernel(const 
 }  // namespace dinvk
 #include "spectral_fast.cuh"
 #include "spectral_pipe.cuh"
+#include "spectral_pipe320.cuh"
 namespace dinvk {
 
 // O(N^2) DFT along one axis of an interleaved (B,H,W) tensor — sizes with prime factors > 5.
@@ -364,6 +365,46 @@ static int try_pipe(const dinvk_spectral_args& a, float2* T1, const Tables& tW, 
   if ((rc = DINVK_POST_LAUNCH())) return rc;
   if ((rc = allow_smem(sp::sp_pass2, sp::P2_SMEM))) return rc;
   launch_pdl(sp::sp_pass2, grid, sp::P2_NT, sp::P2_SMEM, stream, P);
+  return DINVK_POST_LAUNCH();
+}
+// 320x320 two-pass path (spectral_pipe320.cuh): A and A^T, single- or multi-coil.  Returns -1 when the call does not qualify.
+// `coil_ws` != null: pass 2 writes interleaved per-coil images there (the caller runs the coil reduction afterwards).
+static int try_pipe320(const dinvk_spectral_args& a, float2* T1, float2* coil_ws, const Tables& tW, void* stream) {
+  if (a.H != 320 || a.W != 320) return -1;
+  if (getenv("DINVK_NO_PIPE_FFT")) return -1;
+  if (a.fwd == a.inv) return -1;  // fused forward-inverse passes stay on the tile passes
+  if (a.gmode == DINVK_G_CMUL || a.gmode == DINVK_G_CMUL_CONJ) return -1;
+  if (!al16(a.p0) || !al16(a.p1) || !al16(a.out) || !al16(a.coil_maps)) return -1;
+  const int nc = a.ncoil > 1 ? a.ncoil : 1;
+  sp320::Params P = sp320::Params();
+  P.B = a.B;
+  P.p0 = a.p0; P.p1 = a.p1; P.a0 = a.a0; P.a1 = a.p1 ? a.a1 : 0.f;
+  P.src_nc = 1; P.src_div = 1; P.ncoil = nc; P.dst_nc = 1;
+  if (nc > 1 && a.coil_mode == 1) { P.src_div = nc; P.coil = reinterpret_cast<const float2*>(a.coil_maps); P.coil_sb = a.coil_sb; P.dst_nc = nc; }
+  else if (nc > 1) { P.src_nc = nc; }
+  P.gmode = a.gmode; P.g = a.mask; P.gsb = a.mask_sb; P.gsc = a.mask_sc; P.gsh = a.mask_sh; P.gc = a.c; P.gcb = a.c_batch;
+  P.q0 = a.q0; P.q1 = a.q1; P.e0 = a.e0; P.e1 = a.q0 ? a.e1 : 0.f; P.e2 = a.q1 ? a.e2 : 0.f;
+  P.out = a.out; P.tout = coil_ws; P.ws = T1; P.tw = tW.tw; P.centered = a.centered ? 1 : 0;
+  P.inverse = a.inv ? 1 : 0;
+  P.g_at_load = a.inv ? 1 : 0;
+  if (coil_ws) { P.e0 = 1.f; P.q0 = nullptr; P.q1 = nullptr; P.e1 = 0.f; P.e2 = 0.f; }  // e0 is applied by the coil reduction
+  int rc;
+  if ((rc = allow_smem(sp320::sp320_pass1<true>, sp320::P1_SMEM))) return rc;
+  if ((rc = allow_smem(sp320::sp320_pass1<false>, sp320::P1_SMEM))) return rc;
+  if ((rc = allow_smem(sp320::sp320_pass2, sp320::P2_SMEM))) return rc;
+  // one launch pair for the whole batch.  (Chunks of 64 images, whose 52 MB intermediate would stay in L2, measured
+  // 10 % SLOWER at cfg4 — 210 vs 191 us: the passes are bound by issue / shared-memory exchange, not by the intermediate's
+  // HBM round trip, and every extra launch pays a pipeline ramp.  `img0` keeps the chunked form available.)
+  const int CH = 1 << 30;
+  for (int i0 = 0; i0 < a.B; i0 += CH) {
+    P.img0 = i0;
+    P.B = std::min(CH, a.B - i0);
+    const unsigned g1 = (unsigned)std::min(P.B * sp320::HB, 2 * sm_count());
+    const unsigned g2 = (unsigned)std::min(P.B * sp320::HA, 2 * sm_count());
+    if (a.p1) launch_pdl(sp320::sp320_pass1<true>, g1, sp320::NT, sp320::P1_SMEM, stream, P);
+    else launch_pdl(sp320::sp320_pass1<false>, g1, sp320::NT, sp320::P1_SMEM, stream, P);
+    launch_pdl(sp320::sp320_pass2, g2, sp320::NT, sp320::P2_SMEM, stream, P);
+  }
   return DINVK_POST_LAUNCH();
 }
 #endif
@@ -577,6 +618,12 @@ extern "C" int dinvk_spectral(const dinvk_spectral_args* ap, void* workspace, si
   }
 #endif
   if (fast) {
+#ifndef DINVK_EMUL
+    if (a.fwd && !a.inv) {
+      const int prc = try_pipe320(a, T1, nullptr, tW, stream);
+      if (prc >= 0) return prc;
+    }
+#endif
     if (a.fwd && !a.inv) {
       // A: COL(fwd) planar -> T1 ; ROW(fwd, multiplier) T1 -> out
       init_pass(P, a); set_source(P, a); P.dir1 = -1; P.tout = T1; set_axis(P, tH, pH);
@@ -584,7 +631,16 @@ extern "C" int dinvk_spectral(const dinvk_spectral_args* ap, void* workspace, si
       init_pass(P, a); P.tin = T1; P.dir1 = -1; set_mult(P, a, false); set_dest(P, a, nullptr); set_axis(P, tW, pW);
       return launch_pass(false, P, rcfg, stream);
     }
+    int prc320 = -1;
+#ifndef DINVK_EMUL
     if (!a.fwd && a.inv) {
+      prc320 = try_pipe320(a, T1, coil_reduce ? T2 : nullptr, tW, stream);
+      if (prc320 > 0) return prc320;
+    }
+#endif
+    if (!a.fwd && a.inv && prc320 == 0) {
+      // done by the 320 x 320 two-pass kernels; a coil reduction (below) may follow
+    } else if (!a.fwd && a.inv) {
       // A^T: ROW(multiplier at load, inv) planar -> T1 ; COL(inv) T1 -> out (or coil workspace)
       init_pass(P, a); set_source(P, a); set_mult(P, a, true); P.dir1 = +1; P.tout = T1; set_axis(P, tW, pW);
       if ((rc = launch_pass(false, P, rcfg, stream))) return rc;

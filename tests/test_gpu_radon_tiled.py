@@ -1,4 +1,4 @@
-"""GPU parity of the TMA-staged tiled Radon kernels (csrc/radon.cu, radon_tiled_kernel): against the oracle
+"""GPU parity of the shared-memory-tiled Radon kernels (csrc/radon.cu, radon_tiled_kernel): against the oracle
 (CPU restatement of Radon.forward / the autograd transpose, radon.py:252-309, tomography.py:322-342) at sizes that
 exercise partial tiles, several tiles per side and the inscribed-disc option, against the ray-per-thread kernels of the
 same library (`DINVK_NO_TILED_RADON=1`), and the adjoint identity at the cfg3 size.

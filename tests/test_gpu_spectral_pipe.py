@@ -131,3 +131,77 @@ def test_pipe_properties_cfg2(dev):
     nx = float(ops.batched_dot(x, x).double().sum())
     Vx = phys.V_adjoint(x)
     assert abs(float(ops.batched_dot(Vx, Vx).double().sum()) - nx) / nx < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 320 x 320 (cfg4): two-pass kernels of csrc/spectral_pipe320.cuh
+# ---------------------------------------------------------------------------------------------------------------------
+def test_pipe320_vs_oracle(dev):
+    import deepinv_b200 as dinv
+    from oracle import ref_ops as R
+
+    B, Hh, Ww, N = 3, 320, 320, 4
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(B, 2, Hh, Ww, generator=gen)
+    cols = (torch.rand(B, 1, 1, Ww, generator=gen) > 0.8).float().expand(B, 2, Hh, Ww).contiguous()
+    full = (torch.rand(B, 2, Hh, Ww, generator=gen) > 0.5).float()
+    for mask in (cols, full, full[:1].contiguous()):
+        phys = dinv.physics.MRI(mask=mask.to(dev), img_size=(2, Hh, Ww), device=dev)
+        y = R.mri_A(x, mask)
+        assert rel_err(phys.A(x.to(dev)), y) < 1e-5
+        assert rel_err(phys.A_adjoint(y.to(dev)), R.mri_At(y, mask)) < 1e-5
+    maps = torch.view_as_complex(torch.randn(1, N, Hh, Ww, 2, generator=gen).contiguous())
+    maps = maps / maps.abs().pow(2).sum(1, keepdim=True).sqrt()
+    mphys = dinv.physics.MultiCoilMRI(mask=cols.to(dev), coil_maps=maps.to(dev), img_size=(2, Hh, Ww), device=dev)
+    y = R.mcmri_A(x, cols, maps)
+    assert rel_err(mphys.A(x.to(dev)), y) < 1e-5
+    assert rel_err(mphys.A_adjoint(y.to(dev)), R.mcmri_At(y, cols, maps)) < 1e-5
+    assert rel_err(mphys.A_adjoint(y.to(dev), rss=True), R.mcmri_At(y, cols, maps, use_rss=True)) < 1e-5
+
+
+def test_pipe320_vs_tile_passes_many_tiles(dev):
+    from deepinv_b200 import _ffi, ops
+
+    Hh = Ww = 320
+    B, N = 24, 8
+    gen = torch.Generator(device=dev).manual_seed(6)
+    r = lambda *shape: torch.randn(*shape, device=dev, generator=gen)
+    x, p1, q0, q1 = r(B, 2, Hh, Ww), r(B, 2, Hh, Ww), r(B, 2, Hh, Ww), r(B, 2, Hh, Ww)
+    line = ops.mask_spec_from_real((torch.rand(B, 1, 1, Ww, device=dev, generator=gen) > 0.7).float().expand(B, 2, Hh, Ww).contiguous(), Hh, Ww)
+    full = ops.mask_spec_from_real(torch.rand(B, 2, Hh, Ww, device=dev, generator=gen), Hh, Ww)
+    shared = ops.mask_spec_from_real(torch.rand(1, 2, Hh, Ww, device=dev, generator=gen), Hh, Ww)
+    cb = torch.rand(B, device=dev, generator=gen) + 0.5
+    cases = [("A none", dict(fwd=True, inv=False)), ("At none", dict(fwd=False, inv=True)),
+             ("A uncentred", dict(fwd=True, inv=False, centered=False, gmode=_ffi.G_MASK, mask=full)),
+             ("At uncentred", dict(fwd=False, inv=True, centered=False, gmode=_ffi.G_MASK, mask=full))]
+    for mname, m in (("line", line), ("full", full), ("shared", shared)):
+        for gmode in (_ffi.G_MASK, _ffi.G_SQ, _ffi.G_INV_SQ_PLUS_C, _ffi.G_PINV):
+            cases.append((f"A {mname} g{gmode}", dict(fwd=True, inv=False, gmode=gmode, mask=m, c=0.8)))
+            cases.append((f"At {mname} g{gmode}", dict(fwd=False, inv=True, gmode=gmode, mask=m, c=0.8)))
+        ep = dict(gmode=_ffi.G_MASK, mask=m, a0=0.5, p1=p1, a1=-1.5, e0=2.0, q0=q0, e1=0.25, q1=q1, e2=-0.75)
+        cases.append((f"A {mname} epilogue", dict(fwd=True, inv=False, **ep)))
+        cases.append((f"At {mname} epilogue", dict(fwd=False, inv=True, **ep)))
+        cases.append((f"At {mname} c_batch", dict(fwd=False, inv=True, gmode=_ffi.G_INV_SQ_PLUS_C, mask=m, c_batch=cb)))
+    for name, kw in cases:
+        got = ops.spectral(x, Hh, Ww, **kw)
+        with tile_passes():
+            want = ops.spectral(x, Hh, Ww, **kw)
+        assert rel_err(got, want) < 3e-6, name
+    # multi-coil: batch 5 x 8 coils = 40 coil images (800 pass-1 tiles); per-sample and shared maps, per-sample line masks
+    Bm = 5
+    xm = r(Bm, 2, Hh, Ww)
+    for shared_maps in (True, False):
+        maps = torch.view_as_complex(r(1 if shared_maps else Bm, N, Hh, Ww, 2))
+        lm = ops.mask_spec_from_real((torch.rand(Bm, 1, 1, Ww, device=dev, generator=gen) > 0.8).float().expand(Bm, 2, Hh, Ww).contiguous(), Hh, Ww)
+        kwA = dict(fwd=True, inv=False, gmode=_ffi.G_MASK, mask=lm, ncoil=N, coil_mode=1, coil_maps=maps)
+        y = ops.spectral(xm, Hh, Ww, **kwA)
+        with tile_passes():
+            y0 = ops.spectral(xm, Hh, Ww, **kwA)
+        assert y.shape == (Bm, 2, N, Hh, Ww) and rel_err(y, y0) < 3e-6
+        for mode in (2, 3):
+            kwT = dict(fwd=False, inv=True, gmode=_ffi.G_MASK, mask=lm, ncoil=N, coil_mode=mode, coil_maps=maps, e0=(0.7 if mode == 2 else 1.0))
+            v = ops.spectral(y0, Hh, Ww, **kwT)
+            with tile_passes():
+                v0 = ops.spectral(y0, Hh, Ww, **kwT)
+            assert rel_err(v, v0) < 3e-6, (shared_maps, mode)
+    torch.cuda.synchronize()
