@@ -305,7 +305,7 @@ def run_b200(args):
 
         # ---- e2e: host buffers in, host buffer out, every step ------------------------------------
         xh = x_hat.cpu().pin_memory()
-        out_pin = torch.empty_like(xh)
+        out_pin = torch.empty(xh.shape, dtype=xh.dtype, pin_memory=True)  # (empty_like does not inherit pinned-ness)
 
         def e2e_step():
             xd = xh.to(dev, non_blocking=True)

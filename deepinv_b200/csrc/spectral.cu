@@ -341,30 +341,35 @@ static int try_pipe(const dinvk_spectral_args& a, float2* T1, const Tables& tW, 
   P.q0 = a.q0; P.q1 = a.q1; P.e0 = a.e0; P.e1 = a.q0 ? a.e1 : 0.f; P.e2 = a.q1 ? a.e2 : 0.f;
   P.out = a.out; P.ws = T1; P.tw = tW.tw; P.centered = a.centered ? 1 : 0;
   const int ntiles = a.B * 16;
-  const unsigned grid = (unsigned)std::min(ntiles, 2 * sm_count());
+  static const int occ = getenv("DINVK_SP_OCC3") ? 3 : 2;  // CTAs per SM of the row kernels (3 = 24 warps at <= 85 registers: measured no faster)
+  const unsigned grid = (unsigned)std::min(ntiles, occ * sm_count());
+  const unsigned grid2 = (unsigned)std::min(ntiles, 2 * sm_count());
   int rc;
+#define DINVK_SP_LAUNCH(KERN)                                                        \
+  do {                                                                               \
+    if (occ == 2) {                                                                  \
+      if ((rc = allow_smem(KERN<true, 2>, sp::ROW_SMEM))) return rc;                 \
+      if ((rc = allow_smem(KERN<false, 2>, sp::ROW_SMEM))) return rc;                \
+      if (a.p1) launch_pdl(KERN<true, 2>, grid, sp::NT, sp::ROW_SMEM, stream, P);    \
+      else launch_pdl(KERN<false, 2>, grid, sp::NT, sp::ROW_SMEM, stream, P);        \
+    } else {                                                                         \
+      if ((rc = allow_smem(KERN<true, 3>, sp::ROW_SMEM))) return rc;                 \
+      if ((rc = allow_smem(KERN<false, 3>, sp::ROW_SMEM))) return rc;                \
+      if (a.p1) launch_pdl(KERN<true, 3>, grid, sp::NT, sp::ROW_SMEM, stream, P);    \
+      else launch_pdl(KERN<false, 3>, grid, sp::NT, sp::ROW_SMEM, stream, P);        \
+    }                                                                                \
+  } while (0)
   if (fused) {
-    if (a.p1) {
-      if ((rc = allow_smem(sp::sp_row_fused<true>, sp::ROW_SMEM))) return rc;
-      launch_pdl(sp::sp_row_fused<true>, grid, sp::NT, sp::ROW_SMEM, stream, P);
-    } else {
-      if ((rc = allow_smem(sp::sp_row_fused<false>, sp::ROW_SMEM))) return rc;
-      launch_pdl(sp::sp_row_fused<false>, grid, sp::NT, sp::ROW_SMEM, stream, P);
-    }
+    DINVK_SP_LAUNCH(sp::sp_row_fused);
     return DINVK_POST_LAUNCH();
   }
   P.inverse = a.inv ? 1 : 0;
   P.g_at_load = a.inv ? 1 : 0;  // A^T: multiplier on the k-space source; A: multiplier on the k-space result
-  if (a.p1) {
-    if ((rc = allow_smem(sp::sp_pass1<true>, sp::ROW_SMEM))) return rc;
-    launch_pdl(sp::sp_pass1<true>, grid, sp::NT, sp::ROW_SMEM, stream, P);
-  } else {
-    if ((rc = allow_smem(sp::sp_pass1<false>, sp::ROW_SMEM))) return rc;
-    launch_pdl(sp::sp_pass1<false>, grid, sp::NT, sp::ROW_SMEM, stream, P);
-  }
+  DINVK_SP_LAUNCH(sp::sp_pass1);
+#undef DINVK_SP_LAUNCH
   if ((rc = DINVK_POST_LAUNCH())) return rc;
   if ((rc = allow_smem(sp::sp_pass2, sp::P2_SMEM))) return rc;
-  launch_pdl(sp::sp_pass2, grid, sp::P2_NT, sp::P2_SMEM, stream, P);
+  launch_pdl(sp::sp_pass2, grid2, sp::P2_NT, sp::P2_SMEM, stream, P);
   return DINVK_POST_LAUNCH();
 }
 // 320x320 two-pass path (spectral_pipe320.cuh): A and A^T, single- or multi-coil.  Returns -1 when the call does not qualify.
@@ -408,6 +413,7 @@ static int try_pipe320(const dinvk_spectral_args& a, float2* T1, float2* coil_ws
   return DINVK_POST_LAUNCH();
 }
 #endif
+
 
 static int pow2floor(int x) { int p = 1; while (2 * p <= x) p *= 2; return p; }
 

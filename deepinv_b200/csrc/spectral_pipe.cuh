@@ -36,8 +36,7 @@ constexpr int LSTR = 560;               // staged line stride, floats: [re 256 |
                                         // the two lines of a warp hit disjoint banks; reused as 280 float2 for the transpose
 constexpr int STAGE_F = 16 * LSTR;      // floats per staged tile
 constexpr int RLS = 273;                // work-buffer line stride, float2 (pad16 layout)
-constexpr int WORK_F2 = 16 * RLS;
-constexpr size_t ROW_SMEM = (size_t)2 * STAGE_F * 4 + (size_t)WORK_F2 * 8 + 2 * 256 * 8 + 64;
+constexpr size_t ROW_SMEM = (size_t)2 * STAGE_F * 4 + 256 * 8 + 64;  // two staged tiles (lines double as work rows) + twiddles + barriers
 constexpr int P2_NT = 256;
 constexpr int P2_STAGES = 3;
 constexpr int P2_TILE_F = 16 * 256 * 2;  // floats per workspace tile (16 rows of 256 interleaved complex)
@@ -123,22 +122,19 @@ __device__ __forceinline__ void w_stage2(float2 (&v)[16], const float2* wk, int 
   Dft<16>::run(v);
 }
 
-// shared-memory carve-up of the row kernels
+// shared-memory carve-up of the row kernels.  A staged line (re | im planes of one row, LSTR floats) doubles as the line's
+// work row of RLS float2: every lane of the owning warp reads its stage inputs before any lane stores (a __syncwarp apart).
 struct RowSmem {
   float* in0;    // two staged tiles
-  float2* work;  // 16 lines x RLS, rows private to the warp that owns the line
   float2* tws;   // [r][j]: sign(r) * w256^(r j)   (sign = (-1)^r for centred transforms: the (-1)^n pre-phase)
-  float2* twf;   // w256^k, k = 0..255
   uint64_t* full;   // [2] bulk copies landed
   uint64_t* empty;  // [2] all 8 warps released the stage
 };
 __device__ __forceinline__ RowSmem carve_row(unsigned char* raw) {
   RowSmem s;
   s.in0 = reinterpret_cast<float*>(raw);
-  s.work = reinterpret_cast<float2*>(s.in0 + 2 * STAGE_F);
-  s.tws = s.work + WORK_F2;
-  s.twf = s.tws + 256;
-  s.full = reinterpret_cast<uint64_t*>(s.twf + 256);
+  s.tws = reinterpret_cast<float2*>(s.in0 + 2 * STAGE_F);
+  s.full = reinterpret_cast<uint64_t*>(s.tws + 256);
   s.empty = s.full + 2;
   return s;
 }
@@ -147,7 +143,6 @@ __device__ __forceinline__ void fill_tables(const RowSmem& s, const float2* __re
   float2 t = __ldg(tw + ((r * j) & 255));
   if (centered && (r & 1)) { t.x = -t.x; t.y = -t.y; }
   s.tws[tid] = t;
-  s.twf[tid] = __ldg(tw + tid);
 }
 __device__ __forceinline__ void init_row_barriers(const RowSmem& s) {
   mb_init(&s.full[0], 1); mb_init(&s.full[1], 1);
@@ -168,8 +163,8 @@ __device__ __forceinline__ void issue_rows(float* dst, const float* src_img, lon
 // fused row pass (line masks): one tile = 16 consecutive rows of one image.  No CTA-wide barrier in the tile loop: a warp
 // carries its two lines through both transforms; stages are recycled through full / empty mbarriers.
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool HAS_P1>
-__global__ void __launch_bounds__(NT, 2) sp_row_fused(const PipeParams P) {
+template <bool HAS_P1, int OCC>
+__global__ void __launch_bounds__(NT, OCC) sp_row_fused(const PipeParams P) {
   extern __shared__ __align__(128) unsigned char sp_raw[];
   const RowSmem S = carve_row(sp_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -191,11 +186,13 @@ __global__ void __launch_bounds__(NT, 2) sp_row_fused(const PipeParams P) {
   const float scale = 0.0625f;                                   // 1/sqrt(256)
   const float sj = (P.centered && (j & 1)) ? -1.0f : 1.0f;      // (-1)^k post-phase, k = j + 16 r
   const float fmid = sj * scale;                                 // after the forward transform
-  const float fend = sj * scale * P.e0;                          // after the inverse transform (and the epilogue weight)
-  const bool q0_smem = (P.q0 != nullptr) && (P.q0 == P.p0) && !HAS_P1 && P.a0 == 1.0f;
-  const bool ldq0 = (P.q0 != nullptr) && !q0_smem;  // rare: loaded inline in the final pass
+  // e1 * q0 with q0 the (unscaled) source itself: F^-1 (e0 g) F x + e1 x = F^-1 (e0 g + e1) F x — folded into the multiplier,
+  // so the staged source is not needed after the first butterfly
+  const bool fold = (P.q0 != nullptr) && (P.q0 == P.p0) && !HAS_P1 && P.a0 == 1.0f;
+  const float g_scale = fold ? P.e0 : 1.0f, g_shift = fold ? P.e1 : 0.0f;
+  const float fend = sj * scale * (fold ? 1.0f : P.e0);          // after the inverse transform (and the epilogue weight)
+  const bool ldq0 = (P.q0 != nullptr) && !fold;  // rare: loaded inline in the final pass
   const bool ldq1 = P.q1 != nullptr;
-  float2* wk = S.work + line * RLS;
   const float2* twj = S.tws + j;
   auto tw = [&](int r) { return twj[16 * r]; };
 
@@ -211,10 +208,12 @@ __global__ void __launch_bounds__(NT, 2) sp_row_fused(const PipeParams P) {
     }
     mb_wait(&S.full[s], (it >> 1) & 1);
     float* sl = S.in0 + s * STAGE_F + line * LSTR;
+    float2* wk = reinterpret_cast<float2*>(sl);
 
     float2 v[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = make_float2(sl[j + 16 * r], sl[IMO + j + 16 * r]);
+    __syncwarp();  // the line has been read by all of its lanes: it is the work row from here on
     if (HAS_P1) {
       const float* g1 = P.p1 + (long long)img * 2 * HW + (long long)(h0 + line) * N + j;
 #pragma unroll
@@ -239,38 +238,32 @@ __global__ void __launch_bounds__(NT, 2) sp_row_fused(const PipeParams P) {
       gmap<16>(P.gmode, m, c);
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
-        const float mf = m[r] * fmid;
+        const float mf = (g_scale * m[r] + g_shift) * fmid;
         v[r].x *= mf; v[r].y *= -mf;
       }
     } else {
+      const float mf = (g_scale + g_shift) * fmid;
 #pragma unroll
-      for (int r = 0; r < 16; ++r) { v[r].x *= fmid; v[r].y *= -fmid; }
+      for (int r = 0; r < 16; ++r) { v[r].x *= mf; v[r].y *= -mf; }
     }
     __syncwarp();  // every lane has read its stage-2 inputs: the warp's work rows may be overwritten
     w_stage1_store(v, wk, j);
     __syncwarp();
     // the warp writes its own two lines: lane handles 8 x 128 bits, f = lane + 32 i -> (line of the pair, plane, column group)
     const long long gbase = (long long)img * 2 * HW + (long long)(h0 + 2 * warp) * N;
-    float4 qb[8];
-    if (ldq1) {
+    float4 qb[OCC == 2 ? 8 : 1];
+    if (OCC == 2 && ldq1) {  // register budget allows it: second epilogue operand issued before the last butterfly
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < (OCC == 2 ? 8 : 1); ++i) {
         const int f = lane + 32 * i, lp = f >> 7, plane = (f >> 6) & 1, c4 = f & 63;
         qb[i] = __ldg(reinterpret_cast<const float4*>(P.q1 + gbase + plane * HW + lp * N + 4 * c4));
       }
     }
     w_stage2(v, wk, j, tw);
-    // conj, post-phase, scale, e0; + e1 * x when q0 is the staged source; in place into the staged line
-    if (q0_smem) {
+    __syncwarp();  // stage-2 inputs consumed: the work row becomes the planar output row
+    // conj, post-phase, scale, e0 -> planar
 #pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        sl[j + 16 * r] = fend * v[r].x + P.e1 * sl[j + 16 * r];
-        sl[IMO + j + 16 * r] = -fend * v[r].y + P.e1 * sl[IMO + j + 16 * r];
-      }
-    } else {
-#pragma unroll
-      for (int r = 0; r < 16; ++r) { sl[j + 16 * r] = fend * v[r].x; sl[IMO + j + 16 * r] = -fend * v[r].y; }
-    }
+    for (int r = 0; r < 16; ++r) { sl[j + 16 * r] = fend * v[r].x; sl[IMO + j + 16 * r] = -fend * v[r].y; }
     __syncwarp();
     {
       const float* sw2 = S.in0 + s * STAGE_F + (2 * warp) * LSTR;
@@ -283,7 +276,12 @@ __global__ void __launch_bounds__(NT, 2) sp_row_fused(const PipeParams P) {
           const float4 a = __ldg(reinterpret_cast<const float4*>(P.q0 + gbase + plane * HW + lp * N + 4 * c4));
           o.x += P.e1 * a.x; o.y += P.e1 * a.y; o.z += P.e1 * a.z; o.w += P.e1 * a.w;
         }
-        if (ldq1) { o.x += P.e2 * qb[i].x; o.y += P.e2 * qb[i].y; o.z += P.e2 * qb[i].z; o.w += P.e2 * qb[i].w; }
+        if (ldq1) {
+          float4 b4;
+          if (OCC == 2) b4 = qb[OCC == 2 ? i : 0];
+          else b4 = __ldg(reinterpret_cast<const float4*>(P.q1 + gbase + plane * HW + lp * N + 4 * c4));
+          o.x += P.e2 * b4.x; o.y += P.e2 * b4.y; o.z += P.e2 * b4.z; o.w += P.e2 * b4.w;
+        }
         *reinterpret_cast<float4*>(ob + plane * HW + lp * N + 4 * c4) = o;
       }
     }
@@ -297,8 +295,8 @@ __global__ void __launch_bounds__(NT, 2) sp_row_fused(const PipeParams P) {
 // one CTA barrier, then the a-butterfly of the H transform per column, twiddle w256^(b k_lo), store to
 // ws[img][k_lo][b][w] (interleaved)
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool HAS_P1>
-__global__ void __launch_bounds__(NT, 2) sp_pass1(const PipeParams P) {
+template <bool HAS_P1, int OCC>
+__global__ void __launch_bounds__(NT, OCC) sp_pass1(const PipeParams P) {
   extern __shared__ __align__(128) unsigned char sp_raw[];
   const RowSmem S = carve_row(sp_raw);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -319,11 +317,13 @@ __global__ void __launch_bounds__(NT, 2) sp_pass1(const PipeParams P) {
 
   const float sgn_im = P.inverse ? -1.0f : 1.0f;                  // conj of the source for the inverse-by-conjugation
   const float sw = (P.centered && (tid & 1)) ? -1.0f : 1.0f;      // (-1)^k_w post-phase of the W transform, column = tid
-  float2* wk = S.work + line * RLS;
-  float2 twr[16];  // stage-2 twiddles of this thread, kept in registers across tiles
+  float2 twr[OCC == 2 ? 16 : 1];  // OCC == 2: stage-2 twiddles of this thread kept in registers across tiles
+  if (OCC == 2) {
 #pragma unroll
-  for (int r = 0; r < 16; ++r) twr[r] = S.tws[r * 16 + j];
-  auto tw = [&](int r) { return twr[r]; };
+    for (int r = 0; r < (OCC == 2 ? 16 : 1); ++r) twr[r] = S.tws[r * 16 + j];
+  }
+  const float2* twj = S.tws + j;
+  auto tw = [&](int r) { return OCC == 2 ? twr[OCC == 2 ? r : 0] : twj[16 * r]; };
 
   int it = 0;
   for (int t = t0; t < ntiles; t += gridDim.x, ++it) {
@@ -338,11 +338,13 @@ __global__ void __launch_bounds__(NT, 2) sp_pass1(const PipeParams P) {
     mb_wait(&S.full[s], (it >> 1) & 1);
     float* stage = S.in0 + s * STAGE_F;
     float* sl = stage + line * LSTR;
+    float2* wk = reinterpret_cast<float2*>(sl);
     const int h = b + 16 * line;
 
     float2 v[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = make_float2(sl[j + 16 * r], sl[IMO + j + 16 * r]);
+    __syncwarp();  // the line has been read by all of its lanes: it is the work row from here on
     if (HAS_P1) {
       const float* g1 = P.p1 + (long long)img * 2 * HW + (long long)h * N + j;
 #pragma unroll
@@ -357,22 +359,31 @@ __global__ void __launch_bounds__(NT, 2) sp_pass1(const PipeParams P) {
     if (P.g_at_load && P.gmode != DINVK_G_NONE) {
       const float* gp = P.g + (long long)img * P.gsb + (long long)h * P.gsh + j;
       const float c = P.gcb ? __ldg(P.gcb + img) : P.gc;
-      float m0[16], m1[16];
+      float m0[16];
 #pragma unroll
-      for (int r = 0; r < 16; ++r) { m0[r] = __ldg(gp + 16 * r); m1[r] = __ldg(gp + P.gsc + 16 * r); }
+      for (int r = 0; r < 16; ++r) m0[r] = __ldg(gp + 16 * r);
       gmap<16>(P.gmode, m0, c);
-      gmap<16>(P.gmode, m1, c);
+      if (P.gsc == 0) {  // same multiplier on both planes (line masks)
 #pragma unroll
-      for (int r = 0; r < 16; ++r) { v[r].x *= m0[r]; v[r].y *= sgn_im * m1[r]; }
+        for (int r = 0; r < 16; ++r) { v[r].x *= m0[r]; v[r].y *= sgn_im * m0[r]; }
+      } else {
+        float m1[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) m1[r] = __ldg(gp + P.gsc + 16 * r);
+        gmap<16>(P.gmode, m1, c);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) { v[r].x *= m0[r]; v[r].y *= sgn_im * m1[r]; }
+      }
     } else if (P.inverse) {
 #pragma unroll
       for (int r = 0; r < 16; ++r) v[r].y = -v[r].y;
     }
     w_stage1_store(v, wk, j);
-    __syncwarp();  // also: every lane of the warp has consumed its staged line
+    __syncwarp();
     w_stage2(v, wk, j, tw);
+    __syncwarp();  // stage-2 inputs consumed
     {
-      float2* tl = reinterpret_cast<float2*>(sl) + j;  // transpose through the warp's own staged line (280 float2)
+      float2* tl = wk + j;  // transpose through the line's work row
 #pragma unroll
       for (int r = 0; r < 16; ++r) tl[17 * r] = v[r];  // bin j + 16 r -> pad16 index j + 17 r
     }
@@ -393,11 +404,56 @@ __global__ void __launch_bounds__(NT, 2) sp_pass1(const PipeParams P) {
       o[0] = make_float2(sb * v[0].x, sb * v[0].y);
 #pragma unroll
       for (int k = 1; k < 16; ++k) {
-        float2 tk = S.twf[(b * k) & 255];
+        float2 tk = __ldg(P.tw + ((b * k) & 255));  // uniform across the CTA
         tk.x *= sb; tk.y *= sb;
         o[(long long)k * 16 * N] = cmul(v[k], tk);
       }
     }
+  }
+}
+
+// pass-2 work of one column: b-butterfly of the 16 intermediate rows held in u -> rows h = k_lo + 16 k of column `tid`,
+// multiplier (A), scale, conjugation (inverse), epilogue, planar stores
+__device__ __forceinline__ void p2_finish(const PipeParams& P, float2 (&u)[16], int img, int klo, int tid) {
+  constexpr long long HW = (long long)N * N;
+  const float s2 = 1.0f / 256.0f;
+  const float sgn_im = P.inverse ? -1.0f : 1.0f;
+  const bool mult = (P.gmode != DINVK_G_NONE) && !P.g_at_load;
+  Dft<16>::run(u);
+  // (-1)^h post-phase = (-1)^k_lo; scale 1/256; e0
+  const float f = ((P.centered && (klo & 1)) ? -1.0f : 1.0f) * s2 * P.e0;
+  const float fi = sgn_im * f;
+  const long long obase = (long long)img * 2 * HW + (long long)klo * N + tid;
+  if (mult) {  // A: multiplier on the k-space result, rows h = k_lo + 16 k
+    const float c = P.gcb ? __ldg(P.gcb + img) : P.gc;
+    const float* gp = P.g + (long long)img * P.gsb + (long long)klo * P.gsh + tid;
+    if (P.gsh == 0) {  // multiplier independent of the row (line masks): one value per column
+      float m[2] = {__ldg(gp), __ldg(gp + P.gsc)};
+      gmap<2>(P.gmode, m, c);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { u[k].x *= m[0]; u[k].y *= m[1]; }
+    } else {
+      float m0[16], m1[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float* gk = gp + (long long)(16 * k) * P.gsh;
+        m0[k] = __ldg(gk);
+        m1[k] = __ldg(gk + P.gsc);
+      }
+      gmap<16>(P.gmode, m0, c);
+      gmap<16>(P.gmode, m1, c);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { u[k].x *= m0[k]; u[k].y *= m1[k]; }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const long long o = obase + (long long)k * 16 * N;
+    float re = f * u[k].x, im = fi * u[k].y;
+    if (P.q0) { re += P.e1 * __ldg(P.q0 + o); im += P.e1 * __ldg(P.q0 + o + HW); }
+    if (P.q1) { re += P.e2 * __ldg(P.q1 + o); im += P.e2 * __ldg(P.q1 + o + HW); }
+    P.out[o] = re;
+    P.out[o + HW] = im;
   }
 }
 
@@ -413,8 +469,6 @@ __global__ void __launch_bounds__(P2_NT, 2) sp_pass2(const PipeParams P) {
   uint64_t* empty = full + P2_STAGES;
   const int tid = threadIdx.x, lane = tid & 31;
   const int ntiles = P.B * 16;
-  constexpr long long HW = (long long)N * N;
-
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < P2_STAGES; ++i) { mb_init(&full[i], 1); mb_init(&empty[i], P2_NT / 32); }
@@ -431,10 +485,6 @@ __global__ void __launch_bounds__(P2_NT, 2) sp_pass2(const PipeParams P) {
     }
   }
   __syncthreads();
-  const float s2 = 1.0f / 256.0f;
-  const float sgn_im = P.inverse ? -1.0f : 1.0f;
-  const bool mult = (P.gmode != DINVK_G_NONE) && !P.g_at_load;
-
   int it = 0;
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
     const int s = it % P2_STAGES;
@@ -462,35 +512,7 @@ __global__ void __launch_bounds__(P2_NT, 2) sp_pass2(const PipeParams P) {
     }
     __syncwarp();
     if (lane == 0) mb_arrive(&empty[s]);
-    Dft<16>::run(u);
-    // (-1)^h post-phase = (-1)^k_lo; scale 1/256; e0
-    const float f = ((P.centered && (klo & 1)) ? -1.0f : 1.0f) * s2 * P.e0;
-    const float fi = sgn_im * f;
-    const long long obase = (long long)img * 2 * HW + (long long)klo * N + tid;
-    if (mult) {  // A: multiplier on the k-space result, rows h = k_lo + 16 k
-      const float c = P.gcb ? __ldg(P.gcb + img) : P.gc;
-      const float* gp = P.g + (long long)img * P.gsb + (long long)klo * P.gsh + tid;
-      float m0[16], m1[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const float* gk = gp + (long long)(16 * k) * P.gsh;
-        m0[k] = __ldg(gk);
-        m1[k] = __ldg(gk + P.gsc);
-      }
-      gmap<16>(P.gmode, m0, c);
-      gmap<16>(P.gmode, m1, c);
-#pragma unroll
-      for (int k = 0; k < 16; ++k) { u[k].x *= m0[k]; u[k].y *= m1[k]; }
-    }
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const long long o = obase + (long long)k * 16 * N;
-      float re = f * u[k].x, im = fi * u[k].y;
-      if (P.q0) { re += P.e1 * __ldg(P.q0 + o); im += P.e1 * __ldg(P.q0 + o + HW); }
-      if (P.q1) { re += P.e2 * __ldg(P.q1 + o); im += P.e2 * __ldg(P.q1 + o + HW); }
-      P.out[o] = re;
-      P.out[o + HW] = im;
-    }
+    p2_finish(P, u, img, klo, tid);
   }
 }
 

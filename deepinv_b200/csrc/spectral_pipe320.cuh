@@ -154,13 +154,21 @@ __global__ void __launch_bounds__(NT, 2) sp320_pass1(const Params P) {
       const int mb = img / P.ncoil;
       const float* gp = P.g + (long long)mb * P.gsb + (long long)h * P.gsh + j;
       const float c = P.gcb ? __ldg(P.gcb + mb) : P.gc;
-      float m0[16], m1[16];
+      float m0[16];
 #pragma unroll
-      for (int r = 0; r < 16; ++r) { m0[r] = __ldg(gp + 20 * r); m1[r] = __ldg(gp + P.gsc + 20 * r); }
+      for (int r = 0; r < 16; ++r) m0[r] = __ldg(gp + 20 * r);
       gmap<16>(P.gmode, m0, c);
-      gmap<16>(P.gmode, m1, c);
+      if (P.gsc == 0) {  // same multiplier on both planes (line masks)
 #pragma unroll
-      for (int r = 0; r < 16; ++r) { v[r].x *= m0[r]; v[r].y *= sgn_im * m1[r]; }
+        for (int r = 0; r < 16; ++r) { v[r].x *= m0[r]; v[r].y *= sgn_im * m0[r]; }
+      } else {
+        float m1[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) m1[r] = __ldg(gp + P.gsc + 20 * r);
+        gmap<16>(P.gmode, m1, c);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) { v[r].x *= m0[r]; v[r].y *= sgn_im * m1[r]; }
+      }
     } else if (P.inverse) {
 #pragma unroll
       for (int r = 0; r < 16; ++r) v[r].y = -v[r].y;
@@ -266,17 +274,24 @@ __global__ void __launch_bounds__(NT, 2) sp320_pass2(const Params P) {
       const int mb = img / P.ncoil;
       const float c = P.gcb ? __ldg(P.gcb + mb) : P.gc;
       const float* gp = P.g + (long long)mb * P.gsb + (long long)klo * P.gsh + tid;
-      float m0[20], m1[20];
+      if (P.gsh == 0) {  // multiplier independent of the row (line masks): one value per column
+        float m[2] = {__ldg(gp), __ldg(gp + P.gsc)};
+        gmap<2>(P.gmode, m, c);
 #pragma unroll
-      for (int k = 0; k < 20; ++k) {
-        const float* gk = gp + (long long)(16 * k) * P.gsh;
-        m0[k] = __ldg(gk);
-        m1[k] = __ldg(gk + P.gsc);
+        for (int k = 0; k < 20; ++k) { u[k].x *= m[0]; u[k].y *= m[1]; }
+      } else {
+        float m0[20], m1[20];
+#pragma unroll
+        for (int k = 0; k < 20; ++k) {
+          const float* gk = gp + (long long)(16 * k) * P.gsh;
+          m0[k] = __ldg(gk);
+          m1[k] = __ldg(gk + P.gsc);
+        }
+        gmap<20>(P.gmode, m0, c);
+        gmap<20>(P.gmode, m1, c);
+#pragma unroll
+        for (int k = 0; k < 20; ++k) { u[k].x *= m0[k]; u[k].y *= m1[k]; }
       }
-      gmap<20>(P.gmode, m0, c);
-      gmap<20>(P.gmode, m1, c);
-#pragma unroll
-      for (int k = 0; k < 20; ++k) { u[k].x *= m0[k]; u[k].y *= m1[k]; }
     }
     if (P.tout) {
       float2* o = P.tout + (long long)img * HW + (long long)klo * N + tid;
