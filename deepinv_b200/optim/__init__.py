@@ -1,7 +1,9 @@
 from .data_fidelity import L2, DataFidelity, ZeroFidelity  # noqa: F401
+from .dpir import DPIR, get_DPIR_params  # noqa: F401
 from .graphed import GraphedIteration, HostStreamedIteration  # noqa: F401
 from .linear import conjugate_gradient, least_squares  # noqa: F401
-from .optim_iterators import (ADMMIteration, FISTAIteration, HQSIteration, OptimIterator,  # noqa: F401
-                              PGDIteration)
-from .optimizers import ADMM, FISTA, HQS, PGD, BaseOptim, optim_builder  # noqa: F401
-from .prior import PnP, Prior, ZeroPrior  # noqa: F401
+from .optim_iterators import (ADMMIteration, DRSIteration, FISTAIteration, GDIteration, HQSIteration,  # noqa: F401
+                              OptimIterator, PGDIteration)
+from .optimizers import (ADMM, DRS, FISTA, GD, HQS, PGD, BaseOptim, DEQConfig, create_iterator,  # noqa: F401
+                         optim_builder)
+from .prior import RED, PnP, Prior, Tikhonov, ZeroPrior  # noqa: F401

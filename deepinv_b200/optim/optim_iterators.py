@@ -188,3 +188,83 @@ class HQSIteration(OptimIterator):
         super().__init__(**kwargs)
         self.g_step = gStepHQS(**kwargs)
         self.f_step = fStepHQS(**kwargs)
+
+
+# ---- DRS -----------------------------------------------------------------------------------------
+class fStepDRS(fStep):
+    """prox_{gamma f} of z (f first) or of the reflection 2x - z (g first)  (drs.py:76-108)"""
+
+    def forward(self, x, z, cur_data_fidelity, cur_params, y, physics):
+        p = _axpby(2.0, x, -1.0, z) if self.g_first else z
+        return cur_data_fidelity.prox(p, y, physics, gamma=cur_params["stepsize"])
+
+
+class gStepDRS(gStep):
+    """prox_{gamma lambda g} of the reflection 2x - z (f first) or of z (g first)  (drs.py:111-146)"""
+
+    def forward(self, x, z, cur_prior, cur_params):
+        p = z if self.g_first else _axpby(2.0, x, -1.0, z)
+        return cur_prior.prox(p, cur_params["g_param"], gamma=cur_params["lambda"] * cur_params["stepsize"])
+
+
+class DRSIteration(OptimIterator):
+    """Douglas-Rachford splitting (drs.py:12-73): u = prox_f(z); x = prox_g(2u - z); z += beta (x - u)"""
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.g_step = gStepDRS(**kwargs)
+        self.f_step = fStepDRS(**kwargs)
+
+    def forward(self, X, cur_data_fidelity, cur_prior, cur_params, y, physics, *args, **kwargs):
+        x, z = X["est"] if len(X["est"]) == 2 else (None, X["est"])
+        if x is not None and z.shape != x.shape:
+            z = x  # the "dual" variable of DRS lives in the primal space
+        if self.g_first:
+            u = self.g_step(x, z, cur_prior, cur_params)
+            x = self.f_step(u, z, cur_data_fidelity, cur_params, y, physics)
+        else:
+            u = self.f_step(x, z, cur_data_fidelity, cur_params, y, physics)
+            x = self.g_step(u, z, cur_prior, cur_params)
+        beta = cur_params["beta"]
+        if _scalar(beta) and not (torch.is_grad_enabled() and (u.requires_grad or x.requires_grad or z.requires_grad)):
+            z = ops.axpbypcz(z, 1.0, x, float(beta), u, -float(beta))
+        else:
+            z = z + beta * (x - u)
+        return {"est": (x, z), "cost": self._cost(x, cur_data_fidelity, cur_prior, cur_params, y, physics),
+                "aty": X.get("aty")}
+
+
+# ---- GD ------------------------------------------------------------------------------------------
+class fStepGD(fStep):
+    def forward(self, x, cur_data_fidelity, cur_params, y, physics, aty=None):
+        return cur_data_fidelity.grad(x, y, physics)
+
+
+class gStepGD(gStep):
+    def forward(self, x, cur_prior, cur_params):
+        return cur_params["lambda"] * cur_prior.grad(x, cur_params["g_param"])
+
+
+class GDIteration(OptimIterator):
+    """x <- x - gamma (grad f(x) + lambda grad g(x))  (gradient_descent.py:12-66).
+
+    With a plain L2 data term on a physics that has the fused normal-step kernel the data part
+    x - gamma*norm*(A^T A x - A^T y) is one launch; the prior gradient is then subtracted by one axpby."""
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.g_step = gStepGD(**kwargs)
+        self.f_step = fStepGD(**kwargs)
+
+    def forward(self, X, cur_data_fidelity, cur_prior, cur_params, y, physics, *args, **kwargs):
+        x_prev = X["est"][0]
+        aty = X.get("aty")
+        step = cur_params["stepsize"]
+        gg = self.g_step(x_prev, cur_prior, cur_params)
+        fused = (type(cur_data_fidelity) is L2 and hasattr(physics, "normal_step") and _scalar(step) and aty is not None
+                 and not (torch.is_grad_enabled() and (x_prev.requires_grad or gg.requires_grad)))
+        if fused:
+            x = _axpby(1.0, physics.normal_step(x_prev, aty, float(step) * cur_data_fidelity.norm), -float(step), gg)
+        else:
+            x = x_prev - step * (gg + self.f_step(x_prev, cur_data_fidelity, cur_params, y, physics))
+        return {"est": (x,), "cost": self._cost(x, cur_data_fidelity, cur_prior, cur_params, y, physics), "aty": aty}

@@ -16,8 +16,22 @@ import torch
 import torch.nn as nn
 
 from .data_fidelity import ZeroFidelity
-from .optim_iterators import ADMMIteration, FISTAIteration, HQSIteration, OptimIterator, PGDIteration
+from dataclasses import dataclass
+
+from .optim_iterators import (ADMMIteration, DRSIteration, FISTAIteration, GDIteration, HQSIteration, OptimIterator,
+                              PGDIteration)
 from .prior import ZeroPrior
+
+
+@dataclass
+class DEQConfig:
+    """backward-pass settings of a deep-equilibrium model (optimizers.py:44-62)"""
+    max_iter_backward: int = 50
+    anderson_acceleration_backward: bool = False
+    history_size_backward: int = 5
+    beta_backward: float = 1.0
+    eps_backward: float = 1e-4
+    jacobian_free: bool = False
 
 
 def objective_function(x, data_fidelity, prior, cur_params, y, physics):
@@ -28,8 +42,14 @@ class BaseOptim(nn.Module):
     def __init__(self, iterator: OptimIterator, params_algo=None, data_fidelity=None, prior=None, max_iter: int = 100,
                  crit_conv: str = "residual", thres_conv: float = 1e-5, early_stop: bool = False, has_cost: bool = False,
                  custom_metrics=None, custom_init=None, get_output=lambda X: X["est"][0], unfold: bool = False,
-                 trainable_params=None, verbose: bool = False, show_progress_bar: bool = False, **kwargs):
+                 trainable_params=None, verbose: bool = False, show_progress_bar: bool = False, DEQ=None, **kwargs):
         super().__init__()
+        if isinstance(DEQ, bool):
+            self.DEQ, self.DEQ_config = DEQ, (DEQConfig() if DEQ else None)
+        else:
+            self.DEQ, self.DEQ_config = DEQ is not None, (DEQ or DEQConfig())
+        if self.DEQ and self.DEQ_config.anderson_acceleration_backward:
+            raise NotImplementedError("deepinv_b200: Anderson-accelerated DEQ backward is outside the accelerated path")
         self.early_stop, self.crit_conv, self.verbose = early_stop, crit_conv, verbose
         self.max_iter, self.thres_conv = max_iter, thres_conv
         self.custom_metrics, self.custom_init, self.get_output = custom_metrics, custom_init, get_output
@@ -56,8 +76,9 @@ class BaseOptim(nn.Module):
             elif 1 < len(value) < self.max_iter:
                 raise ValueError(f"The number of elements in the parameter {key} is inferior to max_iter.")
         self.init_params_algo = params_algo
+        self._host_schedules = {}
 
-        if self.unfold:
+        if self.unfold or self.DEQ:
             if trainable_params is not None:
                 trainable_params = ["lambda" if p == "lambda_reg" else "g_param" if p == "sigma_denoiser" else p
                                     for p in trainable_params]
@@ -75,7 +96,19 @@ class BaseOptim(nn.Module):
 
     # ---- per-iteration lookups (optimizers.py:464-502) --------------------------------------------
     def update_params_fn(self, it: int) -> dict:
-        return {k: (v[it] if len(v) > 1 else v[0]) for k, v in self.init_params_algo.items()}
+        """parameters of iteration `it` (optimizers.py:464-480).  Fixed (non-trainable) schedules given as tensors — e.g.
+        DPIR's per-iteration sigma / stepsize on the device — are read back to host floats ONCE, so that the loop does not
+        synchronise on a device scalar every iteration (the values are the same fp32 numbers)."""
+        out = {}
+        for k, v in self.init_params_algo.items():
+            if isinstance(v, torch.Tensor) and not v.requires_grad and v.dim() == 1:
+                host = self._host_schedules.get(k)
+                if host is None or host[0] is not v:
+                    host = (v, v.detach().cpu().tolist())
+                    self._host_schedules[k] = host
+                v = host[1]
+            out[k] = v[it] if len(v) > 1 else v[0]
+        return out
 
     def update_prior_fn(self, it: int):
         return self.prior[it] if len(self.prior) > 1 else self.prior[0]
@@ -153,8 +186,30 @@ class BaseOptim(nn.Module):
         return self.iterator(X, self.update_data_fidelity_fn(it), self.update_prior_fn(it), self.update_params_fn(it),
                              y, physics, **kwargs)
 
+    def DEQ_additional_step(self, X, y, physics, **kwargs):
+        """One more iteration WITH gradient tracking at the equilibrium x*, plus a backward hook that replaces the
+        incoming gradient u by the solution of v = J(x*)^T v + u, found by `max_iter_backward` fixed-point sweeps
+        (optimizers.py:741-828; implicit function theorem).  Every J^T v is one autograd pass through the iteration,
+        i.e. the adjoint operator kernels and the denoiser's backward kernels."""
+        it = self.max_iter - 1
+        fid, prior, params = self.update_data_fidelity_fn(it), self.update_prior_fn(it), self.update_params_fn(it)
+        x = self.iterator(X, fid, prior, params, y, physics, **kwargs)["est"][0]
+        if not self.DEQ_config.jacobian_free and x.requires_grad:
+            x0 = x.detach().clone().requires_grad_()
+            f0 = self.iterator({"est": (x0,), "aty": X.get("aty")}, fid, prior, params, y, physics, **kwargs)["est"][0]
+            n_back = int(self.DEQ_config.max_iter_backward)
+
+            def solve_adjoint_fixed_point(grad):
+                v = grad
+                for _ in range(n_back):
+                    v = torch.autograd.grad(f0, x0, v, retain_graph=True)[0] + grad
+                return v
+
+            x.register_hook(solve_adjoint_fixed_point)
+        return x
+
     def forward(self, y, physics, init=None, x_gt=None, compute_metrics: bool = False, **kwargs):
-        ctx = torch.no_grad() if not self.unfold else nullcontext()
+        ctx = torch.no_grad() if (not self.unfold or self.DEQ) else nullcontext()
         with ctx:
             X = self.init_iterate_fn(y, physics, init=init)
             metrics = self._metrics_init(X, x_gt) if compute_metrics else None
@@ -166,7 +221,7 @@ class BaseOptim(nn.Module):
                     metrics = self._metrics_update(metrics, X_prev, X, x_gt)
                 if self.early_stop and it > 1 and self.check_conv_fn(it, X_prev, X):
                     break
-        x = self.get_output(X)
+        x = self.DEQ_additional_step(X, y, physics, **kwargs) if self.DEQ else self.get_output(X)
         return (x, metrics) if compute_metrics else x
 
 
@@ -211,15 +266,39 @@ class ADMM(_named(ADMMIteration)):
 
 
 class HQS(_named(HQSIteration)):
-    """Half-quadratic splitting (optimizers.py:1194-1317)"""
+    """Half-quadratic splitting (optimizers.py:1459-1593)"""
+
+
+class DRS(_named(DRSIteration)):
+    """Douglas-Rachford splitting (optimizers.py:1194-1317)"""
+
+
+class GD(_named(GDIteration)):
+    """Gradient descent on f + lambda g (optimizers.py:1320-1456)"""
+
+
+_ITERATIONS = {"PGD": PGDIteration, "FISTA": FISTAIteration, "ADMM": ADMMIteration, "HQS": HQSIteration,
+               "DRS": DRSIteration, "GD": GDIteration}
+
+
+def create_iterator(iteration, prior=None, cost_fn=None, g_first: bool = False, bregman_potential=None, **kwargs):
+    """name or instance -> OptimIterator (optimizers.py:884-971); an explicit prior switches the cost on"""
+    if prior is None:
+        prior = ZeroPrior()
+    explicit = prior[0].explicit_prior if isinstance(prior, (list, nn.ModuleList)) else prior.explicit_prior
+    has_cost = cost_fn is None and explicit
+    if has_cost:
+        cost_fn = objective_function
+    if isinstance(iteration, str):
+        if iteration not in _ITERATIONS:
+            raise NotImplementedError(f"iteration {iteration!r} is outside the accelerated path "
+                                      f"(have {sorted(_ITERATIONS)})")
+        return _ITERATIONS[iteration](g_first=g_first, cost_fn=cost_fn, has_cost=has_cost)
+    return iteration
 
 
 def optim_builder(iteration, max_iter=100, params_algo=None, data_fidelity=None, prior=None, g_first=False, **kwargs):
     """legacy builder (optimizers.py:2560-2679): iteration given by name or as an OptimIterator"""
-    table = {"PGD": PGDIteration, "FISTA": FISTAIteration, "ADMM": ADMMIteration, "HQS": HQSIteration}
-    if isinstance(iteration, str):
-        if iteration not in table:
-            raise NotImplementedError(f"iteration {iteration!r} is outside the accelerated path")
-        iteration = table[iteration](g_first=g_first)
+    iteration = create_iterator(iteration, prior=prior, g_first=g_first)
     return BaseOptim(iteration, max_iter=max_iter, params_algo=params_algo, data_fidelity=data_fidelity, prior=prior,
                      **kwargs)

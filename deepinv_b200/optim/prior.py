@@ -51,3 +51,37 @@ class PnP(Prior):
 
     def prox(self, x, sigma_denoiser, *args, **kwargs):
         return self.denoiser(x, sigma_denoiser)
+
+
+class RED(Prior):
+    """Regularisation by denoising: grad g(x) = x - D_sigma(x)  (prior.py:112-135); one axpby after the denoiser"""
+
+    def __init__(self, denoiser, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.denoiser = denoiser
+        self.explicit_prior = False
+
+    def grad(self, x, sigma_denoiser, *args, **kwargs):
+        d = self.denoiser(x, sigma_denoiser)
+        if torch.is_grad_enabled() and (x.requires_grad or d.requires_grad):
+            return x - d
+        from .. import ops
+
+        return ops.axpbypcz(x, 1.0, d, -1.0)
+
+
+class Tikhonov(Prior):
+    """g(x) = 1/2 ||x||^2 (prior.py:227-266): grad = x, prox = x / (1 + gamma)"""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.explicit_prior = True
+
+    def fn(self, x, *args, **kwargs):
+        return 0.5 * (x.reshape(x.shape[0], -1) ** 2).sum(-1)
+
+    def grad(self, x, *args, **kwargs):
+        return x
+
+    def prox(self, x, *args, gamma=1.0, **kwargs):
+        return (1 / (gamma + 1)) * x

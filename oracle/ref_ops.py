@@ -590,6 +590,47 @@ def hqs(y, prox_f, At, denoiser, stepsize, sigma_d, max_iter):
     return x
 
 
+def drs(y, prox_f, At, denoiser, stepsize, sigma_d, max_iter, beta=1.0, g_first=False):
+    """Douglas-Rachford splitting (optim_iterators/drs.py:36-73): x0 = z0 = A^T y"""
+    x = z = At(y)
+    for _ in range(max_iter):
+        if g_first:
+            u = denoiser(z, sigma_d)
+            x = prox_f(2 * u - z, stepsize)
+        else:
+            u = prox_f(z, stepsize)
+            x = denoiser(2 * u - z, sigma_d)
+        z = z + beta * (x - u)
+    return x
+
+
+def gd(y, A, At, grad_g, stepsize, lam, max_iter):
+    """gradient descent (optim_iterators/gradient_descent.py:48-56): x <- x - gamma (lambda grad g(x) + A^T(Ax - y))"""
+    x = At(y)
+    for _ in range(max_iter):
+        x = x - stepsize * (lam * grad_g(x) + (At(A(x)) - At(y)))
+    return x
+
+
+def dpir_params(noise_level_img):
+    """optim/dpir.py:11-35"""
+    max_iter = 8
+    s1, s2 = 49.0 / 255.0, noise_level_img
+    sig = torch.logspace(torch.log10(torch.tensor(s1, dtype=torch.float32)), torch.log10(torch.tensor(s2, dtype=torch.float32)),
+                         steps=max_iter, dtype=torch.float32)
+    step = (sig / max(0.01, noise_level_img)) ** 2
+    return sig, (1 / 0.23) * step, max_iter
+
+
+def dpir(y, prox_f, At, denoiser, noise_level_img):
+    """DPIR (optim/dpir.py:38-81): HQS with the per-iteration schedule above"""
+    sig, step, n = dpir_params(noise_level_img)
+    x = At(y)
+    for k in range(n):
+        x = denoiser(prox_f(x, step[k]), sig[k])
+    return x
+
+
 # -------------------------------------------------------------------------------------------------
 # a17: DDRM  (sampling/diffusion.py:149-224) with the noise draws supplied by the caller
 # -------------------------------------------------------------------------------------------------

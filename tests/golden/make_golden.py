@@ -206,6 +206,35 @@ def optim_fixtures():
     save("optim_blur_tiny", x=x, filt=filt, y=y, admm=out, **sd_arrays(dn, "sd__"))
 
 
+def optim2_fixtures():
+    """DRS, GD (explicit + RED priors), DPIR — same miniature MRI problem as optim_mri_tiny"""
+    from deepinv.optim import DPIR, DRS, GD
+    from deepinv.optim.prior import RED, Tikhonov
+
+    B, H, W = 2, 32, 32
+    x = torch.randn(B, 2, H, W, generator=g(1))
+    mask = RandomMaskGenerator((2, H, W), acceleration=4, rng=g(0)).step(B)["mask"]
+    phys = MRI(mask=mask, img_size=(2, H, W))
+    y = phys(x)
+    den = tiny_drunet(2)
+    kw = dict(data_fidelity=L2(), early_stop=False)
+    with torch.no_grad():
+        drs = DRS(prior=PnP(den), stepsize=1.0, sigma_denoiser=0.05, max_iter=3, **kw)(y, phys)
+        drs_relax = DRS(prior=PnP(den), max_iter=3, g_first=True,
+                        params_algo={"stepsize": 0.7, "g_param": 0.05, "lambda": 1.0, "beta": 0.8}, **kw)(y, phys)
+        gd_tik = GD(prior=Tikhonov(), stepsize=0.5, lambda_reg=0.1, max_iter=4, **kw)(y, phys)
+        gd_red = GD(prior=RED(den), stepsize=0.5, lambda_reg=0.3, sigma_denoiser=0.05, max_iter=3, **kw)(y, phys)
+        dpir = DPIR(sigma=0.05, denoiser=den)(y, phys)
+        # the same recipe on a non-decomposable operator: circular Blur -> CG prox inside HQS
+        xb = torch.rand(2, 2, 24, 32, generator=g(18))
+        filt = dinv.physics.functional.gaussian_blur(sigma=(1.0, 1.0))
+        physb = Blur(filter=filt, padding="circular")
+        yb = physb(xb)
+        dpir_blur = DPIR(sigma=0.05, denoiser=den)(yb, physb)
+    save("optim2_mri_tiny", x=x, mask=phys.mask, y=y, drs=drs, drs_relax=drs_relax, gd_tik=gd_tik, gd_red=gd_red,
+         dpir=dpir, xb=xb, filt=filt, yb=yb, dpir_blur=dpir_blur, **sd_arrays(den, "sd__"))
+
+
 def ddrm_fixture():
     B, H, W = 2, 32, 32
     x = torch.randn(B, 2, H, W, generator=g(1)) * 0.3
@@ -229,8 +258,9 @@ def ddrm_fixture():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm"]
+    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm", "optim2"]
     table = {"mri": mri_fixtures, "multicoil": multicoil_fixtures, "tomo": tomo_fixtures, "blur": blur_fixtures,
-             "blurfft": blurfft_fixtures, "model": model_fixtures, "optim": optim_fixtures, "ddrm": ddrm_fixture}
+             "blurfft": blurfft_fixtures, "model": model_fixtures, "optim": optim_fixtures, "ddrm": ddrm_fixture,
+             "optim2": optim2_fixtures}
     for w in which:
         table[w]()

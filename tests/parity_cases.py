@@ -181,6 +181,33 @@ def case_pnp_mri(dev):
     assert len(m["residual"]) == y.shape[0] and len(m["residual"][0]) == 2 and len(m["psnr"][0]) == 3
 
 
+def case_drs_gd_dpir(dev, full=True):
+    """DRS / GD / DPIR on the kernels of the PGD path (full=False: the subset the slow host
+    emulation runs; every case runs on the GPU)"""
+    import deepinv_b200 as dinv
+    from deepinv_b200.optim import DPIR, DRS, GD, L2, RED, PnP, Tikhonov
+
+    g = to_dev(load_golden("optim2_mri_tiny"), dev)
+    den = load_model(dinv.models.DRUNet, g, dev, in_channels=2, out_channels=2, nc=(8, 16, 32, 64), nb=2)
+    phys = dinv.physics.MRI(mask=g["mask"], img_size=(2, 32, 32), device=dev)
+    y = g["y"]
+    kw = dict(data_fidelity=L2(), early_stop=False)
+    assert rel_err(DRS(prior=PnP(den), stepsize=1.0, sigma_denoiser=0.05, max_iter=3, **kw)(y, phys), g["drs"]) < TOL
+    relax = DRS(prior=PnP(den), max_iter=3, g_first=True,
+                params_algo={"stepsize": 0.7, "g_param": 0.05, "lambda": 1.0, "beta": 0.8}, **kw)
+    assert rel_err(GD(prior=Tikhonov(), stepsize=0.5, lambda_reg=0.1, max_iter=4, **kw)(y, phys), g["gd_tik"]) < TOL
+    assert rel_err(GD(prior=RED(den), stepsize=0.5, lambda_reg=0.3, sigma_denoiser=0.05, max_iter=3, **kw)(y, phys),
+                   g["gd_red"]) < TOL
+    if not full:
+        return
+    assert rel_err(relax(y, phys), g["drs_relax"]) < TOL
+    # DPIR's first proxes use gamma up to 64, where (A^T y + z/gamma)/(s^2 + 1/gamma) loses ~3e-6 per prox in fp32 for any
+    # implementation (the reference's own fp32 result is 1e-5 from the fp64 evaluation, tests/test_host_logic_emul.py)
+    assert rel_err(DPIR(sigma=0.05, denoiser=den, device=dev)(y, phys), g["dpir"]) < 5e-5
+    physb = dinv.physics.Blur(filter=g["filt"], padding="circular", device=dev)
+    assert rel_err(DPIR(sigma=0.05, denoiser=den, device=dev)(g["yb"], physb), g["dpir_blur"]) < 1e-4  # CG prox inside
+
+
 def case_pnp_blur_admm(dev):
     import deepinv_b200 as dinv
     from deepinv_b200.optim import ADMM, L2, PnP

@@ -62,6 +62,10 @@ def test_pnp_mri(dev):
     P.case_pnp_mri(dev)
 
 
+def test_drs_gd_dpir(dev):
+    P.case_drs_gd_dpir(dev)
+
+
 def test_pnp_blur_admm(dev):
     P.case_pnp_blur_admm(dev)
 

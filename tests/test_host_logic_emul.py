@@ -78,9 +78,40 @@ def test_pnp_mri():
     P.case_pnp_mri(DEV)
 
 
+def test_drs_gd_dpir():
+    P.case_drs_gd_dpir(DEV, full=False)
+
+
 def test_pnp_blur_admm():
     P.case_pnp_blur_admm(DEV)
 
 
 def test_ddrm():
     P.case_ddrm(DEV)
+
+
+def test_dpir_schedule_toy_denoiser():
+    """DPIR's per-iteration (sigma, stepsize) schedule and HQS step algebra with a closed-form 'denoiser' (the real
+    DRUNet run is the GPU case): package loop on emulated kernels == oracle loop"""
+    from conftest import load_golden, rel_err
+    from oracle import ref_ops as R
+
+    import deepinv_b200 as dinv
+    from deepinv_b200.optim import DPIR, get_DPIR_params
+
+    g = load_golden("optim2_mri_tiny")
+    m, y = g["mask"], g["y"]
+    den = lambda v, s: v * (1.0 - float(s))
+    phys = dinv.physics.MRI(mask=m, img_size=(2, 32, 32), device=DEV)
+    model = DPIR(sigma=0.05, denoiser=den, device=DEV)
+    sig, step, n = get_DPIR_params(0.05)
+    rs, rt, rn = R.dpir_params(0.05)
+    assert n == rn == 8 and torch.equal(sig, rs) and torch.equal(step, rt)
+    # DPIR's first stepsizes are large (gamma = 64 at iteration 0): (A^T y + z/gamma) / (s^2 + 1/gamma) then loses ~3e-6 in
+    # fp32 per prox for ANY implementation, the reference's included.  So the comparison is against the fp64 evaluation of
+    # the same recipe, and the package must be as close to it as the fp32 reference path is.
+    y64, m64 = y.double(), m.double()
+    truth = R.dpir(y64, lambda v, gam: R.mri_prox_l2(v, y64, m64, float(gam)), lambda v: R.mri_At(v, m64), den, 0.05)
+    ref32 = R.dpir(y, lambda v, gam: R.mri_prox_l2(v, y, m, gam), lambda v: R.mri_At(v, m), den, 0.05)
+    e_ref, e_pkg = rel_err(ref32, truth), rel_err(model(y, phys), truth)
+    assert e_pkg < max(2 * e_ref, 1e-5) and e_pkg < 5e-5, (e_pkg, e_ref)
