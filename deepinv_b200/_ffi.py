@@ -52,6 +52,8 @@ _SIGNATURES = {
     "dinvk_blur_adj_workspace_bytes": (c_size_t, [c_int] * 7),
     "dinvk_blur_adj": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_void_p, c_size_t, c_void_p]),
     "dinvk_conv_f32": (c_int, [c_void_p] * 6 + [c_int] * 7 + [c_void_p]),
+    "dinvk_conv_f32_wgrad": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
+    "dinvk_relu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "dinvk_conv3x3_bf16": (c_int, [c_void_p] * 6 + [c_int] * 6 + [c_void_p]),
     "dinvk_conv3x3_bf16_tail": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p]),
     "dinvk_conv3x3_head_bf16": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_void_p, c_int, c_int, c_void_p]),

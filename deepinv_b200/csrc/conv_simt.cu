@@ -210,6 +210,242 @@ __global__ void __launch_bounds__(256) conv2x2_f32_kernel(const float* __restric
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Backward kernels of the fp32 path (training through the denoiser: unfolded / DEQ models,
+// deepinv/unfolded/unfolded.py:9-120, deep_equilibrium.py:70-139 — SURVEY §8(f) item 2).
+// Data gradients reuse the forward kernels (a 3x3 convolution with the transposed, flipped filter;
+// kind 1 <-> kind 2 for the 2x2 pair).  What is new is the weight gradient:
+//   kind 0:  dw[co,ci,ky,kx] = sum_{b,y,x} g[b,co,y,x] * xin[b,ci,y+ky-1,x+kx-1]
+// A CTA owns one 8-row band of one image, 32 output channels and 8 input channels; it walks the
+// band tile by tile with the forward kernel's staging (input halo tile + the matching 8x32x32
+// block of g, channel-fastest so that a thread reads its 4 output channels as one float4).  Thread
+// = (4 output channels, 1 input channel, 2 of the 8 rows): 36 accumulators, a sliding 3x3 input
+// window (3 new shared loads per pixel) -> 36 FMAs per 4 shared loads.  The 4 row groups are
+// summed through shared memory and leave as one atomicAdd per weight per CTA; the bias gradient
+// (sum of g) rides along in the CTAs of input-channel chunk 0.
+constexpr int WG_CI = 8;   // input channels per CTA
+constexpr int WG_CO = 32;  // output channels per CTA
+
+__global__ void __launch_bounds__(256) conv3x3_wgrad_f32_kernel(const float* __restrict__ x, const float* __restrict__ xadd,
+                                                                const float* __restrict__ g, float* __restrict__ dw,
+                                                                float* __restrict__ dbias, int Cin, int Cout, int H, int W,
+                                                                int tiles_x, int nci) {
+  __shared__ __align__(16) float s_in[WG_CI][C3_TH + 2][C3_ROWP];
+  __shared__ __align__(16) float s_g[C3_TH * C3_TW * WG_CO];  // [row][col][co]; reused for the final reduction
+  const int tid = threadIdx.x;
+  const int lane64 = tid & 63, rg = tid >> 6;
+  const int cg = lane64 & 7, ci = lane64 >> 3;
+  const int ty0 = blockIdx.x * C3_TH;
+  const int co0 = blockIdx.y * WG_CO;
+  const int b = blockIdx.z / nci, c0 = (blockIdx.z % nci) * WG_CI;
+  const long long HW = (long long)H * W;
+  const float* xb = x + (long long)b * Cin * HW;
+  const float* ab = xadd ? xadd + (long long)b * Cin * HW : nullptr;
+  const float* gb = g + (long long)b * Cout * HW;
+  const bool do_bias = dbias != nullptr && c0 == 0 && ci == 0;
+
+  float acc[4][9];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[q][k] = 0.f;
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+
+  for (int t = 0; t < tiles_x; ++t) {
+    const int tx0 = t * C3_TW;
+    for (int idx = tid; idx < WG_CI * (C3_TH + 2) * (C3_TW + 2); idx += 256) {
+      const int c = idx / ((C3_TH + 2) * (C3_TW + 2));
+      const int rem = idx - c * ((C3_TH + 2) * (C3_TW + 2));
+      const int r = rem / (C3_TW + 2), col = rem - r * (C3_TW + 2);
+      const int gy = ty0 + r - 1, gx = tx0 + col - 1;
+      float v = 0.f;
+      if (c0 + c < Cin && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        const long long o = (long long)(c0 + c) * HW + (long long)gy * W + gx;
+        v = __ldg(xb + o);
+        if (ab) v += __ldg(ab + o);
+      }
+      s_in[c][r][col] = v;
+    }
+    for (int idx = tid; idx < WG_CO * C3_TH * C3_TW; idx += 256) {
+      const int co = idx / (C3_TH * C3_TW);
+      const int rem = idx - co * (C3_TH * C3_TW);
+      const int r = rem / C3_TW, col = rem - r * C3_TW;
+      const int gy = ty0 + r, gx = tx0 + col;
+      float v = 0.f;
+      if (co0 + co < Cout && gy < H && gx < W) v = __ldg(gb + (long long)(co0 + co) * HW + (long long)gy * W + gx);
+      s_g[(r * C3_TW + col) * WG_CO + co] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int r = rg * 2 + rr;
+      float win[3][3];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        win[ky][1] = s_in[ci][r + ky][0];
+        win[ky][2] = s_in[ci][r + ky][1];
+      }
+      for (int col = 0; col < C3_TW; ++col) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          win[ky][0] = win[ky][1];
+          win[ky][1] = win[ky][2];
+          win[ky][2] = s_in[ci][r + ky][col + 2];
+        }
+        const float4 g4 = *reinterpret_cast<const float4*>(&s_g[(r * C3_TW + col) * WG_CO + cg * 4]);
+        const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          bsum[q] += gv[q];
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) acc[q][ky * 3 + kx] = fmaf(gv[q], win[ky][kx], acc[q][ky * 3 + kx]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // sum the 4 row groups: groups 2,3 -> smem -> groups 0,1 ; group 1 -> smem -> group 0
+  float* red = s_g;  // 2 * 64 * 40 floats <= 8192
+#pragma unroll
+  for (int round = 0; round < 2; ++round) {
+    const int half = round == 0 ? 2 : 1;
+    if (rg >= half && rg < 2 * half) {
+      float* dst = red + ((rg - half) * 64 + lane64) * 40;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) dst[q * 9 + k] = acc[q][k];
+        dst[36 + q] = bsum[q];
+      }
+    }
+    __syncthreads();
+    if (rg < half) {
+      const float* src = red + (rg * 64 + lane64) * 40;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[q][k] += src[q * 9 + k];
+        bsum[q] += src[36 + q];
+      }
+    }
+    __syncthreads();
+  }
+  if (rg == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int co = co0 + cg * 4 + q;
+      if (co >= Cout) continue;
+      if (c0 + ci < Cin) {
+        float* d = dw + ((long long)co * Cin + (c0 + ci)) * 9;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) atomicAdd(d + k, acc[q][k]);
+      }
+      if (do_bias) atomicAdd(dbias + co, bsum[q]);
+    }
+  }
+}
+
+// weight gradient of the 2x2 pair as D[k][n] = sum_m A(m,k) * G(m,n) with the forward kernel's gathers:
+//   mode 1: A(m,k) = (x+xadd)[b, k/4, 2yo + (k/2)%2, 2xo + k%2],  G(m,n) = g[b, n, yo, xo],          dw[n*K + k]
+//   mode 2: A(m,k) = (x+xadd)[b, k, y, x],                        G(m,n) = g[b, n/4, 2y+(n/2)%2, 2x+n%2],  dw[k*N + n]
+// CTA = 32x32 block of D over a chunk of WG2_MCHUNK rows m; thread = 2x2 outputs; one atomicAdd per output.
+constexpr int WG2_MCHUNK = 4096;
+
+__global__ void __launch_bounds__(256) conv2x2_wgrad_f32_kernel(const float* __restrict__ x, const float* __restrict__ xadd,
+                                                                const float* __restrict__ g, float* __restrict__ dw,
+                                                                float* __restrict__ dbias, int B, int Cin, int Cout, int H,
+                                                                int W, int mode) {
+  __shared__ float sA[G_TM][32 + 1];
+  __shared__ float sG[G_TM][32 + 1];
+  const int tid = threadIdx.x;
+  const int Ho = H / 2, Wo = W / 2;
+  const long long M = mode == 1 ? (long long)B * Ho * Wo : (long long)B * H * W;
+  const int N = mode == 1 ? Cout : 4 * Cout;
+  const int K = mode == 1 ? 4 * Cin : Cin;
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  const long long mbeg = (long long)blockIdx.z * WG2_MCHUNK;
+  const long long mend = mbeg + WG2_MCHUNK < M ? mbeg + WG2_MCHUNK : M;
+  const int tk = (tid & 15) * 2, tn = (tid >> 4) * 2;
+  const long long HW = (long long)H * W;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  float bs = 0.f;  // bias gradient: thread tid < 32 of the k-block 0 sums column n0 + tid (mode 1 only)
+
+  for (long long m0 = mbeg; m0 < mend; m0 += G_TM) {
+    for (int idx = tid; idx < G_TM * 32; idx += 256) {
+      const int mm = idx & (G_TM - 1), kk = idx / G_TM;  // m fastest: coalesced along pixels
+      const long long m = m0 + mm;
+      const int k = k0 + kk;
+      float v = 0.f;
+      if (m < mend && k < K) {
+        long long o;
+        if (mode == 1) {
+          const int xo = (int)(m % Wo), yo = (int)((m / Wo) % Ho);
+          const long long bb = m / ((long long)Wo * Ho);
+          const int c = k >> 2, dy = (k >> 1) & 1, dx = k & 1;
+          o = (bb * Cin + c) * HW + (long long)(2 * yo + dy) * W + (2 * xo + dx);
+        } else {
+          const long long bb = m / HW, p = m - bb * HW;
+          o = (bb * Cin + k) * HW + p;
+        }
+        v = __ldg(x + o);
+        if (xadd) v += __ldg(xadd + o);
+      }
+      sA[mm][kk] = v;
+    }
+    for (int idx = tid; idx < G_TM * 32; idx += 256) {
+      const int mm = idx & (G_TM - 1), nn = idx / G_TM;
+      const long long m = m0 + mm;
+      const int n = n0 + nn;
+      float v = 0.f;
+      if (m < mend && n < N) {
+        if (mode == 1) {
+          const long long bb = m / ((long long)Wo * Ho), p = m - bb * ((long long)Wo * Ho);
+          v = __ldg(g + (bb * Cout + n) * ((long long)Ho * Wo) + p);
+        } else {
+          const long long bb = m / HW, p = m - bb * HW;
+          const int y = (int)(p / W), xx = (int)(p - (long long)y * W);
+          const int co = n >> 2, dy = (n >> 1) & 1, dx = n & 1;
+          v = __ldg(g + (bb * Cout + co) * (4 * HW) + (long long)(2 * y + dy) * (2 * W) + (2 * xx + dx));
+        }
+      }
+      sG[mm][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int mm = 0; mm < G_TM; ++mm) {
+      const float a0 = sA[mm][tk], a1 = sA[mm][tk + 1];
+      const float g0 = sG[mm][tn], g1 = sG[mm][tn + 1];
+      acc[0][0] = fmaf(a0, g0, acc[0][0]);
+      acc[0][1] = fmaf(a0, g1, acc[0][1]);
+      acc[1][0] = fmaf(a1, g0, acc[1][0]);
+      acc[1][1] = fmaf(a1, g1, acc[1][1]);
+    }
+    if (dbias && blockIdx.x == 0 && tid < 32)
+      for (int mm = 0; mm < G_TM; ++mm) bs += sG[mm][tid];
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int k = k0 + tk + i, n = n0 + tn + j;
+      if (k < K && n < N) atomicAdd(dw + (mode == 1 ? (long long)n * K + k : (long long)k * N + n), acc[i][j]);
+    }
+  if (dbias && blockIdx.x == 0 && tid < 32 && n0 + tid < N) atomicAdd(dbias + (mode == 1 ? n0 + tid : (n0 + tid) >> 2), bs);
+}
+
+// g_in = g * [out > 0]  (backward of the ReLU fused into the forward launch; `out` is the forward's output)
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ g, const float* __restrict__ out,
+                                                       float* __restrict__ gin, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    gin[i] = out[i] > 0.f ? g[i] : 0.f;
+}
+
 }  // namespace dinvk
 
 using namespace dinvk;
@@ -233,5 +469,41 @@ extern "C" int dinvk_conv_f32(const float* x, const float* xadd, const float* we
     DINVK_LAUNCH(conv2x2_f32_kernel, dim3((unsigned)ceil_div(M, G_TM), ceil_div(N, G_TN)), dim3(256), 0, stream, x, xadd,
                  weight, bias, res, out, B, Cin, Cout, H, W, kind, act);
   }
+  return DINVK_POST_LAUNCH();
+}
+
+extern "C" int dinvk_conv_f32_wgrad(const float* x, const float* xadd, const float* gout, float* dweight, float* dbias,
+                                    int B, int Cin, int Cout, int H, int W, int kind, void* stream) {
+  DINVK_CHECK_ARG(x && gout && dweight, "dinvk_conv_f32_wgrad: null pointer");
+  DINVK_CHECK_ARG(B >= 0 && Cin >= 1 && Cout >= 1 && H >= 1 && W >= 1, "dinvk_conv_f32_wgrad: bad shape");
+  DINVK_CHECK_ARG(kind >= 0 && kind <= 2, "dinvk_conv_f32_wgrad: kind %d", kind);
+  const size_t wn = (size_t)Cout * Cin * (kind == 0 ? 9 : 4);
+  if (cudaMemsetAsync(dweight, 0, wn * sizeof(float), (cudaStream_t)stream) != cudaSuccess)
+    return set_error(DINVK_ECUDA, "dinvk_conv_f32_wgrad: memset failed");
+  if (dbias && cudaMemsetAsync(dbias, 0, (size_t)Cout * sizeof(float), (cudaStream_t)stream) != cudaSuccess)
+    return set_error(DINVK_ECUDA, "dinvk_conv_f32_wgrad: memset failed");
+  if (B == 0) return DINVK_OK;
+  if (kind == 0) {
+    const int tiles_x = ceil_div(W, C3_TW), tiles_y = ceil_div(H, C3_TH), nci = ceil_div(Cin, WG_CI);
+    DINVK_CHECK_ARG((long long)B * nci <= 65535 && ceil_div(Cout, WG_CO) <= 65535, "dinvk_conv_f32_wgrad: grid too large");
+    DINVK_LAUNCH(conv3x3_wgrad_f32_kernel, dim3(tiles_y, ceil_div(Cout, WG_CO), B * nci), dim3(256), 0, stream, x, xadd, gout,
+                 dweight, dbias, Cin, Cout, H, W, tiles_x, nci);
+  } else {
+    if (kind == 1) DINVK_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "dinvk_conv_f32_wgrad: strided conv needs even H, W");
+    const long long M = kind == 1 ? (long long)B * (H / 2) * (W / 2) : (long long)B * H * W;
+    const int N = kind == 1 ? Cout : 4 * Cout, K = kind == 1 ? 4 * Cin : Cin;
+    DINVK_CHECK_ARG(ceil_div(M, WG2_MCHUNK) <= 65535, "dinvk_conv_f32_wgrad: grid too large");
+    DINVK_LAUNCH(conv2x2_wgrad_f32_kernel, dim3(ceil_div(K, 32), ceil_div(N, 32), (unsigned)ceil_div(M, WG2_MCHUNK)), dim3(256),
+                 0, stream, x, xadd, gout, dweight, dbias, B, Cin, Cout, H, W, kind);
+  }
+  return DINVK_POST_LAUNCH();
+}
+
+extern "C" int dinvk_relu_bwd(const float* gout, const float* out, float* gin, long long n, void* stream) {
+  DINVK_CHECK_ARG(gout && out && gin && n >= 0, "dinvk_relu_bwd: bad argument");
+  if (n == 0) return DINVK_OK;
+  const long long want = (n + 255) / 256;
+  const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+  DINVK_LAUNCH(relu_bwd_kernel, dim3(grid), dim3(256), 0, stream, gout, out, gin, n);
   return DINVK_POST_LAUNCH();
 }

@@ -32,6 +32,6 @@ class Denoiser(nn.Module):
 def _no_grad_guard(name: str, *tensors) -> None:
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
         raise NotImplementedError(
-            f"{name}: the sm_100a denoiser kernels are inference-only in this round (SURVEY.md §8(f) item 2); "
-            "run the denoiser under torch.no_grad()."
+            f"{name}: the tensor-core (bf16) denoiser kernels are inference-only; train with precision='fp32' "
+            "(differentiable: ops._ConvF32Fn) or run the bf16 denoiser under torch.no_grad()."
         )

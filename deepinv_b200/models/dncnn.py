@@ -44,12 +44,12 @@ class DnCNN(Denoiser):
             self.to(device)
 
     def forward(self, x: torch.Tensor, sigma=None) -> torch.Tensor:
-        _no_grad_guard("DnCNN", x, self.in_conv.weight)
         if self.precision == "bf16":
+            _no_grad_guard("DnCNN(precision='bf16')", x, self.in_conv.weight)
             from .tc_engine import dncnn_forward_bf16
 
             return dncnn_forward_bf16(self, x)
-        t = ops.conv_f32(x, self.in_conv.weight, bias=self.in_conv.bias, relu=True)
+        t = ops.conv_f32_ag(x, self.in_conv.weight, bias=self.in_conv.bias, relu=True)
         for conv in self.conv_list:
-            t = ops.conv_f32(t, conv.weight, bias=conv.bias, relu=True)
-        return ops.conv_f32(t, self.out_conv.weight, bias=self.out_conv.bias, res=x)
+            t = ops.conv_f32_ag(t, conv.weight, bias=conv.bias, relu=True)
+        return ops.conv_f32_ag(t, self.out_conv.weight, bias=self.out_conv.bias, res=x)

@@ -84,25 +84,25 @@ class DRUNet(Denoiser):
     @staticmethod
     def _resblocks_f32(t, blocks):
         for rb in blocks:
-            u = ops.conv_f32(t, rb.res[0].weight, relu=True)
-            t = ops.conv_f32(u, rb.res[2].weight, res=t)
+            u = ops.conv_f32_ag(t, rb.res[0].weight, relu=True)
+            t = ops.conv_f32_ag(u, rb.res[2].weight, res=t)
         return t
 
     def _forward_unet_f32(self, x0):
         nb = self.nb
-        x1 = ops.conv_f32(x0, self.m_head.weight)
-        x2 = ops.conv_f32(self._resblocks_f32(x1, list(self.m_down1)[:nb]), self.m_down1[nb].weight, kind=1)
-        x3 = ops.conv_f32(self._resblocks_f32(x2, list(self.m_down2)[:nb]), self.m_down2[nb].weight, kind=1)
-        x4 = ops.conv_f32(self._resblocks_f32(x3, list(self.m_down3)[:nb]), self.m_down3[nb].weight, kind=1)
+        x1 = ops.conv_f32_ag(x0, self.m_head.weight)
+        x2 = ops.conv_f32_ag(self._resblocks_f32(x1, list(self.m_down1)[:nb]), self.m_down1[nb].weight, kind=1)
+        x3 = ops.conv_f32_ag(self._resblocks_f32(x2, list(self.m_down2)[:nb]), self.m_down2[nb].weight, kind=1)
+        x4 = ops.conv_f32_ag(self._resblocks_f32(x3, list(self.m_down3)[:nb]), self.m_down3[nb].weight, kind=1)
         x = self._resblocks_f32(x4, list(self.m_body))
-        x = self._resblocks_f32(ops.conv_f32(x, self.m_up3[0].weight, kind=2, xadd=x4), list(self.m_up3)[1:])
-        x = self._resblocks_f32(ops.conv_f32(x, self.m_up2[0].weight, kind=2, xadd=x3), list(self.m_up2)[1:])
-        x = self._resblocks_f32(ops.conv_f32(x, self.m_up1[0].weight, kind=2, xadd=x2), list(self.m_up1)[1:])
-        return ops.conv_f32(x, self.m_tail.weight, xadd=x1)
+        x = self._resblocks_f32(ops.conv_f32_ag(x, self.m_up3[0].weight, kind=2, xadd=x4), list(self.m_up3)[1:])
+        x = self._resblocks_f32(ops.conv_f32_ag(x, self.m_up2[0].weight, kind=2, xadd=x3), list(self.m_up2)[1:])
+        x = self._resblocks_f32(ops.conv_f32_ag(x, self.m_up1[0].weight, kind=2, xadd=x2), list(self.m_up1)[1:])
+        return ops.conv_f32_ag(x, self.m_tail.weight, xadd=x1)
 
     def forward_unet(self, x0: torch.Tensor) -> torch.Tensor:
-        _no_grad_guard("DRUNet", x0, self.m_head.weight)
         if self.precision == "bf16":
+            _no_grad_guard("DRUNet(precision='bf16')", x0, self.m_head.weight)
             from .tc_engine import drunet_forward_bf16
 
             return drunet_forward_bf16(self, x0)

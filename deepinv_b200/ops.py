@@ -240,6 +240,70 @@ def conv_f32(x, weight, *, kind: int = 0, bias=None, xadd=None, res=None, relu: 
     return out
 
 
+def conv_f32_wgrad(x, xadd, gout, weight_shape, kind: int = 0, want_bias: bool = False):
+    """weight (and bias) gradient of `conv_f32`: x [+ xadd] is the forward input, gout the gradient of the
+    pre-residual output; returns (dweight, dbias | None)"""
+    dev = _require_cuda(x, xadd, gout)
+    x, xadd, gout = _f32c(x), _f32c(xadd), _f32c(gout)
+    B, Cin, H, W = x.shape
+    Cout = weight_shape[1] if kind == 2 else weight_shape[0]
+    dw = torch.empty(tuple(weight_shape), dtype=torch.float32, device=dev)
+    db = torch.empty(Cout, dtype=torch.float32, device=dev) if want_bias else None
+    check(get_lib().dinvk_conv_f32_wgrad(_p(x), _p(xadd), _p(gout), _p(dw), _p(db), B, Cin, Cout, H, W, kind, _stream(dev)))
+    return dw, db
+
+
+def relu_bwd(gout, out) -> torch.Tensor:
+    dev = _require_cuda(gout, out)
+    gout, out = _f32c(gout), _f32c(out)
+    gin = torch.empty_like(gout)
+    check(get_lib().dinvk_relu_bwd(_p(gout), _p(out), _p(gin), gout.numel(), _stream(dev)))
+    return gin
+
+
+class _ConvF32Fn(torch.autograd.Function):
+    """differentiable `conv_f32`: out = act(conv(x + xadd, w) + bias) + res.  Backward (first order) runs on the same
+    library: ReLU mask, data gradient through the forward entry (3x3: transposed + flipped filter; the 2x2 strided conv
+    and its transpose are each other's data gradient), weight / bias gradient through `dinvk_conv_f32_wgrad`."""
+
+    @staticmethod
+    def forward(ctx, x, xadd, weight, bias, res, kind, relu):
+        out = conv_f32(x, weight, kind=kind, bias=bias, xadd=xadd, res=res, relu=relu)
+        if relu and res is not None:
+            raise NotImplementedError("conv_f32 backward: ReLU together with a residual is not used by DRUNet / DnCNN")
+        ctx.kind, ctx.relu = kind, relu
+        ctx.has = (xadd is not None, bias is not None, res is not None)
+        ctx.save_for_backward(x, xadd, weight, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, xadd, weight, out = ctx.saved_tensors
+        kind = ctx.kind
+        has_xadd, has_bias, has_res = ctx.has
+        need = ctx.needs_input_grad
+        g = _f32c(g)
+        gp = relu_bwd(g, out) if ctx.relu else g
+        dx = dw = db = None
+        if need[0] or (has_xadd and need[1]):
+            if kind == 0:
+                wt = weight.detach().transpose(0, 1).flip(2, 3).contiguous()
+                dx = conv_f32(gp, wt)
+            else:
+                dx = conv_f32(gp, weight.detach(), kind=2 if kind == 1 else 1)
+        if need[2] or (has_bias and need[3]):
+            dw, db = conv_f32_wgrad(x, xadd, gp, weight.shape, kind=kind, want_bias=has_bias and need[3])
+        return (dx if need[0] else None, dx if (has_xadd and need[1]) else None, dw if need[2] else None,
+                db if (has_bias and need[3]) else None, g if (has_res and need[4]) else None, None, None)
+
+
+def conv_f32_ag(x, weight, *, kind: int = 0, bias=None, xadd=None, res=None, relu: bool = False) -> torch.Tensor:
+    """`conv_f32` that records a backward when (and only when) a gradient is being tracked"""
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, weight, bias, xadd, res)):
+        return _ConvF32Fn.apply(x, xadd, weight, bias, res, kind, relu)
+    return conv_f32(x, weight, kind=kind, bias=bias, xadd=xadd, res=res, relu=relu)
+
+
 # --------------------------------------------------------------------------------------------
 # Radon family (sinograms live in angle-major memory (B, C, A, P); see csrc/radon.cu)
 # --------------------------------------------------------------------------------------------

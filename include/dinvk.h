@@ -207,6 +207,18 @@ int dinvk_conv_f32(const float* x, const float* xadd, const float* weight, const
                    const float* res, float* out, int B, int Cin, int Cout, int H, int W,
                    int kind, int act, void* stream);
 
+/* backward of dinvk_conv_f32 (training through the denoiser inside unfolded / deep-equilibrium models,
+ * deepinv/unfolded/unfolded.py:9-120, deep_equilibrium.py:70-139; replaces ATen's convolution_backward):
+ *   data gradient: the forward entry itself — kind 0 with the transposed + flipped filter, kind 1 <-> kind 2;
+ *   weight (+ bias) gradient: dweight has the forward weight's layout, dbias (Cout) optional; both are zeroed
+ *   here and accumulated with fp32 atomics (summation order is not deterministic);
+ *   x [+ xadd] is the forward input, gout the gradient w.r.t. the pre-residual output (after dinvk_relu_bwd
+ *   when the forward had act = 1).  B, Cin, Cout, H, W are the FORWARD call's arguments. */
+int dinvk_conv_f32_wgrad(const float* x, const float* xadd, const float* gout, float* dweight, float* dbias,
+                         int B, int Cin, int Cout, int H, int W, int kind, void* stream);
+/* gin = gout * [out > 0] : backward of the fused ReLU, `out` being the forward output */
+int dinvk_relu_bwd(const float* gout, const float* out, float* gin, long long n, void* stream);
+
 /* bf16 tensor-core path (tcgen05 implicit GEMM, TMA-fed), NHWC bf16 activations:
  *   x (B,H,W,Cin) bf16, weight (Cout, 9*Cin) bf16 K-major with k = (ky*3+kx)*Cin + c,
  *   out (B,H,W,Cout) bf16;  out = act(conv3x3(x) + bias) + res + res2   (bias fp32 (Cout) optional;

@@ -115,3 +115,56 @@ def test_dpir_schedule_toy_denoiser():
     ref32 = R.dpir(y, lambda v, gam: R.mri_prox_l2(v, y, m, gam), lambda v: R.mri_At(v, m), den, 0.05)
     e_ref, e_pkg = rel_err(ref32, truth), rel_err(model(y, phys), truth)
     assert e_pkg < max(2 * e_ref, 1e-5) and e_pkg < 5e-5, (e_pkg, e_ref)
+
+
+# ---- training closure (backward kernels of the fp32 denoiser path) ---------------------------
+@pytest.mark.parametrize("kind,cin,cout,h,w", [(0, 5, 7, 11, 37), (0, 16, 40, 16, 64), (1, 6, 10, 8, 12), (2, 10, 6, 5, 7)])
+def test_conv_backward_kernels(kind, cin, cout, h, w):
+    """data / weight / bias / residual / skip-input gradients of `ops.conv_f32_ag` == torch autograd of the same op"""
+    import torch.nn.functional as F
+    from conftest import rel_err
+
+    from deepinv_b200 import ops
+
+    torch.manual_seed(kind * 7 + cin)
+    B = 2
+    x = torch.randn(B, cin, h, w, requires_grad=True)
+    xadd = torch.randn(B, cin, h, w, requires_grad=True)
+    wshape = (cin, cout, 2, 2) if kind == 2 else (cout, cin, 3, 3) if kind == 0 else (cout, cin, 2, 2)
+    wt = (torch.randn(wshape) / 4).requires_grad_()
+    bias = torch.randn(cout, requires_grad=True)
+    for relu, use_res in ((True, False), (False, True)):
+        conv = {0: lambda t: F.conv2d(t, wt, bias, padding=1), 1: lambda t: F.conv2d(t, wt, bias, stride=2),
+                2: lambda t: F.conv_transpose2d(t, wt, bias, stride=2)}[kind]
+        ref = conv(x + xadd)
+        res = torch.randn_like(ref).requires_grad_() if use_res else None
+        ref = torch.relu(ref) if relu else ref
+        ref = ref + res if use_res else ref
+        r = torch.randn_like(ref)
+        leaves = [x, xadd, wt, bias] + ([res] if use_res else [])
+        want = torch.autograd.grad((ref * r).sum(), leaves)
+        out = ops.conv_f32_ag(x, wt, kind=kind, bias=bias, xadd=xadd, res=res, relu=relu)
+        assert rel_err(out, ref) < 1e-5
+        got = torch.autograd.grad((out * r).sum(), leaves)
+        for a, b in zip(got, want):
+            assert a.shape == b.shape and rel_err(a, b) < 1e-5
+
+
+def test_drunet_gradients():
+    """d loss / d (input, every weight) of the tiny DRUNet through the library's backward == autograd of the oracle"""
+    from conftest import load_golden, rel_err
+    from oracle import ref_ops as R
+
+    import deepinv_b200 as dinv
+
+    g = load_golden("drunet_tiny")
+    den = P.load_model(dinv.models.DRUNet, g, DEV, in_channels=2, out_channels=2, nc=(8, 16, 32, 64), nb=2)
+    x = g["x"][:1, :, :, :32].clone().requires_grad_()
+    r = torch.randn(1, 2, 32, 32)
+    (den(x, 0.05) * r).sum().backward()
+    sd = {k: v.clone().requires_grad_() for k, v in g["sd"].items()}
+    x2 = x.detach().clone().requires_grad_()
+    (R.drunet_forward(x2, 0.05, sd, nb=2) * r).sum().backward()
+    assert rel_err(x.grad, x2.grad) < 1e-5
+    for k, p in den.named_parameters():
+        assert rel_err(p.grad, sd[k].grad) < 2e-5, k
