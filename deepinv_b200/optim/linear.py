@@ -55,22 +55,94 @@ def conjugate_gradient(A: Callable, b: torch.Tensor, max_iter: int = 100, tol: f
     return x
 
 
+def _solve_normal(physics, y, z, init, g, g_batch, max_iter, tol, verbose, kwargs):
+    """CG on (A^T A + I/gamma) x = A^T y + z/gamma; gamma: None, a host float `g`, or a (B,) device tensor `g_batch`"""
+    b = physics.A_adjoint(y, **kwargs)
+    if g_batch is not None:
+        inv = torch.reciprocal(g_batch)
+        if z is not None:
+            b = ops.batched_axpy(b, z, inv, 1.0)
+        H = lambda v: ops.batched_axpy(physics.A_adjoint_A(v, **kwargs), v, inv, 1.0)
+    elif g is not None:
+        if z is not None:
+            b = ops.axpbypcz(b, 1.0, z, 1.0 / g)
+        H = lambda v: ops.axpbypcz(physics.A_adjoint_A(v, **kwargs), 1.0, v, 1.0 / g)
+    else:
+        H = lambda v: physics.A_adjoint_A(v, **kwargs)
+    return conjugate_gradient(H, b, max_iter=max_iter, tol=tol, init=init, verbose=verbose)
+
+
+class _LeastSquaresFn(torch.autograd.Function):
+    """h(z, y, gamma) = argmin_x gamma/2 ||Ax - y||^2 + 1/2 ||x - z||^2 with O(1)-memory backward by implicit
+    differentiation (deepinv/optim/linear/least_squares.py:200-342): with M = (A^T A + I/gamma)^-1 and v the incoming
+    gradient, ONE more CG solve gives Mv, and  dL/dy = A Mv,  dL/dz = Mv / gamma,  dL/dgamma = <Mv, h - z> / gamma^2.
+    Both solves run on the operator kernels; nothing of the forward iteration is stored."""
+
+    @staticmethod
+    def forward(ctx, physics, y, z, init, gamma, opts):
+        g, g_batch = _split_gamma(gamma, y.shape[0])
+        with torch.no_grad():
+            h = _solve_normal(physics, y, z, init, g, g_batch, opts["max_iter"], opts["tol"], opts["verbose"], opts["kwargs"])
+        ctx.physics, ctx.opts, ctx.g, ctx.gamma_shape = physics, opts, g, (gamma.shape if isinstance(gamma, torch.Tensor) else None)
+        ctx.save_for_backward(h, y, z, g_batch)
+        return h
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        h, y, z, g_batch = ctx.saved_tensors
+        physics, opts, g = ctx.physics, ctx.opts, ctx.g
+        # (A^T A + I/gamma) mv = grad_output   <=>   the forward problem with y = 0, z = gamma * grad_output
+        if g_batch is not None:
+            zz = ops.batched_axpy(torch.zeros_like(grad_output), grad_output, g_batch, 1.0)
+        else:
+            zz = ops.axpbypcz(grad_output, g)
+        mv = _solve_normal(physics, torch.zeros_like(y), zz, None, g, g_batch, opts["max_iter"], opts["tol"], False, opts["kwargs"])
+        need = ctx.needs_input_grad
+        gy = physics.A(mv, **opts["kwargs"]) if need[1] else None
+        gz = None
+        if need[2]:
+            gz = ops.batched_axpy(torch.zeros_like(mv), mv, torch.reciprocal(g_batch), 1.0) if g_batch is not None \
+                else ops.axpbypcz(mv, 1.0 / g)
+        ggam = None
+        if need[4]:
+            per = ops.batched_dot(mv, ops.axpbypcz(h, 1.0, z, -1.0))
+            if g_batch is not None:
+                ggam = (per / g_batch ** 2).reshape(ctx.gamma_shape)
+            else:
+                ggam = (per.sum() / g ** 2).reshape(ctx.gamma_shape)
+        return None, gy, gz, None, ggam, None
+
+
+def _split_gamma(gamma, batch):
+    """-> (host float | None, (B,) device tensor | None)"""
+    if gamma is None:
+        return None, None
+    if isinstance(gamma, torch.Tensor) and gamma.numel() > 1:
+        if gamma.shape[0] != batch or gamma.numel() != batch:
+            raise ValueError("If gamma is batched, its batch size must match the one of y.")
+        return None, gamma.detach().reshape(-1).float()
+    return float(gamma), None
+
+
 def least_squares(physics, y: torch.Tensor, z: torch.Tensor | None = None, init: torch.Tensor | None = None,
                   gamma=None, solver: str = "CG", max_iter: int = 100, tol: float = 1e-6, verbose: bool = False,
                   **kwargs) -> torch.Tensor:
     r"""argmin_x gamma/2 ||A x - y||^2 + 1/2 ||x - z||^2 via the normal equations
-    (A^T A + I/gamma) x = A^T y + z/gamma  (least_squares.py:148-151)."""
+    (A^T A + I/gamma) x = A^T y + z/gamma  (least_squares.py:148-151); gamma may be a scalar or one value per sample.
+    When a gradient w.r.t. y, z or gamma is being tracked the result carries the implicit-differentiation backward of the
+    reference's `least_squares_implicit_backward` (least_squares.py:345-469)."""
     if solver not in ("CG", "cg", None):
         raise NotImplementedError(f"deepinv_b200: solver {solver!r} is outside the accelerated path (CG only, SURVEY §8 a12)")
-    if isinstance(gamma, torch.Tensor) and gamma.numel() > 1:
-        raise NotImplementedError("per-sample gamma is not supported by the CG path")
-    g = None if gamma is None else float(gamma)
-    b = physics.A_adjoint(y, **kwargs)
-    if g is not None and z is not None:
-        b = ops.axpbypcz(b, 1.0, z, 1.0 / g)
-    if g is None:
-        H = lambda v: physics.A_adjoint_A(v, **kwargs)
-    else:
-        H = lambda v: ops.axpbypcz(physics.A_adjoint_A(v, **kwargs), 1.0, v, 1.0 / g)
-    x = conjugate_gradient(H, b, max_iter=max_iter, tol=tol, init=init, verbose=verbose)
-    return x
+    kwargs.pop("parallel_dim", None)
+    tracked = torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in (y, z, gamma))
+    if tracked:
+        if z is None:
+            z = torch.zeros_like(physics.A_adjoint(y.detach(), **kwargs))
+        if gamma is None:
+            gamma = 1e8  # "no regularisation" of a tracked solve = the reference's pseudo-inverse branch (forward.py:850-862)
+        gam = gamma if isinstance(gamma, torch.Tensor) else torch.tensor(float(gamma), device=y.device)
+        opts = {"max_iter": max_iter, "tol": tol, "verbose": verbose, "kwargs": kwargs}
+        return _LeastSquaresFn.apply(physics, y, z, init, gam, opts)
+    g, g_batch = _split_gamma(gamma, y.shape[0])
+    return _solve_normal(physics, y, z, init, g, g_batch, max_iter, tol, verbose, kwargs)

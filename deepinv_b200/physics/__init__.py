@@ -1,5 +1,5 @@
 from .blur import Blur, BlurFFT  # noqa: F401
 from .forward import DecomposablePhysics, LinearPhysics, Physics  # noqa: F401
-from .mri import MRI, MRIMixin, MultiCoilMRI  # noqa: F401
+from .mri import MRI, DynamicMRI, MRIMixin, MultiCoilMRI, SequentialMRI, TimeMixin  # noqa: F401
 from .noise import GaussianNoise, NoiseModel, ZeroNoise  # noqa: F401
 from .tomography import Tomography  # noqa: F401

@@ -1,7 +1,7 @@
 """MRI / MultiCoilMRI on the fused sm_100a spectral kernels.
 
-Drop-in for deepinv/physics/mri.py:11-497 (2-D; `three_d=True`, DynamicMRI, SequentialMRI are out of
-scope).  Same constructor, buffers (`mask`, `coil_maps`), kwargs-store-as-buffer side
+Drop-in for deepinv/physics/mri.py:11-695 (2-D and 2-D+t: MRI, MultiCoilMRI, DynamicMRI, SequentialMRI;
+`three_d=True` is out of scope).  Same constructor, buffers (`mask`, `coil_maps`), kwargs-store-as-buffer side
 effects and error types.  Every method below is one or two launches of `dinvk_spectral`
 (csrc/spectral.cu); nothing is computed with torch.fft.
 """
@@ -241,6 +241,157 @@ class MRI(MRIMixin, DecomposablePhysics):
         if mask is not None:
             mask = self.check_mask(mask=mask, three_d=getattr(self, "three_d", False)) if check_mask else mask
         super().update_parameters(mask=mask, **kwargs)
+
+
+class TimeMixin:
+    """time <-> batch folding helpers (deepinv/utils/mixins.py:19-115)"""
+
+    @staticmethod
+    def flatten(x: Tensor) -> Tensor:
+        B, C, T, H, W = x.shape
+        return x.permute(0, 2, 1, 3, 4).reshape(B * T, C, H, W)
+
+    @staticmethod
+    def unflatten(x: Tensor, batch_size: int = 1) -> Tensor:
+        BT, C, H, W = x.shape
+        return x.reshape(batch_size, BT // batch_size, C, H, W).permute(0, 2, 1, 3, 4)
+
+    @staticmethod
+    def flatten_C(x: Tensor) -> Tensor:
+        return x.reshape(x.shape[0], x.shape[1] * x.shape[2], x.shape[3], x.shape[4])
+
+    @staticmethod
+    def average(x: Tensor, mask: Tensor = None, dim: int = 2) -> Tensor:
+        _x = x.sum(dim)
+        out = torch.zeros_like(_x)
+        m = (mask if mask is not None else (x != 0)).sum(dim)
+        out[m != 0] = _x[m != 0] / m[m != 0]
+        return out
+
+    @staticmethod
+    def repeat(x: Tensor, target: Tensor, dim: int = 2) -> Tensor:
+        return x.unsqueeze(dim=dim).expand_as(target)
+
+
+class DynamicMRI(MRI, TimeMixin):
+    r"""Single-coil dynamic (2-D + t) MRI  y_t = M_t F x_t  on (B,2,T,H,W) tensors (mri.py:499-598).
+
+    Time frames are independent 2-D problems, so the operator is the static one on the time-folded batch: an internal
+    `MRI` whose mask is the (B*T,2,H,W) folding of the 5-D `mask` buffer runs the same fused spectral kernels
+    (A, A^T, A^T A, prox_l2, data step); only the fold / unfold permutes are extra.  Mask shapes accepted: (H,W), (T,H,W),
+    (C,T,H,W), (B,C,T,H,W) like the reference."""
+
+    def __init__(self, mask: Tensor | None = None, img_size: tuple | None = (320, 320), three_d: bool = False,
+                 device="cpu", **kwargs):
+        super().__init__(mask=mask, img_size=img_size, three_d=three_d, device=device, **kwargs)
+        self._flat = None
+        self._flat_key = None
+
+    def check_mask(self, mask: Tensor = None, **kwargs) -> Tensor:
+        if isinstance(mask, np.ndarray):
+            mask = torch.from_numpy(mask)
+        while mask is not None and len(mask.shape) < 5:  # to B,C,T,H,W
+            mask = mask.unsqueeze(0)
+        return MRIMixin.check_mask(mask, three_d=True)  # only pads C to 2 at this point
+
+    def _static(self, batch: int) -> MRI:
+        """the static operator on the time-folded batch (rebuilt when the mask buffer or the batch size changes)"""
+        m = self.mask
+        key = (m.data_ptr(), m._version, tuple(m.shape), m.device, batch)
+        if key != self._flat_key:
+            T = m.shape[2]
+            mb = m if (m.shape[0] == batch or batch == 1) else m.expand(batch, *m.shape[1:])
+            self._flat = MRI(mask=self.flatten(mb).contiguous(), img_size=(2, *m.shape[-2:]), device=m.device)
+            self._flat_key = key
+        return self._flat
+
+    def _check(self, t: Tensor):
+        Bm, _, T, H, W = self.mask.shape
+        if t.dim() != 5 or t.shape[1] != 2 or tuple(t.shape[2:]) != (T, H, W):
+            raise ValueError(f"expected a (B,2,{T},{H},{W}) tensor, got {tuple(t.shape)}")
+        if Bm != 1 and Bm != t.shape[0]:
+            raise ValueError(f"mask batch {Bm} does not match input batch {t.shape[0]}")
+
+    def _fold(self, name: str, t: Tensor, *extra, **kw) -> Tensor:
+        self._check(t)
+        B = t.shape[0]
+        out = getattr(self._static(B), name)(self.flatten(t), *extra, **kw)
+        return self.unflatten(out, batch_size=B)
+
+    def A(self, x: Tensor, mask: Tensor = None, **kwargs) -> Tensor:
+        self.update_parameters(mask=mask, **kwargs)
+        return self._fold("A", x)
+
+    def A_adjoint(self, y: Tensor, mask: Tensor = None, mag: bool = False, **kwargs) -> Tensor:
+        self.update_parameters(mask=mask, **kwargs)
+        return self._fold("A_adjoint", y, mag=mag)
+
+    def A_dagger(self, y: Tensor, mask: Tensor = None, **kwargs) -> Tensor:
+        return self.A_adjoint(y, mask=mask, **kwargs)
+
+    def A_adjoint_A(self, x: Tensor, mask: Tensor = None, **kwargs) -> Tensor:
+        self.update_parameters(mask=mask, **kwargs)
+        return self._fold("A_adjoint_A", x)
+
+    def A_A_adjoint(self, y: Tensor, mask: Tensor = None, **kwargs) -> Tensor:
+        self.update_parameters(mask=mask, **kwargs)
+        return self._fold("A_A_adjoint", y)
+
+    def V_adjoint(self, x: Tensor) -> Tensor:
+        return self._fold("V_adjoint", x)
+
+    def V(self, x: Tensor, **kwargs) -> Tensor:
+        return self._fold("V", x)
+
+    def prox_l2(self, z: Tensor, y: Tensor, gamma, **kwargs) -> Tensor:
+        self._check(z)
+        B, T = z.shape[0], z.shape[2]
+        if isinstance(gamma, Tensor) and gamma.numel() > 1:
+            gamma = gamma.reshape(B, 1).expand(B, T).reshape(-1)
+        return self.unflatten(self._static(B).prox_l2(self.flatten(z), self.flatten(y), gamma, **kwargs), batch_size=B)
+
+    def normal_step(self, x: Tensor, aty: Tensor, gamma: float) -> Tensor:
+        self._check(x)
+        B = x.shape[0]
+        return self.unflatten(self._static(B).normal_step(self.flatten(x), self.flatten(aty), gamma), batch_size=B)
+
+    def noise(self, x, **kwargs):
+        return self.noise_model(x, **kwargs) * self.mask
+
+    def update_parameters(self, mask: Tensor = None, check_mask: bool = True, **kwargs):
+        if mask is not None and check_mask:
+            mask = self.check_mask(mask=mask)
+        DecomposablePhysics.update_parameters(self, mask=mask, **kwargs)
+
+    def to_static(self, mask: Tensor | None = None, device="cpu") -> MRI:
+        """drop the time dimension: union of the per-frame masks (mri.py:583-598)"""
+        return MRI(mask=torch.clip(self.mask.sum(2), 0.0, 1.0) if mask is None else mask, img_size=self.img_size,
+                   device=device)
+
+
+class SequentialMRI(DynamicMRI):
+    r"""Sequential sampling of ONE static image: y_t = M_t F x, x (B,2,H,W), y (B,2,T,H,W) (mri.py:601-695).
+
+    F x does not depend on t, so `A` runs ONE 2-D transform (the reference repeats x T times and transforms every copy)
+    and then applies the T frame masks; the default adjoint averages the frames in k-space and runs one fused
+    mask + inverse-transform launch of the static operator."""
+
+    def A(self, x: Tensor, mask: Tensor = None, **kwargs) -> Tensor:
+        self.update_parameters(mask=mask, **kwargs)
+        if torch.is_grad_enabled() and x.requires_grad:
+            return DynamicMRI.A(self, self.repeat(x, self.mask if x.shape[0] == self.mask.shape[0] else
+                                                  self.mask.expand(x.shape[0], *self.mask.shape[1:])))
+        k = MRIMixin.im_to_kspace(self, x)
+        return k.unsqueeze(2) * self.mask
+
+    def A_adjoint(self, y: Tensor, mask: Tensor = None, keep_time_dim: bool = False, **kwargs) -> Tensor:
+        if keep_time_dim:
+            return super().A_adjoint(y, mask, **kwargs)
+        mask = self.check_mask(mask) if mask is not None else self.mask
+        return self.to_static(device=y.device).A_adjoint(self.average(y, mask), mask=self.average(mask), **kwargs)
+
+    def A_dagger(self, y: Tensor, mask: Tensor = None, **kwargs) -> Tensor:
+        return self.A_adjoint(y, mask=mask, **kwargs)
 
 
 class MultiCoilMRI(MRIMixin, LinearPhysics):

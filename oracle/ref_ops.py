@@ -106,6 +106,24 @@ def rss(x, multicoil=True, mag=True):  # mixins.py:249-287
     return ss.sqrt()
 
 
+# DynamicMRI / SequentialMRI (physics/mri.py:499-695): the functions above act on the last two dims, so a (B,2,T,H,W) video
+# with a (B|1,2,T,H,W) mask goes through mri_A / mri_At / mri_AtA / mri_prox_l2 unchanged (the reference folds T into B)
+def seqmri_A(x, mask5):  # mri.py:672-676: repeat the static image over T, then the dynamic operator
+    return mri_A(x.unsqueeze(2).expand(x.shape[0], 2, *mask5.shape[2:]), mask5)
+
+
+def time_average(x, mask=None):  # mixins.py:83-101
+    _x = x.sum(2)
+    m = (mask if mask is not None else (x != 0)).sum(2)
+    out = torch.zeros_like(_x)
+    out[m != 0] = _x[m != 0] / m[m != 0]
+    return out
+
+
+def seqmri_At(y, mask5):  # mri.py:678-695 (keep_time_dim=False): static adjoint of the time-averaged k-space
+    return mri_At(time_average(y, mask5), time_average(mask5))
+
+
 # a6: MultiCoilMRI (physics/mri.py:254-324)
 def mcmri_A(x, mask, coil_maps):
     Sx = coil_maps * to_complex(x)[:, None]  # (B,N,H,W)

@@ -63,6 +63,32 @@ def mri_fixtures():
              At_mag=phys.A_adjoint(y, mag=True), gamma=np.float32(0.7))
 
 
+def dynamic_fixtures():
+    """DynamicMRI / SequentialMRI (mri.py:499-695)"""
+    from deepinv.physics import DynamicMRI, SequentialMRI
+
+    B, T, H, W = 2, 3, 16, 12
+    x = torch.randn(B, 2, T, H, W, generator=g(1))
+    z = torch.randn(B, 2, T, H, W, generator=g(3))
+    for tag, mask in [("dynmri_batched", RandomMaskGenerator((2, T, H, W), acceleration=4, rng=g(0)).step(B)["mask"]),
+                      ("dynmri_shared_thw", (torch.rand(T, H, W, generator=g(2)) > 0.5).float())]:
+        phys = DynamicMRI(mask=mask, img_size=(2, T, H, W))
+        y = phys.A(x)
+        save(tag, x=x, mask_in=mask, mask=phys.mask, y=y, At=phys.A_adjoint(y), At_mag=phys.A_adjoint(y, mag=True),
+             AtA=phys.A_adjoint_A(x), z=z, prox=phys.prox_l2(z, y, 0.7), dagger=phys.A_dagger(y), gamma=np.float32(0.7))
+    # sequential: T disjoint line sets of one static image
+    xs = torch.randn(B, 2, H, W, generator=g(4))
+    cols = torch.randperm(W, generator=g(5))
+    mask = torch.zeros(T, H, W)
+    for t in range(T):
+        mask[t, :, cols[t::T][:3]] = 1
+    mask = mask[None, None].expand(B, 2, T, H, W).contiguous()  # the reference needs the mask batch to equal x's
+    phys = SequentialMRI(mask=mask, img_size=(2, T, H, W))
+    y = phys.A(xs)
+    save("seqmri_lines", x=xs, mask_in=mask, mask=phys.mask, y=y, At=phys.A_adjoint(y),
+         At_keep=phys.A_adjoint(y, keep_time_dim=True), dagger=phys.A_dagger(y))
+
+
 def multicoil_fixtures():
     B, N, H, W = 2, 3, 16, 20
     x = torch.randn(B, 2, H, W, generator=g(1))
@@ -235,6 +261,64 @@ def optim2_fixtures():
          dpir=dpir, xb=xb, filt=filt, yb=yb, dpir_blur=dpir_blur, **sd_arrays(den, "sd__"))
 
 
+def _grads(model, names=None):
+    out = {}
+    for k, p_ in model.named_parameters():
+        if p_.grad is not None and (names is None or any(n in k for n in names)):
+            out["grad__" + k.replace(".", "__")] = p_.grad.detach().clone()
+    return out
+
+
+def train_fixtures():
+    """gradients of unfolded / deep-equilibrium models from the real reference (one backward each)"""
+    from deepinv.optim import GD
+    from deepinv.optim.prior import Tikhonov
+    from deepinv.unfolded import unfolded_builder
+
+    B, H, W = 2, 32, 32
+    x = torch.randn(B, 2, H, W, generator=g(1))
+    mask = RandomMaskGenerator((2, H, W), acceleration=4, rng=g(0)).step(B)["mask"]
+    phys = MRI(mask=mask, img_size=(2, H, W))
+    y = phys(x)
+    # (1) unfolded PGD, 2 iterations, trainable stepsize + sigma + DRUNet weights
+    den = tiny_drunet(2).train()
+    model = unfolded_builder("PGD", params_algo={"stepsize": [1.0, 0.8], "g_param": [0.05, 0.03], "lambda": 1.0},
+                             trainable_params=["stepsize", "g_param"], data_fidelity=L2(), prior=PnP(den), max_iter=2)
+    out = model(y, phys)
+    loss = ((out - x) ** 2).mean()
+    loss.backward()
+    save("train_unfolded_pgd_mri", x=x, mask=phys.mask, y=y, out=out, loss=loss, **sd_arrays(den, "sd__"), **_grads(model))
+    # (2) deep equilibrium: PGD, 6 forward iterations, 8 backward fixed-point sweeps
+    den = tiny_drunet(2).train()
+    from deepinv.optim import DEQConfig
+    deq = PGD(data_fidelity=L2(), prior=PnP(den), stepsize=0.9, sigma_denoiser=0.05, max_iter=6, early_stop=False,
+              DEQ=DEQConfig(max_iter_backward=8), trainable_params=["stepsize"])
+    out = deq(y, phys)
+    loss = ((out - x) ** 2).mean()
+    loss.backward()
+    save("train_deq_pgd_mri", out=out, loss=loss, **_grads(deq))
+    # (3) DEQ with an explicit prior (cheap enough for the CPU host-logic test): GD + Tikhonov, trainable stepsize / lambda
+    deq2 = GD(data_fidelity=L2(), prior=Tikhonov(), stepsize=0.5, lambda_reg=0.2, max_iter=10, early_stop=False,
+              DEQ=DEQConfig(max_iter_backward=12), trainable_params=["stepsize", "lambda"])
+    out = deq2(y, phys)
+    loss = ((out - x) ** 2).mean()
+    loss.backward()
+    save("train_deq_gd_tikhonov", out=out, loss=loss, **_grads(deq2))
+    # (4) unfolded ADMM on a non-decomposable operator: circular Blur, CG prox with implicit-differentiation backward
+    Bb, C, Hb, Wb = 2, 1, 24, 28
+    xb = torch.rand(Bb, C, Hb, Wb, generator=g(18))
+    filt = dinv.physics.functional.gaussian_blur(sigma=(1.0, 1.0))
+    physb = Blur(filter=filt, padding="circular")
+    yb = physb(xb)
+    dn = tiny_dncnn(1).train()
+    modelb = unfolded_builder("ADMM", params_algo={"stepsize": [1.0, 1.2], "g_param": 0.05, "lambda": 1.0, "beta": 1.0},
+                              trainable_params=["stepsize"], data_fidelity=L2(), prior=PnP(dn), max_iter=2)
+    out = modelb(yb, physb)
+    loss = ((out - xb) ** 2).mean()
+    loss.backward()
+    save("train_unfolded_admm_blur", x=xb, filt=filt, y=yb, out=out, loss=loss, **sd_arrays(dn, "sd__"), **_grads(modelb))
+
+
 def ddrm_fixture():
     B, H, W = 2, 32, 32
     x = torch.randn(B, 2, H, W, generator=g(1)) * 0.3
@@ -258,9 +342,10 @@ def ddrm_fixture():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm", "optim2"]
+    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm", "optim2", "train", "dynamic"]
     table = {"mri": mri_fixtures, "multicoil": multicoil_fixtures, "tomo": tomo_fixtures, "blur": blur_fixtures,
              "blurfft": blurfft_fixtures, "model": model_fixtures, "optim": optim_fixtures, "ddrm": ddrm_fixture,
-             "optim2": optim2_fixtures}
+             "optim2": optim2_fixtures, "train": train_fixtures,
+             "dynamic": dynamic_fixtures}
     for w in which:
         table[w]()

@@ -3,6 +3,8 @@ package code driving the emulated kernels).  Every case compares the package's p
 vectors produced by the real reference (tests/golden)."""
 import math
 
+import pytest
+
 import torch
 
 from conftest import load_golden, rel_err
@@ -44,6 +46,40 @@ def case_mri(name, dev):
     xr = x.clone().requires_grad_(True)  # autograd: backward of A is A^T
     phys.A(xr).backward(y)
     assert rel_err(xr.grad, phys.A_adjoint(y)) < TOL
+
+
+def case_dynamic_mri(name, dev):
+    """DynamicMRI / SequentialMRI on the time-folded static kernels vs the real reference"""
+    import deepinv_b200 as dinv
+
+    g = to_dev(load_golden(name), dev)
+    x, y = g["x"], g["y"]
+    if name.startswith("seq"):
+        phys = dinv.physics.SequentialMRI(mask=g["mask_in"], img_size=tuple(g["mask"].shape[1:]), device=dev)
+        assert torch.equal(phys.mask, g["mask"])
+        yk = phys.A(x)
+        assert yk.shape == y.shape and rel_err(yk, y) < TOL and torch.equal(yk == 0, y == 0)
+        assert rel_err(phys.A_adjoint(y), g["At"]) < TOL
+        assert rel_err(phys.A_adjoint(y, keep_time_dim=True), g["At_keep"]) < TOL
+        assert rel_err(phys.A_dagger(y), g["dagger"]) < TOL
+        xr = x.clone().requires_grad_(True)
+        phys.A(xr).backward(y)
+        assert rel_err(xr.grad, phys.A_adjoint(y, keep_time_dim=True).sum(2)) < TOL
+        return
+    phys = dinv.physics.DynamicMRI(mask=g["mask_in"], img_size=tuple(x.shape[1:]), device=dev)
+    assert torch.equal(phys.mask, g["mask"])
+    yk = phys.A(x)
+    assert rel_err(yk, y) < TOL and torch.equal(yk == 0, y == 0)
+    assert rel_err(phys.A_adjoint(y), g["At"]) < TOL
+    assert rel_err(phys.A_adjoint(y, mag=True), g["At_mag"]) < TOL
+    assert rel_err(phys.A_adjoint_A(x), g["AtA"]) < TOL
+    assert rel_err(phys.prox_l2(g["z"], y, float(g["gamma"])), g["prox"]) < TOL
+    assert rel_err(phys.A_dagger(y), g["dagger"]) < TOL
+    assert rel_err(phys.normal_step(x, phys.A_adjoint(y), 0.8), x - 0.8 * (g["AtA"] - g["At"])) < TOL
+    st = phys.to_static(device=dev)
+    assert torch.equal(st.mask, torch.clip(g["mask"].sum(2), 0.0, 1.0))
+    with pytest.raises(ValueError):
+        phys.A(x[:, :, :2])
 
 
 def case_multicoil(name, dev):
@@ -206,6 +242,84 @@ def case_drs_gd_dpir(dev, full=True):
     assert rel_err(DPIR(sigma=0.05, denoiser=den, device=dev)(y, phys), g["dpir"]) < 5e-5
     physb = dinv.physics.Blur(filter=g["filt"], padding="circular", device=dev)
     assert rel_err(DPIR(sigma=0.05, denoiser=den, device=dev)(g["yb"], physb), g["dpir_blur"]) < 1e-4  # CG prox inside
+
+
+def _check_param_grads(model, g, tol_w=2e-5, tol_p=2e-4):
+    """gradients of every parameter against the reference's (fixture keys `grad__<name>`); the reference registers the
+    unfolded parameters under `init_params_algo` (BaseUnfold) or `params_algo` (BaseOptim): same tensors"""
+    want = {k[6:].replace("__", ".").replace("init_params_algo", "params_algo"): v for k, v in g.items() if k.startswith("grad__")}
+    scale = max(float(v.abs().max()) for k, v in want.items() if k.startswith("params_algo"))
+    seen = 0
+    for k, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        assert k in want, k
+        seen += 1
+        if k.startswith("params_algo"):
+            assert abs(float(p.grad) - float(want[k])) < tol_p * scale, (k, float(p.grad), float(want[k]))
+        else:
+            assert rel_err(p.grad, want[k]) < tol_w, (k, rel_err(p.grad, want[k]))
+    assert seen == len(want), (seen, len(want))
+
+
+def case_train_deq_explicit(dev):
+    """deep equilibrium GD + Tikhonov on MRI: forward value, loss and d loss / d (stepsize, lambda) through the backward
+    fixed-point hook == the real reference"""
+    import deepinv_b200 as dinv
+    from deepinv_b200.optim import GD, L2, DEQConfig, Tikhonov
+
+    g0 = to_dev(load_golden("train_unfolded_pgd_mri"), dev)
+    g = to_dev(load_golden("train_deq_gd_tikhonov"), dev)
+    phys = dinv.physics.MRI(mask=g0["mask"], img_size=(2, 32, 32), device=dev)
+    deq = GD(data_fidelity=L2(), prior=Tikhonov(), stepsize=0.5, lambda_reg=0.2, max_iter=10, early_stop=False,
+             DEQ=DEQConfig(max_iter_backward=12), trainable_params=["stepsize", "lambda"]).to(dev)
+    out = deq(g0["y"], phys)
+    loss = ((out - g0["x"]) ** 2).mean()
+    loss.backward()
+    assert rel_err(out, g["out"]) < TOL and abs(float(loss) - float(g["loss"])) < 1e-5 * float(g["loss"])
+    _check_param_grads(deq, g)
+
+
+def case_train_unfolded(dev):
+    """one training step (forward, MSE loss, backward) of unfolded PGD (MRI, DRUNet), a deep-equilibrium PGD and unfolded
+    ADMM (circular Blur: CG prox with implicit-differentiation backward, DnCNN): outputs, losses and the gradient of
+    every trainable parameter == the real reference"""
+    import deepinv_b200 as dinv
+    from deepinv_b200.optim import PGD, L2, DEQConfig, PnP
+    from deepinv_b200.unfolded import unfolded_builder
+
+    g = to_dev(load_golden("train_unfolded_pgd_mri"), dev)
+    phys = dinv.physics.MRI(mask=g["mask"], img_size=(2, 32, 32), device=dev)
+    x, y = g["x"], g["y"]
+    den = load_model(dinv.models.DRUNet, g, dev, in_channels=2, out_channels=2, nc=(8, 16, 32, 64), nb=2).train()
+    model = unfolded_builder("PGD", params_algo={"stepsize": [1.0, 0.8], "g_param": [0.05, 0.03], "lambda": 1.0},
+                             trainable_params=["stepsize", "g_param"], data_fidelity=L2(), prior=PnP(den), max_iter=2).to(dev)
+    out = model(y, phys)
+    loss = ((out - x) ** 2).mean()
+    loss.backward()
+    assert rel_err(out, g["out"]) < TOL and abs(float(loss) - float(g["loss"])) < 1e-5 * float(g["loss"])
+    _check_param_grads(model, g)
+
+    gd = to_dev(load_golden("train_deq_pgd_mri"), dev)
+    den = load_model(dinv.models.DRUNet, g, dev, in_channels=2, out_channels=2, nc=(8, 16, 32, 64), nb=2).train()
+    deq = PGD(data_fidelity=L2(), prior=PnP(den), stepsize=0.9, sigma_denoiser=0.05, max_iter=6, early_stop=False,
+              DEQ=DEQConfig(max_iter_backward=8), trainable_params=["stepsize"]).to(dev)
+    out = deq(y, phys)
+    loss = ((out - x) ** 2).mean()
+    loss.backward()
+    assert rel_err(out, gd["out"]) < TOL and abs(float(loss) - float(gd["loss"])) < 1e-5 * float(gd["loss"])
+    _check_param_grads(deq, gd, tol_w=5e-5)
+
+    gb = to_dev(load_golden("train_unfolded_admm_blur"), dev)
+    physb = dinv.physics.Blur(filter=gb["filt"], padding="circular", device=dev)
+    dn = load_model(dinv.models.DnCNN, gb, dev, in_channels=1, out_channels=1, depth=5, nf=8).train()
+    modelb = unfolded_builder("ADMM", params_algo={"stepsize": [1.0, 1.2], "g_param": 0.05, "lambda": 1.0, "beta": 1.0},
+                              trainable_params=["stepsize"], data_fidelity=L2(), prior=PnP(dn), max_iter=2).to(dev)
+    out = modelb(gb["y"], physb)
+    loss = ((out - gb["x"]) ** 2).mean()
+    loss.backward()
+    assert rel_err(out, gb["out"]) < 1e-4 and abs(float(loss) - float(gb["loss"])) < 1e-4 * float(gb["loss"])
+    _check_param_grads(modelb, gb, tol_w=2e-3, tol_p=2e-3)  # CG solves (tol 1e-4) inside forward and backward
 
 
 def case_pnp_blur_admm(dev):

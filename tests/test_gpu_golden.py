@@ -22,6 +22,11 @@ def test_mri(name, dev):
     P.case_mri(name, dev)
 
 
+@pytest.mark.parametrize("name", golden_names("dynmri_") + golden_names("seqmri_"))
+def test_dynamic_mri(name, dev):
+    P.case_dynamic_mri(name, dev)
+
+
 @pytest.mark.parametrize("name", golden_names("mcmri_"))
 def test_multicoil(name, dev):
     P.case_multicoil(name, dev)
@@ -64,6 +69,14 @@ def test_pnp_mri(dev):
 
 def test_drs_gd_dpir(dev):
     P.case_drs_gd_dpir(dev)
+
+
+def test_train_deq_explicit(dev):
+    P.case_train_deq_explicit(dev)
+
+
+def test_train_unfolded(dev):
+    P.case_train_unfolded(dev)
 
 
 def test_pnp_blur_admm(dev):

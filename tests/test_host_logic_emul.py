@@ -37,6 +37,11 @@ def test_mri(name):
     P.case_mri(name, DEV)
 
 
+@pytest.mark.parametrize("name", golden_names("dynmri_") + golden_names("seqmri_"))
+def test_dynamic_mri(name):
+    P.case_dynamic_mri(name, DEV)
+
+
 @pytest.mark.parametrize("name", golden_names("mcmri_"))
 def test_multicoil(name):
     P.case_multicoil(name, DEV)
@@ -80,6 +85,10 @@ def test_pnp_mri():
 
 def test_drs_gd_dpir():
     P.case_drs_gd_dpir(DEV, full=False)
+
+
+def test_train_deq_explicit():
+    P.case_train_deq_explicit(DEV)
 
 
 def test_pnp_blur_admm():
@@ -168,3 +177,41 @@ def test_drunet_gradients():
     assert rel_err(x.grad, x2.grad) < 1e-5
     for k, p in den.named_parameters():
         assert rel_err(p.grad, sd[k].grad) < 2e-5, k
+
+
+@pytest.mark.parametrize("batched_gamma", [False, True])
+def test_least_squares_implicit_backward(batched_gamma):
+    """prox_l2 of a non-decomposable operator (circular Blur, CG on the kernels): value and the implicit-differentiation
+    gradients w.r.t. y, z, gamma == autograd through a dense fp64 solve of the same normal equations"""
+    from conftest import rel_err
+    from oracle import ref_ops as R
+
+    import deepinv_b200 as dinv
+
+    torch.manual_seed(3)
+    B, H, W = 2, 8, 10
+    filt = torch.rand(1, 1, 3, 3)
+    filt = filt / filt.sum()
+    phys = dinv.physics.Blur(filter=filt, padding="circular", device=DEV)
+    phys.max_iter, phys.tol = 25, 1e-5
+    y = torch.randn(B, 1, H, W, requires_grad=True)
+    z = torch.randn(B, 1, H, W, requires_grad=True)
+    gamma = (torch.tensor([0.7, 2.5]) if batched_gamma else torch.tensor(1.3)).requires_grad_()
+    r = torch.randn(B, 1, H, W)
+    out = phys.prox_l2(z, y, gamma)
+    gy, gz, gg = torch.autograd.grad((out * r).sum(), [y, z, gamma])
+    # dense reference
+    n = H * W
+    eye = torch.eye(n, dtype=torch.float64).reshape(n, 1, H, W)
+    A = R.blur_A(eye.float(), filt, "circular").double().reshape(n, n).T  # columns = A e_i
+    y64, z64, g64 = (t.detach().double().requires_grad_() for t in (y, z, gamma))
+    gb = g64.reshape(-1, 1) if batched_gamma else g64
+    rhs = y64.reshape(B, n) @ A + z64.reshape(B, n) / gb
+    hs = []
+    for b in range(B):
+        gcur = g64[b] if batched_gamma else g64
+        hs.append(torch.linalg.solve(A.T @ A + torch.eye(n, dtype=torch.float64) / gcur, rhs[b]))
+    h = torch.stack(hs).reshape(B, 1, H, W)
+    wy, wz, wg = torch.autograd.grad((h * r.double()).sum(), [y64, z64, g64])
+    assert rel_err(out, h) < 1e-5
+    assert rel_err(gy, wy) < 2e-4 and rel_err(gz, wz) < 2e-4 and rel_err(gg, wg) < 2e-4
