@@ -268,3 +268,158 @@ class BlurFFT(DecomposablePhysics):
 
     def U_adjoint(self, x: Tensor, **kwargs) -> Tensor:
         return torch.view_as_real(self._rfft2(x) * torch.conj(self.angle))
+
+
+class Downsampling(LinearPhysics):
+    r"""y = S_f (h * x): anti-aliasing blur followed by decimation by `factor` (deepinv/physics/blur.py:15-440).
+
+    `A` is the tiled correlation kernel (`dinvk_blur_fwd`) followed by the strided pick, `A_adjoint` the zero-stuffed
+    upsampling followed by the exact transposed kernel (`dinvk_blur_adj`), for all five paddings.  With circular padding
+    `prox_l2` is the closed form of Zhao et al. (blur.py:332-364): the f x f aliasing fold of |h^|^2 is inverted bin by
+    bin; the two 2-D transforms run on the library's spectral kernel (`dinvk_spectral`, un-centred), the fold itself is
+    a handful of elementwise passes on the spectrum.  Other paddings: CG on the operator kernels (LinearPhysics)."""
+
+    def __init__(self, img_size=None, filter="warn", factor: int = 2, device="cpu", padding: str = "circular", **kwargs):
+        if isinstance(filter, str) and filter == "warn":
+            warn("Leaving the filter as default is deprecated and will be removed in future versions. Please specify "
+                 "filter=None for bare decimation, or one of the available filters (gaussian, bilinear, bicubic, sinc).",
+                 stacklevel=2)
+            filter = None
+        super().__init__(device=device, **kwargs)
+        self.imsize = tuple(img_size) if isinstance(img_size, list) else img_size
+        self.imsize_dynamic = (3, 128, 128)
+        self.padding = padding
+        _padding_code(padding)
+        self.factor = self.check_factor(factor)
+        self.register_buffer("filter", self._make_filter(filter, self.factor, device))
+        self._fh_key = None
+        self.to(device)
+
+    @staticmethod
+    def check_factor(factor) -> int:
+        if isinstance(factor, (int, float)):
+            return int(factor)
+        if isinstance(factor, Tensor):
+            if factor.ndim > 1:
+                raise ValueError("Factor tensor must be 1D.")
+            u = torch.unique(factor)
+            if len(u) > 1:
+                raise ValueError(f"Downsampling only supports one unique factor per batch, but got factors {u.tolist()}.")
+            return int(u.item())
+        raise ValueError(f"Factor must be an int, float or a 1D Tensor, got {type(factor)}.")
+
+    @staticmethod
+    def _make_filter(filter, factor, device):
+        from . import functional as dF
+
+        if filter is None:
+            return None
+        if isinstance(filter, list):
+            if len(set(filter)) == 1 and isinstance(filter[0], str):
+                filter = filter[0]
+            else:
+                raise ValueError("Downsampling supports filter string lists if they are identical, but got unique filters "
+                                 f"{set(filter)}.")
+        if isinstance(filter, Tensor):
+            return filter.to(device)
+        if filter == "gaussian":
+            return dF.gaussian_blur(sigma=(factor, factor), device=device)
+        if filter == "bilinear":
+            return dF.bilinear_filter(factor, device=device)
+        if filter == "bicubic":
+            return dF.bicubic_filter(factor, device=device)
+        if filter == "sinc":
+            return dF.sinc_filter(factor, length=4 * factor, device=device)
+        raise ValueError(f"unknown filter {filter!r}")
+
+    def update_parameters(self, filter=None, factor=None, **kwargs):
+        if factor is not None:
+            if filter is None and self.filter is not None:
+                warn("Updating factor but not filter. Filter will not be valid for new factor. Pass filter string or new "
+                     "filter to resolve this.")
+            self.factor = self.check_factor(factor)
+        if filter is not None:
+            dev = self.filter.device if isinstance(self.filter, Tensor) else \
+                (filter.device if isinstance(filter, Tensor) else kwargs.get("device", "cpu"))
+            f = self._make_filter(filter, self.factor, dev)
+            if self.filter is None:
+                self.register_buffer("filter", f)
+            else:
+                self.filter = f.to(self.filter.device)
+        kwargs.pop("device", None)
+        super().update_parameters(**kwargs)
+
+    # ---- operator -------------------------------------------------------------------------------------------
+    def _blur(self, x):
+        return x if self.filter is None else ops.blur_fwd(x, self.filter, _padding_code(self.padding))
+
+    def _blur_t(self, v, H, W):
+        return v if self.filter is None else ops.blur_adj(v, self.filter, _padding_code(self.padding), H, W)
+
+    def _down(self, x):
+        f = self.factor
+        return self._blur(x)[:, :, ::f, ::f].contiguous()
+
+    def _up(self, y, H, W):
+        """A^T: zero-stuffing to the blurred image's size (H', W'), then the transposed blur back to (H, W)"""
+        f = self.factor
+        valid = self.filter is not None and _padding_code(self.padding) == _ffi.PAD_VALID
+        Hb, Wb = (H - self.filter.shape[-2] + 1, W - self.filter.shape[-1] + 1) if valid else (H, W)
+        v = torch.zeros(y.shape[0], y.shape[1], Hb, Wb, device=y.device, dtype=torch.float32)
+        v[:, :, ::f, ::f] = y
+        return self._blur_t(v, H, W)
+
+    def A(self, x: Tensor, filter=None, factor=None, **kwargs) -> Tensor:
+        self.imsize_dynamic = tuple(x.shape[-3:])
+        self.update_parameters(filter=filter, factor=factor, device=x.device, **kwargs)
+        if x.dim() != 4:
+            raise ValueError(f"Expected Tensor dimension to be 4, is {x.dim()}")
+        if self.filter is not None:
+            _check_filter(self.filter, x.shape[0], x.shape[1])
+        H, W = x.shape[-2:]
+        return linear_apply(x, self._down, lambda t: self._up(t, H, W))
+
+    def A_adjoint(self, y: Tensor, filter=None, factor=None, **kwargs) -> Tensor:
+        f = self.check_factor(factor) if factor is not None else self.factor
+        self.imsize_dynamic = (y.shape[-3], y.shape[-2] * f, y.shape[-1] * f)
+        self.update_parameters(filter=filter, factor=factor, device=y.device, **kwargs)
+        imsize = self.imsize if self.imsize is not None else self.imsize_dynamic
+        H, W = imsize[-2:]
+        return linear_apply(y, lambda t: self._up(t, H, W), self._down)
+
+    # ---- closed-form prox for circular padding ------------------------------------------------------------------
+    def _spectrum(self, C, H, W):
+        """F h (un-normalised 2-D DFT of the zero-padded, centre-rolled filter): (1|B, C, H, W) complex"""
+        f = self.filter
+        key = (f.data_ptr(), f._version, C, H, W)
+        if key != self._fh_key:
+            ff = f if f.shape[1] == C else f.expand(f.shape[0], C, *f.shape[-2:])
+            self._Fh = BlurFFT._full_spectrum(ff, (C, H, W))
+            self._fh_key = key
+        return self._Fh
+
+    def prox_l2(self, z: Tensor, y: Tensor, gamma, use_fft: bool = True, **kwargs) -> Tensor:
+        tracked = torch.is_grad_enabled() and (z.requires_grad or y.requires_grad or
+                                               (isinstance(gamma, Tensor) and gamma.requires_grad))
+        if not (use_fft and self.padding == "circular" and self.filter is not None) or tracked or \
+                (isinstance(gamma, Tensor) and gamma.numel() > 1):
+            return LinearPhysics.prox_l2(self, z, y, gamma, **kwargs)
+        g = float(gamma)
+        B, C, H, W = z.shape
+        sf = self.factor
+        z_hat = ops.axpbypcz(self.A_adjoint(y), 1.0, z, 1.0 / g)
+        planar = torch.zeros(B * C, 2, H, W, device=z.device)
+        planar[:, 0] = z_hat.reshape(B * C, H, W)
+        s = ops.spectral(planar, H, W, fwd=True, inv=False, centered=False)  # orthonormal: linear, undone by the inverse
+        Fz = torch.complex(s[:, 0], s[:, 1]).reshape(B, C, H, W)
+        Fh = self._spectrum(C, H, W)
+
+        def fold(a):  # mean over the sf x sf aliases: (.., H, W) -> (.., H/sf, W/sf)
+            return a.reshape(*a.shape[:-2], sf, H // sf, sf, W // sf).mean(dim=(-4, -2))
+
+        top = fold(Fh * Fz)
+        below = fold((Fh.conj() * Fh).real) + 1.0 / g
+        rc = Fh.conj() * (top / below).repeat(1, 1, sf, sf)
+        rp = torch.stack([rc.real, rc.imag], 2).reshape(B * C, 2, H, W).contiguous()
+        r = ops.spectral(rp, H, W, fwd=False, inv=True, centered=False)[:, 0].reshape(B, C, H, W)
+        return ops.axpbypcz(z_hat, g, r, -g)

@@ -407,13 +407,38 @@ def blur_At(y: torch.Tensor, filt: torch.Tensor, padding: str, H: int, W: int) -
     return flat.reshape(B, C, H, W)
 
 
+# Downsampling (physics/blur.py:280-364): blur, then keep every factor-th pixel; transpose = zero-stuffing + transposed blur
+def down_A(x, filt, factor, padding="circular"):
+    xb = x if filt is None else blur_A(x, filt, padding)
+    return xb[:, :, ::factor, ::factor]
+
+
+def down_At(y, filt, factor, padding, H, W):
+    Hb, Wb = (H - filt.shape[-2] + 1, W - filt.shape[-1] + 1) if (filt is not None and padding == "valid") else (H, W)
+    v = torch.zeros(y.shape[0], y.shape[1], Hb, Wb, dtype=y.dtype)
+    v[:, :, ::factor, ::factor] = y
+    return v if filt is None else blur_At(v, filt, padding, H, W)
+
+
+def down_prox_l2(z, y, filt, factor, gamma):
+    """closed form for circular padding (blur.py:332-364, Zhao et al. 2016)"""
+    B, C, H, W = z.shape
+    Fh = filter_fft(filt.expand(filt.shape[0], C, *filt.shape[-2:]) if filt.shape[1] != C else filt, (C, H, W), real_fft=False)
+    z_hat = down_At(y, filt, factor, "circular", H, W) + z / gamma
+    Fz = torch.fft.fft2(z_hat)
+    fold = lambda a: a.reshape(*a.shape[:-2], factor, H // factor, factor, W // factor).mean(dim=(-4, -2))
+    top, below = fold(Fh * Fz), fold(Fh.conj() * Fh) + 1 / gamma
+    r = torch.real(torch.fft.ifft2(Fh.conj() * (top / below).repeat(1, 1, factor, factor)))
+    return (z_hat - r) * gamma
+
+
 # a11: BlurFFT (physics/blur.py:639-692, convolution.py:790-812)
-def filter_fft(filt: torch.Tensor, img_size) -> torch.Tensor:
+def filter_fft(filt: torch.Tensor, img_size, real_fft: bool = True) -> torch.Tensor:
     H, W = img_size[-2:]
     h, w = filt.shape[-2:]
     f = F.pad(filt, (0, W - w, 0, H - h))
     f = torch.roll(f, shifts=(-int(h / 2), -int(w / 2)), dims=(-2, -1))
-    return torch.fft.rfftn(f, dim=(-2, -1))
+    return torch.fft.rfftn(f, dim=(-2, -1)) if real_fft else torch.fft.fftn(f, dim=(-2, -1))
 
 
 def blurfft_params(filt: torch.Tensor, img_size):

@@ -89,6 +89,29 @@ def dynamic_fixtures():
          At_keep=phys.A_adjoint(y, keep_time_dim=True), dagger=phys.A_dagger(y))
 
 
+def down_fixtures():
+    """Downsampling (blur.py:15-440) and the filter constructors it uses"""
+    from deepinv.physics import Downsampling
+    from deepinv.physics import functional as dF
+
+    save("filters", gaussian=dF.gaussian_blur(sigma=(2.0, 2.0)), gaussian_aniso=dF.gaussian_blur(sigma=(1.0, 2.5), angle=30.0),
+         bilinear2=dF.bilinear_filter(2), bicubic2=dF.bicubic_filter(2), bicubic4=dF.bicubic_filter(4),
+         sinc2=dF.sinc_filter(2, length=8), sinc3=dF.sinc_filter(3, length=12))
+    B, C, H, W = 2, 3, 24, 32
+    x = torch.rand(B, C, H, W, generator=g(21))
+    z = torch.rand(B, C, H, W, generator=g(22))
+    for tag, filt, factor, pad in [("down_gauss_f2_circular", "gaussian", 2, "circular"), ("down_bicubic_f4_circular", "bicubic", 4, "circular"),
+                                   ("down_none_f2_circular", None, 2, "circular"), ("down_bilinear_f2_valid", "bilinear", 2, "valid"),
+                                   ("down_sinc_f2_reflect", "sinc", 2, "reflect")]:
+        phys = Downsampling(img_size=(C, H, W), filter=filt, factor=factor, padding=pad)
+        y = phys.A(x)
+        v = torch.rand(*y.shape, generator=g(23))
+        arrs = dict(x=x, y=y, v=v, At=phys.A_adjoint(v), factor=np.int32(factor))
+        if pad == "circular" and filt is not None:
+            arrs.update(z=z, prox=phys.prox_l2(z, y, 1.5), gamma=np.float32(1.5))
+        save(tag, **arrs)
+
+
 def multicoil_fixtures():
     B, N, H, W = 2, 3, 16, 20
     x = torch.randn(B, 2, H, W, generator=g(1))
@@ -342,10 +365,10 @@ def ddrm_fixture():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm", "optim2", "train", "dynamic"]
+    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm", "optim2", "train", "dynamic", "down"]
     table = {"mri": mri_fixtures, "multicoil": multicoil_fixtures, "tomo": tomo_fixtures, "blur": blur_fixtures,
              "blurfft": blurfft_fixtures, "model": model_fixtures, "optim": optim_fixtures, "ddrm": ddrm_fixture,
              "optim2": optim2_fixtures, "train": train_fixtures,
-             "dynamic": dynamic_fixtures}
+             "dynamic": dynamic_fixtures, "down": down_fixtures}
     for w in which:
         table[w]()

@@ -82,6 +82,42 @@ def case_dynamic_mri(name, dev):
         phys.A(x[:, :, :2])
 
 
+def case_filters(dev):
+    from deepinv_b200.physics import functional as dF
+
+    g = load_golden("filters")
+    got = dict(gaussian=dF.gaussian_blur(sigma=(2.0, 2.0), device=dev), gaussian_aniso=dF.gaussian_blur(sigma=(1.0, 2.5), angle=30.0, device=dev),
+               bilinear2=dF.bilinear_filter(2, device=dev), bicubic2=dF.bicubic_filter(2, device=dev),
+               bicubic4=dF.bicubic_filter(4, device=dev), sinc2=dF.sinc_filter(2, length=8, device=dev),
+               sinc3=dF.sinc_filter(3, length=12, device=dev))
+    for k, v in got.items():
+        assert v.shape == g[k].shape and rel_err(v, g[k]) < 1e-6, k
+
+
+def case_downsampling(name, dev):
+    """Downsampling: blur kernel + decimation, exact transpose, closed-form circular prox"""
+    import deepinv_b200 as dinv
+
+    g = to_dev(load_golden(name), dev)
+    _, filt, fac, pad = name.split("_")
+    filt = None if filt == "none" else {"gauss": "gaussian"}.get(filt, filt)
+    x = g["x"]
+    phys = dinv.physics.Downsampling(img_size=tuple(x.shape[1:]), filter=filt, factor=int(g["factor"]), padding=pad, device=dev)
+    y = phys.A(x)
+    assert y.shape == g["y"].shape and rel_err(y, g["y"]) < TOL
+    assert rel_err(phys.A_adjoint(g["v"]), g["At"]) < TOL
+    u = torch.randn_like(x)
+    lhs, rhs = (phys.A(u) * g["v"]).sum().double(), (u * phys.A_adjoint(g["v"])).sum().double()
+    assert abs(float(lhs - rhs)) < 1e-4 * max(1.0, abs(float(lhs)))
+    if "prox" in g:
+        assert rel_err(phys.prox_l2(g["z"], g["y"], float(g["gamma"])), g["prox"]) < TOL
+        cg = phys.prox_l2(g["z"], g["y"], float(g["gamma"]), use_fft=False)  # the CG route agrees with the closed form
+        assert rel_err(cg, g["prox"]) < 1e-3
+    xr = x.clone().requires_grad_(True)
+    phys.A(xr).backward(g["v"])
+    assert rel_err(xr.grad, g["At"]) < TOL
+
+
 def case_multicoil(name, dev):
     import deepinv_b200 as dinv
 

@@ -27,6 +27,15 @@ def test_dynamic_mri(name, dev):
     P.case_dynamic_mri(name, dev)
 
 
+@pytest.mark.parametrize("name", golden_names("down_"))
+def test_downsampling(name, dev):
+    P.case_downsampling(name, dev)
+
+
+def test_filters(dev):
+    P.case_filters(dev)
+
+
 @pytest.mark.parametrize("name", golden_names("mcmri_"))
 def test_multicoil(name, dev):
     P.case_multicoil(name, dev)

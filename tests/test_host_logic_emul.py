@@ -42,6 +42,15 @@ def test_dynamic_mri(name):
     P.case_dynamic_mri(name, DEV)
 
 
+@pytest.mark.parametrize("name", golden_names("down_"))
+def test_downsampling(name):
+    P.case_downsampling(name, DEV)
+
+
+def test_filters():
+    P.case_filters(DEV)
+
+
 @pytest.mark.parametrize("name", golden_names("mcmri_"))
 def test_multicoil(name):
     P.case_multicoil(name, DEV)

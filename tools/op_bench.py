@@ -122,3 +122,37 @@ with torch.no_grad():
         report("MultiCoilMRI.A 32x8x320^2", t(lambda: p.A(x), 10, 2), mb)
         report("MultiCoilMRI.A_adjoint", t(lambda: p.A_adjoint(y), 10, 2), mb)
         report("MultiCoilMRI.A_dagger (CG)", t(lambda: p.A_dagger(y), 1, 1, graph=False))
+if "train" in which:  # backward kernels of the fp32 denoiser path + one unfolded training step
+    from deepinv_b200 import ops
+    from deepinv_b200.optim import L2, PnP
+    from deepinv_b200.unfolded import unfolded_builder
+
+    B, C, H, W = 8, 64, 256, 256
+    x = torch.randn(B, C, H, W, device=dev, generator=g)
+    w = torch.randn(C, C, 3, 3, device=dev, generator=g) / 24
+    gout = torch.randn(B, C, H, W, device=dev, generator=g)
+    gf = 2 * 9 * C * C * B * H * W / 1e9
+    with torch.no_grad():
+        report("conv3x3 fp32 forward 8x64x256^2 (64->64)", t(lambda: ops.conv_f32(x, w), 5, 2, graph=False), gflop=gf)
+        wt = w.transpose(0, 1).flip(2, 3).contiguous()
+        report("conv3x3 fp32 data gradient", t(lambda: ops.conv_f32(gout, wt), 5, 2, graph=False), gflop=gf)
+        report("conv3x3 fp32 weight gradient", t(lambda: ops.conv_f32_wgrad(x, None, gout, w.shape), 5, 2, graph=False), gflop=gf)
+        report("relu backward 8x64x256^2", t(lambda: ops.relu_bwd(gout, x), 5, 2, graph=False), 3 * x.numel() * 4 / 1e6)
+    Bt = 4
+    xt = torch.randn(Bt, 2, 256, 256, device=dev, generator=g)
+    cols = (torch.rand(Bt, 1, 1, 256, device=dev, generator=g) > 0.75).float().expand(Bt, 2, 256, 256).contiguous()
+    p = dinv.physics.MRI(mask=cols, img_size=(2, 256, 256), device=dev)
+    with torch.no_grad():
+        yt = p.A(xt)
+    den = dinv.models.DRUNet(in_channels=2, out_channels=2, pretrained=None, device=dev).train()
+    model = unfolded_builder("PGD", params_algo={"stepsize": [1.0, 1.0], "g_param": [0.05, 0.03], "lambda": 1.0},
+                             trainable_params=["stepsize", "g_param"], data_fidelity=L2(), prior=PnP(den), max_iter=2).to(dev)
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        loss = ((model(yt, p) - xt) ** 2).mean()
+        loss.backward()
+
+    # 2 unfolded iterations x (forward 277 GFLOP + data gradient 277 + weight gradient 277) per image
+    report("unfolded PGD (2 it, DRUNet fp32) training step, batch 4 x 256^2", t(step, 2, 1, graph=False),
+           gflop=2 * 3 * 277.4 * Bt)
