@@ -144,5 +144,6 @@ def least_squares(physics, y: torch.Tensor, z: torch.Tensor | None = None, init:
         gam = gamma if isinstance(gamma, torch.Tensor) else torch.tensor(float(gamma), device=y.device)
         opts = {"max_iter": max_iter, "tol": tol, "verbose": verbose, "kwargs": kwargs}
         return _LeastSquaresFn.apply(physics, y, z, init, gam, opts)
-    g, g_batch = _split_gamma(gamma, y.shape[0])
+    y0 = y if isinstance(y, torch.Tensor) else y[0]  # stacked operators measure TensorLists (physics/combine.py)
+    g, g_batch = _split_gamma(gamma, y0.shape[0])
     return _solve_normal(physics, y, z, init, g, g_batch, max_iter, tol, verbose, kwargs)

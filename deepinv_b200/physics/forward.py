@@ -107,6 +107,21 @@ class Physics(nn.Module):
     def clone(self):
         return copy.deepcopy(self)
 
+    def __mul__(self, other):
+        """A = self o other  (forward.py:73-88, 573-583); keeps self's noise and sensor models"""
+        from .combine import compose
+
+        if not isinstance(self, LinearPhysics) or not isinstance(other, LinearPhysics):
+            warnings.warn("You are composing two physics objects. The resulting physics will not retain the original attributes. "
+                          "You may instead retrieve attributes of the original physics by indexing the resulting physics.")
+        return compose(other, self, max_iter=self.max_iter, tol=self.tol)
+
+    def stack(self, other):
+        """[self; other] with TensorList measurements (forward.py:90-107, 585-601)"""
+        from .combine import stack
+
+        return stack(self, other)
+
     def set_ls_solver(self, solver, max_iter=None, tol=None):
         if max_iter is not None:
             self.max_iter = max_iter

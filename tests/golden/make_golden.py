@@ -112,6 +112,32 @@ def down_fixtures():
         save(tag, **arrs)
 
 
+def combine_fixtures():
+    """§8(b): `__mul__` (composition) and `stack` of operators on the path"""
+    from deepinv.physics import Downsampling
+
+    B, C, H, W = 2, 1, 24, 32
+    x = torch.rand(B, C, H, W, generator=g(31))
+    z = torch.rand(B, C, H, W, generator=g(32))
+    filt = dinv.physics.functional.gaussian_blur(sigma=(1.0, 1.5))
+    blur = Blur(filter=filt, padding="circular")
+    down = Downsampling(img_size=(C, H, W), filter="bilinear", factor=2, padding="circular")
+    comp = down * blur  # y = down(blur(x))
+    y = comp.A(x)
+    v = torch.rand(*y.shape, generator=g(33))
+    save("combine_down_blur", x=x, filt=filt, y=y, v=v, At=comp.A_adjoint(v), z=z, prox=comp.prox_l2(z, y, 2.0),
+         gamma=np.float32(2.0))
+    Bm, Hm, Wm = 2, 16, 20
+    xm = torch.randn(Bm, 2, Hm, Wm, generator=g(34))
+    zm = torch.randn(Bm, 2, Hm, Wm, generator=g(35))
+    m1 = (torch.rand(Bm, 2, Hm, Wm, generator=g(36)) > 0.6).float()
+    m2 = RandomMaskGenerator((2, Hm, Wm), acceleration=4, rng=g(0)).step(Bm)["mask"]
+    st = MRI(mask=m1, img_size=(2, Hm, Wm)).stack(MRI(mask=m2, img_size=(2, Hm, Wm)))
+    ys = st.A(xm)
+    save("combine_stack_mri", x=xm, m1=m1, m2=m2, y0=ys[0], y1=ys[1], At=st.A_adjoint(ys), z=zm,
+         prox=st.prox_l2(zm, ys, 0.9), gamma=np.float32(0.9), dagger=st.A_dagger(ys))
+
+
 def multicoil_fixtures():
     B, N, H, W = 2, 3, 16, 20
     x = torch.randn(B, 2, H, W, generator=g(1))
@@ -365,10 +391,11 @@ def ddrm_fixture():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm", "optim2", "train", "dynamic", "down"]
+    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm", "optim2", "train", "dynamic", "down", "combine"]
     table = {"mri": mri_fixtures, "multicoil": multicoil_fixtures, "tomo": tomo_fixtures, "blur": blur_fixtures,
              "blurfft": blurfft_fixtures, "model": model_fixtures, "optim": optim_fixtures, "ddrm": ddrm_fixture,
              "optim2": optim2_fixtures, "train": train_fixtures,
-             "dynamic": dynamic_fixtures, "down": down_fixtures}
+             "dynamic": dynamic_fixtures, "down": down_fixtures,
+             "combine": combine_fixtures}
     for w in which:
         table[w]()

@@ -118,6 +118,35 @@ def case_downsampling(name, dev):
     assert rel_err(xr.grad, g["At"]) < TOL
 
 
+def case_combine(dev):
+    """§8(b): composition (`*`) and stacking (`stack`) of operators — member kernels + CG prox vs the real reference"""
+    import deepinv_b200 as dinv
+
+    g = to_dev(load_golden("combine_down_blur"), dev)
+    x = g["x"]
+    blur = dinv.physics.Blur(filter=g["filt"], padding="circular", device=dev)
+    down = dinv.physics.Downsampling(img_size=tuple(x.shape[1:]), filter="bilinear", factor=2, padding="circular", device=dev)
+    comp = down * blur
+    assert isinstance(comp, dinv.physics.ComposedLinearPhysics) and comp[0] is blur and comp[1] is down
+    assert rel_err(comp.A(x), g["y"]) < TOL
+    assert rel_err(comp.A_adjoint(g["v"]), g["At"]) < TOL
+    assert rel_err(comp.prox_l2(g["z"], g["y"], float(g["gamma"])), g["prox"]) < 1e-4
+
+    g = to_dev(load_golden("combine_stack_mri"), dev)
+    x = g["x"]
+    p1 = dinv.physics.MRI(mask=g["m1"], img_size=tuple(x.shape[1:]), device=dev)
+    p2 = dinv.physics.MRI(mask=g["m2"], img_size=tuple(x.shape[1:]), device=dev)
+    st = p1.stack(p2)
+    assert isinstance(st, dinv.physics.StackedLinearPhysics) and len(st) == 2
+    y = st.A(x)
+    assert rel_err(y[0], g["y0"]) < TOL and rel_err(y[1], g["y1"]) < TOL
+    assert rel_err(st.A_adjoint(y), g["At"]) < TOL
+    assert rel_err(st.prox_l2(g["z"], y, float(g["gamma"])), g["prox"]) < 1e-4
+    assert rel_err(st.A_dagger(y), g["dagger"]) < 5e-3
+    yy = st(x)  # forward = sensor(noise(A)) per member
+    assert isinstance(yy, dinv.physics.TensorList) and rel_err(yy[1], g["y1"]) < TOL
+
+
 def case_multicoil(name, dev):
     import deepinv_b200 as dinv
 

@@ -32,6 +32,10 @@ def test_downsampling(name, dev):
     P.case_downsampling(name, dev)
 
 
+def test_combine(dev):
+    P.case_combine(dev)
+
+
 def test_filters(dev):
     P.case_filters(dev)
 

@@ -47,6 +47,10 @@ def test_downsampling(name):
     P.case_downsampling(name, DEV)
 
 
+def test_combine():
+    P.case_combine(DEV)
+
+
 def test_filters():
     P.case_filters(DEV)
 
