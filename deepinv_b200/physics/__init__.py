@@ -1,4 +1,4 @@
-from . import functional  # noqa: F401
+from . import functional, generator  # noqa: F401
 from .blur import Blur, BlurFFT, Downsampling  # noqa: F401
 from .forward import DecomposablePhysics, LinearPhysics, Physics  # noqa: F401
 from .mri import MRI, DynamicMRI, MRIMixin, MultiCoilMRI, SequentialMRI, TimeMixin  # noqa: F401

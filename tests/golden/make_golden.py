@@ -138,6 +138,24 @@ def combine_fixtures():
          prox=st.prox_l2(zm, ys, 0.9), gamma=np.float32(0.9), dagger=st.A_dagger(ys))
 
 
+def maskgen_fixtures():
+    """§8(f) item 4: the LAW of the reference's mask generators (inclusion frequencies, equispaced pattern set)"""
+    from deepinv.physics.generator import EquispacedMaskGenerator, GaussianMaskGenerator
+
+    W, N = 64, 6000
+    out = {}
+    for tag, cls, acc in [("random4", RandomMaskGenerator, 4), ("gauss4", GaussianMaskGenerator, 4), ("gauss8", GaussianMaskGenerator, 8)]:
+        gen = cls((2, 8, W), acceleration=acc, rng=g(0))
+        m = gen.step(N)["mask"]
+        out[f"freq_{tag}"] = m[:, 0, 0].mean(0)
+        out[f"count_{tag}"] = m[:, 0, 0].sum(-1).unique()
+    out["n_rows"] = np.int64(N)
+    gen = EquispacedMaskGenerator((2, 6, 8, W), acceleration=4, rng=g(0))
+    pats = torch.unique(gen.step(200)["mask"][:, 0, :, 0], dim=0)  # (n_offsets, T, W)
+    out["equi_patterns"] = pats
+    save("maskgen_stats", **out)
+
+
 def multicoil_fixtures():
     B, N, H, W = 2, 3, 16, 20
     x = torch.randn(B, 2, H, W, generator=g(1))
@@ -391,11 +409,11 @@ def ddrm_fixture():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm", "optim2", "train", "dynamic", "down", "combine"]
+    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm", "optim2", "train", "dynamic", "down", "combine", "maskgen"]
     table = {"mri": mri_fixtures, "multicoil": multicoil_fixtures, "tomo": tomo_fixtures, "blur": blur_fixtures,
              "blurfft": blurfft_fixtures, "model": model_fixtures, "optim": optim_fixtures, "ddrm": ddrm_fixture,
              "optim2": optim2_fixtures, "train": train_fixtures,
              "dynamic": dynamic_fixtures, "down": down_fixtures,
-             "combine": combine_fixtures}
+             "combine": combine_fixtures, "maskgen": maskgen_fixtures}
     for w in which:
         table[w]()
