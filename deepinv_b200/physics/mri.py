@@ -1,7 +1,7 @@
 """MRI / MultiCoilMRI on the fused sm_100a spectral kernels.
 
-Drop-in for deepinv/physics/mri.py:11-695 (2-D and 2-D+t: MRI, MultiCoilMRI, DynamicMRI, SequentialMRI;
-`three_d=True` is out of scope).  Same constructor, buffers (`mask`, `coil_maps`), kwargs-store-as-buffer side
+Drop-in for deepinv/physics/mri.py:11-695 (2-D and 2-D+t: MRI, MultiCoilMRI, DynamicMRI, SequentialMRI; single-coil
+`three_d=True` runs the separable 3-D transform on the 2-D kernels — a correctness-level path; 3-D multi-coil is out of scope).  Same constructor, buffers (`mask`, `coil_maps`), kwargs-store-as-buffer side
 effects and error types.  Every method below is one or two launches of `dinvk_spectral`
 (csrc/spectral.cu); nothing is computed with torch.fft.
 """
@@ -40,15 +40,29 @@ class MRIMixin:
         return torch.view_as_real(x).moveaxis(-1, 1)
 
     # centred orthonormal 2-D DFT on planar (B,2,H,W) tensors (mixins.py:158-206)
+    @staticmethod
+    def _transform3(x: Tensor, inverse: bool) -> Tensor:
+        """centred orthonormal 3-D DFT of a planar (B,2,D,H,W) volume, separable on the 2-D kernels: the (H,W) transform with
+        the depth folded into the batch, then the depth transform as 1 x D "images" with depth made the fastest axis (two
+        permute copies around it).  Correctness-level path (the 2-D operators are the tuned ones)."""
+        B, _, D, H, W = x.shape
+        t = x.permute(0, 2, 1, 3, 4).reshape(B * D, 2, H, W)
+        t = ops.spectral(t, H, W, fwd=not inverse, inv=inverse)
+        t = t.reshape(B, D, 2, H, W).permute(0, 3, 4, 2, 1).reshape(B * H * W, 2, 1, D)
+        t = ops.spectral(t, 1, D, fwd=not inverse, inv=inverse)
+        return t.reshape(B, H, W, 2, D).permute(0, 3, 4, 1, 2)
+
     def im_to_kspace(self, x: Tensor, three_d: bool = False) -> Tensor:
-        _no_3d(three_d)
+        if three_d:
+            return linear_apply(x, lambda t: MRIMixin._transform3(t, False), lambda t: MRIMixin._transform3(t, True))
         H, W = x.shape[-2:]
         f = lambda t: ops.spectral(t, H, W, fwd=True, inv=False)
         g = lambda t: ops.spectral(t, H, W, fwd=False, inv=True)
         return linear_apply(x, f, g)
 
     def kspace_to_im(self, y: Tensor, three_d: bool = False) -> Tensor:
-        _no_3d(three_d)
+        if three_d:
+            return linear_apply(y, lambda t: MRIMixin._transform3(t, True), lambda t: MRIMixin._transform3(t, False))
         H, W = y.shape[-2:]
         f = lambda t: ops.spectral(t, H, W, fwd=True, inv=False)
         g = lambda t: ops.spectral(t, H, W, fwd=False, inv=True)
@@ -88,7 +102,7 @@ class MRIMixin:
 
 def _no_3d(three_d: bool) -> None:
     if three_d:
-        raise NotImplementedError("deepinv_b200: 3-D MRI is outside the accelerated path (SURVEY.md §8); use the reference")
+        raise NotImplementedError("deepinv_b200: 3-D multi-coil MRI is outside the accelerated path (SURVEY.md §8); use the reference")
 
 
 class _MaskCache:
@@ -112,12 +126,11 @@ class MRI(MRIMixin, DecomposablePhysics):
     def __init__(self, mask: Tensor | None = None, img_size: tuple | None = (320, 320), three_d: bool = False,
                  device="cpu", **kwargs):
         super().__init__(device=device, **kwargs)
-        _no_3d(three_d)
         self.three_d = three_d
         self.img_size = img_size
         if mask is None:
             mask = torch.ones(*img_size, device=device)
-        m = self.check_mask(mask)
+        m = self.check_mask(mask, three_d=three_d)
         self.register_buffer("mask", m if m.is_floating_point() else m.to(torch.float32))
         self.img_size = self.mask.shape[1:]
         self._mcache = _MaskCache()
@@ -164,11 +177,17 @@ class MRI(MRIMixin, DecomposablePhysics):
 
     def A(self, x: Tensor, mask: Tensor = None, **kwargs) -> Tensor:
         self.update_parameters(mask=mask, **kwargs)
+        if self.three_d:  # 3-D volumes: generic SVD bodies (forward.py:1080-1252) on the separable 3-D transform
+            return DecomposablePhysics.A(self, x)
         self._check(x)
         return linear_apply(x, self._A, self._At)
 
     def A_adjoint(self, y: Tensor, mask: Tensor = None, mag: bool = False, crop: bool = False, **kwargs) -> Tensor:
         self.update_parameters(mask=mask, **kwargs)
+        if self.three_d:
+            x = DecomposablePhysics.A_adjoint(self, y)
+            x = self.rss(x, multicoil=False) if mag else x
+            return self.crop(x, crop=crop) if crop else x
         self._check(y)
         x = linear_apply(y, self._At, self._A)
         if mag:
@@ -179,6 +198,8 @@ class MRI(MRIMixin, DecomposablePhysics):
 
     def A_adjoint_A(self, x: Tensor, mask: Tensor = None, **kwargs) -> Tensor:
         self.update_parameters(mask=mask, **kwargs)
+        if self.three_d:
+            return DecomposablePhysics.A_adjoint_A(self, x)
         self._check(x)
         H, W = self._hw()
         f = lambda t: ops.spectral(t, H, W, fwd=True, inv=True, gmode=_ffi.G_SQ, mask=self._spec())
@@ -186,6 +207,8 @@ class MRI(MRIMixin, DecomposablePhysics):
 
     def A_A_adjoint(self, y: Tensor, mask: Tensor = None, **kwargs) -> Tensor:
         self.update_parameters(mask=mask, **kwargs)
+        if self.three_d:
+            return DecomposablePhysics.A_A_adjoint(self, y)
         self._check(y)
         H, W = self._hw()
         f = lambda t: ops.spectral(t, H, W, fwd=False, inv=False, gmode=_ffi.G_SQ, mask=self._spec())
@@ -193,6 +216,8 @@ class MRI(MRIMixin, DecomposablePhysics):
 
     def A_dagger(self, y: Tensor, mask: Tensor = None, **kwargs) -> Tensor:
         self.update_parameters(mask=mask, **kwargs)
+        if self.three_d:
+            return DecomposablePhysics.A_dagger(self, y)
         self._check(y)
         if torch.is_grad_enabled() and y.requires_grad:
             return super().A_dagger(y)
@@ -210,7 +235,7 @@ class MRI(MRIMixin, DecomposablePhysics):
         r"""argmin_x gamma/2 ||Ax-y||^2 + 1/2 ||x-z||^2 = V((V^T(A^T y + z/gamma)) / (s^2 + 1/gamma)) (forward.py:1212-1234)"""
         needs_grad = torch.is_grad_enabled() and (z.requires_grad or y.requires_grad or
                                                   (isinstance(gamma, Tensor) and gamma.requires_grad))
-        if needs_grad:
+        if needs_grad or self.three_d:
             return super().prox_l2(z, y, gamma, **kwargs)
         self._check(z)
         H, W = self._hw()
@@ -229,6 +254,8 @@ class MRI(MRIMixin, DecomposablePhysics):
     def normal_step(self, x: Tensor, aty: Tensor, gamma: float) -> Tensor:
         r"""fused gradient step of the L2 data term: x - gamma * (A^T A x - A^T y)
         (optim_iterators/pgd.py:137-139 with data_fidelity.py:335-336) in one launch for line masks"""
+        if self.three_d:
+            return x - gamma * (DecomposablePhysics.A_adjoint_A(self, x) - aty)
         self._check(x)
         H, W = self._hw()
         return ops.spectral(x, H, W, fwd=True, inv=True, gmode=_ffi.G_SQ, mask=self._spec(),

@@ -56,6 +56,21 @@ def kspace_to_im(y):  # mixins.py:195-206
     return from_complex(cifft2(to_complex(y)))
 
 
+def cfft3(xc: torch.Tensor, inverse: bool = False) -> torch.Tensor:
+    """three_d=True: the same centred orthonormal transform over the last THREE dims (mixins.py:158-180, dim=(-3,-2,-1))"""
+    d = (-3, -2, -1)
+    f = torch.fft.ifftn if inverse else torch.fft.fftn
+    return torch.fft.fftshift(f(torch.fft.ifftshift(xc, dim=d), dim=d, norm="ortho"), dim=d)
+
+
+def im_to_kspace3(x):
+    return from_complex(cfft3(to_complex(x)))
+
+
+def kspace_to_im3(y):
+    return from_complex(cfft3(to_complex(y), inverse=True))
+
+
 def check_mask(mask: torch.Tensor) -> torch.Tensor:
     """to (B,2,H,W), duplicating a real mask on both planes (mixins.py:125-146)"""
     while mask.dim() < 4:

@@ -156,6 +156,17 @@ def maskgen_fixtures():
     save("maskgen_stats", **out)
 
 
+def mri3d_fixture():
+    B, D, H, W = 2, 6, 8, 12
+    x = torch.randn(B, 2, D, H, W, generator=g(41))
+    z = torch.randn(B, 2, D, H, W, generator=g(42))
+    mask = (torch.rand(B, 1, D, H, W, generator=g(43)) > 0.5).float()
+    phys = MRI(mask=mask, img_size=(2, D, H, W), three_d=True)
+    y = phys.A(x)
+    save("mri3d_6x8x12", x=x, mask_in=mask, mask=phys.mask, y=y, At=phys.A_adjoint(y), AtA=phys.A_adjoint_A(x), z=z,
+         prox=phys.prox_l2(z, y, 0.7), dagger=phys.A_dagger(y), Vt=phys.V_adjoint(x), gamma=np.float32(0.7))
+
+
 def multicoil_fixtures():
     B, N, H, W = 2, 3, 16, 20
     x = torch.randn(B, 2, H, W, generator=g(1))
@@ -409,11 +420,12 @@ def ddrm_fixture():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm", "optim2", "train", "dynamic", "down", "combine", "maskgen"]
+    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm", "optim2", "train", "dynamic", "down", "combine", "maskgen", "mri3d"]
     table = {"mri": mri_fixtures, "multicoil": multicoil_fixtures, "tomo": tomo_fixtures, "blur": blur_fixtures,
              "blurfft": blurfft_fixtures, "model": model_fixtures, "optim": optim_fixtures, "ddrm": ddrm_fixture,
              "optim2": optim2_fixtures, "train": train_fixtures,
              "dynamic": dynamic_fixtures, "down": down_fixtures,
-             "combine": combine_fixtures, "maskgen": maskgen_fixtures}
+             "combine": combine_fixtures, "maskgen": maskgen_fixtures,
+             "mri3d": mri3d_fixture}
     for w in which:
         table[w]()

@@ -147,6 +147,26 @@ def case_combine(dev):
     assert isinstance(yy, dinv.physics.TensorList) and rel_err(yy[1], g["y1"]) < TOL
 
 
+def case_mri_3d(dev):
+    """single-coil 3-D MRI (three_d=True): separable 3-D transform on the 2-D kernels vs the real reference"""
+    import deepinv_b200 as dinv
+
+    g = to_dev(load_golden("mri3d_6x8x12"), dev)
+    x, y = g["x"], g["y"]
+    phys = dinv.physics.MRI(mask=g["mask_in"], img_size=tuple(x.shape[1:]), three_d=True, device=dev)
+    assert torch.equal(phys.mask, g["mask"])
+    yk = phys.A(x)
+    assert rel_err(yk, y) < TOL and torch.equal(yk == 0, y == 0)
+    assert rel_err(phys.V_adjoint(x), g["Vt"]) < TOL
+    assert rel_err(phys.A_adjoint(y), g["At"]) < TOL
+    assert rel_err(phys.A_adjoint_A(x), g["AtA"]) < TOL
+    assert rel_err(phys.prox_l2(g["z"], y, float(g["gamma"])), g["prox"]) < TOL
+    assert rel_err(phys.A_dagger(y), g["dagger"]) < TOL
+    xr = x.clone().requires_grad_(True)
+    phys.A(xr).backward(y)
+    assert rel_err(xr.grad, g["At"]) < TOL
+
+
 def case_multicoil(name, dev):
     import deepinv_b200 as dinv
 

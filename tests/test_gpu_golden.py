@@ -36,6 +36,10 @@ def test_combine(dev):
     P.case_combine(dev)
 
 
+def test_mri_3d(dev):
+    P.case_mri_3d(dev)
+
+
 def test_filters(dev):
     P.case_filters(dev)
 

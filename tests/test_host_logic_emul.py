@@ -51,6 +51,10 @@ def test_combine():
     P.case_combine(DEV)
 
 
+def test_mri_3d():
+    P.case_mri_3d(DEV)
+
+
 def test_filters():
     P.case_filters(DEV)
 
