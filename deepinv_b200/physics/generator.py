@@ -149,3 +149,62 @@ class EquispacedMaskGenerator(BaseMaskGenerator):
         cols = cols[..., :W]
         cols[..., pad: pad + self.n_center] = 1
         return cols
+
+
+class PSFGenerator(PhysicsGenerator):
+    """base class of PSF generators (generator/blur.py:16-60): holds `psf_size`"""
+
+    def __init__(self, psf_size: tuple = (31, 31), num_channels: int = 1, **kwargs):
+        extra = {k: kwargs.pop(k) for k in list(kwargs) if k not in ("rng", "device", "dtype", "step")}
+        super().__init__(**kwargs)
+        self.psf_size = psf_size
+        self.num_channels = num_channels
+        for k, v in extra.items():
+            setattr(self, k, v)
+
+
+class MotionBlurGenerator(PSFGenerator):
+    r"""Random motion-blur PSFs (generator/blur.py:209-352, after Schuler et al. 2015): x(t), y(t) ~ GP(0, Matern-5/2-type
+    kernel k), sampled by circulant embedding (irfft(rfft(noise) * sqrt(rfft(k)))) and rasterised as a 2-D histogram of the
+    mean-free trajectory on [-1,1]^2, normalised to sum 1.  Same random draws as the reference (two `randn(B, n_steps)` from
+    the generator), so a CPU generator with the same seed gives the reference's PSFs exactly; the per-trajectory Python loop of
+    `histogramdd` calls is ONE batched `scatter_add` here, so a whole batch of PSFs is produced on the device in a few launches."""
+
+    def __init__(self, psf_size: tuple, rng: torch.Generator | None = None, device="cpu", dtype=torch.float32, l: float = 0.3,
+                 sigma: float = 0.25, n_steps: int = 1000):
+        if isinstance(psf_size, int):
+            psf_size = (psf_size, psf_size)
+        if len(psf_size) != 2:
+            raise ValueError("psf_size must 2D.")
+        super().__init__(psf_size=psf_size, device=device, dtype=dtype, rng=rng, l=l, sigma=sigma, n_steps=n_steps)
+
+    def matern_kernel(self, diff, sigma: float | None = None, l: float | None = None):
+        sigma = self.sigma if sigma is None else sigma
+        l = self.l if l is None else l
+        fraction = 5 ** 0.5 * diff.abs() / l
+        return sigma ** 2 * (1 + fraction + fraction ** 2 / 3) * torch.exp(-fraction)
+
+    def f_matern(self, batch_size: int = 1, sigma: float | None = None, l: float | None = None):
+        vec = torch.randn(batch_size, self.n_steps, generator=self.rng, **self.factory_kwargs)
+        time = torch.linspace(-torch.pi, torch.pi, self.n_steps, **self.factory_kwargs)[None]
+        kernel_fft = torch.fft.rfft(self.matern_kernel(time, sigma, l))
+        traj = torch.fft.irfft(torch.fft.rfft(vec) * torch.sqrt(kernel_fft)).real
+        keep = int(self.n_steps // (2 * torch.pi))
+        return traj[:, :keep]
+
+    def step(self, batch_size: int = 1, sigma: float | None = None, l: float | None = None, seed: int | None = None, **kwargs):
+        self.rng_manual_seed(seed)
+        fx = self.f_matern(batch_size, sigma, l)
+        fy = self.f_matern(batch_size, sigma, l)
+        pts = torch.stack([fx - fx.mean(1, keepdim=True), fy - fy.mean(1, keepdim=True)], dim=-1)  # (B, n, 2)
+        h, w = self.psf_size
+        bins = torch.tensor([h, w], device=pts.device)
+        inside = ((pts >= -1) & (pts <= 1)).all(-1)
+        idx = (bins * ((pts + 1) / 2)).long()
+        idx = torch.minimum(idx, bins - 1).clamp_min_(0)  # the last bin includes the upper bound
+        flat = idx[..., 0] * w + idx[..., 1]
+        hist = torch.zeros(batch_size, h * w, **self.factory_kwargs)
+        hist.scatter_add_(1, flat, inside.to(hist.dtype))
+        kernel = hist.reshape(batch_size, 1, h, w)
+        kernel = kernel / (kernel.sum(dim=(-2, -1), keepdim=True) + 1e-6)
+        return {"filter": kernel}

@@ -154,6 +154,10 @@ def maskgen_fixtures():
     pats = torch.unique(gen.step(200)["mask"][:, 0, :, 0], dim=0)  # (n_offsets, T, W)
     out["equi_patterns"] = pats
     save("maskgen_stats", **out)
+    from deepinv.physics.generator import MotionBlurGenerator
+
+    mb = MotionBlurGenerator((31, 31), rng=g(0))  # cfg5's PSF generator, seed 0
+    save("motionblur_psf", filt=mb.step(3)["filter"], filt_l=mb.step(2, sigma=0.4, l=0.5, seed=7)["filter"])
 
 
 def mri3d_fixture():

@@ -35,6 +35,21 @@ def _check(dev):
         RandomMaskGenerator((2, 32, 32), acceleration=4, center_fraction=0.5, device=dev)
 
 
+def test_motion_blur_generator_matches_reference_draws():
+    """same generator seed on CPU -> the reference's PSFs (tests/golden/motionblur_psf.npz, produced by the real reference)"""
+    from conftest import rel_err
+
+    from deepinv_b200.physics.generator import MotionBlurGenerator
+
+    g = load_golden("motionblur_psf")
+    mb = MotionBlurGenerator((31, 31), rng=torch.Generator().manual_seed(0))
+    f = mb.step(3)["filter"]
+    assert f.shape == (3, 1, 31, 31) and rel_err(f, g["filt"]) < 1e-6
+    f2 = mb.step(2, sigma=0.4, l=0.5, seed=7)["filter"]
+    assert rel_err(f2, g["filt_l"]) < 1e-6
+    assert torch.allclose(f.sum(dim=(-2, -1)), torch.ones(3, 1), atol=1e-5)
+
+
 def test_mask_generators_cpu():
     _check("cpu")
 
