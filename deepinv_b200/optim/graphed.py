@@ -57,6 +57,45 @@ class GraphedIteration:
         return self.x
 
 
+class GraphedSolve:
+    """A WHOLE reconstruction `algo(y, physics)` — every iteration, per-iteration schedules (DPIR's sigma / stepsize) baked
+    in as constants — captured once as one CUDA graph and replayed per measurement: `solve(y)` costs one copy of y into the
+    static input buffer plus one graph launch instead of max_iter x ~70 ctypes launches.  Requires a run without host
+    synchronisation: `early_stop=False`, no metrics, closed-form data steps (MRI / BlurFFT prox, fused gradient step); the
+    CG-based prox polls a device flag from the host and cannot be captured."""
+
+    def __init__(self, algo, y: torch.Tensor, physics, warmup: int = 1):
+        if getattr(algo, "early_stop", False):
+            raise ValueError("early_stop=True needs a host decision per iteration and cannot be captured")
+        self.algo, self.physics = algo, physics
+        self.y = y.clone()
+        dev = y.device
+        with torch.no_grad():
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    out = algo(self.y, physics)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            from .._lib import launch_count
+
+            n0 = launch_count()
+            self.out = torch.empty_like(out)
+            self.y.add_(0)  # bump the version: operators that memoise A^T y per (buffer, version) recompute it INSIDE the graph
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out.copy_(algo(self.y, physics))
+            self.launches = launch_count() - n0
+
+    def solve(self, y: torch.Tensor) -> torch.Tensor:
+        """reconstruction of `y` (same shape as the capture's); the returned tensor is the static output buffer"""
+        self.y.copy_(y)
+        self.graph.replay()
+        return self.out
+
+
 class HostStreamedIteration:
     """A stream of independent single-iteration requests whose inputs AND outputs live in pinned host memory.
 
