@@ -111,3 +111,33 @@ def test_library_loaded_is_in_tree(dev):
     n0 = dinv.launch_count()
     dinv.physics.MRI(img_size=(2, 8, 8), device=dev).A(torch.randn(1, 2, 8, 8, device=dev))
     assert dinv.launch_count() > n0
+
+
+def test_training_loop_reduces_loss(dev):
+    """end to end: a few Adam steps on an unfolded PGD model (trainable stepsizes + DRUNet weights) whose every forward
+    and backward op is a libdinvk launch; the supervised loss must go down"""
+    import deepinv_b200 as dinv
+    from deepinv_b200.optim import L2, PnP
+    from deepinv_b200.unfolded import unfolded_builder
+
+    torch.manual_seed(0)
+    B, H, W = 4, 32, 32
+    x = torch.randn(B, 2, H, W, device=dev) * 0.5
+    cols = (torch.rand(B, 1, 1, W) > 0.6).float().expand(B, 2, H, W).contiguous().to(dev)
+    phys = dinv.physics.MRI(mask=cols, img_size=(2, H, W), device=dev)
+    with torch.no_grad():
+        y = phys.A(x)
+    den = dinv.models.DRUNet(in_channels=2, out_channels=2, nc=(8, 16, 32, 64), nb=1, pretrained=None, device=dev).train()
+    model = unfolded_builder("PGD", params_algo={"stepsize": [1.0, 1.0, 1.0], "g_param": 0.05, "lambda": 1.0},
+                             trainable_params=["stepsize"], data_fidelity=L2(), prior=PnP(den), max_iter=3).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=2e-3)
+    n0 = dinv.launch_count()
+    losses = []
+    for _ in range(8):
+        opt.zero_grad(set_to_none=True)
+        loss = ((model(y, phys) - x) ** 2).mean()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert dinv.launch_count() - n0 > 8 * 3 * 20
+    assert all(torch.isfinite(torch.tensor(losses))) and losses[-1] < 0.9 * losses[0], losses
