@@ -61,26 +61,3 @@ def test_host_streamed_requests(dev):
             xd, yd = xs[k].to(dev), ys[k].to(dev)
             ref = algo.single_iteration({"est": (xd, xd), "aty": None}, 0, yd, physics)["est"][0]
             assert torch.equal(outs[k].to(dev), ref), f"request {k}"
-
-
-def test_graphed_solve_dpir(dev):
-    """a whole DPIR reconstruction (8 HQS iterations with their sigma / stepsize schedule) as ONE graph: replays on new
-    measurements reproduce the eager runs bit for bit"""
-    import deepinv_b200 as dinv
-    from deepinv_b200.optim import DPIR, GraphedSolve
-
-    torch.manual_seed(0)
-    B, H, W = 2, 64, 64
-    den = dinv.models.DRUNet(in_channels=2, out_channels=2, pretrained=None, precision="bf16").to(dev).eval()
-    cols = (torch.rand(B, 1, 1, W) > 0.7).float().expand(B, 2, H, W).contiguous()
-    physics = dinv.physics.MRI(mask=cols.to(dev), img_size=(2, H, W), device=dev)
-    algo = DPIR(sigma=0.05, denoiser=den, device=dev)
-    with torch.no_grad():
-        ys = [physics.A(torch.randn(B, 2, H, W, device=dev)) for _ in range(3)]
-        g = GraphedSolve(algo, ys[0], physics)
-        assert g.launches > 8 * 60
-        for y in ys[::-1]:
-            want = algo(y.clone(), physics)
-            got = g.solve(y)
-            torch.cuda.synchronize()
-            assert torch.equal(got, want)
