@@ -58,12 +58,14 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
-    cmd = [nvcc, *flags, "-I", str(ROOT / "include"), *_cutlass_include(), "-o", str(LIB), *map(str, sources())]
+    tmp = LIB.with_suffix(".so.tmp")  # link to a scratch name, then rename: a reader never sees a half-written library
+    cmd = [nvcc, *flags, "-I", str(ROOT / "include"), *_cutlass_include(), "-o", str(tmp), *map(str, sources())]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
         print(" ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True, cwd=str(ROOT))
+    os.replace(tmp, LIB)
     STAMP.write_text(dig)
     return LIB
 

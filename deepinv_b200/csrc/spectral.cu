@@ -309,8 +309,15 @@ static int get_tables(int n, int centered, Tables* out) {
 }
 
 
-#ifndef DINVK_EMUL
 static inline bool al16(const void* p);
+#ifdef DINVK_EMUL
+template <typename K, typename... Args>
+static void launch_pdl(K kern, unsigned grid, unsigned block, size_t smem, void* stream, const Args&... args) {
+  (void)stream;
+  count_launch();
+  ::emul::launch(dim3(grid), dim3(block), smem, [&]() { kern(args...); });
+}
+#else
 // launch with programmatic stream serialization (PDL): the kernel may begin its prologue while the previous kernel in the
 // stream drains; it executes griddepcontrol.wait before touching memory (see spectral_pipe.cuh)
 template <typename K, typename... Args>
@@ -324,6 +331,7 @@ static void launch_pdl(K kern, unsigned grid, unsigned block, size_t smem, void*
   cfg.attrs = at; cfg.numAttrs = 1;
   (void)cudaLaunchKernelEx(&cfg, kern, args...);
 }
+#endif
 // 256x256 single-coil fast path (spectral_pipe.cuh).  Returns -1 when the call does not qualify.
 static int try_pipe(const dinvk_spectral_args& a, float2* T1, const Tables& tW, void* stream) {
   if (a.H != 256 || a.W != 256 || a.ncoil > 1) return -1;
@@ -412,7 +420,6 @@ static int try_pipe320(const dinvk_spectral_args& a, float2* T1, float2* coil_ws
   }
   return DINVK_POST_LAUNCH();
 }
-#endif
 
 
 static int pow2floor(int x) { int p = 1; while (2 * p <= x) p *= 2; return p; }
@@ -617,19 +624,15 @@ extern "C" int dinvk_spectral(const dinvk_spectral_args* ap, void* workspace, si
     return launch_pass(false, P, ecfg, stream);
   }
 
-#ifndef DINVK_EMUL
   if (fast) {
     const int prc = try_pipe(a, T1, tW, stream);
     if (prc >= 0) return prc;
   }
-#endif
   if (fast) {
-#ifndef DINVK_EMUL
     if (a.fwd && !a.inv) {
       const int prc = try_pipe320(a, T1, nullptr, tW, stream);
       if (prc >= 0) return prc;
     }
-#endif
     if (a.fwd && !a.inv) {
       // A: COL(fwd) planar -> T1 ; ROW(fwd, multiplier) T1 -> out
       init_pass(P, a); set_source(P, a); P.dir1 = -1; P.tout = T1; set_axis(P, tH, pH);
@@ -638,12 +641,10 @@ extern "C" int dinvk_spectral(const dinvk_spectral_args* ap, void* workspace, si
       return launch_pass(false, P, rcfg, stream);
     }
     int prc320 = -1;
-#ifndef DINVK_EMUL
     if (!a.fwd && a.inv) {
       prc320 = try_pipe320(a, T1, coil_reduce ? T2 : nullptr, tW, stream);
       if (prc320 > 0) return prc320;
     }
-#endif
     if (!a.fwd && a.inv && prc320 == 0) {
       // done by the 320 x 320 two-pass kernels; a coil reduction (below) may follow
     } else if (!a.fwd && a.inv) {

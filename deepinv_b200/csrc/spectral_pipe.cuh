@@ -23,7 +23,6 @@
 //           sp_pass2       workspace -> H stage 2 -> multiplier / epilogue -> planar rows
 // Restricted to H = W = 256, single-coil planar (B,2,H,W) tensors; everything else takes the tile passes.
 #pragma once
-#ifndef DINVK_EMUL
 #include "fft_core.cuh"
 
 namespace dinvk {
@@ -55,6 +54,44 @@ struct PipeParams {
   int g_at_load;      // pass1 applies the multiplier to the source (A^T); pass2 applies it to the result (A)
 };
 
+#ifdef DINVK_EMUL
+// TEST-ONLY host model of the mbarrier / bulk-copy primitives (tests/emul): one 64-bit word per barrier holding
+// [phase:1 | init:15 | pending:16 | tx bytes:32]; a phase completes when every expected arrival has happened AND the expected
+// bytes have landed, exactly like the hardware object; the bulk copy is a synchronous memcpy followed by complete_tx.
+#define DINVK_SP_DYN_SMEM() unsigned char* sp_raw = reinterpret_cast<unsigned char*>(::emul::dyn_smem())
+namespace mbemul {
+inline uint64_t pack(uint64_t phase, uint64_t init, uint64_t pending, int32_t tx) {
+  return (phase << 63) | (init << 48) | (pending << 32) | (uint64_t)(uint32_t)tx;
+}
+inline void update(uint64_t* bar, int darrive, int32_t dtx) {
+  for (;;) {
+    uint64_t o = __atomic_load_n(bar, __ATOMIC_SEQ_CST);
+    uint64_t phase = o >> 63, init = (o >> 48) & 0x7fff, pending = (o >> 32) & 0xffff;
+    int32_t tx = (int32_t)(uint32_t)o;
+    pending -= (uint64_t)darrive;
+    tx += dtx;
+    if (pending == 0 && tx == 0) { phase ^= 1; pending = init; }
+    const uint64_t n = pack(phase, init, pending, tx);
+    if (__atomic_compare_exchange_n(bar, &o, n, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) return;
+  }
+}
+}  // namespace mbemul
+inline void mb_init(uint64_t* bar, uint32_t count) { __atomic_store_n(bar, mbemul::pack(0, count, count, 0), __ATOMIC_SEQ_CST); }
+inline void mb_expect_tx(uint64_t* bar, uint32_t bytes) { mbemul::update(bar, 1, (int32_t)bytes); }
+inline void mb_arrive(uint64_t* bar) { mbemul::update(bar, 1, 0); }
+inline void mb_wait(uint64_t* bar, uint32_t parity) {
+  while ((__atomic_load_n(bar, __ATOMIC_SEQ_CST) >> 63) == (uint64_t)(parity & 1)) std::this_thread::yield();
+}
+inline void griddep_wait() {}
+inline void griddep_launch() {}
+inline void fence_async_smem() {}
+inline void fence_mbar_init() {}
+inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  std::memcpy(dst, src, bytes);
+  mbemul::update(bar, 0, -(int32_t)bytes);
+}
+#else
+#define DINVK_SP_DYN_SMEM() extern __shared__ __align__(128) unsigned char sp_raw[]
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
@@ -86,6 +123,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(s_u32(bar))
                : "memory");
 }
+
+#endif  // DINVK_EMUL
 
 // multiplier transform applied to K raw mask values at once: the mode switch sits outside the element loop
 template <int K>
@@ -165,7 +204,7 @@ __device__ __forceinline__ void issue_rows(float* dst, const float* src_img, lon
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool HAS_P1, int OCC>
 __global__ void __launch_bounds__(NT, OCC) sp_row_fused(const PipeParams P) {
-  extern __shared__ __align__(128) unsigned char sp_raw[];
+  DINVK_SP_DYN_SMEM();
   const RowSmem S = carve_row(sp_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int line = tid >> 4, j = tid & 15;
@@ -297,7 +336,7 @@ __global__ void __launch_bounds__(NT, OCC) sp_row_fused(const PipeParams P) {
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool HAS_P1, int OCC>
 __global__ void __launch_bounds__(NT, OCC) sp_pass1(const PipeParams P) {
-  extern __shared__ __align__(128) unsigned char sp_raw[];
+  DINVK_SP_DYN_SMEM();
   const RowSmem S = carve_row(sp_raw);
   const int tid = threadIdx.x, lane = tid & 31;
   const int line = tid >> 4, j = tid & 15;
@@ -463,7 +502,7 @@ __device__ __forceinline__ void p2_finish(const PipeParams& P, float2 (&u)[16], 
 // 3-stage ring recycled through full / empty mbarriers (no CTA barrier in the loop).
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(P2_NT, 2) sp_pass2(const PipeParams P) {
-  extern __shared__ __align__(128) unsigned char sp_raw[];
+  DINVK_SP_DYN_SMEM();
   float* ring = reinterpret_cast<float*>(sp_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + P2_STAGES * P2_TILE_F);
   uint64_t* empty = full + P2_STAGES;
@@ -518,4 +557,3 @@ __global__ void __launch_bounds__(P2_NT, 2) sp_pass2(const PipeParams P) {
 
 }  // namespace sp
 }  // namespace dinvk
-#endif  // DINVK_EMUL

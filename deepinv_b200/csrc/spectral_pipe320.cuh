@@ -15,7 +15,6 @@
 // pass-1 load, the per-coil k-space goes straight to the (batch, 2, ncoil, H, W) output, the adjoint's pass 2 writes the
 // interleaved per-coil images that coil_combine_kernel reduces.
 #pragma once
-#ifndef DINVK_EMUL
 #include "spectral_pipe.cuh"
 
 namespace dinvk {
@@ -77,7 +76,7 @@ __device__ __forceinline__ void issue_rows(float* dst, const Params& P, int img,
 
 template <bool HAS_P1>
 __global__ void __launch_bounds__(NT, 2) sp320_pass1(const Params P) {
-  extern __shared__ __align__(128) unsigned char sp_raw[];
+  DINVK_SP_DYN_SMEM();
   float* in0 = reinterpret_cast<float*>(sp_raw);
   float2* tws = reinterpret_cast<float2*>(in0 + 2 * STAGE_F);  // [r < 20][j < 16]: sign(r) w320^(r j)
   float2* twf = tws + 320;                                     // w320^k
@@ -219,7 +218,7 @@ __global__ void __launch_bounds__(NT, 2) sp320_pass1(const Params P) {
 }
 
 __global__ void __launch_bounds__(NT, 2) sp320_pass2(const Params P) {
-  extern __shared__ __align__(128) unsigned char sp_raw[];
+  DINVK_SP_DYN_SMEM();
   float* ring = reinterpret_cast<float*>(sp_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + P2_STAGES * P2_TILE_F);
   uint64_t* empty = full + P2_STAGES;
@@ -315,4 +314,3 @@ __global__ void __launch_bounds__(NT, 2) sp320_pass2(const Params P) {
 
 }  // namespace sp320
 }  // namespace dinvk
-#endif  // DINVK_EMUL

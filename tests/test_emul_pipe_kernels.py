@@ -1,0 +1,87 @@
+"""The benchmark-size spectral kernels — the persistent, bulk-copy-pipelined 256x256 (cfg2) and 320x320 (cfg4) kernels of
+csrc/spectral_pipe*.cuh — executed on the host: tests/emul models the mbarrier / cp.async.bulk primitives (a phase completes
+when all expected arrivals AND bytes are in), so tile schedule, ring indexing, barrier parities, butterflies, twiddles and
+epilogues of the very kernels bench.py times are checked against the oracle in the GPU-less container.  (The same cases run
+on the device in tests/test_gpu_spectral_pipe.py.)"""
+import pytest
+import torch
+
+from conftest import rel_err
+
+
+@pytest.fixture(autouse=True)
+def emul_backend(monkeypatch):
+    from emul_util import emul_lib
+
+    from deepinv_b200 import ops
+
+    lib = emul_lib()
+
+    def check(rc):
+        assert rc == 0, lib.dinvk_last_error()
+
+    monkeypatch.setattr(ops, "_require_cuda", lambda *ts: torch.device("cpu"))
+    monkeypatch.setattr(ops, "_stream", lambda dev: None)
+    monkeypatch.setattr(ops, "get_lib", lambda: lib)
+    monkeypatch.setattr(ops, "check", check)
+    ops._ws_cache.clear()
+    yield lib
+    ops._ws_cache.clear()
+
+
+def _masks(kind, B, H, W, gen):
+    if kind == "lines":
+        return (torch.rand(B, 1, 1, W, generator=gen) > 0.75).float().expand(B, 2, H, W).contiguous()
+    if kind == "shared":
+        return (torch.rand(1, 1, H, W, generator=gen) > 0.5).float().expand(1, 2, H, W).contiguous()
+    return (torch.rand(B, 2, H, W, generator=gen) > 0.5).float()
+
+
+@pytest.mark.parametrize("kind", ["lines", "full"])
+def test_pipe256_operators(kind, emul_backend, monkeypatch):
+    import deepinv_b200 as dinv
+    from oracle import ref_ops as R
+
+    gen = torch.Generator().manual_seed(7)
+    B, H, W = 3, 256, 256  # 48 tiles: several tiles per "CTA" ring in the emulated persistent grid
+    x = torch.randn(B, 2, H, W, generator=gen)
+    z = torch.randn(B, 2, H, W, generator=gen)
+    mask = _masks(kind, B, H, W, gen)
+    p = dinv.physics.MRI(mask=mask, img_size=(2, H, W))
+    n0 = emul_backend.dinvk_launch_count()
+    y = p.A(x)
+    assert emul_backend.dinvk_launch_count() - n0 == 2  # pass 1 + pass 2 of the pipelined path (tile passes: also 2)
+    ref_y = R.mri_A(x, mask)
+    assert rel_err(y, ref_y) < 1e-6 and torch.equal(y == 0, ref_y == 0)
+    aty = R.mri_At(ref_y, mask)
+    assert rel_err(p.A_adjoint(ref_y), aty) < 1e-6
+    if kind != "lines":  # fused passes with h-dependent masks take the general tile passes (tests/test_emul_kernels.py)
+        return
+    assert rel_err(p.A_adjoint_A(x), R.mri_AtA(x, mask)) < 1e-6
+    assert rel_err(p.normal_step(x, aty, 0.8), x - 0.8 * (R.mri_AtA(x, mask) - aty)) < 1e-6
+    assert rel_err(p.prox_l2(z, ref_y, 0.7), R.mri_prox_l2(z, ref_y, mask, 0.7)) < 1e-6
+    assert rel_err(p.V_adjoint(x), R.im_to_kspace(x)) < 1e-6 and rel_err(p.V(x), R.kspace_to_im(x)) < 1e-6
+    # the pipelined kernels against the general tile passes on the same operands
+    got = p.A_adjoint(ref_y)
+    monkeypatch.setenv("DINVK_NO_PIPE_FFT", "1")
+    assert rel_err(got, p.A_adjoint(ref_y)) < 5e-7
+
+
+def test_pipe320_single_and_multicoil(emul_backend):
+    import deepinv_b200 as dinv
+    from oracle import ref_ops as R
+
+    gen = torch.Generator().manual_seed(9)
+    B, N, H, W = 2, 3, 320, 320
+    x = torch.randn(B, 2, H, W, generator=gen)
+    mask = _masks("lines", B, H, W, gen)
+    p = dinv.physics.MRI(mask=mask, img_size=(2, H, W))
+    y = R.mri_A(x, mask)
+    assert rel_err(p.A(x), y) < 1e-6 and rel_err(p.A_adjoint(y), R.mri_At(y, mask)) < 1e-6
+    maps = torch.randn(B, N, H, W, generator=gen, dtype=torch.complex64)
+    maps = maps / maps.abs().pow(2).sum(1, keepdim=True).sqrt()
+    pm = dinv.physics.MultiCoilMRI(mask=mask, coil_maps=maps, img_size=(2, H, W))
+    ym = R.mcmri_A(x, mask, maps)
+    assert rel_err(pm.A(x), ym) < 1e-6
+    assert rel_err(pm.A_adjoint(ym), R.mcmri_At(ym, mask, maps)) < 1e-6
+    assert rel_err(pm.A_adjoint(ym, rss=True), R.mcmri_At(ym, mask, maps, use_rss=True)) < 1e-6
