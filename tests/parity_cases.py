@@ -283,7 +283,7 @@ def case_dncnn(dev):
         assert rel_err(den(g["x"], 0.1), g["out"]) < TOL
 
 
-def case_pnp_mri(dev):
+def case_pnp_mri(dev, full=True):
     import deepinv_b200 as dinv
     from deepinv_b200.optim import ADMM, FISTA, HQS, L2, PGD, PnP
 
@@ -293,10 +293,11 @@ def case_pnp_mri(dev):
     y = g["y"]
     kw = dict(data_fidelity=L2(), prior=PnP(den), early_stop=False)
     assert rel_err(PGD(stepsize=1.0, sigma_denoiser=0.05, max_iter=4, **kw)(y, phys), g["pgd"]) < TOL
-    relax = PGD(max_iter=3, params_algo={"stepsize": 0.8, "g_param": 0.05, "lambda": 1.0, "beta": 0.9}, **kw)
-    assert rel_err(relax(y, phys), g["pgd_relax"]) < TOL
-    assert rel_err(HQS(stepsize=1.0, sigma_denoiser=0.05, max_iter=3, **kw)(y, phys), g["hqs"]) < TOL
     assert rel_err(ADMM(stepsize=1.0, sigma_denoiser=0.05, max_iter=3, **kw)(y, phys), g["admm"]) < TOL
+    if full:  # (the slow host emulation runs PGD / ADMM / FISTA / metrics; every algorithm runs on the GPU)
+        relax = PGD(max_iter=3, params_algo={"stepsize": 0.8, "g_param": 0.05, "lambda": 1.0, "beta": 0.9}, **kw)
+        assert rel_err(relax(y, phys), g["pgd_relax"]) < TOL
+        assert rel_err(HQS(stepsize=1.0, sigma_denoiser=0.05, max_iter=3, **kw)(y, phys), g["hqs"]) < TOL
     assert rel_err(FISTA(stepsize=1.0, sigma_denoiser=0.05, max_iter=3, **kw)(y, phys), g["fista"]) < TOL
     x, m = PGD(stepsize=1.0, sigma_denoiser=0.05, max_iter=2, **kw)(y, phys, compute_metrics=True, x_gt=g["x"])
     assert len(m["residual"]) == y.shape[0] and len(m["residual"][0]) == 2 and len(m["psnr"][0]) == 3

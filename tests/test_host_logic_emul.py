@@ -97,7 +97,7 @@ def test_dncnn():
 
 
 def test_pnp_mri():
-    P.case_pnp_mri(DEV)
+    P.case_pnp_mri(DEV, full=False)
 
 
 def test_drs_gd_dpir():
