@@ -17,7 +17,7 @@ import torch
 from torch import Tensor
 
 from .. import _ffi, ops
-from .forward import DecomposablePhysics, LinearPhysics, linear_apply
+from .forward import DecomposablePhysics, LinearPhysics, TensorKey, cache_hit, linear_apply
 
 
 def _padding_code(padding: str) -> int:
@@ -141,8 +141,7 @@ class BlurFFT(DecomposablePhysics):
     # ---- device-side multipliers derived from (mask, angle) -------------------------------------------
     def _mult(self):
         m, a = self.mask, self.angle
-        key = (m.data_ptr(), m._version, a.data_ptr(), a._version)
-        if key != self._spec_key:
+        if not cache_hit(self._spec_key, m, a):
             H, W = self.img_size[-2:]
             half = m[..., 0] * a                       # h^ on the half spectrum (1, C, H, W/2+1)
             C = half.shape[1]
@@ -159,7 +158,7 @@ class BlurFFT(DecomposablePhysics):
             self._hdag = ops.MaskSpec(torch.view_as_real(torch.conj(ang) * pinv).contiguous(), H * W if not same else 0, 0, W, True)
             self._habs = ops.MaskSpec(mag.contiguous(), H * W if not same else 0, 0, W, False)
             self._same = same
-            self._spec_key = key
+            self._spec_key = TensorKey(m, a)
         return self._h, self._hdag, self._habs, self._same
 
     # ---- packing of real images into complex ones --------------------------------------------------------
@@ -391,11 +390,10 @@ class Downsampling(LinearPhysics):
     def _spectrum(self, C, H, W):
         """F h (un-normalised 2-D DFT of the zero-padded, centre-rolled filter): (1|B, C, H, W) complex"""
         f = self.filter
-        key = (f.data_ptr(), f._version, C, H, W)
-        if key != self._fh_key:
+        if not cache_hit(self._fh_key, f, extra=(C, H, W)):
             ff = f if f.shape[1] == C else f.expand(f.shape[0], C, *f.shape[-2:])
             self._Fh = BlurFFT._full_spectrum(ff, (C, H, W))
-            self._fh_key = key
+            self._fh_key = TensorKey(f, extra=(C, H, W))
         return self._Fh
 
     def prox_l2(self, z: Tensor, y: Tensor, gamma, use_fft: bool = True, **kwargs) -> Tensor:

@@ -44,6 +44,28 @@ def linear_apply(x: torch.Tensor, op: Callable, adj: Callable) -> torch.Tensor:
     return op(x)
 
 
+class TensorKey:
+    """Identity + version of the tensors a derived quantity (compressed mask, spectrum, trig table, memoised A^T y) was
+    computed from.  It holds STRONG references to them: a key made of `(data_ptr(), _version)` alone collides when a tensor
+    is freed and the caching allocator hands its address to the next tensor of the same shape (e.g. `algo(y.clone(), physics)`
+    in a loop) — the stale entry would then be served for new data."""
+
+    __slots__ = ("refs", "vers", "extra")
+
+    def __init__(self, *tensors, extra=()):
+        self.refs = tensors
+        self.vers = tuple(t._version for t in tensors)
+        self.extra = extra
+
+    def matches(self, *tensors, extra=()) -> bool:
+        return (len(tensors) == len(self.refs) and all(a is b for a, b in zip(tensors, self.refs))
+                and self.vers == tuple(t._version for t in tensors) and self.extra == extra)
+
+
+def cache_hit(key, *tensors, extra=()) -> bool:
+    return key is not None and key.matches(*tensors, extra=extra)
+
+
 class Physics(nn.Module):
     r"""y = N(A(x))  (forward.py:19-351)"""
 

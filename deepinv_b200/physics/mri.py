@@ -14,7 +14,7 @@ import torch
 from torch import Tensor
 
 from .. import _ffi, ops
-from .forward import DecomposablePhysics, LinearPhysics, linear_apply
+from .forward import DecomposablePhysics, LinearPhysics, TensorKey, cache_hit, linear_apply
 
 
 class MRIMixin:
@@ -113,10 +113,9 @@ class _MaskCache:
         self.spec = None
 
     def get(self, mask: Tensor, H: int, W: int) -> ops.MaskSpec:
-        key = (mask.data_ptr(), mask._version, tuple(mask.shape), mask.device)
-        if key != self.key:
+        if not cache_hit(self.key, mask):
             self.spec = ops.mask_spec_from_real(mask, H, W)
-            self.key = key
+            self.key = TensorKey(mask)
         return self.spec
 
 
@@ -225,10 +224,9 @@ class MRI(MRIMixin, DecomposablePhysics):
 
     def _cached_At(self, y: Tensor) -> Tensor:
         """A^T y for a constant y (the reference recomputes it every iteration, data_fidelity.py:335-336)"""
-        key = (y.data_ptr(), y._version, tuple(y.shape), self.mask.data_ptr(), self.mask._version)
-        if key != self._aty_key:
+        if not cache_hit(self._aty_key, y, self.mask):
             self._aty = self._At(y)
-            self._aty_key = key
+            self._aty_key = TensorKey(y, self.mask)
         return self._aty
 
     def prox_l2(self, z: Tensor, y: Tensor, gamma, **kwargs) -> Tensor:
@@ -324,12 +322,10 @@ class DynamicMRI(MRI, TimeMixin):
     def _static(self, batch: int) -> MRI:
         """the static operator on the time-folded batch (rebuilt when the mask buffer or the batch size changes)"""
         m = self.mask
-        key = (m.data_ptr(), m._version, tuple(m.shape), m.device, batch)
-        if key != self._flat_key:
-            T = m.shape[2]
+        if not cache_hit(self._flat_key, m, extra=(batch,)):
             mb = m if (m.shape[0] == batch or batch == 1) else m.expand(batch, *m.shape[1:])
             self._flat = MRI(mask=self.flatten(mb).contiguous(), img_size=(2, *m.shape[-2:]), device=m.device)
-            self._flat_key = key
+            self._flat_key = TensorKey(m, extra=(batch,))
         return self._flat
 
     def _check(self, t: Tensor):

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from .. import ops
-from .forward import LinearPhysics, linear_apply
+from .forward import LinearPhysics, TensorKey, cache_hit, linear_apply
 
 
 def _deg2rad(theta: torch.Tensor) -> torch.Tensor:
@@ -71,11 +71,10 @@ class Tomography(LinearPhysics):
     # ---- geometry tables -------------------------------------------------------------------------------
     def _trig(self):
         a = self.angles
-        key = (a.data_ptr(), a._version, a.device)
-        if key != self._trig_key:
+        if not cache_hit(self._trig_key, a):
             th = _deg2rad(a.to(torch.float32))
             self._cos, self._sin = th.cos().contiguous(), th.sin().contiguous()
-            self._trig_key = key
+            self._trig_key = TensorKey(a)
         return self._cos, self._sin
 
     def _norm(self) -> float:

@@ -232,3 +232,27 @@ def test_least_squares_implicit_backward(batched_gamma):
     wy, wz, wg = torch.autograd.grad((h * r.double()).sum(), [y64, z64, g64])
     assert rel_err(out, h) < 1e-5
     assert rel_err(gy, wy) < 2e-4 and rel_err(gz, wz) < 2e-4 and rel_err(gg, wg) < 2e-4
+
+
+def test_memoised_adjoint_is_not_served_for_a_new_tensor_at_the_same_address():
+    """regression: prox_l2 memoises A^T y per measurement tensor; a freed y whose address is handed to the next y (same
+    shape, version 0) must not hit the stale entry — the cache key holds the tensor itself, not its pointer"""
+    from conftest import load_golden, rel_err
+    from oracle import ref_ops as R
+
+    import deepinv_b200 as dinv
+
+    g = load_golden("optim2_mri_tiny")
+    m = g["mask"]
+    phys = dinv.physics.MRI(mask=m, img_size=(2, 32, 32), device=DEV)
+    z = torch.randn(2, 2, 32, 32)
+    seen = set()
+    for k in range(6):
+        y = R.mri_A(torch.randn(2, 2, 32, 32), m).clone()  # freed at the end of the iteration: the allocator reuses the block
+        seen.add(y.data_ptr())
+        assert rel_err(phys.prox_l2(z, y, 0.7), R.mri_prox_l2(z, y, m, 0.7)) < 1e-5
+        del y
+    y = R.mri_A(torch.randn(2, 2, 32, 32), m)
+    a = phys.prox_l2(z, y, 0.7)
+    y.mul_(2.0)  # in-place change of the SAME tensor: version bump -> recomputed
+    assert rel_err(phys.prox_l2(z, y, 0.7), R.mri_prox_l2(z, y, m, 0.7)) < 1e-5 and rel_err(a, phys.prox_l2(z, y, 0.7)) > 1e-2
