@@ -220,8 +220,8 @@ __global__ void __launch_bounds__(256) conv2x2_f32_kernel(const float* __restric
 // A CTA owns one 8-row band of one image, 32 output channels and 8 input channels; it walks the
 // band tile by tile with the forward kernel's staging (input halo tile + the matching 8x32x32
 // block of g, channel-fastest so that a thread reads its 4 output channels as one float4).  Thread
-// = (4 output channels, 1 input channel, 2 of the 8 rows): 36 accumulators, a sliding 3x3 input
-// window (3 new shared loads per pixel) -> 36 FMAs per 4 shared loads.  The 4 row groups are
+// = (4 output channels, 1 input channel, 2 of the 8 rows): 36 accumulators; 4 columns per step from a
+// 3x6 register patch (float4 + float2 per row) and four float4 of g -> 144 FMAs per 10 shared loads.  The 4 row groups are
 // summed through shared memory and leave as one atomicAdd per weight per CTA; the bias gradient
 // (sum of g) rides along in the CTAs of input-channel chunk 0.
 constexpr int WG_CI = 8;   // input channels per CTA
@@ -243,7 +243,8 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_f32_kernel(const float* __r
   const float* xb = x + (long long)b * Cin * HW;
   const float* ab = xadd ? xadd + (long long)b * Cin * HW : nullptr;
   const float* gb = g + (long long)b * Cout * HW;
-  const bool do_bias = dbias != nullptr && c0 == 0 && ci == 0;
+  const bool cta_bias = dbias != nullptr && c0 == 0;  // CTA-uniform: the bias gradient rides in the chunk-0 CTAs only
+  const bool do_bias = cta_bias && ci == 0;
 
   float acc[4][9];
 #pragma unroll
@@ -280,28 +281,29 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_f32_kernel(const float* __r
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
       const int r = rg * 2 + rr;
-      float win[3][3];
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        win[ky][1] = s_in[ci][r + ky][0];
-        win[ky][2] = s_in[ci][r + ky][1];
-      }
-      for (int col = 0; col < C3_TW; ++col) {
+      // 4 output columns at a time: the 3 x 6 input patch they need comes in as one float4 + one float2 per row (compile-time
+      // indexed from then on: no window shifting), the 4 x 4 block of g as four float4 -> 10 shared loads per 144 FMAs
+#pragma unroll 2
+      for (int c4 = 0; c4 < C3_TW; c4 += 4) {
+        float in[3][6];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-          win[ky][0] = win[ky][1];
-          win[ky][1] = win[ky][2];
-          win[ky][2] = s_in[ci][r + ky][col + 2];
+          const float4 i0 = *reinterpret_cast<const float4*>(&s_in[ci][r + ky][c4]);
+          const float2 i1 = *reinterpret_cast<const float2*>(&s_in[ci][r + ky][c4 + 4]);
+          in[ky][0] = i0.x; in[ky][1] = i0.y; in[ky][2] = i0.z; in[ky][3] = i0.w; in[ky][4] = i1.x; in[ky][5] = i1.y;
         }
-        const float4 g4 = *reinterpret_cast<const float4*>(&s_g[(r * C3_TW + col) * WG_CO + cg * 4]);
-        const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          bsum[q] += gv[q];
+        for (int p = 0; p < 4; ++p) {
+          const float4 g4 = *reinterpret_cast<const float4*>(&s_g[(r * C3_TW + c4 + p) * WG_CO + cg * 4]);
+          const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
+          for (int q = 0; q < 4; ++q) {
+            if (cta_bias) bsum[q] += gv[q];
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) acc[q][ky * 3 + kx] = fmaf(gv[q], win[ky][kx], acc[q][ky * 3 + kx]);
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) acc[q][ky * 3 + kx] = fmaf(gv[q], in[ky][p + kx], acc[q][ky * 3 + kx]);
+          }
         }
       }
     }
