@@ -66,7 +66,11 @@ def cartesian_mask(batch: int, h: int, w: int, accel: int, seed: int) -> torch.T
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """`nvidia-smi -lms 20` running from before the warm-up; every sample carries the driver's timestamp, so the samples that
+    fall INSIDE a host-side window (the timed region, or — when that is shorter than a few sampler periods — a replay of the
+    same workload right after it) can be picked out afterwards."""
+
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
@@ -76,12 +80,21 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                        "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
-    def stop(self) -> dict:
+    @staticmethod
+    def now():
+        import datetime
+
+        return datetime.datetime.now()
+
+    def stop(self, windows) -> dict:
+        """windows: list of (label, t_begin, t_end) in preference order; the first one holding >= 3 samples is reported"""
+        import datetime
+
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -90,18 +103,33 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.p.kill()
         self.f.flush()
-        rows = [r.split(",") for r in Path(self.f.name).read_text().strip().splitlines() if r.count(",") >= 8]
+        rows = []
+        for r in Path(self.f.name).read_text().strip().splitlines():
+            c = [v.strip() for v in r.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                rows.append((datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f"), c))
+            except ValueError:
+                continue
         os.unlink(self.f.name)
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(float(r[1]) for r in rows)
+        pick, label = rows, "whole run (no sample inside the windows)"
+        for lab, t0, t1 in windows:
+            inside = [rc for rc in rows if t0 <= rc[0] <= t1]
+            if len(inside) >= 3:
+                pick, label = inside, lab
+                break
+        cols = [c for _, c in pick]
+        sm = sorted(float(c[1]) for c in cols)
         reasons = set()
-        for r in rows:
+        for c in cols:
             for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
-                if r[col].strip().lower().startswith("active"):
+                if c[col].lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "power_w_max": max(float(r[3]) for r in rows),
-                "samples": len(rows), "reasons": sorted(reasons)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(cols[0][2]), "power_w_max": max(float(c[3]) for c in cols),
+                "samples": len(cols), "window": label, "reasons": sorted(reasons)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -257,6 +285,9 @@ def run_b200(args):
         return algo.single_iteration(X, it, y, physics)
 
     graphed = None
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()  # from before the warm-up: the sampler needs ~100 ms to deliver its first line
     with torch.no_grad():
         X = algo.init_iterate_fn(y, physics)
         for it in range(args.warmup):
@@ -273,12 +304,10 @@ def run_b200(args):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        clocks = ClockSampler(local)
-        if rank == 0:
-            clocks.start()
         launches0 = lib.dinvk_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
+        t_w0 = ClockSampler.now()
         e0.record()
         if graphed is not None:
             x_hat = graphed.run(args.steps)
@@ -291,11 +320,26 @@ def run_b200(args):
             dist.all_gather_into_tensor(gathered, x_hat.contiguous())
         e1.record()
         torch.cuda.synchronize()
+        t_w1 = ClockSampler.now()
         ms_total = e0.elapsed_time(e1)
         launches = lib.dinvk_launch_count() - launches0
         if graphed is not None:
             launches = graphed.launches_per_step * args.steps
-        clk = clocks.stop() if rank == 0 else None
+        windows = [("timed region", t_w0, t_w1)]
+        if rank == 0 and ms_total < 400.0:
+            # the timed region is shorter than a handful of sampler periods: replay the SAME workload (untimed) for ~1 s
+            # right away, back to back with the timed region, and read the clocks / throttle reasons from that window
+            n_probe = max(1, int(1000.0 / max(ms_total / args.steps, 1e-3)))
+            t_p0 = ClockSampler.now()
+            if graphed is not None:
+                graphed.run(n_probe)
+            else:
+                Xp = X
+                for it in range(n_probe):
+                    Xp = iteration(Xp, it)
+            torch.cuda.synchronize()
+            windows.append(("same workload replayed (untimed) for ~1 s right after the timed region", t_p0, ClockSampler.now()))
+        clk = clocks.stop(windows) if rank == 0 else None
         if world > 1:
             t = torch.tensor([ms_total], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
