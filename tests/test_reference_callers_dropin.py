@@ -51,21 +51,25 @@ def emul_backend(monkeypatch):
 
 
 def test_reference_pgd_and_hqs_drive_dropin_mri_and_denoiser():
-    """reference BaseOptim / L2.grad / L2.prox / PnP.prox -> deepinv_b200 MRI.A, A_adjoint, A_adjoint_A, prox_l2, DRUNet
-    (HQS with a closed-form toy denoiser to keep the emulated run short)"""
+    """reference BaseOptim / L2.grad / L2.prox / PnP.prox -> deepinv_b200 MRI.A, A_adjoint, A_adjoint_A, prox_l2, DRUNet; the
+    yardstick is the same reference algorithm on the reference's own MRI and DRUNet (same weights).  Two PGD iterations with the
+    real denoiser, HQS with a closed-form toy denoiser: keeps the emulated run short."""
     import deepinv_b200 as dinv
 
     g = load_golden("optim_mri_tiny")
     den = P.load_model(dinv.models.DRUNet, g, DEV, in_channels=2, out_channels=2, nc=(8, 16, 32, 64), nb=2)
+    refden = ref.models.DRUNet(in_channels=2, out_channels=2, nc=(8, 16, 32, 64), nb=2, pretrained=None).eval()
+    refden.load_state_dict(g["sd"], strict=True)
     phys = dinv.physics.MRI(mask=g["mask"], img_size=(2, 32, 32), device=DEV)
-    kw = dict(data_fidelity=ref.optim.L2(), prior=ref.optim.PnP(den), early_stop=False)
+    refphys = ref.physics.MRI(mask=g["mask"], img_size=(2, 32, 32))
+    pgd = lambda d: ref.optim.PGD(data_fidelity=ref.optim.L2(), prior=ref.optim.PnP(d), stepsize=1.0, sigma_denoiser=0.05,
+                                  max_iter=2, early_stop=False)
+    toy = lambda v, s: v * (1.0 - float(s))
+    hqs = lambda: ref.optim.HQS(data_fidelity=ref.optim.L2(), prior=ref.optim.PnP(toy), stepsize=0.8, sigma_denoiser=0.05,
+                                max_iter=3, early_stop=False)
     with torch.no_grad():
-        assert rel_err(ref.optim.PGD(stepsize=1.0, sigma_denoiser=0.05, max_iter=4, **kw)(g["y"], phys), g["pgd"]) < 1e-5
-        toy = lambda v, s: v * (1.0 - float(s))
-        refphys = ref.physics.MRI(mask=g["mask"], img_size=(2, 32, 32))
-        mk = lambda: ref.optim.HQS(data_fidelity=ref.optim.L2(), prior=ref.optim.PnP(toy), stepsize=0.8, sigma_denoiser=0.05,
-                                   max_iter=3, early_stop=False)
-        assert rel_err(mk()(g["y"], phys), mk()(g["y"], refphys)) < 1e-5
+        assert rel_err(pgd(den)(g["y"], phys), pgd(refden)(g["y"], refphys)) < 1e-5
+        assert rel_err(hqs()(g["y"], phys), hqs()(g["y"], refphys)) < 1e-5
 
 
 def test_reference_least_squares_solver_drives_dropin_blur():
@@ -81,21 +85,25 @@ def test_reference_least_squares_solver_drives_dropin_blur():
 
 
 def test_reference_ddrm_drives_dropin_mri():
-    """reference DDRM (sampling/diffusion.py:149-224) -> deepinv_b200 MRI.U_adjoint / V / V_adjoint / mask + DRUNet"""
+    """reference DDRM (sampling/diffusion.py:149-224) -> deepinv_b200 MRI.U_adjoint / V / V_adjoint / mask; same sampler on the
+    reference's MRI as yardstick, recorded noise draws, closed-form toy denoiser"""
     import deepinv_b200 as dinv
 
     g = load_golden("ddrm_mri_tiny")
-    den = P.load_model(dinv.models.DRUNet, g, DEV, in_channels=2, out_channels=2, nc=(8, 16, 32, 64), nb=2)
-    phys = dinv.physics.MRI(mask=g["mask"], img_size=(2, 32, 32), device=DEV,
-                            noise_model=dinv.physics.GaussianNoise(sigma=float(g["sigma_noise"])))
-    it = iter(list(g["noises"]))
-    orig = torch.randn_like
-    torch.randn_like = lambda t, **kw: next(it).to(t)
-    try:
-        out = ref.sampling.DDRM(denoiser=den, sigmas=g["sigmas"].numpy())(g["y"], phys)
-    finally:
-        torch.randn_like = orig
-    assert rel_err(out, g["out"]) < 1e-5
+    toy = lambda v, s: v * (1.0 / (1.0 + float(s)))
+    sig = float(g["sigma_noise"])
+    phys = dinv.physics.MRI(mask=g["mask"], img_size=(2, 32, 32), device=DEV, noise_model=dinv.physics.GaussianNoise(sigma=sig))
+    refphys = ref.physics.MRI(mask=g["mask"], img_size=(2, 32, 32), noise_model=ref.physics.GaussianNoise(sigma=sig))
+    outs = []
+    for ph in (phys, refphys):
+        it = iter(list(g["noises"]))
+        orig = torch.randn_like
+        torch.randn_like = lambda t, **kw: next(it).to(t)
+        try:
+            outs.append(ref.sampling.DDRM(denoiser=toy, sigmas=g["sigmas"].numpy())(g["y"], ph))
+        finally:
+            torch.randn_like = orig
+    assert rel_err(outs[0], outs[1]) < 1e-5
 
 
 def test_reference_trainer_trains_dropin_unfolded_model():
