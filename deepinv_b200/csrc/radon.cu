@@ -344,6 +344,68 @@ static int launch_tiled(bool adj, const float* x_img, const float* sino_in, floa
 }
 #endif  // DINVK_EMUL
 
+
+// ---- fan-beam projector and its exact transpose (physics/functional/radon.py:16-52 + 252-309 with fan_beam=True) ----
+// The reference samples the padded image on a grid that is, for angle t, the rotation of the points
+//   (x_i, y_j * d_i),  x_i = linspace(-1,1,G)[i],  y_j = linspace(-1,1,D)[j],  d_i = (half_len * (x_i + src)) / den
+// (a fan of straight rays: the detector coordinate scales linearly with the distance from the source) and sums over i.
+// One thread per ray (bc, t, j) walks its G samples; the forward gathers into a register, the transpose scatters
+// y[t,j] * w with the forward's fp32 weights (global fp32 atomics into the zeroed image).
+struct FanGeom {
+  int W, G, D, A, pb, circle;
+  float step_g, step_d, half_len, src, den;
+};
+
+template <bool ADJ>
+__global__ void __launch_bounds__(128) fanbeam_kernel(const float* __restrict__ src, float* __restrict__ dst, FanGeom F,
+                                                      const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                                                      float scale) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y, bc = blockIdx.z;
+  if (j >= F.D) return;
+  const float c = __ldg(cos_t + t), s = __ldg(sin_t + t);
+  const float gm1 = (float)(F.G - 1);
+  const float yj = lin_at(j, F.D, F.step_d);
+  RadonGeom R;
+  R.W = F.W; R.P = F.G; R.A = F.A; R.pb = F.pb; R.circle = F.circle; R.step = F.step_g;
+  const long long WW = (long long)F.W * F.W;
+  const float* img = ADJ ? nullptr : src + (long long)bc * WW;
+  float* oimg = ADJ ? dst + (long long)bc * WW : nullptr;
+  const float yv = ADJ ? __ldg(src + ((long long)bc * F.A + t) * F.D + j) * scale : 0.f;
+  float acc = 0.f;
+  for (int i = 0; i < F.G; ++i) {
+    const float xi = lin_at(i, F.G, F.step_g);
+    const float d = (F.half_len * (xi + F.src)) / F.den;
+    const float y = yj * d;
+    const float gx = fmaf(y, s, xi * c);
+    const float gy = fmaf(y, c, -(xi * s));
+    const float px = ((gx + 1.0f) * 0.5f) * gm1, py = ((gy + 1.0f) * 0.5f) * gm1;
+    const float fx = floorf(px), fy = floorf(py);
+    if (!(fx >= (float)(F.pb - 1) && fx < (float)(F.pb + F.W) && fy >= (float)(F.pb - 1) && fy < (float)(F.pb + F.W))) continue;
+    const int X0 = (int)fx, Y0 = (int)fy;
+    const float wx1 = px - fx, wy1 = py - fy, wx0 = (fx + 1.0f) - px, wy0 = (fy + 1.0f) - py;
+    if (!ADJ) {
+      const float v00 = img_at(img, R, X0, Y0), v01 = img_at(img, R, X0 + 1, Y0);
+      const float v10 = img_at(img, R, X0, Y0 + 1), v11 = img_at(img, R, X0 + 1, Y0 + 1);
+      acc += v00 * (wx0 * wy0) + v01 * (wx1 * wy0) + v10 * (wx0 * wy1) + v11 * (wx1 * wy1);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int X = X0 + (k & 1), Y = Y0 + (k >> 1);
+        const int x = X - F.pb, yy = Y - F.pb;
+        if (x < 0 || x >= F.W || yy < 0 || yy >= F.W) continue;
+        if (F.circle) {
+          const float ax = 2.0f * (float)x / (float)(F.W - 1) - 1.0f, ay = 2.0f * (float)yy / (float)(F.W - 1) - 1.0f;
+          if (!(ax * ax + ay * ay <= 1.0f)) continue;
+        }
+        const float w = ((k & 1) ? wx1 : wx0) * ((k >> 1) ? wy1 : wy0);
+        atomicAdd(oimg + (long long)yy * F.W + x, yv * w);
+      }
+    }
+  }
+  if (!ADJ) dst[((long long)bc * F.A + t) * F.D + j] = acc * scale;
+}
+
 static int make_geom(RadonGeom* G, int W, int P, int A, int circle) {
   if (W < 1 || P < W || A < 1) return set_error(DINVK_EINVAL, "radon: bad geometry W=%d P=%d A=%d", W, P, A);
   if (circle && P != W) return set_error(DINVK_EINVAL, "radon: circle=1 requires P == W");
@@ -404,5 +466,28 @@ extern "C" int dinvk_iradon_bp(const float* sino, float* x, int BC, int W, int P
   DINVK_CHECK_ARG(BC <= 65535 && A <= 4096, "dinvk_iradon_bp: grid too large");
   DINVK_LAUNCH(iradon_bp_kernel, dim3(ceil_div((long long)W * W, 256), BC), dim3(256), 2 * A * sizeof(float), stream, sino, x, G,
                cos_t, sin_t, scale);
+  return DINVK_POST_LAUNCH();
+}
+
+extern "C" int dinvk_fanbeam(const float* in, float* out, int BC, int W, int G, int D, int A, int circle, const float* cos_t,
+                             const float* sin_t, float half_len, float src, float den, float scale, int adjoint, void* stream) {
+  DINVK_CHECK_ARG(in && out && cos_t && sin_t && BC >= 0, "dinvk_fanbeam: bad arguments");
+  DINVK_CHECK_ARG(W >= 1 && G >= W && D >= 1 && A >= 1, "dinvk_fanbeam: bad geometry W=%d G=%d D=%d A=%d", W, G, D, A);
+  DINVK_CHECK_ARG(!circle || G == W, "dinvk_fanbeam: circle=1 requires G == W");
+  DINVK_CHECK_ARG(A <= 65535 && BC <= 65535, "dinvk_fanbeam: grid too large");
+  if (BC == 0) return DINVK_OK;
+  FanGeom F;
+  F.W = W; F.G = G; F.D = D; F.A = A; F.circle = circle ? 1 : 0;
+  F.pb = circle ? 0 : (G / 2 - W / 2);
+  F.step_g = G > 1 ? 2.0f / (float)(G - 1) : 0.f;
+  F.step_d = D > 1 ? 2.0f / (float)(D - 1) : 0.f;
+  F.half_len = half_len; F.src = src; F.den = den;
+  if (adjoint) {
+    if (cudaMemsetAsync(out, 0, (size_t)BC * W * W * sizeof(float), (cudaStream_t)stream) != cudaSuccess)
+      return set_error(DINVK_ECUDA, "dinvk_fanbeam: memset failed");
+    DINVK_LAUNCH(fanbeam_kernel<true>, dim3(ceil_div(D, 128), A, BC), dim3(128), 0, stream, in, out, F, cos_t, sin_t, scale);
+  } else {
+    DINVK_LAUNCH(fanbeam_kernel<false>, dim3(ceil_div(D, 128), A, BC), dim3(128), 0, stream, in, out, F, cos_t, sin_t, scale);
+  }
   return DINVK_POST_LAUNCH();
 }

@@ -328,6 +328,19 @@ def radon_adj(sino_am, W: int, cos_t, sin_t, circle: bool, scale: float, iradon:
     return x
 
 
+def fanbeam(t, W: int, G: int, D: int, cos_t, sin_t, circle: bool, half_len: float, src: float, den: float, scale: float,
+            adjoint: bool) -> torch.Tensor:
+    """fan-beam projector: image (B,C,W,W) -> angle-major sinogram (B,C,A,D), or its exact transpose"""
+    dev = _require_cuda(t, cos_t, sin_t)
+    t = _f32c(t)
+    B, C = t.shape[:2]
+    A = cos_t.numel()
+    out = torch.empty((B, C, W, W) if adjoint else (B, C, A, D), dtype=torch.float32, device=dev)
+    check(get_lib().dinvk_fanbeam(_p(t), _p(out), B * C, W, G, D, A, int(circle), _p(cos_t), _p(sin_t), half_len, src, den,
+                                  scale, int(adjoint), _stream(dev)))
+    return out
+
+
 def ramp_filter(sino_am) -> torch.Tensor:
     """ramp-filter every detector row of an angle-major sinogram (B, C, A, P)"""
     dev = _require_cuda(sino_am)

@@ -31,8 +31,6 @@ class Tomography(LinearPhysics):
                  fan_beam: bool = False, fan_parameters: dict = None, device="cpu", dtype: torch.dtype = torch.float,
                  **kwargs):
         super().__init__(device=device, **kwargs)
-        if fan_beam:
-            raise NotImplementedError("deepinv_b200: fan-beam geometry is outside the accelerated path (SURVEY.md §8)")
         if dtype != torch.float:
             raise NotImplementedError("deepinv_b200.Tomography computes in float32")
         if isinstance(angles, int):
@@ -42,7 +40,17 @@ class Tomography(LinearPhysics):
         elif not isinstance(angles, torch.Tensor):
             raise ValueError(f"angles must be int, float, iterable or Tensor, but got {type(angles)}")
         self.register_buffer("angles", angles)
-        self.fan_beam = False
+        self.fan_beam = bool(fan_beam)
+        self.fan_parameters = None
+        if self.fan_beam:
+            # defaults of radon.py:224-240; the grid is built on the padded image of size G = W (circle) or ceil(sqrt(2) W)
+            fp = dict(fan_parameters or {})
+            fp.setdefault("pixel_spacing", 0.5 / img_width)
+            fp.setdefault("source_radius", 57.5)
+            fp.setdefault("detector_radius", 57.5)
+            fp.setdefault("n_detector_pixels", 258)
+            fp.setdefault("detector_spacing", 0.077)
+            self.fan_parameters = fp
         self.adjoint_via_backprop = adjoint_via_backprop
         if circle and fbp_interpolate_boundary:
             warn("The argument fbp_interpolate_boundary=True is not applicable if circle=True. The value "
@@ -54,6 +62,13 @@ class Tomography(LinearPhysics):
         self.dtype = dtype
         # P = ceil(sqrt(2) W) in float32 (radon.py:60-61, 319)
         self.P = img_width if circle else int(((2 * torch.ones(1)).sqrt() * img_width).ceil())
+        self.G = self.P  # grid size of the padded image
+        if self.fan_beam:
+            fp = self.fan_parameters
+            self.P = int(fp["n_detector_pixels"])  # detector cells of a sinogram row
+            sf = 2.0 / (self.G * fp["pixel_spacing"])  # radon.py:23-28, python floats like the reference
+            src, det, spacing = fp["source_radius"] * sf, fp["detector_radius"] * sf, fp["detector_spacing"] * sf
+            self._fan = (0.5 * (spacing * (self.P - 1)), src, src + det)
         self._trig_key = None
         if normalize is None:
             warn("The default value of `normalize` is not specified and will be automatically set to `True`. Set "
@@ -89,10 +104,14 @@ class Tomography(LinearPhysics):
     # ---- raw kernels (angle-major sinograms) ---------------------------------------------------------------
     def _fwd_am(self, x, scale):
         c, s = self._trig()
+        if self.fan_beam:
+            return ops.fanbeam(x, self.img_width, self.G, self.P, c, s, self.circle, *self._fan, scale, adjoint=False)
         return ops.radon_fwd(x, self.P, c, s, self.circle, scale)
 
     def _adj_am(self, y_am, scale, iradon=False):
         c, s = self._trig()
+        if self.fan_beam:  # always the exact transpose (tomography.py:322-342: fan_beam forces the autograd adjoint)
+            return ops.fanbeam(y_am, self.img_width, self.G, self.P, c, s, self.circle, *self._fan, scale, adjoint=True)
         return ops.radon_adj(y_am, self.img_width, c, s, self.circle, scale, iradon=iradon)
 
     @staticmethod
@@ -105,7 +124,7 @@ class Tomography(LinearPhysics):
 
     def _At(self, y):
         n = self._norm()
-        if self.adjoint_via_backprop:
+        if self.adjoint_via_backprop or self.fan_beam:
             return self._adj_am(self._to_am(y), 1.0 / n)
         # ApplyRadon adjoint = iradon(y, filtering=False) / pi * 2A (radon.py:512-514), iradon itself carries pi/(2A)
         return self._adj_am(self._to_am(y), 1.0 / n, iradon=True)
@@ -126,7 +145,7 @@ class Tomography(LinearPhysics):
         A = self.angles.numel()
         yf = ops.ramp_filter(self._to_am(y))
         n = self._norm()
-        if self.adjoint_via_backprop:
+        if self.adjoint_via_backprop or self.fan_beam:
             # A_adjoint(filter(y)) * pi/(2A) * norm^2  with A_adjoint = R^T / norm
             out = self._adj_am(yf, (math.pi / (2 * A)) * n)
         else:

@@ -179,6 +179,16 @@ int dinvk_radon_adj(const float* sino, float* x, int BC, int W, int P, int A, in
 int dinvk_iradon_bp(const float* sino, float* x, int BC, int W, int P, int A, int circle,
                     const float* cos_t, const float* sin_t, float scale, void* stream);
 
+/* fan-beam projector (adjoint = 0: image (BC,W,W) -> sinogram (BC,A,D)) and its exact transpose (adjoint = 1), replacing
+ * grid_sample over fan_beam_grid + sum (deepinv/physics/functional/radon.py:16-52, 252-309 with fan_beam=True) and its
+ * autograd transpose (tomography.py:322-342).  G = grid size (W if circle else ceil(sqrt(2) W)), D = detector pixels;
+ * the sample of ray j at step i is R_t(x_i, y_j * ((half_len * (x_i + src)) / den)) with x = linspace(-1,1,G),
+ * y = linspace(-1,1,D); half_len, src, den are the reference's scaled fp32 constants (0.5 * detector_length,
+ * source_radius, source_radius + detector_radius).  The transpose accumulates with fp32 atomics. */
+int dinvk_fanbeam(const float* in, float* out, int BC, int W, int G, int D, int A, int circle,
+                  const float* cos_t, const float* sin_t, float half_len, float src, float den, float scale,
+                  int adjoint, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Blur (deepinv/physics/functional/convolution.py:42-164 conv2d / conv_transpose2d)
  * ------------------------------------------------------------------------------------------

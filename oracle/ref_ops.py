@@ -235,6 +235,56 @@ def radon_forward(x: torch.Tensor, angles_deg: torch.Tensor, circle: bool = Fals
     return out.reshape(B, C, P, len(angles_deg))
 
 
+def fan_parameters_default(W: int, fan_parameters=None) -> dict:
+    """radon.py:224-240"""
+    fp = dict(fan_parameters or {})
+    fp.setdefault("pixel_spacing", 0.5 / W)
+    fp.setdefault("source_radius", 57.5)
+    fp.setdefault("detector_radius", 57.5)
+    fp.setdefault("n_detector_pixels", 258)
+    fp.setdefault("detector_spacing", 0.077)
+    return fp
+
+
+def fanbeam_forward(x: torch.Tensor, angles_deg: torch.Tensor, circle: bool = False, fan_parameters=None) -> torch.Tensor:
+    """(B,C,W,W) -> (B,C,D,A): Radon.forward with fan_beam=True — the sampling grid of fan_beam_grid (radon.py:16-52): the
+    points (x_i, y_j * d_i), d_i = 0.5 L (x_i + r_s) / (r_s + r_d) in units scaled by 2 / (G * pixel_spacing), rotated by theta;
+    bilinear samples (align_corners=True, zeros) summed over i.  Differentiable: its vjp is the reference's adjoint."""
+    B, C, W, _ = x.shape
+    G, pb = radon_geometry(W, circle)
+    fp = fan_parameters_default(W, fan_parameters)
+    dt = x.dtype
+    if circle:
+        ax = 2 * torch.arange(W, dtype=torch.float32) / (W - 1) - 1.0
+        xp = x * ((ax[None, :] ** 2 + ax[:, None] ** 2) <= 1).to(dt)
+    else:
+        xp = F.pad(x, (pb, G - W - pb, pb, G - W - pb))
+    img = xp.reshape(B * C, G, G)
+    D = int(fp["n_detector_pixels"])
+    sf = 2.0 / (G * fp["pixel_spacing"])
+    rs, rd, sp = fp["source_radius"] * sf, fp["detector_radius"] * sf, fp["detector_spacing"] * sf
+    L = sp * (D - 1)
+    xi = torch.linspace(-1, 1, G, dtype=dt)[None, :].expand(D, G)   # along the ray (grid width)
+    yj = torch.linspace(-1, 1, D, dtype=dt)[:, None].expand(D, G)   # detector coordinate (grid height)
+    yy = yj * (0.5 * L * (xi + rs) / (rs + rd))
+    outs = []
+    for th in angles_deg:
+        th = deg2rad(th.to(dt).reshape(1))
+        c, s = th.cos(), th.sin()
+        px = ((c * xi + s * yy) + 1) / 2 * (G - 1)
+        py = ((-s * xi + c * yy) + 1) / 2 * (G - 1)
+        outs.append(_bilinear_zeros(img, px, py).sum(2))  # sum over the ray samples i -> (BC, D)
+    return torch.stack(outs, dim=-1).reshape(B, C, D, len(angles_deg))
+
+
+def fanbeam_adjoint(y: torch.Tensor, angles_deg: torch.Tensor, W: int, circle: bool = False, fan_parameters=None) -> torch.Tensor:
+    """the autograd transpose the reference uses for fan-beam (tomography.py:322-342)"""
+    x0 = torch.zeros(y.shape[0], y.shape[1], W, W, dtype=y.dtype, requires_grad=True)
+    with torch.enable_grad():
+        out = fanbeam_forward(x0, angles_deg, circle, fan_parameters)
+    return torch.autograd.grad(out, x0, y)[0]
+
+
 def radon_adjoint(y: torch.Tensor, angles_deg: torch.Tensor, W: int, circle: bool = False) -> torch.Tensor:
     """exact transpose of radon_forward (the autograd adjoint of Tomography, tomography.py:322-342):
     every sample scatters sino[b,c,j,theta]*w into its bilinear neighbours, then crop (pad^T)."""

@@ -208,6 +208,18 @@ def tomo_fixtures():
          fbp=phys.A_dagger(y, fbp=True), dagger=phys.A_dagger(y))
 
 
+def fanbeam_fixtures():
+    """§8(f) item 3: fan-beam Tomography (functional/radon.py:16-52; tomography.py fan_beam=True)"""
+    for tag, W, circle, fp in [("fan_24_default", 24, False, None),
+                               ("fan_20_circle_custom", 20, True, {"n_detector_pixels": 37, "detector_spacing": 0.31,
+                                                                   "source_radius": 40.0, "detector_radius": 25.0})]:
+        x = torch.randn(2, 1, W, W, generator=g(51))
+        phys = Tomography(angles=9, img_width=W, circle=circle, fan_beam=True, fan_parameters=fp, normalize=False)
+        y = phys.A(x)
+        v = torch.randn(*y.shape, generator=g(52))
+        save(tag, x=x, angles=phys.angles, y=y.contiguous(), v=v, At=phys.A_adjoint(v), fbp=phys.A_dagger(y, fbp=True))
+
+
 def blur_fixtures():
     B, C, H, W = 2, 2, 17, 19
     x = torch.rand(B, C, H, W, generator=g(8))
@@ -424,12 +436,12 @@ def ddrm_fixture():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm", "optim2", "train", "dynamic", "down", "combine", "maskgen", "mri3d"]
+    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm", "optim2", "train", "dynamic", "down", "combine", "maskgen", "mri3d", "fan"]
     table = {"mri": mri_fixtures, "multicoil": multicoil_fixtures, "tomo": tomo_fixtures, "blur": blur_fixtures,
              "blurfft": blurfft_fixtures, "model": model_fixtures, "optim": optim_fixtures, "ddrm": ddrm_fixture,
              "optim2": optim2_fixtures, "train": train_fixtures,
              "dynamic": dynamic_fixtures, "down": down_fixtures,
              "combine": combine_fixtures, "maskgen": maskgen_fixtures,
-             "mri3d": mri3d_fixture}
+             "mri3d": mri3d_fixture, "fan": fanbeam_fixtures}
     for w in which:
         table[w]()

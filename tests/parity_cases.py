@@ -202,6 +202,25 @@ def case_tomography(name, dev):
     assert abs(float(lhs - rhs)) < 1e-4 * max(1.0, abs(float(lhs)))  # exact transpose (reference asserts 1e-3)
 
 
+def case_fanbeam(name, dev):
+    """fan-beam Tomography: forward, exact transpose, FBP vs the real reference"""
+    import deepinv_b200 as dinv
+
+    g = to_dev(load_golden(name), dev)
+    W = g["x"].shape[-1]
+    fp = None if "default" in name else {"n_detector_pixels": 37, "detector_spacing": 0.31, "source_radius": 40.0,
+                                         "detector_radius": 25.0}
+    phys = dinv.physics.Tomography(angles=g["angles"], img_width=W, circle="circle" in name, fan_beam=True, fan_parameters=fp,
+                                   normalize=False, device=dev)
+    y = phys.A(g["x"])
+    assert y.shape == g["y"].shape and rel_err(y, g["y"]) < TOL
+    assert rel_err(phys.A_adjoint(g["v"]), g["At"]) < TOL
+    assert rel_err(phys.A_dagger(g["y"], fbp=True), g["fbp"]) < TOL
+    u = torch.randn_like(g["x"])
+    lhs, rhs = (phys.A(u) * g["v"]).sum().double(), (u * phys.A_adjoint(g["v"])).sum().double()
+    assert abs(float(lhs - rhs)) < 1e-4 * max(1.0, abs(float(lhs)))
+
+
 def case_tomography_normalised(dev):
     import deepinv_b200 as dinv
 

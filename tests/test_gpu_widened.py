@@ -23,6 +23,11 @@ def test_dynamic_mri(name, dev):
     P.case_dynamic_mri(name, dev)
 
 
+@pytest.mark.parametrize("name", golden_names("fan_"))
+def test_fanbeam(name, dev):
+    P.case_fanbeam(name, dev)
+
+
 @pytest.mark.parametrize("name", golden_names("down_"))
 def test_downsampling(name, dev):
     P.case_downsampling(name, dev)

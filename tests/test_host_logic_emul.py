@@ -42,6 +42,11 @@ def test_dynamic_mri(name):
     P.case_dynamic_mri(name, DEV)
 
 
+@pytest.mark.parametrize("name", golden_names("fan_"))
+def test_fanbeam(name):
+    P.case_fanbeam(name, DEV)
+
+
 @pytest.mark.parametrize("name", golden_names("down_"))
 def test_downsampling(name):
     P.case_downsampling(name, DEV)
