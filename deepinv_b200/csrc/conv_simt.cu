@@ -19,13 +19,14 @@ constexpr int C3_TH = 8;     // tile rows
 constexpr int C3_TW = 32;    // tile cols
 constexpr int C3_TC = 32;    // output channels per CTA
 constexpr int C3_ROWP = 36;  // padded smem row (34 used)
+constexpr int C3_WS = 36;    // padded weight row in shared memory (32 used): keeps float4 alignment, spreads the staging stores
 
 __global__ void __launch_bounds__(256) conv3x3_f32_kernel(const float* __restrict__ x, const float* __restrict__ xadd,
                                                           const float* __restrict__ w, const float* __restrict__ bias,
                                                           const float* __restrict__ res, float* __restrict__ out,
                                                           int Cin, int Cout, int H, int W, int tiles_x, int act) {
   __shared__ __align__(16) float s_in[C3_CC][C3_TH + 2][C3_ROWP];
-  __shared__ __align__(16) float s_w[C3_CC][9][C3_TC];
+  __shared__ __align__(16) float s_w[C3_CC * 9][C3_WS];
   const int tid = threadIdx.x;
   const int tx = tid & 7, ty = (tid >> 3) & 7, tz = tid >> 6;
   const int ty0 = (blockIdx.x / tiles_x) * C3_TH, tx0 = (blockIdx.x % tiles_x) * C3_TW;
@@ -56,14 +57,14 @@ __global__ void __launch_bounds__(256) conv3x3_f32_kernel(const float* __restric
       }
       s_in[c][r][col] = v;
     }
-    // stage weights: w[(co, ci, ky, kx)]
+    // stage weights w[(co, ci, ky, kx)] as s_w[(ci, tap)][co] (rows padded to C3_WS = 36 floats).  A warp covers 8 consecutive
+    // (ci, tap) entries x 4 output channels: 32-byte global segments, and shared banks 4*(ci,tap) + co -> all 32 distinct
     for (int idx = tid; idx < C3_CC * 9 * C3_TC; idx += 256) {
-      const int co = idx / (C3_CC * 9);
-      const int rem = idx - co * (C3_CC * 9);
-      const int c = rem / 9, k = rem - c * 9;
+      const int blk = idx >> 5;
+      const int ck = (blk % 9) * 8 + (idx & 7), co = (blk / 9) * 4 + ((idx >> 3) & 3);
       float v = 0.f;
-      if (c0 + c < Cin && co0 + co < Cout) v = __ldg(w + ((long long)(co0 + co) * Cin + (c0 + c)) * 9 + k);
-      s_w[c][k][co] = v;
+      if (c0 + ck / 9 < Cin && co0 + co < Cout) v = __ldg(w + ((long long)(co0 + co) * Cin + c0) * 9 + ck);
+      s_w[ck][co] = v;
     }
     __syncthreads();
 #pragma unroll
@@ -75,8 +76,8 @@ __global__ void __launch_bounds__(256) conv3x3_f32_kernel(const float* __restric
         const float in6[6] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y};
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const float4 w0 = *reinterpret_cast<const float4*>(&s_w[c][ky * 3 + kx][tz * 8]);
-          const float4 w1 = *reinterpret_cast<const float4*>(&s_w[c][ky * 3 + kx][tz * 8 + 4]);
+          const float4 w0 = *reinterpret_cast<const float4*>(&s_w[c * 9 + ky * 3 + kx][tz * 8]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&s_w[c * 9 + ky * 3 + kx][tz * 8 + 4]);
           const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
           for (int p = 0; p < 4; ++p)
@@ -226,13 +227,14 @@ __global__ void __launch_bounds__(256) conv2x2_f32_kernel(const float* __restric
 // (sum of g) rides along in the CTAs of input-channel chunk 0.
 constexpr int WG_CI = 8;   // input channels per CTA
 constexpr int WG_CO = 32;  // output channels per CTA
+constexpr int WG_GS = 36;  // shared row of the g tile (32 channels + 4 pad)
 
 __global__ void __launch_bounds__(256) conv3x3_wgrad_f32_kernel(const float* __restrict__ x, const float* __restrict__ xadd,
                                                                 const float* __restrict__ g, float* __restrict__ dw,
                                                                 float* __restrict__ dbias, int Cin, int Cout, int H, int W,
                                                                 int tiles_x, int nci) {
   __shared__ __align__(16) float s_in[WG_CI][C3_TH + 2][C3_ROWP];
-  __shared__ __align__(16) float s_g[C3_TH * C3_TW * WG_CO];  // [row][col][co]; reused for the final reduction
+  __shared__ __align__(16) float s_g[C3_TH * C3_TW * WG_GS];  // [row][col][co (+4 pad)]; reused for the final reduction
   const int tid = threadIdx.x;
   const int lane64 = tid & 63, rg = tid >> 6;
   const int cg = lane64 & 7, ci = lane64 >> 3;
@@ -268,14 +270,17 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_f32_kernel(const float* __r
       }
       s_in[c][r][col] = v;
     }
+    // g tile, channel-fastest with rows of WG_GS = 36 floats.  A warp covers 8 consecutive pixels x 4 channels: 32-byte global
+    // segments, shared banks 4*pixel + channel -> all 32 distinct (a plain [pixel][32] layout filled pixel-fastest is a 32-way
+    // bank conflict on every store: measured 2x the kernel's whole compute-phase shared traffic)
     for (int idx = tid; idx < WG_CO * C3_TH * C3_TW; idx += 256) {
-      const int co = idx / (C3_TH * C3_TW);
-      const int rem = idx - co * (C3_TH * C3_TW);
-      const int r = rem / C3_TW, col = rem - r * C3_TW;
+      const int blk = idx >> 5;
+      const int pix = (blk & 31) * 8 + (idx & 7), co = (blk >> 5) * 4 + ((idx >> 3) & 3);
+      const int r = pix / C3_TW, col = pix - r * C3_TW;
       const int gy = ty0 + r, gx = tx0 + col;
       float v = 0.f;
       if (co0 + co < Cout && gy < H && gx < W) v = __ldg(gb + (long long)(co0 + co) * HW + (long long)gy * W + gx);
-      s_g[(r * C3_TW + col) * WG_CO + co] = v;
+      s_g[pix * WG_GS + co] = v;
     }
     __syncthreads();
 #pragma unroll
@@ -294,7 +299,7 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_f32_kernel(const float* __r
         }
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-          const float4 g4 = *reinterpret_cast<const float4*>(&s_g[(r * C3_TW + c4 + p) * WG_CO + cg * 4]);
+          const float4 g4 = *reinterpret_cast<const float4*>(&s_g[(r * C3_TW + c4 + p) * WG_GS + cg * 4]);
           const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -311,7 +316,7 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_f32_kernel(const float* __r
   }
 
   // sum the 4 row groups: groups 2,3 -> smem -> groups 0,1 ; group 1 -> smem -> group 0
-  float* red = s_g;  // 2 * 64 * 40 floats <= 8192
+  float* red = s_g;  // 2 * 64 * 40 floats <= 9216
 #pragma unroll
   for (int round = 0; round < 2; ++round) {
     const int half = round == 0 ? 2 : 1;
