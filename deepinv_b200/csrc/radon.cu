@@ -189,7 +189,6 @@ __global__ void __launch_bounds__(256) iradon_bp_kernel(const float* __restrict_
 }
 
 
-#ifndef DINVK_EMUL
 // ---------------------------------------------------------------------------------------------------------------------
 // Tiled forward projection and exact transpose (the default path on the GPU).
 //
@@ -214,7 +213,11 @@ template <bool ADJ>
 __global__ void __launch_bounds__(RT_THREADS) radon_tiled_kernel(const float* __restrict__ src,
                                                                  float* __restrict__ out, RadonGeom G, const float* __restrict__ cos_t,
                                                                  const float* __restrict__ sin_t, float scale, int tps) {
+#ifdef DINVK_EMUL
+  unsigned char* rt_raw = reinterpret_cast<unsigned char*>(::emul::dyn_smem());
+#else
   extern __shared__ __align__(128) unsigned char rt_raw[];
+#endif
   float* T = reinterpret_cast<float*>(rt_raw);                 // [RTH][RTW]
   float* s_cs = T + RTH * RTW;                                  // cos[A], sin[A]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -342,7 +345,6 @@ static int launch_tiled(bool adj, const float* x_img, const float* sino_in, floa
   }
   return DINVK_POST_LAUNCH();
 }
-#endif  // DINVK_EMUL
 
 
 // ---- fan-beam projector and its exact transpose (physics/functional/radon.py:16-52 + 252-309 with fan_beam=True) ----
@@ -427,12 +429,10 @@ extern "C" int dinvk_radon_fwd(const float* x, float* sino, int BC, int W, int P
   if (rc) return rc;
   if (BC == 0) return DINVK_OK;
   DINVK_CHECK_ARG(A <= 65535 && BC <= 65535, "dinvk_radon_fwd: grid too large");
-#ifndef DINVK_EMUL
   if (tiled_ok(x, W, A)) {
     rc = launch_tiled(false, x, nullptr, sino, BC, G, cos_t, sin_t, scale, stream);
     if (rc >= 0) return rc;
   }
-#endif
   DINVK_LAUNCH(radon_fwd_kernel, dim3(ceil_div(P, 128), A, BC), dim3(128), 0, stream, x, sino, G, cos_t, sin_t, scale);
   return DINVK_POST_LAUNCH();
 }
@@ -445,12 +445,10 @@ extern "C" int dinvk_radon_adj(const float* sino, float* x, int BC, int W, int P
   if (rc) return rc;
   if (BC == 0) return DINVK_OK;
   DINVK_CHECK_ARG(BC <= 65535 && A <= 4096, "dinvk_radon_adj: grid too large");
-#ifndef DINVK_EMUL
   if (tiled_ok(x, W, A)) {
     rc = launch_tiled(true, nullptr, sino, x, BC, G, cos_t, sin_t, scale, stream);
     if (rc >= 0) return rc;
   }
-#endif
   DINVK_LAUNCH(radon_adj_kernel, dim3(ceil_div((long long)W * W, 256), BC), dim3(256), 2 * A * sizeof(float), stream, sino, x, G,
                cos_t, sin_t, scale);
   return DINVK_POST_LAUNCH();
