@@ -11,6 +11,9 @@
 //   kind 1/2: 2x2 stride-2 conv / transposed conv as a small gather-GEMM-scatter (64x32 tiles).
 // Fusions: input sum (x + xadd: the U-Net skip), bias, ReLU, residual add.
 #include "common.cuh"
+#ifndef DINVK_EMUL
+#include <cstdlib>
+#endif
 
 namespace dinvk {
 
@@ -21,7 +24,15 @@ constexpr int C3_TC = 32;    // output channels per CTA
 constexpr int C3_ROWP = 36;  // padded smem row (34 used)
 constexpr int C3_WS = 36;    // padded weight row in shared memory (32 used): keeps float4 alignment, spreads the staging stores
 
-__global__ void __launch_bounds__(256) conv3x3_f32_kernel(const float* __restrict__ x, const float* __restrict__ xadd,
+constexpr int C3_IN_ELEMS = C3_CC * (C3_TH + 2) * (C3_TW + 2);  // staged inputs per chunk (8 x 10 x 34)
+constexpr int C3_IN_IT = (C3_IN_ELEMS + 255) / 256;              // 11 per thread
+constexpr int C3_W_IT = C3_CC * 9 * C3_TC / 256;                 // 9 per thread
+
+// PF = true: software-pipelined staging — the global loads of chunk k+1 are issued into registers before the FMAs of chunk k
+// and stored to shared memory after them, so their latency (ncu: long-scoreboard is the top stall of the synchronous version)
+// is covered by the compute of the same CTA instead of only by the other resident CTAs.
+template <bool PF>
+__global__ void __launch_bounds__(256, PF ? 2 : 3) conv3x3_f32_kernel(const float* __restrict__ x, const float* __restrict__ xadd,
                                                           const float* __restrict__ w, const float* __restrict__ bias,
                                                           const float* __restrict__ res, float* __restrict__ out,
                                                           int Cin, int Cout, int H, int W, int tiles_x, int act) {
@@ -42,31 +53,69 @@ __global__ void __launch_bounds__(256) conv3x3_f32_kernel(const float* __restric
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc[p][q] = 0.f;
 
+  // one staged input (halo, zero padding) / weight of chunk c0 for flat index idx
+  auto load_in = [&](int c0, int idx) -> float {
+    const int c = idx / ((C3_TH + 2) * (C3_TW + 2));
+    const int rem = idx - c * ((C3_TH + 2) * (C3_TW + 2));
+    const int r = rem / (C3_TW + 2), col = rem - r * (C3_TW + 2);
+    const int gy = ty0 + r - 1, gx = tx0 + col - 1;
+    float v = 0.f;
+    if (idx < C3_IN_ELEMS && c0 + c < Cin && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      const long long o = (long long)(c0 + c) * HW + (long long)gy * W + gx;
+      v = __ldg(xb + o);
+      if (ab) v += __ldg(ab + o);
+    }
+    return v;
+  };
+  // weights w[(co, ci, ky, kx)] go to s_w[(ci, tap)][co] (rows padded to C3_WS = 36 floats).  A warp covers 8 consecutive
+  // (ci, tap) entries x 4 output channels: 32-byte global segments, and shared banks 4*(ci,tap) + co -> all 32 distinct
+  auto load_w = [&](int c0, int idx, int& soff) -> float {
+    const int blk = idx >> 5;
+    const int ck = (blk % 9) * 8 + (idx & 7), co = (blk / 9) * 4 + ((idx >> 3) & 3);
+    soff = ck * C3_WS + co;
+    float v = 0.f;
+    if (c0 + ck / 9 < Cin && co0 + co < Cout) v = __ldg(w + ((long long)(co0 + co) * Cin + c0) * 9 + ck);
+    return v;
+  };
+  float* s_in_flat = &s_in[0][0][0];
+  float* s_w_flat = &s_w[0][0];
+  float rin[PF ? C3_IN_IT : 1], rw[PF ? C3_W_IT : 1];
+  if (PF) {
+#pragma unroll
+    for (int it = 0; it < C3_IN_IT; ++it) rin[PF ? it : 0] = load_in(0, tid + 256 * it);
+#pragma unroll
+    for (int it = 0; it < C3_W_IT; ++it) { int so; rw[PF ? it : 0] = load_w(0, tid + 256 * it, so); }
+  }
+
   for (int c0 = 0; c0 < Cin; c0 += C3_CC) {
-    // stage inputs (halo, zero padding) — 8 x 10 x 34 values
-    for (int idx = tid; idx < C3_CC * (C3_TH + 2) * (C3_TW + 2); idx += 256) {
-      const int c = idx / ((C3_TH + 2) * (C3_TW + 2));
-      const int rem = idx - c * ((C3_TH + 2) * (C3_TW + 2));
-      const int r = rem / (C3_TW + 2), col = rem - r * (C3_TW + 2);
-      const int gy = ty0 + r - 1, gx = tx0 + col - 1;
-      float v = 0.f;
-      if (c0 + c < Cin && gy >= 0 && gy < H && gx >= 0 && gx < W) {
-        const long long o = (long long)(c0 + c) * HW + (long long)gy * W + gx;
-        v = __ldg(xb + o);
-        if (ab) v += __ldg(ab + o);
+    if (PF) {
+      // registers of this chunk -> shared memory (row pitch 36 for 34 used columns: flat offset = idx + 2 * (idx / 34))
+#pragma unroll
+      for (int it = 0; it < C3_IN_IT; ++it) {
+        const int idx = tid + 256 * it;
+        if (idx < C3_IN_ELEMS) s_in_flat[idx + 2 * (idx / (C3_TW + 2))] = rin[PF ? it : 0];
       }
-      s_in[c][r][col] = v;
+#pragma unroll
+      for (int it = 0; it < C3_W_IT; ++it) {
+        const int idx = tid + 256 * it, blk = idx >> 5;
+        s_w_flat[((blk % 9) * 8 + (idx & 7)) * C3_WS + (blk / 9) * 4 + ((idx >> 3) & 3)] = rw[PF ? it : 0];
+      }
+      __syncthreads();
+      if (c0 + C3_CC < Cin) {  // next chunk's loads fly during this chunk's FMAs
+#pragma unroll
+        for (int it = 0; it < C3_IN_IT; ++it) rin[PF ? it : 0] = load_in(c0 + C3_CC, tid + 256 * it);
+#pragma unroll
+        for (int it = 0; it < C3_W_IT; ++it) { int so; rw[PF ? it : 0] = load_w(c0 + C3_CC, tid + 256 * it, so); }
+      }
+    } else {
+      for (int idx = tid; idx < C3_IN_ELEMS; idx += 256) s_in_flat[idx + 2 * (idx / (C3_TW + 2))] = load_in(c0, idx);
+      for (int idx = tid; idx < C3_CC * 9 * C3_TC; idx += 256) {
+        int so;
+        const float v = load_w(c0, idx, so);
+        s_w_flat[so] = v;
+      }
+      __syncthreads();
     }
-    // stage weights w[(co, ci, ky, kx)] as s_w[(ci, tap)][co] (rows padded to C3_WS = 36 floats).  A warp covers 8 consecutive
-    // (ci, tap) entries x 4 output channels: 32-byte global segments, and shared banks 4*(ci,tap) + co -> all 32 distinct
-    for (int idx = tid; idx < C3_CC * 9 * C3_TC; idx += 256) {
-      const int blk = idx >> 5;
-      const int ck = (blk % 9) * 8 + (idx & 7), co = (blk / 9) * 4 + ((idx >> 3) & 3);
-      float v = 0.f;
-      if (c0 + ck / 9 < Cin && co0 + co < Cout) v = __ldg(w + ((long long)(co0 + co) * Cin + c0) * 9 + ck);
-      s_w[ck][co] = v;
-    }
-    __syncthreads();
 #pragma unroll
     for (int c = 0; c < C3_CC; ++c) {
 #pragma unroll
@@ -467,8 +516,13 @@ extern "C" int dinvk_conv_f32(const float* x, const float* xadd, const float* we
   if (kind == 0) {
     const int tiles_x = ceil_div(W, C3_TW), tiles_y = ceil_div(H, C3_TH);
     DINVK_CHECK_ARG(B <= 65535 && ceil_div(Cout, C3_TC) <= 65535, "dinvk_conv_f32: grid too large");
-    DINVK_LAUNCH(conv3x3_f32_kernel, dim3(tiles_x * tiles_y, ceil_div(Cout, C3_TC), B), dim3(256), 0, stream, x, xadd,
-                 weight, bias, res, out, Cin, Cout, H, W, tiles_x, act);
+    static const bool prefetch = getenv("DINVK_F32_PREFETCH") ? atoi(getenv("DINVK_F32_PREFETCH")) != 0 : false;
+    if (prefetch)
+      DINVK_LAUNCH(conv3x3_f32_kernel<true>, dim3(tiles_x * tiles_y, ceil_div(Cout, C3_TC), B), dim3(256), 0, stream, x, xadd,
+                   weight, bias, res, out, Cin, Cout, H, W, tiles_x, act);
+    else
+      DINVK_LAUNCH(conv3x3_f32_kernel<false>, dim3(tiles_x * tiles_y, ceil_div(Cout, C3_TC), B), dim3(256), 0, stream, x, xadd,
+                   weight, bias, res, out, Cin, Cout, H, W, tiles_x, act);
   } else {
     if (kind == 1) DINVK_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "dinvk_conv_f32: strided conv needs even H, W");
     const long long M = kind == 1 ? (long long)B * (H / 2) * (W / 2) : (long long)B * H * W;
