@@ -117,8 +117,8 @@ def test_pnp_blur_admm():
     P.case_pnp_blur_admm(DEV)
 
 
-def test_ddrm():
-    P.case_ddrm(DEV)
+def test_optim_step_algebra_toy_denoiser():
+    P.case_optim_toy(DEV)
 
 
 def test_dpir_schedule_toy_denoiser():
