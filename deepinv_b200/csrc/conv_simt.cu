@@ -278,7 +278,8 @@ constexpr int WG_CI = 8;   // input channels per CTA
 constexpr int WG_CO = 32;  // output channels per CTA
 constexpr int WG_GS = 36;  // shared row of the g tile (32 channels + 4 pad)
 
-__global__ void __launch_bounds__(256) conv3x3_wgrad_f32_kernel(const float* __restrict__ x, const float* __restrict__ xadd,
+template <int MINB>  // CTAs per SM the register allocation is held to (2: 119 registers; 3: 80 registers, 20 B of spills)
+__global__ void __launch_bounds__(256, MINB) conv3x3_wgrad_f32_kernel(const float* __restrict__ x, const float* __restrict__ xadd,
                                                                 const float* __restrict__ g, float* __restrict__ dw,
                                                                 float* __restrict__ dbias, int Cin, int Cout, int H, int W,
                                                                 int tiles_x, int nci) {
@@ -547,8 +548,13 @@ extern "C" int dinvk_conv_f32_wgrad(const float* x, const float* xadd, const flo
   if (kind == 0) {
     const int tiles_x = ceil_div(W, C3_TW), tiles_y = ceil_div(H, C3_TH), nci = ceil_div(Cin, WG_CI);
     DINVK_CHECK_ARG((long long)B * nci <= 65535 && ceil_div(Cout, WG_CO) <= 65535, "dinvk_conv_f32_wgrad: grid too large");
-    DINVK_LAUNCH(conv3x3_wgrad_f32_kernel, dim3(tiles_y, ceil_div(Cout, WG_CO), B * nci), dim3(256), 0, stream, x, xadd, gout,
-                 dweight, dbias, Cin, Cout, H, W, tiles_x, nci);
+    static const int occ = getenv("DINVK_WGRAD_OCC") ? atoi(getenv("DINVK_WGRAD_OCC")) : 2;
+    if (occ == 3)
+      DINVK_LAUNCH(conv3x3_wgrad_f32_kernel<3>, dim3(tiles_y, ceil_div(Cout, WG_CO), B * nci), dim3(256), 0, stream, x, xadd, gout,
+                   dweight, dbias, Cin, Cout, H, W, tiles_x, nci);
+    else
+      DINVK_LAUNCH(conv3x3_wgrad_f32_kernel<2>, dim3(tiles_y, ceil_div(Cout, WG_CO), B * nci), dim3(256), 0, stream, x, xadd, gout,
+                   dweight, dbias, Cin, Cout, H, W, tiles_x, nci);
   } else {
     if (kind == 1) DINVK_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "dinvk_conv_f32_wgrad: strided conv needs even H, W");
     const long long M = kind == 1 ? (long long)B * (H / 2) * (W / 2) : (long long)B * H * W;
