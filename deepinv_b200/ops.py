@@ -268,9 +268,9 @@ class _ConvF32Fn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, xadd, weight, bias, res, kind, relu):
-        out = conv_f32(x, weight, kind=kind, bias=bias, xadd=xadd, res=res, relu=relu)
-        if relu and res is not None:
+        if relu and res is not None:  # the ReLU mask is recovered from the output, which the residual would hide
             raise NotImplementedError("conv_f32 backward: ReLU together with a residual is not used by DRUNet / DnCNN")
+        out = conv_f32(x, weight, kind=kind, bias=bias, xadd=xadd, res=res, relu=relu)
         ctx.kind, ctx.relu = kind, relu
         ctx.has = (xadd is not None, bias is not None, res is not None)
         ctx.save_for_backward(x, xadd, weight, out if relu else None)
