@@ -24,6 +24,54 @@ from .prior import ZeroPrior
 
 
 @dataclass
+class AndersonAccelerationConfig:
+    """Anderson acceleration of the fixed-point loop (optimizers.py:64-78)"""
+    history_size: int = 10
+    beta: float = 0.9
+    eps: float = 0.1
+    full_backprop: bool = False
+
+
+class _AndersonState:
+    """Type-II Anderson mixing of the last m iterates (fixed_point.py:117-260): with G = T - X the residuals of the stored
+    pairs, solve the bordered system [[0, 1^T], [1, G G^T + eps I]] [nu; p] = [1; 0] per sample (weights p sum to 1) and take
+    x = beta * p^T T + (1 - beta) * p^T X.  The iterates are whatever the kernels produced; the mixing itself is two small
+    batched GEMMs (m <= history_size rows) and an (m+1) x (m+1) solve per sample — library calls, not a hot path."""
+
+    def __init__(self, cfg: AndersonAccelerationConfig, x: torch.Tensor):
+        B, d, m = x.shape[0], x[0].numel(), cfg.history_size
+        self.cfg = cfg
+        self.x_hist = torch.zeros(B, m, d, dtype=x.dtype, device=x.device)
+        self.t_hist = torch.zeros(B, m, d, dtype=x.dtype, device=x.device)
+        self.H = torch.zeros(B, m + 1, m + 1, dtype=x.dtype, device=x.device)
+        self.H[:, 0, 1:] = 1.0
+        self.H[:, 1:, 0] = 1.0
+        self.q = torch.zeros(B, m + 1, 1, dtype=x.dtype, device=x.device)
+        self.q[:, 0] = 1.0
+
+    def step(self, it: int, x_prev: torch.Tensor, tx: torch.Tensor) -> torch.Tensor:
+        cfg = self.cfg
+        B = x_prev.shape[0]
+        slot, m = it % cfg.history_size, min(it + 1, cfg.history_size)
+        self.x_hist[:, slot] = x_prev.reshape(B, -1).detach()
+        self.t_hist[:, slot] = tx.reshape(B, -1).detach()
+        X, T = self.x_hist[:, :m], self.t_hist[:, :m]
+        if torch.is_grad_enabled() and (x_prev.requires_grad or tx.requires_grad):
+            # gradient through the current pair only (full_backprop=False semantics, fixed_point.py:218-235)
+            sel = torch.zeros(1, m, 1, dtype=X.dtype, device=X.device)
+            sel[:, slot] = 1.0
+            X = X + sel * (x_prev.reshape(B, 1, -1) - X[:, slot: slot + 1])
+            T = T + sel * (tx.reshape(B, 1, -1) - T[:, slot: slot + 1])
+        G = T - X
+        H = self.H.clone()
+        H[:, 1: m + 1, 1: m + 1] = torch.bmm(G, G.transpose(1, 2)) + cfg.eps * torch.eye(m, dtype=X.dtype, device=X.device)[None]
+        p = torch.linalg.solve(H[:, : m + 1, : m + 1], self.q[:, : m + 1])[:, 1: m + 1, 0]
+        self.H = H.detach()
+        x = cfg.beta * (p[:, None] @ T)[:, 0] + (1 - cfg.beta) * (p[:, None] @ X)[:, 0]
+        return x.view_as(x_prev)
+
+
+@dataclass
 class DEQConfig:
     """backward-pass settings of a deep-equilibrium model (optimizers.py:44-62)"""
     max_iter_backward: int = 50
@@ -42,8 +90,16 @@ class BaseOptim(nn.Module):
     def __init__(self, iterator: OptimIterator, params_algo=None, data_fidelity=None, prior=None, max_iter: int = 100,
                  crit_conv: str = "residual", thres_conv: float = 1e-5, early_stop: bool = False, has_cost: bool = False,
                  custom_metrics=None, custom_init=None, get_output=lambda X: X["est"][0], unfold: bool = False,
-                 trainable_params=None, verbose: bool = False, show_progress_bar: bool = False, DEQ=None, **kwargs):
+                 trainable_params=None, verbose: bool = False, show_progress_bar: bool = False, DEQ=None,
+                 anderson_acceleration=False, **kwargs):
         super().__init__()
+        if isinstance(anderson_acceleration, bool):
+            self.anderson_acceleration_config = AndersonAccelerationConfig() if anderson_acceleration else None
+        else:
+            self.anderson_acceleration_config = anderson_acceleration
+        if self.anderson_acceleration_config is not None and self.anderson_acceleration_config.full_backprop:
+            raise NotImplementedError("deepinv_b200: Anderson acceleration with full_backprop=True is not supported")
+        self._anderson = None
         if isinstance(DEQ, bool):
             self.DEQ, self.DEQ_config = DEQ, (DEQConfig() if DEQ else None)
         else:
@@ -183,8 +239,17 @@ class BaseOptim(nn.Module):
         return m
 
     def single_iteration(self, X, it, y, physics, **kwargs):
-        return self.iterator(X, self.update_data_fidelity_fn(it), self.update_prior_fn(it), self.update_params_fn(it),
-                             y, physics, **kwargs)
+        fid, prior, params = self.update_data_fidelity_fn(it), self.update_prior_fn(it), self.update_params_fn(it)
+        Xn = self.iterator(X, fid, prior, params, y, physics, **kwargs)
+        if self.anderson_acceleration_config is not None:  # mix the new iterate with the history (fixed_point.py:391-400)
+            if self._anderson is None or it == 0:
+                self._anderson = _AndersonState(self.anderson_acceleration_config, X["est"][0])
+            x = self._anderson.step(it, X["est"][0], Xn["est"][0])
+            Xn = dict(Xn)
+            Xn["est"] = (x, *Xn["est"][1:])
+            if self.has_cost and self.iterator.cost_fn is not None:
+                Xn["cost"] = self.iterator.cost_fn(x, fid, prior, params, y, physics)
+        return Xn
 
     def DEQ_additional_step(self, X, y, physics, **kwargs):
         """One more iteration WITH gradient tracking at the equilibrium x*, plus a backward hook that replaces the

@@ -413,6 +413,25 @@ def train_fixtures():
     save("train_unfolded_admm_blur", x=xb, filt=filt, y=yb, out=out, loss=loss, **sd_arrays(dn, "sd__"), **_grads(modelb))
 
 
+def anderson_fixtures():
+    """Anderson-accelerated fixed-point loops (fixed_point.py:117-260) from the real reference"""
+    from deepinv.optim import GD, AndersonAccelerationConfig
+    from deepinv.optim.prior import Tikhonov
+
+    B, H, W = 2, 32, 32
+    x = torch.randn(B, 2, H, W, generator=g(1))
+    mask = RandomMaskGenerator((2, H, W), acceleration=4, rng=g(0)).step(B)["mask"]
+    phys = MRI(mask=mask, img_size=(2, H, W))
+    y = phys(x)
+    den = tiny_drunet(2)
+    with torch.no_grad():
+        pgd = PGD(data_fidelity=L2(), prior=PnP(den), stepsize=1.0, sigma_denoiser=0.05, max_iter=4, early_stop=False,
+                  anderson_acceleration=True)(y, phys)
+        gd = GD(data_fidelity=L2(), prior=Tikhonov(), stepsize=0.5, lambda_reg=0.2, max_iter=12, early_stop=False,
+                anderson_acceleration=AndersonAccelerationConfig(history_size=3, beta=1.0, eps=1e-3))(y, phys)
+    save("optim_anderson", x=x, mask=phys.mask, y=y, pgd=pgd, gd=gd, **sd_arrays(den, "sd__"))
+
+
 def ddrm_fixture():
     B, H, W = 2, 32, 32
     x = torch.randn(B, 2, H, W, generator=g(1)) * 0.3
@@ -436,12 +455,12 @@ def ddrm_fixture():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm", "optim2", "train", "dynamic", "down", "combine", "maskgen", "mri3d", "fan"]
+    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm", "optim2", "train", "dynamic", "down", "combine", "maskgen", "mri3d", "fan", "anderson"]
     table = {"mri": mri_fixtures, "multicoil": multicoil_fixtures, "tomo": tomo_fixtures, "blur": blur_fixtures,
              "blurfft": blurfft_fixtures, "model": model_fixtures, "optim": optim_fixtures, "ddrm": ddrm_fixture,
              "optim2": optim2_fixtures, "train": train_fixtures,
              "dynamic": dynamic_fixtures, "down": down_fixtures,
              "combine": combine_fixtures, "maskgen": maskgen_fixtures,
-             "mri3d": mri3d_fixture, "fan": fanbeam_fixtures}
+             "mri3d": mri3d_fixture, "fan": fanbeam_fixtures, "anderson": anderson_fixtures}
     for w in which:
         table[w]()

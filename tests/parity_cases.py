@@ -465,6 +465,24 @@ def case_train_unfolded(dev):
     _check_param_grads(modelb, gb, tol_w=2e-3, tol_p=2e-3)  # CG solves (tol 1e-4) inside forward and backward
 
 
+def case_anderson(dev, full=True):
+    """Anderson-accelerated loops (fixed_point.py:117-260) vs the real reference"""
+    import deepinv_b200 as dinv
+    from deepinv_b200.optim import GD, L2, PGD, AndersonAccelerationConfig, PnP, Tikhonov
+
+    g = to_dev(load_golden("optim_anderson"), dev)
+    phys = dinv.physics.MRI(mask=g["mask"], img_size=(2, 32, 32), device=dev)
+    gd = GD(data_fidelity=L2(), prior=Tikhonov(), stepsize=0.5, lambda_reg=0.2, max_iter=12, early_stop=False,
+            anderson_acceleration=AndersonAccelerationConfig(history_size=3, beta=1.0, eps=1e-3))
+    assert rel_err(gd(g["y"], phys), g["gd"]) < 2e-5  # 12 small linear solves on top of the iterates
+    if not full:
+        return
+    den = load_model(dinv.models.DRUNet, g, dev, in_channels=2, out_channels=2, nc=(8, 16, 32, 64), nb=2)
+    pgd = PGD(data_fidelity=L2(), prior=PnP(den), stepsize=1.0, sigma_denoiser=0.05, max_iter=4, early_stop=False,
+              anderson_acceleration=True)
+    assert rel_err(pgd(g["y"], phys), g["pgd"]) < 2e-5
+
+
 def case_pnp_blur_admm(dev):
     import deepinv_b200 as dinv
     from deepinv_b200.optim import ADMM, L2, PnP

@@ -41,6 +41,10 @@ def test_mri_3d(dev):
     P.case_mri_3d(dev)
 
 
+def test_anderson(dev):
+    P.case_anderson(dev)
+
+
 def test_filters(dev):
     P.case_filters(dev)
 

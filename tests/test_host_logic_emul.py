@@ -60,6 +60,10 @@ def test_mri_3d():
     P.case_mri_3d(DEV)
 
 
+def test_anderson():
+    P.case_anderson(DEV, full=False)
+
+
 def test_filters():
     P.case_filters(DEV)
 
