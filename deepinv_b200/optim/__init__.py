@@ -4,7 +4,8 @@ from .graphed import GraphedIteration, GraphedSolve, HostStreamedIteration  # no
 from .linear import conjugate_gradient, least_squares  # noqa: F401
 from .optim_iterators import (ADMMIteration, DRSIteration, FISTAIteration, GDIteration, HQSIteration,  # noqa: F401
                               OptimIterator, PGDIteration)
-from .optimizers import (ADMM, DRS, FISTA, GD, HQS, PGD, AndersonAccelerationConfig, BaseOptim, DEQConfig,  # noqa: F401
+from .optimizers import (ADMM, DRS, FISTA, GD, HQS, PGD, AndersonAccelerationConfig, BacktrackingConfig, BaseOptim,
+                         DEQConfig,  # noqa: F401
                          create_iterator,
                          optim_builder)
 from .prior import RED, PnP, Prior, Tikhonov, ZeroPrior  # noqa: F401

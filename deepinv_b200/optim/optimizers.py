@@ -32,6 +32,14 @@ class AndersonAccelerationConfig:
     full_backprop: bool = False
 
 
+@dataclass
+class BacktrackingConfig:
+    """Armijo-type backtracking on the stepsize (optimizers.py:80-91)"""
+    gamma: float = 0.1
+    eta: float = 0.9
+    max_iter: int = 20
+
+
 class _AndersonState:
     """Type-II Anderson mixing of the last m iterates (fixed_point.py:117-260): with G = T - X the residuals of the stored
     pairs, solve the bordered system [[0, 1^T], [1, G G^T + eps I]] [nu; p] = [1; 0] per sample (weights p sum to 1) and take
@@ -91,8 +99,12 @@ class BaseOptim(nn.Module):
                  crit_conv: str = "residual", thres_conv: float = 1e-5, early_stop: bool = False, has_cost: bool = False,
                  custom_metrics=None, custom_init=None, get_output=lambda X: X["est"][0], unfold: bool = False,
                  trainable_params=None, verbose: bool = False, show_progress_bar: bool = False, DEQ=None,
-                 anderson_acceleration=False, **kwargs):
+                 anderson_acceleration=False, backtracking=None, **kwargs):
         super().__init__()
+        if isinstance(backtracking, bool):
+            self.backtracking, self.backtracking_config = backtracking, (BacktrackingConfig() if backtracking else None)
+        else:
+            self.backtracking, self.backtracking_config = backtracking is not None, (backtracking or BacktrackingConfig())
         if isinstance(anderson_acceleration, bool):
             self.anderson_acceleration_config = AndersonAccelerationConfig() if anderson_acceleration else None
         else:
@@ -133,6 +145,12 @@ class BaseOptim(nn.Module):
                 raise ValueError(f"The number of elements in the parameter {key} is inferior to max_iter.")
         self.init_params_algo = params_algo
         self._host_schedules = {}
+        if self.backtracking and len(params_algo["stepsize"]) > 1:
+            warnings.warn("Backtracking impossible when stepsize is predefined as a list. Setting backtracking to False.")
+            self.backtracking = False
+        if self.backtracking and not self.has_cost:
+            warnings.warn("Backtracking impossible when no cost function is given. Setting backtracking to False.")
+            self.backtracking = False
 
         if self.unfold or self.DEQ:
             if trainable_params is not None:
@@ -192,7 +210,27 @@ class BaseOptim(nn.Module):
             aty = physics.A_adjoint(y)
             X = {"est": (aty, aty.clone()), "aty": aty}
         X["cost"] = None
+        if self.has_cost and self.iterator.cost_fn is not None:  # F(x0): backtracking / cost-based stopping compare against it
+            X["cost"] = self.iterator.cost_fn(X["est"][0], self.update_data_fidelity_fn(0), self.update_prior_fn(0),
+                                              self.update_params_fn(0), y, physics)
         return X
+
+    def backtracking_check_fn(self, X_prev, X) -> bool:
+        """sufficient-decrease test F(x_prev) - F(x) >= gamma / stepsize * ||x - x_prev||^2 (batch means); on failure the
+        stepsize is multiplied by eta and the iterate is rejected (optimizers.py:668-701)"""
+        if not (self.backtracking and self.has_cost and X_prev is not None and X_prev.get("cost") is not None):
+            return True
+        x_prev = X_prev["est"][0].reshape(X_prev["est"][0].shape[0], -1)
+        x = X["est"][0].reshape(x_prev.shape[0], -1)
+        diff_F = (X_prev["cost"] - X["cost"]).mean()
+        diff_x = torch.linalg.vector_norm(x - x_prev, dim=-1, ord=2).pow(2).mean()
+        stepsize = self.init_params_algo["stepsize"][0]
+        if diff_F < (self.backtracking_config.gamma / stepsize) * diff_x:
+            self.init_params_algo["stepsize"] = [self.backtracking_config.eta * stepsize]
+            if self.verbose:
+                print(f"Backtracking : new stepsize = {float(self.init_params_algo['stepsize'][0]):.6f}")
+            return False
+        return True
 
     def check_conv_fn(self, it, X_prev, X) -> bool:
         if self.crit_conv == "residual":
@@ -279,9 +317,17 @@ class BaseOptim(nn.Module):
             X = self.init_iterate_fn(y, physics, init=init)
             metrics = self._metrics_init(X, x_gt) if compute_metrics else None
             self.has_converged = False
+            failed = 0
             for it in range(self.max_iter):
                 X_prev = X
                 X = self.single_iteration(X, it, y, physics, **kwargs)
+                if not self.backtracking_check_fn(X_prev, X):  # rejected step: keep the iterate, retry with the smaller stepsize
+                    X = X_prev
+                    failed += 1
+                    if failed >= self.backtracking_config.max_iter:
+                        break
+                    continue
+                failed = 0
                 if compute_metrics:
                     metrics = self._metrics_update(metrics, X_prev, X, x_gt)
                 if self.early_stop and it > 1 and self.check_conv_fn(it, X_prev, X):

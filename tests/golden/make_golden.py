@@ -429,7 +429,18 @@ def anderson_fixtures():
                   anderson_acceleration=True)(y, phys)
         gd = GD(data_fidelity=L2(), prior=Tikhonov(), stepsize=0.5, lambda_reg=0.2, max_iter=12, early_stop=False,
                 anderson_acceleration=AndersonAccelerationConfig(history_size=3, beta=1.0, eps=1e-3))(y, phys)
-    save("optim_anderson", x=x, mask=phys.mask, y=y, pgd=pgd, gd=gd, **sd_arrays(den, "sd__"))
+    from deepinv.optim import BacktrackingConfig
+
+    with torch.no_grad():
+        gd_bt = GD(data_fidelity=L2(), prior=Tikhonov(), stepsize=2.5, lambda_reg=0.2, max_iter=15, early_stop=False,
+                   backtracking=BacktrackingConfig(gamma=0.1, eta=0.5, max_iter=20))
+        out_bt = gd_bt(y, phys)
+        pgd_bt = PGD(data_fidelity=L2(), prior=Tikhonov(), stepsize=3.0, lambda_reg=0.5, max_iter=10, early_stop=False,
+                     backtracking=True)
+        out_pgd_bt = pgd_bt(y, phys)
+    save("optim_anderson", x=x, mask=phys.mask, y=y, pgd=pgd, gd=gd, gd_bt=out_bt,
+         gd_bt_step=np.float32(gd_bt.params_algo["stepsize"][0]), pgd_bt=out_pgd_bt,
+         pgd_bt_step=np.float32(pgd_bt.params_algo["stepsize"][0]), **sd_arrays(den, "sd__"))
 
 
 def ddrm_fixture():

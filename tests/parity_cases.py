@@ -475,6 +475,15 @@ def case_anderson(dev, full=True):
     gd = GD(data_fidelity=L2(), prior=Tikhonov(), stepsize=0.5, lambda_reg=0.2, max_iter=12, early_stop=False,
             anderson_acceleration=AndersonAccelerationConfig(history_size=3, beta=1.0, eps=1e-3))
     assert rel_err(gd(g["y"], phys), g["gd"]) < 2e-5  # 12 small linear solves on top of the iterates
+    from deepinv_b200.optim import BacktrackingConfig
+
+    bt = GD(data_fidelity=L2(), prior=Tikhonov(), stepsize=2.5, lambda_reg=0.2, max_iter=15, early_stop=False,
+            backtracking=BacktrackingConfig(gamma=0.1, eta=0.5, max_iter=20))  # starts too large: rejected steps shrink it
+    assert rel_err(bt(g["y"], phys), g["gd_bt"]) < TOL
+    assert abs(float(bt.init_params_algo["stepsize"][0]) - float(g["gd_bt_step"])) < 1e-6
+    pbt = PGD(data_fidelity=L2(), prior=Tikhonov(), stepsize=3.0, lambda_reg=0.5, max_iter=10, early_stop=False, backtracking=True)
+    assert rel_err(pbt(g["y"], phys), g["pgd_bt"]) < TOL
+    assert abs(float(pbt.init_params_algo["stepsize"][0]) - float(g["pgd_bt_step"])) < 1e-6
     if not full:
         return
     den = load_model(dinv.models.DRUNet, g, dev, in_channels=2, out_channels=2, nc=(8, 16, 32, 64), nb=2)
