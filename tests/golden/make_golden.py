@@ -432,7 +432,7 @@ def anderson_fixtures():
     from deepinv.optim import BacktrackingConfig
 
     with torch.no_grad():
-        gd_bt = GD(data_fidelity=L2(), prior=Tikhonov(), stepsize=2.5, lambda_reg=0.2, max_iter=15, early_stop=False,
+        gd_bt = GD(data_fidelity=L2(), prior=Tikhonov(), stepsize=2.5, lambda_reg=0.2, max_iter=8, early_stop=False,
                    backtracking=BacktrackingConfig(gamma=0.1, eta=0.5, max_iter=20))
         out_bt = gd_bt(y, phys)
         pgd_bt = PGD(data_fidelity=L2(), prior=Tikhonov(), stepsize=3.0, lambda_reg=0.5, max_iter=10, early_stop=False,
