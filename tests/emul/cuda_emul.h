@@ -16,6 +16,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
+#include <pthread.h>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -51,24 +53,30 @@ inline dim3 blockDim, gridDim;
 
 namespace emul {
 
+// pthread barriers are futex-based: a waiter sleeps in the kernel and the last arrival wakes the group with one syscall,
+// far cheaper than a mutex + condition variable when 256 host threads share 8 cores
 class Barrier {
  public:
-  void reset(int n) { n_ = n; count_ = 0; gen_ = 0; }
-  void wait() {
-    std::unique_lock<std::mutex> lk(m_);
-    int g = gen_;
-    if (++count_ == n_) { count_ = 0; ++gen_; cv_.notify_all(); }
-    else cv_.wait(lk, [&] { return gen_ != g; });
+  Barrier() = default;
+  Barrier(const Barrier&) = delete;
+  Barrier& operator=(const Barrier&) = delete;
+  ~Barrier() { if (init_) pthread_barrier_destroy(&b_); }
+  void reset(int n) {
+    if (init_ && n == n_) return;
+    if (init_) pthread_barrier_destroy(&b_);
+    pthread_barrier_init(&b_, nullptr, (unsigned)n);
+    n_ = n; init_ = true;
   }
+  void wait() { pthread_barrier_wait(&b_); }
  private:
-  std::mutex m_;
-  std::condition_variable cv_;
-  int n_ = 1, count_ = 0, gen_ = 0;
+  pthread_barrier_t b_;
+  int n_ = 0;
+  bool init_ = false;
 };
 
 struct State {
   Barrier block_bar;
-  std::vector<Barrier> warp_bar;
+  std::vector<std::unique_ptr<Barrier>> warp_bar;
   std::vector<uint64_t> xchg;  // per-thread exchange slot for shuffles
   std::vector<unsigned char> dyn;
   int nthreads = 0;
@@ -78,6 +86,59 @@ inline void* dyn_smem() { return state().dyn.data(); }
 
 inline int linear_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); }
 
+// Persistent worker pool: one host thread per CUDA thread slot, created once and reused by every launch (a 256-thread
+// CTA used to cost 256 pthread_create / join per launch).  Worker t runs the kernel body for thread t of every block.
+class Pool {
+ public:
+  static Pool& get() { static Pool p; return p; }
+  void run(int nt, const std::function<void(int)>& job) {
+    std::unique_lock<std::mutex> lk(m_);
+    while ((int)workers_.size() < nt) {
+      const int t = (int)workers_.size();
+      workers_.emplace_back([this, t]() { loop(t); });
+    }
+    job_ = &job; nt_ = nt; pending_ = nt; ++gen_;
+    cv_start_.notify_all();
+    cv_done_.wait(lk, [&] { return pending_ == 0; });
+    job_ = nullptr;
+  }
+ private:
+  Pool() = default;
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true; ++gen_;
+    }
+    cv_start_.notify_all();
+    for (auto& w : workers_) w.join();
+  }
+  void loop(int t) {
+    unsigned long seen = 0;
+    for (;;) {
+      const std::function<void(int)>* job = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_start_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        if (t < nt_) job = job_;
+      }
+      if (job) {
+        (*job)(t);
+        std::lock_guard<std::mutex> lk(m_);
+        if (--pending_ == 0) cv_done_.notify_all();
+      }
+    }
+  }
+  std::mutex m_;
+  std::condition_variable cv_start_, cv_done_;
+  std::vector<std::thread> workers_;
+  const std::function<void(int)>* job_ = nullptr;
+  int nt_ = 0, pending_ = 0;
+  unsigned long gen_ = 0;
+  bool stop_ = false;
+};
+
 template <typename F>
 void launch(dim3 grid, dim3 block, size_t smem, F body) {
   State& s = state();
@@ -86,28 +147,24 @@ void launch(dim3 grid, dim3 block, size_t smem, F body) {
   s.nthreads = nt;
   s.block_bar.reset(nt);
   const int nwarps = (nt + 31) / 32;
-  s.warp_bar = std::vector<Barrier>(nwarps);
-  for (int w = 0; w < nwarps; ++w) s.warp_bar[w].reset(std::min(32, nt - 32 * w));
+  while ((int)s.warp_bar.size() < nwarps) s.warp_bar.emplace_back(new Barrier());
+  for (int w = 0; w < nwarps; ++w) s.warp_bar[w]->reset(std::min(32, nt - 32 * w));
   s.xchg.assign(nt, 0);
   s.dyn.assign(smem + 64, 0);
   const long nblocks = (long)grid.x * grid.y * grid.z;
-  std::vector<std::thread> th;
-  th.reserve(nt);
-  for (int t = 0; t < nt; ++t) {
-    th.emplace_back([&, t]() {
-      threadIdx.x = t % block.x;
-      threadIdx.y = (t / block.x) % block.y;
-      threadIdx.z = t / (block.x * block.y);
-      for (long b = 0; b < nblocks; ++b) {
-        blockIdx.x = (unsigned)(b % grid.x);
-        blockIdx.y = (unsigned)((b / grid.x) % grid.y);
-        blockIdx.z = (unsigned)(b / ((long)grid.x * grid.y));
-        body();
-        s.block_bar.wait();  // block boundary: statics / dyn smem are reused by the next block
-      }
-    });
-  }
-  for (auto& x : th) x.join();
+  const std::function<void(int)> job = [&](int t) {
+    threadIdx.x = t % block.x;
+    threadIdx.y = (t / block.x) % block.y;
+    threadIdx.z = t / (block.x * block.y);
+    for (long b = 0; b < nblocks; ++b) {
+      blockIdx.x = (unsigned)(b % grid.x);
+      blockIdx.y = (unsigned)((b / grid.x) % grid.y);
+      blockIdx.z = (unsigned)(b / ((long)grid.x * grid.y));
+      body();
+      s.block_bar.wait();  // block boundary: statics / dyn smem are reused by the next block
+    }
+  };
+  Pool::get().run(nt, job);
 }
 
 template <typename T>
@@ -118,11 +175,11 @@ inline T shfl_generic(T v, int src_lane) {
   static_assert(sizeof(T) <= 8, "shuffle payload too large");
   std::memcpy(&bits, &v, sizeof(T));
   s.xchg[tid] = bits;
-  s.warp_bar[warp].wait();
+  s.warp_bar[warp]->wait();
   int src = warp * 32 + (src_lane & 31);
   if (src >= s.nthreads) src = tid;
   uint64_t r = s.xchg[src];
-  s.warp_bar[warp].wait();
+  s.warp_bar[warp]->wait();
   T out;
   std::memcpy(&out, &r, sizeof(T));
   (void)lane;
@@ -131,7 +188,7 @@ inline T shfl_generic(T v, int src_lane) {
 }  // namespace emul
 
 static inline void __syncthreads() { emul::state().block_bar.wait(); }
-static inline void __syncwarp(unsigned = 0xffffffffu) { emul::state().warp_bar[emul::linear_tid() / 32].wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emul::state().warp_bar[emul::linear_tid() / 32]->wait(); }
 
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m, int = 32) { return emul::shfl_generic(v, (emul::linear_tid() % 32) ^ m); }
 template <typename T> static inline T __shfl_down_sync(unsigned, T v, int d, int = 32) {
