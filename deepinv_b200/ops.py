@@ -135,6 +135,8 @@ def spectral(
         out = torch.empty(out_shape, dtype=torch.float32, device=dev)
     else:
         assert out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == tuple(out_shape)
+    if out.numel() == 0:  # empty batch: nothing to launch (an empty tensor has a null data pointer)
+        return out
     a = _ffi.SpectralArgs()
     a.B, a.H, a.W = nimg, H, W
     a.fwd, a.inv, a.centered, a.gmode = int(fwd), int(inv), int(centered), gmode
@@ -173,6 +175,8 @@ def axpbypcz(x, a: float, y=None, b: float = 0.0, z=None, c: float = 0.0, out=No
     x, y, z = _f32c(x), _f32c(y), _f32c(z)
     if out is None:
         out = torch.empty_like(x)
+    if x.numel() == 0:
+        return out
     check(get_lib().dinvk_axpbypcz(_p(out), _p(x), a, _p(y), b, _p(z), c, x.numel(), _stream(dev)))
     return out
 
@@ -184,6 +188,10 @@ def batched_dot(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     B = x.shape[0]
     n_per = x.numel() // max(B, 1)
     out = torch.empty(B, dtype=torch.float32, device=dev)
+    if B == 0:
+        return out
+    if n_per == 0:
+        return out.zero_()
     lib = get_lib()
     nb = lib.dinvk_batched_dot_workspace_bytes(B, n_per)
     ws = workspace(dev, nb, "dot")
@@ -198,6 +206,8 @@ def batched_axpy(x: torch.Tensor, y: torch.Tensor, s: torch.Tensor, sa: float = 
     B = x.shape[0]
     if out is None:
         out = torch.empty_like(x)
+    if x.numel() == 0:
+        return out
     check(get_lib().dinvk_batched_axpy(_p(out), _p(x), _p(y), _p(s), sa, B, x.numel() // max(B, 1), _stream(dev)))
     return out
 
@@ -205,6 +215,8 @@ def batched_axpy(x: torch.Tensor, y: torch.Tensor, s: torch.Tensor, sa: float = 
 def cg_scalars(mode: int, num, den, eps: float, bnorm2=None, tol2: float = 0.0, done_flag=None) -> torch.Tensor:
     dev = _require_cuda(num, den)
     out = torch.empty_like(num)
+    if num.numel() == 0:
+        return out
     check(get_lib().dinvk_cg_scalars(mode, _p(out), _p(num), _p(den), eps, _p(bnorm2), tol2, _p(done_flag), num.numel(),
                                      _stream(dev)))
     return out
@@ -235,6 +247,8 @@ def conv_f32(x, weight, *, kind: int = 0, bias=None, xadd=None, res=None, relu: 
     else:
         Cout = weight.shape[0]
         out = torch.empty(B, Cout, H, W, dtype=torch.float32, device=dev)
+    if out.numel() == 0:
+        return out
     check(get_lib().dinvk_conv_f32(_p(x), _p(xadd), _p(weight), _p(bias), _p(res), _p(out), B, Cin, Cout, H, W, kind,
                                    int(relu), _stream(dev)))
     return out
@@ -313,6 +327,8 @@ def radon_fwd(x, P: int, cos_t, sin_t, circle: bool, scale: float) -> torch.Tens
     B, C, W, _ = x.shape
     A = cos_t.numel()
     sino = torch.empty(B, C, A, P, dtype=torch.float32, device=dev)
+    if sino.numel() == 0:
+        return sino
     check(get_lib().dinvk_radon_fwd(_p(x), _p(sino), B * C, W, P, A, int(circle), _p(cos_t), _p(sin_t), scale, _stream(dev)))
     return sino
 
@@ -323,6 +339,8 @@ def radon_adj(sino_am, W: int, cos_t, sin_t, circle: bool, scale: float, iradon:
     sino_am = _f32c(sino_am)
     B, C, A, P = sino_am.shape
     x = torch.empty(B, C, W, W, dtype=torch.float32, device=dev)
+    if x.numel() == 0:
+        return x
     fn = get_lib().dinvk_iradon_bp if iradon else get_lib().dinvk_radon_adj
     check(fn(_p(sino_am), _p(x), B * C, W, P, A, int(circle), _p(cos_t), _p(sin_t), scale, _stream(dev)))
     return x
@@ -336,6 +354,8 @@ def fanbeam(t, W: int, G: int, D: int, cos_t, sin_t, circle: bool, half_len: flo
     B, C = t.shape[:2]
     A = cos_t.numel()
     out = torch.empty((B, C, W, W) if adjoint else (B, C, A, D), dtype=torch.float32, device=dev)
+    if out.numel() == 0:
+        return out
     check(get_lib().dinvk_fanbeam(_p(t), _p(out), B * C, W, G, D, A, int(circle), _p(cos_t), _p(sin_t), half_len, src, den,
                                   scale, int(adjoint), _stream(dev)))
     return out
@@ -346,7 +366,9 @@ def ramp_filter(sino_am) -> torch.Tensor:
     dev = _require_cuda(sino_am)
     sino_am = _f32c(sino_am)
     P = sino_am.shape[-1]
-    rows = sino_am.numel() // P
+    rows = sino_am.numel() // max(P, 1)
+    if sino_am.numel() == 0:
+        return torch.empty_like(sino_am)
     if rows == 1:  # the kernel filters rows in pairs
         two = torch.cat([sino_am.reshape(1, P), torch.zeros(1, P, device=dev)], 0)
         return ramp_filter(two.reshape(1, 1, 2, P))[..., :1, :].reshape(sino_am.shape)
@@ -365,6 +387,8 @@ def blur_fwd(x, filt, padding: int) -> torch.Tensor:
     FB, FC, h, w = filt.shape
     shape = (B, C, H - h + 1, W - w + 1) if padding == _ffi.PAD_VALID else (B, C, H, W)
     y = torch.empty(shape, dtype=torch.float32, device=dev)
+    if y.numel() == 0:
+        return y
     check(get_lib().dinvk_blur_fwd(_p(x), _p(filt), _p(y), B, C, H, W, FB, FC, h, w, padding, _stream(dev)))
     return y
 
@@ -375,6 +399,8 @@ def blur_adj(y, filt, padding: int, H: int, W: int) -> torch.Tensor:
     B, C = y.shape[:2]
     FB, FC, h, w = filt.shape
     x = torch.empty(B, C, H, W, dtype=torch.float32, device=dev)
+    if x.numel() == 0:
+        return x
     lib = get_lib()
     nb = lib.dinvk_blur_adj_workspace_bytes(B, C, H, W, h, w, padding)
     ws = workspace(dev, nb, "blur")

@@ -277,9 +277,10 @@ class TimeMixin:
         return x.permute(0, 2, 1, 3, 4).reshape(B * T, C, H, W)
 
     @staticmethod
-    def unflatten(x: Tensor, batch_size: int = 1) -> Tensor:
+    def unflatten(x: Tensor, batch_size: int = 1, frames: int | None = None) -> Tensor:
         BT, C, H, W = x.shape
-        return x.reshape(batch_size, BT // batch_size, C, H, W).permute(0, 2, 1, 3, 4)
+        T = frames if frames is not None else BT // batch_size  # `frames` makes the empty batch well defined
+        return x.reshape(batch_size, T, C, H, W).permute(0, 2, 1, 3, 4)
 
     @staticmethod
     def flatten_C(x: Tensor) -> Tensor:
@@ -339,7 +340,7 @@ class DynamicMRI(MRI, TimeMixin):
         self._check(t)
         B = t.shape[0]
         out = getattr(self._static(B), name)(self.flatten(t), *extra, **kw)
-        return self.unflatten(out, batch_size=B)
+        return self.unflatten(out, batch_size=B, frames=t.shape[2])
 
     def A(self, x: Tensor, mask: Tensor = None, **kwargs) -> Tensor:
         self.update_parameters(mask=mask, **kwargs)
@@ -371,12 +372,13 @@ class DynamicMRI(MRI, TimeMixin):
         B, T = z.shape[0], z.shape[2]
         if isinstance(gamma, Tensor) and gamma.numel() > 1:
             gamma = gamma.reshape(B, 1).expand(B, T).reshape(-1)
-        return self.unflatten(self._static(B).prox_l2(self.flatten(z), self.flatten(y), gamma, **kwargs), batch_size=B)
+        return self.unflatten(self._static(B).prox_l2(self.flatten(z), self.flatten(y), gamma, **kwargs), batch_size=B, frames=T)
 
     def normal_step(self, x: Tensor, aty: Tensor, gamma: float) -> Tensor:
         self._check(x)
         B = x.shape[0]
-        return self.unflatten(self._static(B).normal_step(self.flatten(x), self.flatten(aty), gamma), batch_size=B)
+        return self.unflatten(self._static(B).normal_step(self.flatten(x), self.flatten(aty), gamma), batch_size=B,
+                              frames=x.shape[2])
 
     def noise(self, x, **kwargs):
         return self.noise_model(x, **kwargs) * self.mask
