@@ -55,7 +55,45 @@ def conjugate_gradient(A: Callable, b: torch.Tensor, max_iter: int = 100, tol: f
     return x
 
 
-def _solve_normal(physics, y, z, init, g, g_batch, max_iter, tol, verbose, kwargs):
+def bicgstab(A: Callable, b: torch.Tensor, init: torch.Tensor | None = None, max_iter: int = 100, tol: float = 1e-5,
+             verbose: bool = False) -> torch.Tensor:
+    """Stabilised bi-conjugate gradients for a square (not necessarily symmetric) operator, batch dimension in parallel
+    (deepinv/optim/linear/bicgstab.py:8-107, van der Vorst 1992; same breakdown safeguards and stopping rule).  The seven
+    inner products per iteration are `dinvk_batched_dot` launches, the vector updates `dinvk_batched_axpy` with the (B,) scalars
+    staying on the device; only the convergence test reads one boolean back per iteration."""
+    x = torch.zeros_like(b) if init is None else init
+    r = ops.axpbypcz(b, 1.0, A(x), -1.0)
+    r_hat = r.clone()
+    rho = _dot(r, r_hat)
+    p = r
+    tol2 = _dot(b, b) * (float(tol) ** 2)
+    eps = torch.finfo(torch.float32).eps
+    safe = lambda num, den: torch.where(den.abs() > eps, num / den, torch.zeros_like(num))
+    for i in range(int(max_iter)):
+        v = A(p)
+        alpha = safe(rho, _dot(r_hat, v))
+        h = ops.batched_axpy(x, p, alpha, 1.0)
+        s_ = ops.batched_axpy(r, v, alpha, -1.0)
+        t = A(s_)
+        omega = safe(_dot(t, s_), _dot(t, t))
+        x = ops.batched_axpy(h, s_, omega, 1.0)
+        r = ops.batched_axpy(s_, t, omega, -1.0)
+        if bool(torch.all(_dot(r, r) < tol2)):
+            if verbose:
+                print("BiCGSTAB Converged at iteration", i)
+            break
+        rho_new = _dot(r, r_hat)
+        ok = (rho.abs() > eps) & (omega.abs() > eps)
+        beta = torch.where(ok, (rho_new / rho) * (alpha / omega), torch.zeros_like(rho_new))
+        p = ops.batched_axpy(r, ops.batched_axpy(p, v, omega, -1.0), beta, 1.0)
+        rho = rho_new
+    else:
+        if verbose:
+            print("BiCGSTAB did not converge")
+    return x
+
+
+def _solve_normal(physics, y, z, init, g, g_batch, max_iter, tol, verbose, kwargs, solver="CG"):
     """CG on (A^T A + I/gamma) x = A^T y + z/gamma; gamma: None, a host float `g`, or a (B,) device tensor `g_batch`"""
     b = physics.A_adjoint(y, **kwargs)
     if g_batch is not None:
@@ -69,6 +107,8 @@ def _solve_normal(physics, y, z, init, g, g_batch, max_iter, tol, verbose, kwarg
         H = lambda v: ops.axpbypcz(physics.A_adjoint_A(v, **kwargs), 1.0, v, 1.0 / g)
     else:
         H = lambda v: physics.A_adjoint_A(v, **kwargs)
+    if solver == "BiCGStab":
+        return bicgstab(H, b, init=init, max_iter=max_iter, tol=tol, verbose=verbose)
     return conjugate_gradient(H, b, max_iter=max_iter, tol=tol, init=init, verbose=verbose)
 
 
@@ -82,7 +122,8 @@ class _LeastSquaresFn(torch.autograd.Function):
     def forward(ctx, physics, y, z, init, gamma, opts):
         g, g_batch = _split_gamma(gamma, y.shape[0])
         with torch.no_grad():
-            h = _solve_normal(physics, y, z, init, g, g_batch, opts["max_iter"], opts["tol"], opts["verbose"], opts["kwargs"])
+            h = _solve_normal(physics, y, z, init, g, g_batch, opts["max_iter"], opts["tol"], opts["verbose"], opts["kwargs"],
+                              opts["solver"])
         ctx.physics, ctx.opts, ctx.g, ctx.gamma_shape = physics, opts, g, (gamma.shape if isinstance(gamma, torch.Tensor) else None)
         ctx.save_for_backward(h, y, z, g_batch)
         return h
@@ -97,7 +138,8 @@ class _LeastSquaresFn(torch.autograd.Function):
             zz = ops.batched_axpy(torch.zeros_like(grad_output), grad_output, g_batch, 1.0)
         else:
             zz = ops.axpbypcz(grad_output, g)
-        mv = _solve_normal(physics, torch.zeros_like(y), zz, None, g, g_batch, opts["max_iter"], opts["tol"], False, opts["kwargs"])
+        mv = _solve_normal(physics, torch.zeros_like(y), zz, None, g, g_batch, opts["max_iter"], opts["tol"], False, opts["kwargs"],
+                           opts["solver"])
         need = ctx.needs_input_grad
         gy = physics.A(mv, **opts["kwargs"]) if need[1] else None
         gz = None
@@ -132,8 +174,10 @@ def least_squares(physics, y: torch.Tensor, z: torch.Tensor | None = None, init:
     (A^T A + I/gamma) x = A^T y + z/gamma  (least_squares.py:148-151); gamma may be a scalar or one value per sample.
     When a gradient w.r.t. y, z or gamma is being tracked the result carries the implicit-differentiation backward of the
     reference's `least_squares_implicit_backward` (least_squares.py:345-469)."""
-    if solver not in ("CG", "cg", None):
-        raise NotImplementedError(f"deepinv_b200: solver {solver!r} is outside the accelerated path (CG only, SURVEY §8 a12)")
+    if solver not in ("CG", "cg", "BiCGStab", None):
+        raise NotImplementedError(f"deepinv_b200: solver {solver!r} is outside the accelerated path (CG and BiCGStab on the "
+                                  "normal equations; SURVEY §8 a12)")
+    solver = "BiCGStab" if solver == "BiCGStab" else "CG"
     kwargs.pop("parallel_dim", None)
     tracked = torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in (y, z, gamma))
     if tracked:
@@ -142,8 +186,8 @@ def least_squares(physics, y: torch.Tensor, z: torch.Tensor | None = None, init:
         if gamma is None:
             gamma = 1e8  # "no regularisation" of a tracked solve = the reference's pseudo-inverse branch (forward.py:850-862)
         gam = gamma if isinstance(gamma, torch.Tensor) else torch.tensor(float(gamma), device=y.device)
-        opts = {"max_iter": max_iter, "tol": tol, "verbose": verbose, "kwargs": kwargs}
+        opts = {"max_iter": max_iter, "tol": tol, "verbose": verbose, "kwargs": kwargs, "solver": solver}
         return _LeastSquaresFn.apply(physics, y, z, init, gam, opts)
     y0 = y if isinstance(y, torch.Tensor) else y[0]  # stacked operators measure TensorLists (physics/combine.py)
     g, g_batch = _split_gamma(gamma, y0.shape[0])
-    return _solve_normal(physics, y, z, init, g, g_batch, max_iter, tol, verbose, kwargs)
+    return _solve_normal(physics, y, z, init, g, g_batch, max_iter, tol, verbose, kwargs, solver)

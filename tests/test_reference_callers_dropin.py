@@ -143,3 +143,20 @@ def test_reference_trainer_trains_dropin_unfolded_model():
     assert all(not torch.equal(a, b) for a, b in zip(p0, model.parameters()))
     res = trainer.test(dl)
     assert "PSNR" in res and res["PSNR"] == res["PSNR"]
+
+
+@pytest.mark.parametrize("solver", ["CG", "BiCGStab"])
+def test_least_squares_solvers_match_the_reference_solvers(solver):
+    """deepinv_b200.optim.least_squares (CG / BiCGStab on the kernels) == the reference's least_squares with the same solver on the
+    same (drop-in) operator: same iterates, same stopping rule"""
+    import deepinv_b200 as dinv
+    from deepinv.optim.linear import least_squares as ref_ls
+
+    g = load_golden("blur_gauss_circular_prox")
+    phys = dinv.physics.Blur(filter=g["filt"], padding="circular", device=DEV)
+    gam = float(g["gamma"])
+    want = ref_ls(phys.A, phys.A_adjoint, g["y"], z=g["z"], init=g["z"], gamma=gam, parallel_dim=[0], AAT=phys.A_A_adjoint,
+                  ATA=phys.A_adjoint_A, max_iter=40, tol=1e-5, solver=solver)
+    got = dinv.optim.least_squares(phys, g["y"], z=g["z"], init=g["z"], gamma=gam, solver=solver, max_iter=40, tol=1e-5)
+    assert rel_err(got, want) < 2e-5
+    assert rel_err(got, g["prox"]) < 1e-3  # the fixture was produced with tol = 1e-4 (LinearPhysics default)
