@@ -189,5 +189,11 @@ def least_squares(physics, y: torch.Tensor, z: torch.Tensor | None = None, init:
         opts = {"max_iter": max_iter, "tol": tol, "verbose": verbose, "kwargs": kwargs, "solver": solver}
         return _LeastSquaresFn.apply(physics, y, z, init, gam, opts)
     y0 = y if isinstance(y, torch.Tensor) else y[0]  # stacked operators measure TensorLists (physics/combine.py)
+    if solver == "BiCGStab" and isinstance(y, torch.Tensor):
+        # the reference hands a "complete" system (A^T y has the shape of y) to BiCGStab as A x = y itself — gamma and z do not
+        # enter (least_squares.py:131-134); mirrored so that solver="BiCGStab" returns what the reference returns
+        probe = physics.A_adjoint(y, **kwargs)
+        if probe.shape == y.shape:
+            return bicgstab(lambda v: physics.A(v, **kwargs), y, init=init, max_iter=max_iter, tol=tol, verbose=verbose)
     g, g_batch = _split_gamma(gamma, y0.shape[0])
     return _solve_normal(physics, y, z, init, g, g_batch, max_iter, tol, verbose, kwargs, solver)
