@@ -11,7 +11,6 @@ scalings (:258-293), `A_dagger()` / `prox_l2` are CG on the normal equations (fo
 from __future__ import annotations
 
 import math
-from collections.abc import Iterable
 from warnings import warn
 
 import numpy as np
