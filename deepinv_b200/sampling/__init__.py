@@ -1,1 +1,1 @@
-from .diffusion import DDRM  # noqa: F401
+from .diffusion import DDRM, DiffPIR  # noqa: F401

@@ -464,14 +464,35 @@ def ddrm_fixture():
          sigma_noise=np.float32(0.02), **sd_arrays(den, "sd__"))
 
 
+def diffpir_fixture():
+    """DiffPIR (sampling/diffusion.py:227-513) on a circular blur with a recorded noise sequence"""
+    B, H, W = 2, 32, 32
+    x = torch.rand(B, 1, H, W, generator=g(61))
+    filt = dinv.physics.functional.gaussian_blur(sigma=(1.0, 1.0))
+    phys = BlurFFT(img_size=(1, H, W), filter=filt, noise_model=dinv.physics.GaussianNoise(sigma=0.03, rng=g(62)))
+    y = phys(x)
+    den = tiny_drunet(1)
+    noises = [torch.randn(B, 1, H, W, generator=g(200 + t)) for t in range(8)]
+    it = iter(noises)
+    orig = torch.randn_like
+    torch.randn_like = lambda t, **kw: next(it).to(t)
+    try:
+        out = dinv.sampling.DiffPIR(den, L2(), sigma=0.03, max_iter=6, zeta=0.3, lambda_=7.0)(y, phys)
+    finally:
+        torch.randn_like = orig
+    save("diffpir_blurfft_tiny", x=x, filt=filt, y=y, noises=torch.stack(noises), out=out, sigma_noise=np.float32(0.03),
+         **sd_arrays(den, "sd__"))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm", "optim2", "train", "dynamic", "down", "combine", "maskgen", "mri3d", "fan", "anderson"]
+    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm", "optim2", "train", "dynamic", "down", "combine", "maskgen", "mri3d", "fan", "anderson", "diffpir"]
     table = {"mri": mri_fixtures, "multicoil": multicoil_fixtures, "tomo": tomo_fixtures, "blur": blur_fixtures,
              "blurfft": blurfft_fixtures, "model": model_fixtures, "optim": optim_fixtures, "ddrm": ddrm_fixture,
              "optim2": optim2_fixtures, "train": train_fixtures,
              "dynamic": dynamic_fixtures, "down": down_fixtures,
              "combine": combine_fixtures, "maskgen": maskgen_fixtures,
-             "mri3d": mri3d_fixture, "fan": fanbeam_fixtures, "anderson": anderson_fixtures}
+             "mri3d": mri3d_fixture, "fan": fanbeam_fixtures, "anderson": anderson_fixtures,
+             "diffpir": diffpir_fixture}
     for w in which:
         table[w]()

@@ -121,6 +121,10 @@ def test_pnp_blur_admm():
     P.case_pnp_blur_admm(DEV)
 
 
+def test_diffpir():
+    P.case_diffpir(DEV)
+
+
 def test_optim_step_algebra_toy_denoiser():
     P.case_optim_toy(DEV)
 
