@@ -45,6 +45,10 @@ def test_anderson(dev):
     P.case_anderson(dev)
 
 
+def test_diffpir(dev):
+    P.case_diffpir(dev)
+
+
 def test_filters(dev):
     P.case_filters(dev)
 
