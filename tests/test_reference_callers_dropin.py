@@ -156,8 +156,8 @@ def test_least_squares_solvers_match_the_reference_solvers(solver):
     phys = dinv.physics.Blur(filter=g["filt"], padding="circular", device=DEV)
     gam = float(g["gamma"])
     want = ref_ls(phys.A, phys.A_adjoint, g["y"], z=g["z"], init=g["z"], gamma=gam, parallel_dim=[0], AAT=phys.A_A_adjoint,
-                  ATA=phys.A_adjoint_A, max_iter=40, tol=1e-5, solver=solver)
-    got = dinv.optim.least_squares(phys, g["y"], z=g["z"], init=g["z"], gamma=gam, solver=solver, max_iter=40, tol=1e-5)
+                  ATA=phys.A_adjoint_A, max_iter=25, tol=1e-5, solver=solver)
+    got = dinv.optim.least_squares(phys, g["y"], z=g["z"], init=g["z"], gamma=gam, solver=solver, max_iter=25, tol=1e-5)
     # CG: regularised normal equations, well conditioned.  BiCGStab on this square operator: the UNregularised deblurring system
     # A x = y (see below) — 40 iterations of it amplify the round-off differences of the inner products to a few 1e-4
     assert rel_err(got, want) < (2e-5 if solver == "CG" else 2e-3)
@@ -168,6 +168,6 @@ def test_least_squares_solvers_match_the_reference_solvers(solver):
         valid = dinv.physics.Blur(filter=g["filt"], padding="valid", device=DEV)   # rectangular: normal equations with gamma
         yv = valid.A(g["z"])
         want_v = ref_ls(valid.A, valid.A_adjoint, yv, z=g["z"], init=g["z"], gamma=gam, parallel_dim=[0], AAT=valid.A_A_adjoint,
-                        ATA=valid.A_adjoint_A, max_iter=40, tol=1e-5, solver=solver)
-        got_v = dinv.optim.least_squares(valid, yv, z=g["z"], init=g["z"], gamma=gam, solver=solver, max_iter=40, tol=1e-5)
+                        ATA=valid.A_adjoint_A, max_iter=25, tol=1e-5, solver=solver)
+        got_v = dinv.optim.least_squares(valid, yv, z=g["z"], init=g["z"], gamma=gam, solver=solver, max_iter=25, tol=1e-5)
         assert rel_err(got_v, want_v) < 2e-5
