@@ -20,6 +20,9 @@ def load_golden(name: str) -> dict:
     z = np.load(GOLDEN / f"{name}.npz")
     out, sd = {}, {}
     for k in z.files:
+        if k == "sd_from":  # the state_dict lives in another fixture (the seed-0 tiny DRUNet is shared by several cases)
+            sd = dict(load_golden(str(z[k]))["sd"])
+            continue
         t = torch.from_numpy(np.asarray(z[k]))
         if k.startswith("sd__"):
             sd[k[4:].replace("__", ".")] = t

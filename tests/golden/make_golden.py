@@ -271,7 +271,16 @@ def tiny_dncnn(cin):
 
 
 def sd_arrays(model, prefix):
-    return {f"{prefix}{k.replace('.', '__')}": v for k, v in model.state_dict().items()}
+    """state_dict entries of a fixture; the seed-0 tiny 2-channel DRUNet is stored once (drunet_tiny.npz) and referenced"""
+    sd = model.state_dict()
+    ref = OUT / "drunet_tiny.npz"
+    if ref.exists():
+        base = np.load(ref)
+        keys = {f"sd__{k.replace('.', '__')}" for k in sd}
+        if keys == {k for k in base.files if k.startswith("sd__")} and all(
+                np.array_equal(base[f"sd__{k.replace('.', '__')}"], v.numpy()) for k, v in sd.items()):
+            return {"sd_from": np.array("drunet_tiny")}
+    return {f"{prefix}{k.replace('.', '__')}": v for k, v in sd.items()}
 
 
 def model_fixtures():
@@ -283,7 +292,8 @@ def model_fixtures():
         out_b = den(x, sig)
         xs = torch.randn(1, 2, 20, 36, generator=g(16))  # needs the replicate-pad path
         out_s = den(xs, 0.05)
-    save("drunet_tiny", x=x, out=out, sig=sig, out_b=out_b, xs=xs, out_s=out_s, **sd_arrays(den, "sd__"))
+    save("drunet_tiny", x=x, out=out, sig=sig, out_b=out_b, xs=xs, out_s=out_s,
+         **{f"sd__{k.replace('.', '__')}": v for k, v in den.state_dict().items()})
     dn = tiny_dncnn(1)
     x = torch.randn(2, 1, 24, 28, generator=g(17))
     with torch.no_grad():
