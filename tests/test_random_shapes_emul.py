@@ -143,3 +143,88 @@ def test_downsampling_shapes(H, W, factor, filt, pad):
     assert phys.A(x).shape == y.shape and rel_err(phys.A(x), y) < 1e-5
     v = torch.randn(y.shape, generator=g)
     assert rel_err(phys.A_adjoint(v), R.down_At(v, f, factor, pad, H, W)) < 1e-5
+
+
+@settings(**COMMON)
+@given(B=st.integers(1, 2), N=st.integers(1, 5), H=st.integers(2, 24), W=st.integers(2, 24), shared_maps=st.booleans(), rss=st.booleans())
+def test_multicoil_shapes(B, N, H, W, shared_maps, rss):
+    import deepinv_b200 as dinv
+    from oracle import ref_ops as R
+
+    g = torch.Generator().manual_seed(N * 97 + H * 5 + W)
+    x = torch.randn(B, 2, H, W, generator=g)
+    maps = torch.randn(1 if shared_maps else B, N, H, W, generator=g, dtype=torch.complex64)
+    maps = maps / maps.abs().pow(2).sum(1, keepdim=True).sqrt()
+    m = (torch.rand(B, 1, 1, W, generator=g) > 0.4).float().expand(B, 2, H, W).contiguous()
+    p = dinv.physics.MultiCoilMRI(mask=m, coil_maps=maps, img_size=(2, H, W))
+    y = R.mcmri_A(x, m, maps)
+    assert p.A(x).shape == y.shape and rel_err(p.A(x), y) < 2e-6
+    assert rel_err(p.A_adjoint(y, rss=rss), R.mcmri_At(y, m, maps, use_rss=rss)) < 2e-6
+
+
+@settings(**COMMON)
+@given(B=st.integers(1, 3), C=st.integers(1, 3), H=st.integers(4, 33), W=st.integers(4, 33), h=st.integers(1, 5), w=st.integers(1, 5),
+       gamma=st.floats(0.3, 4.0))
+def test_blurfft_shapes(B, C, H, W, h, w, gamma):
+    import deepinv_b200 as dinv
+    from oracle import ref_ops as R
+
+    h, w = min(h, H), min(w, W)
+    g = torch.Generator().manual_seed(H * 37 + W * 3 + h)
+    filt = torch.rand(1, 1, h, w, generator=g) + 0.1
+    filt = filt / filt.sum()
+    x = torch.randn(B, C, H, W, generator=g)
+    z = torch.randn(B, C, H, W, generator=g)
+    p = dinv.physics.BlurFFT(img_size=(C, H, W), filter=filt)
+    mask, angle = R.blurfft_params(filt, (C, H, W))
+    y = R.blurfft_A(x, mask, angle, (C, H, W))
+    assert rel_err(p.A(x), y) < 1e-5
+    assert rel_err(p.A_adjoint(y), R.blurfft_At(y, mask, angle, (C, H, W))) < 1e-5
+    assert rel_err(p.prox_l2(z, y, gamma), R.blurfft_prox_l2(z, y, mask, angle, (C, H, W), gamma)) < 1e-5
+
+
+@settings(**COMMON)
+@given(W=st.integers(6, 30), A=st.integers(1, 6), D=st.integers(3, 40), circle=st.booleans(), src=st.floats(20.0, 80.0), det=st.floats(10.0, 80.0),
+       spacing=st.floats(0.03, 0.5))
+def test_fanbeam_geometries(W, A, D, circle, src, det, spacing):
+    import deepinv_b200 as dinv
+    from oracle import ref_ops as R
+
+    g = torch.Generator().manual_seed(W * 13 + D)
+    fp = {"n_detector_pixels": D, "detector_spacing": spacing, "source_radius": src, "detector_radius": det}
+    angles = torch.rand(A, generator=g) * 360
+    x = torch.randn(1, 1, W, W, generator=g)
+    phys = dinv.physics.Tomography(angles=angles, img_width=W, circle=circle, fan_beam=True, fan_parameters=dict(fp), normalize=False)
+    y = R.fanbeam_forward(x, angles, circle, dict(fp))
+    got = phys.A(x)
+    assert got.shape == y.shape
+    # wide fans put most sample coordinates far outside [-1, 1]; the reference's own fp32 grid then carries errors of a few 1e-5
+    # of the (small) output.  Yardstick: the fp64 evaluation — the kernel must be at least as close to it as the reference is
+    y64 = R.fanbeam_forward(x.double(), angles.double(), circle, dict(fp))
+    scale = max(float(y64.norm()), 1e-3 * float(x.norm()))
+    assert float((got.double() - y64).norm()) < max(2e-5 * scale, 1.5 * float((y.double() - y64).norm()))
+    v = torch.randn(y.shape, generator=g)
+    xt = R.fanbeam_adjoint(v, angles, W, circle, dict(fp))
+    xt64 = R.fanbeam_adjoint(v.double(), angles.double(), W, circle, dict(fp))
+    scale = max(float(xt64.norm()), 1e-3 * float(v.norm()))
+    assert float((phys.A_adjoint(v).double() - xt64).norm()) < max(2e-5 * scale, 1.5 * float((xt.double() - xt64).norm()))
+
+
+@settings(**COMMON)
+@given(B=st.integers(1, 2), T=st.integers(1, 4), H=st.integers(2, 18), W=st.integers(2, 18), form=st.sampled_from(["hw", "thw", "cthw", "bcthw"]))
+def test_dynamic_mri_mask_forms(B, T, H, W, form):
+    import deepinv_b200 as dinv
+    from oracle import ref_ops as R
+
+    g = torch.Generator().manual_seed(T * 50 + H * 3 + W)
+    shape = {"hw": (H, W), "thw": (T, H, W), "cthw": (2, T, H, W), "bcthw": (B, 2, T, H, W)}[form]
+    m_in = (torch.rand(*shape, generator=g) > 0.5).float()
+    p = dinv.physics.DynamicMRI(mask=m_in, img_size=(2, T, H, W))
+    m = m_in
+    while m.dim() < 5:
+        m = m.unsqueeze(0)
+    if m.shape[1] == 1:
+        m = torch.cat([m, m], 1)
+    x = torch.randn(B, 2, p.mask.shape[2], H, W, generator=g)
+    y = R.mri_A(x, m)
+    assert rel_err(p.A(x), y) < 2e-6 and rel_err(p.A_adjoint(y), R.mri_At(y, m)) < 2e-6
