@@ -108,3 +108,48 @@ def test_tiled_radon_forward_and_transpose(W, circle, emul_backend, monkeypatch)
     assert abs(float(lhs - rhs)) < 1e-4 * max(1.0, abs(float(lhs)))
     monkeypatch.setenv("DINVK_NO_TILED_RADON", "1")
     assert rel_err(phys.A(x), y) < 3e-6 and rel_err(phys.A_adjoint(v), xt) < 3e-6
+
+
+def test_pipe256_every_operand_combination_vs_tile_passes(emul_backend, monkeypatch):
+    """the operand / multiplier / epilogue combinations of `dinvk_spectral` that reach the pipelined kernels (the list of
+    tests/test_gpu_spectral_pipe.py), pipelined kernels vs the general tile passes on the same operands, on the host"""
+    import os
+
+    from deepinv_b200 import _ffi, ops
+
+    H = W = 256
+    B = 2  # 32 tiles over the emulated persistent grid (8 CTAs): every CTA refills its ring
+    gen = torch.Generator().manual_seed(2)
+    r = lambda: torch.randn(B, 2, H, W, generator=gen)
+    x, p1, q0, q1 = r(), r(), r(), r()
+    line = ops.mask_spec_from_real((torch.rand(B, 1, 1, W, generator=gen) > 0.7).float().expand(B, 2, H, W).contiguous(), H, W)
+    full = ops.mask_spec_from_real(torch.rand(B, 2, H, W, generator=gen), H, W)
+    shared = ops.mask_spec_from_real(torch.rand(1, 2, H, W, generator=gen), H, W)
+    assert line.sh == 0 and full.sh == W
+    cb = torch.rand(B, generator=gen) + 0.5
+    cases = []
+    for mname, m in (("line", line), ("full", full), ("shared", shared)):
+        for gmode in ((_ffi.G_MASK, _ffi.G_INV_SQ_PLUS_C, _ffi.G_PINV) if mname == "line" else (_ffi.G_MASK,)):
+            cases.append((f"A {mname} g{gmode}", dict(fwd=True, inv=False, gmode=gmode, mask=m, c=0.8)))
+            cases.append((f"At {mname} g{gmode}", dict(fwd=False, inv=True, gmode=gmode, mask=m, c=0.8)))
+        cases.append((f"A {mname} epilogue", dict(fwd=True, inv=False, gmode=_ffi.G_MASK, mask=m, a0=0.5, p1=p1, a1=-1.5, e0=2.0,
+                                                   q0=q0, e1=0.25, q1=q1, e2=-0.75)))
+        cases.append((f"At {mname} c_batch", dict(fwd=False, inv=True, gmode=_ffi.G_INV_SQ_PLUS_C, mask=m, c_batch=cb)))
+    for gmode in (_ffi.G_MASK, _ffi.G_SQ, _ffi.G_INV_SQ_PLUS_C, _ffi.G_PINV):
+        cases.append((f"fused line g{gmode}", dict(fwd=True, inv=True, gmode=gmode, mask=line, c=1.3)))
+    cases += [
+        ("fused none", dict(fwd=True, inv=True)),
+        ("A none", dict(fwd=True, inv=False)),
+        ("At uncentred", dict(fwd=False, inv=True, centered=False, gmode=_ffi.G_MASK, mask=full)),
+        ("fused uncentred", dict(fwd=True, inv=True, centered=False, gmode=_ffi.G_SQ, mask=line)),
+        ("normal step", dict(fwd=True, inv=True, gmode=_ffi.G_SQ, mask=line, e0=-0.9, q0=x, e1=1.0, q1=q1, e2=0.9)),
+        ("fused q0 != p0", dict(fwd=True, inv=True, gmode=_ffi.G_SQ, mask=line, e0=-0.9, q0=q0, e1=1.0, q1=q1, e2=0.9)),
+        ("prox", dict(fwd=True, inv=True, gmode=_ffi.G_INV_SQ_PLUS_C, mask=line, p1=p1, a1=1.0 / 0.7, c=1.0 / 0.7)),
+        ("prox c_batch", dict(fwd=True, inv=True, gmode=_ffi.G_INV_SQ_PLUS_C, mask=line, p1=p1, a1=1.0, c_batch=cb)),
+    ]
+    for name, kw in cases:
+        got = ops.spectral(x, H, W, **kw)
+        monkeypatch.setenv("DINVK_NO_PIPE_FFT", "1")
+        want = ops.spectral(x, H, W, **kw)
+        monkeypatch.delenv("DINVK_NO_PIPE_FFT")
+        assert rel_err(got, want) < 3e-6, name
