@@ -12,7 +12,13 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent.parent
 CSRC = ROOT / "deepinv_b200" / "csrc"
-OUT = HERE / "_build" / "libdinvk_emul.so"
+import os
+
+# DINVK_EMUL_SANITIZE=1: AddressSanitizer + UBSan build of the emulated kernels — the CPU stand-in for compute-sanitizer's
+# memcheck (out-of-bounds shared / global accesses, misaligned vector loads, signed overflow in index math).  Run with
+#   DINVK_EMUL_SANITIZE=1 LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 python -m pytest tests/test_emul_kernels.py ...
+SANITIZE = os.environ.get("DINVK_EMUL_SANITIZE") == "1"
+OUT = HERE / "_build" / ("libdinvk_emul_asan.so" if SANITIZE else "libdinvk_emul.so")
 # SIMT-only translation units (the tcgen05/TMA kernels cannot be emulated)
 SOURCES = ["core.cu", "spectral.cu", "elementwise.cu", "radon.cu", "blur.cu", "conv_simt.cu"]
 
@@ -29,15 +35,17 @@ def build() -> Path:
     objs = []
     procs = []
     for s in srcs:
-        o = OUT.parent / (s.stem + ".o")
+        o = OUT.parent / (s.stem + ("_asan.o" if SANITIZE else ".o"))
         objs.append(o)
-        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-DDINVK_EMUL", "-x", "c++", "-I", str(HERE), "-I", str(ROOT / "include"),
+        san = ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-g", "-O1"] if SANITIZE else ["-O2"]
+        cmd = ["g++", *san, "-std=c++17", "-fPIC", "-DDINVK_EMUL", "-x", "c++", "-I", str(HERE), "-I", str(ROOT / "include"),
                "-Wno-unknown-pragmas", "-c", str(s), "-o", str(o)]
         procs.append((cmd, subprocess.Popen(cmd)))
     for cmd, p in procs:
         if p.wait() != 0:
             raise RuntimeError("emul build failed: " + " ".join(cmd))
-    subprocess.run(["g++", "-shared", "-o", str(OUT), *map(str, objs), "-lpthread"], check=True)
+    subprocess.run(["g++", "-shared", *(["-fsanitize=address,undefined"] if SANITIZE else []), "-o", str(OUT), *map(str, objs),
+                    "-lpthread"], check=True)
     stamp.write_text(h.hexdigest())
     return OUT
 
