@@ -17,8 +17,12 @@ import os
 # DINVK_EMUL_SANITIZE=1: AddressSanitizer + UBSan build of the emulated kernels — the CPU stand-in for compute-sanitizer's
 # memcheck (out-of-bounds shared / global accesses, misaligned vector loads, signed overflow in index math).  Run with
 #   DINVK_EMUL_SANITIZE=1 LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 python -m pytest tests/test_emul_kernels.py ...
-SANITIZE = os.environ.get("DINVK_EMUL_SANITIZE") == "1"
-OUT = HERE / "_build" / ("libdinvk_emul_asan.so" if SANITIZE else "libdinvk_emul.so")
+SANITIZE = os.environ.get("DINVK_EMUL_SANITIZE") in ("1", "thread")
+# DINVK_EMUL_SANITIZE=thread: ThreadSanitizer build — every CUDA thread is a host thread and __syncthreads / __syncwarp are real
+# barriers, so a missing barrier between a shared-memory write and another thread's read is a data race TSan reports: the CPU
+# stand-in for compute-sanitizer's racecheck (LD_PRELOAD=$(gcc -print-file-name=libtsan.so)).
+TSAN = os.environ.get("DINVK_EMUL_SANITIZE") == "thread"
+OUT = HERE / "_build" / ("libdinvk_emul_tsan.so" if TSAN else "libdinvk_emul_asan.so" if SANITIZE else "libdinvk_emul.so")
 # SIMT-only translation units (the tcgen05/TMA kernels cannot be emulated)
 SOURCES = ["core.cu", "spectral.cu", "elementwise.cu", "radon.cu", "blur.cu", "conv_simt.cu"]
 
@@ -35,16 +39,17 @@ def build() -> Path:
     objs = []
     procs = []
     for s in srcs:
-        o = OUT.parent / (s.stem + ("_asan.o" if SANITIZE else ".o"))
+        o = OUT.parent / (s.stem + ("_tsan.o" if TSAN else "_asan.o" if SANITIZE else ".o"))
         objs.append(o)
-        san = ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-g", "-O1"] if SANITIZE else ["-O2"]
+        san = (["-fsanitize=thread", "-g", "-O1"] if TSAN else
+               ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-g", "-O1"] if SANITIZE else ["-O2"])
         cmd = ["g++", *san, "-std=c++17", "-fPIC", "-DDINVK_EMUL", "-x", "c++", "-I", str(HERE), "-I", str(ROOT / "include"),
                "-Wno-unknown-pragmas", "-c", str(s), "-o", str(o)]
         procs.append((cmd, subprocess.Popen(cmd)))
     for cmd, p in procs:
         if p.wait() != 0:
             raise RuntimeError("emul build failed: " + " ".join(cmd))
-    subprocess.run(["g++", "-shared", *(["-fsanitize=address,undefined"] if SANITIZE else []), "-o", str(OUT), *map(str, objs),
+    subprocess.run(["g++", "-shared", *(["-fsanitize=thread"] if TSAN else ["-fsanitize=address,undefined"] if SANITIZE else []), "-o", str(OUT), *map(str, objs),
                     "-lpthread"], check=True)
     stamp.write_text(h.hexdigest())
     return OUT
