@@ -93,6 +93,64 @@ def bicgstab(A: Callable, b: torch.Tensor, init: torch.Tensor | None = None, max
     return x
 
 
+def lsqr(A: Callable, AT: Callable, b: torch.Tensor, eta=0.0, x0: torch.Tensor | None = None, tol: float = 1e-6,
+         max_iter: int = 100, verbose: bool = False) -> torch.Tensor:
+    r"""LSQR (Paige & Saunders 1982) for min_x ||A x - b||^2 + eta ||x - x0||^2 on rectangular operators, batch dimension in
+    parallel (deepinv/optim/linear/lsqr.py:5-230; that file adapts SciPy's lsqr).  Golub-Kahan bidiagonalisation with the damped
+    Givens update; per iteration one `A`, one `A^T`, two norms (`dinvk_batched_dot`) and five `dinvk_batched_axpy`, the
+    (B,)-sized rotation scalars stay on the device; one boolean is read back per iteration for the stopping rule
+    ||r|| <= tol ||b||.  eta: float or (B,) tensor."""
+    nrm = lambda t: _dot(t, t).sqrt()
+    scale = lambda t, s_: ops.batched_axpy(t, t, s_ - 1.0, 1.0)          # t * s[b]
+    B = b.shape[0]
+    dev = b.device
+    eta_t = (eta.reshape(-1).float() if isinstance(eta, torch.Tensor) else torch.full((B,), float(eta or 0.0), device=dev))
+    if bool((eta_t < 0).any()):
+        raise ValueError("Damping parameter eta must be non-negative. LSQR cannot be applied to problems with negative eta.")
+    damp = eta_t.sqrt()
+    bnorm = nrm(b)
+    if x0 is None:
+        x = torch.zeros_like(AT(b))
+        u = b
+    else:
+        x = x0.clone()
+        u = ops.axpbypcz(b, 1.0, A(x), -1.0)
+    beta = nrm(u)
+    safe_inv = lambda t: torch.where(t > 0, 1.0 / t, torch.zeros_like(t))
+    u = scale(u, safe_inv(beta))
+    v = AT(u)
+    alpha = nrm(v)
+    v = scale(v, safe_inv(alpha))
+    w = v
+    rhobar, phibar = alpha, beta
+    if bool(((alpha * beta) == 0).all()):
+        return x
+    for itn in range(int(max_iter)):
+        u = ops.batched_axpy(A(v), u, alpha, -1.0)
+        beta = nrm(u)
+        u = scale(u, safe_inv(beta))
+        v = ops.batched_axpy(AT(u), v, beta, -1.0)
+        alpha = nrm(v)
+        v = scale(v, safe_inv(alpha))
+        rhobar1 = torch.sqrt(rhobar ** 2 + eta_t)
+        cs1, sn1 = rhobar / rhobar1, damp / rhobar1
+        psi, phibar = sn1 * phibar, cs1 * phibar
+        rho = torch.hypot(rhobar1, beta)
+        cs, sn = rhobar1 / rho, beta / rho
+        theta, rhobar = sn * alpha, -cs * alpha
+        phi, phibar = cs * phibar, sn * phibar
+        x = ops.batched_axpy(x, w, phi / rho, 1.0)
+        w = ops.batched_axpy(v, w, theta / rho, -1.0)
+        if bool((torch.sqrt(phibar ** 2 + psi ** 2) <= tol * bnorm).all()):
+            if verbose:
+                print("LSQR converged at iteration", itn)
+            break
+    else:
+        if verbose:
+            print("LSQR did not converge")
+    return x
+
+
 def _solve_normal(physics, y, z, init, g, g_batch, max_iter, tol, verbose, kwargs, solver="CG"):
     """CG on (A^T A + I/gamma) x = A^T y + z/gamma; gamma: None, a host float `g`, or a (B,) device tensor `g_batch`"""
     b = physics.A_adjoint(y, **kwargs)
@@ -174,12 +232,14 @@ def least_squares(physics, y: torch.Tensor, z: torch.Tensor | None = None, init:
     (A^T A + I/gamma) x = A^T y + z/gamma  (least_squares.py:148-151); gamma may be a scalar or one value per sample.
     When a gradient w.r.t. y, z or gamma is being tracked the result carries the implicit-differentiation backward of the
     reference's `least_squares_implicit_backward` (least_squares.py:345-469)."""
-    if solver not in ("CG", "cg", "BiCGStab", None):
-        raise NotImplementedError(f"deepinv_b200: solver {solver!r} is outside the accelerated path (CG and BiCGStab on the "
-                                  "normal equations; SURVEY §8 a12)")
-    solver = "BiCGStab" if solver == "BiCGStab" else "CG"
+    if solver not in ("CG", "cg", "BiCGStab", "lsqr", None):
+        raise NotImplementedError(f"deepinv_b200: solver {solver!r} is outside the accelerated path (CG, BiCGStab, lsqr; "
+                                  "SURVEY §8 a12)")
+    solver = solver if solver in ("BiCGStab", "lsqr") else "CG"
     kwargs.pop("parallel_dim", None)
     tracked = torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in (y, z, gamma))
+    if tracked and solver == "lsqr":
+        solver = "CG"  # the implicit-differentiation backward needs the normal-equation solve
     if tracked:
         if z is None:
             z = torch.zeros_like(physics.A_adjoint(y.detach(), **kwargs))
@@ -189,6 +249,13 @@ def least_squares(physics, y: torch.Tensor, z: torch.Tensor | None = None, init:
         opts = {"max_iter": max_iter, "tol": tol, "verbose": verbose, "kwargs": kwargs, "solver": solver}
         return _LeastSquaresFn.apply(physics, y, z, init, gam, opts)
     y0 = y if isinstance(y, torch.Tensor) else y[0]  # stacked operators measure TensorLists (physics/combine.py)
+    if solver == "lsqr":  # rectangular solver on (A, A^T) directly: eta = 1/gamma, x0 = z (least_squares.py:118-130)
+        if not isinstance(y, torch.Tensor):
+            raise NotImplementedError("deepinv_b200: lsqr on stacked (TensorList) measurements is not supported; use CG")
+        eta = 0.0 if gamma is None else (1.0 / gamma.reshape(-1).float() if isinstance(gamma, torch.Tensor) and gamma.numel() > 1
+                                         else 1.0 / float(gamma))
+        return lsqr(lambda v: physics.A(v, **kwargs), lambda v: physics.A_adjoint(v, **kwargs), y, eta=eta, x0=z, tol=tol,
+                    max_iter=max_iter, verbose=verbose)
     if solver == "BiCGStab" and isinstance(y, torch.Tensor):
         # the reference hands a "complete" system (A^T y has the shape of y) to BiCGStab as A x = y itself — gamma and z do not
         # enter (least_squares.py:131-134); mirrored so that solver="BiCGStab" returns what the reference returns

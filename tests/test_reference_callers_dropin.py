@@ -171,3 +171,20 @@ def test_least_squares_solvers_match_the_reference_solvers(solver):
                         ATA=valid.A_adjoint_A, max_iter=25, tol=1e-5, solver=solver)
         got_v = dinv.optim.least_squares(valid, yv, z=g["z"], init=g["z"], gamma=gam, solver=solver, max_iter=25, tol=1e-5)
         assert rel_err(got_v, want_v) < 2e-5
+
+
+def test_lsqr_matches_the_reference_lsqr_on_a_rectangular_operator():
+    """deepinv_b200.optim.lsqr (Golub-Kahan on the kernels) vs the reference's lsqr (optim/linear/lsqr.py) on the drop-in valid-padding
+    Blur (rectangular): damped problem with a warm start, and the plain pseudo-inverse"""
+    import deepinv_b200 as dinv
+    from deepinv.optim.linear import least_squares as ref_ls
+
+    g = load_golden("blur_gauss_circular_prox")
+    phys = dinv.physics.Blur(filter=g["filt"], padding="valid", device=DEV)
+    y = phys.A(g["z"]) + 0.01 * torch.randn(phys.A(g["z"]).shape, generator=torch.Generator().manual_seed(0))
+    for gam, batched in ((2.0, False), (torch.tensor([0.5, 3.0]), True)):
+        want = ref_ls(phys.A, phys.A_adjoint, y, z=g["x"], init=g["x"], gamma=gam, parallel_dim=[0], max_iter=30, tol=1e-6, solver="lsqr")
+        got = dinv.optim.least_squares(phys, y, z=g["x"], init=g["x"], gamma=gam, solver="lsqr", max_iter=30, tol=1e-6)
+        assert rel_err(got, want) < 1e-4, batched
+    cg = dinv.optim.least_squares(phys, y, z=g["x"], init=g["x"], gamma=2.0, solver="CG", max_iter=60, tol=1e-6)
+    assert rel_err(dinv.optim.least_squares(phys, y, z=g["x"], gamma=2.0, solver="lsqr", max_iter=60, tol=1e-7), cg) < 1e-3
