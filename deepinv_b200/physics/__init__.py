@@ -6,3 +6,4 @@ from .noise import GaussianNoise, NoiseModel, ZeroNoise  # noqa: F401
 from .tomography import Tomography  # noqa: F401
 from .combine import (ComposedLinearPhysics, ComposedPhysics, StackedLinearPhysics, StackedPhysics, TensorList,  # noqa: F401
                       compose, stack)
+from .inpainting import Denoising, Inpainting  # noqa: F401

@@ -38,7 +38,10 @@ class DDRM(nn.Module):
                 np.random.seed(seed)
                 torch.manual_seed(seed)
             sigma_noise = float(physics.noise_model.sigma) if hasattr(physics.noise_model, "sigma") else 0.01
-            mask = physics.mask.abs().to(torch.float32).contiguous()
+            mask = physics.mask.abs().to(torch.float32)
+            if mask.dim() == 0:  # Denoising: all singular values equal (diffusion.py:168-171 uses ones_like(y))
+                mask = mask * torch.ones((1, *y.shape[1:]), dtype=torch.float32, device=y.device)
+            mask = mask.contiguous()
             if mask.shape[0] != 1:
                 raise IndexError("DDRM requires a batch-1 mask (deepinv/sampling/diffusion.py:173)")
             c = math.sqrt(1 - self.eta ** 2)

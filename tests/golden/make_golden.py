@@ -474,6 +474,31 @@ def ddrm_fixture():
          sigma_noise=np.float32(0.02), **sd_arrays(den, "sd__"))
 
 
+def inpainting_fixture():
+    """DDRM on Inpainting (the reference's own sampling test, tests/test_sampling.py:147-195) with a recorded noise sequence"""
+    from deepinv.physics import Denoising, Inpainting
+
+    B, H, W = 2, 32, 32
+    x = torch.rand(B, 2, H, W, generator=g(71))
+    mask = (torch.rand(1, 2, H, W, generator=g(72)) > 0.4).float()
+    phys = Inpainting(img_size=(2, H, W), mask=mask, noise_model=dinv.physics.GaussianNoise(sigma=0.05, rng=g(73)))
+    y = phys(x)
+    den = tiny_drunet(2)
+    sigmas = np.linspace(1, 0, 5)
+    noises = [torch.randn(B, 2, H, W, generator=g(300 + t)) for t in range(len(sigmas))]
+    it = iter(noises)
+    orig = torch.randn_like
+    torch.randn_like = lambda t, **kw: next(it).to(t)
+    try:
+        out = dinv.sampling.DDRM(denoiser=den, sigmas=sigmas)(y, phys)
+        it = iter(noises)
+        out_den = dinv.sampling.DDRM(denoiser=den, sigmas=sigmas)(y, Denoising(dinv.physics.GaussianNoise(sigma=0.05)))
+    finally:
+        torch.randn_like = orig
+    save("ddrm_inpainting_tiny", x=x, mask=mask, y=y, sigmas=sigmas, noises=torch.stack(noises), out=out, out_denoising=out_den,
+         At=phys.A_adjoint(y), prox=phys.prox_l2(x, y, 0.8), sigma_noise=np.float32(0.05), **sd_arrays(den, "sd__"))
+
+
 def diffpir_fixture():
     """DiffPIR (sampling/diffusion.py:227-513) on a circular blur with a recorded noise sequence"""
     B, H, W = 2, 32, 32
@@ -496,13 +521,13 @@ def diffpir_fixture():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm", "optim2", "train", "dynamic", "down", "combine", "maskgen", "mri3d", "fan", "anderson", "diffpir"]
+    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm", "optim2", "train", "dynamic", "down", "combine", "maskgen", "mri3d", "fan", "anderson", "diffpir", "inpainting"]
     table = {"mri": mri_fixtures, "multicoil": multicoil_fixtures, "tomo": tomo_fixtures, "blur": blur_fixtures,
              "blurfft": blurfft_fixtures, "model": model_fixtures, "optim": optim_fixtures, "ddrm": ddrm_fixture,
              "optim2": optim2_fixtures, "train": train_fixtures,
              "dynamic": dynamic_fixtures, "down": down_fixtures,
              "combine": combine_fixtures, "maskgen": maskgen_fixtures,
              "mri3d": mri3d_fixture, "fan": fanbeam_fixtures, "anderson": anderson_fixtures,
-             "diffpir": diffpir_fixture}
+             "diffpir": diffpir_fixture, "inpainting": inpainting_fixture}
     for w in which:
         table[w]()

@@ -506,6 +506,23 @@ def case_pnp_blur_admm(dev):
     assert rel_err(out, g["admm"]) < 1e-4  # three CG solves inside
 
 
+def case_ddrm_inpainting(dev):
+    """DDRM on Inpainting and Denoising (identity singular vectors): the reference's own sampling demo, recorded noise draws"""
+    import deepinv_b200 as dinv
+
+    g = to_dev(load_golden("ddrm_inpainting_tiny"), dev)
+    den = load_model(dinv.models.DRUNet, g, dev, in_channels=2, out_channels=2, nc=(8, 16, 32, 64), nb=2)
+    sig = float(g["sigma_noise"])
+    phys = dinv.physics.Inpainting(img_size=(2, 32, 32), mask=g["mask"], device=dev, noise_model=dinv.physics.GaussianNoise(sigma=sig))
+    assert rel_err(phys.A_adjoint(g["y"]), g["At"]) < TOL and rel_err(phys.prox_l2(g["x"], g["y"], 0.8), g["prox"]) < TOL
+    sigmas = [float(s_) for s_ in g["sigmas"]]
+    out = dinv.sampling.DDRM(denoiser=den, sigmas=sigmas)(g["y"], phys, noises=list(g["noises"]))
+    assert rel_err(out, g["out"]) < TOL
+    dn = dinv.physics.Denoising(dinv.physics.GaussianNoise(sigma=sig), device=dev)
+    out = dinv.sampling.DDRM(denoiser=den, sigmas=sigmas)(g["y"], dn, noises=list(g["noises"]))
+    assert rel_err(out, g["out_denoising"]) < TOL
+
+
 def case_diffpir(dev):
     """DiffPIR on BlurFFT with the reference's recorded noise draws (host-planned schedule vs the reference's device lookups)"""
     import deepinv_b200 as dinv

@@ -121,6 +121,10 @@ def test_pnp_blur_admm():
     P.case_pnp_blur_admm(DEV)
 
 
+def test_ddrm_inpainting_and_denoising():
+    P.case_ddrm_inpainting(DEV)
+
+
 def test_diffpir():
     P.case_diffpir(DEV)
 
