@@ -69,3 +69,23 @@ def test_state_dict_compatibility_with_reference_layout():
     m.load_state_dict(sd, strict=True)
     full = dinv.models.DRUNet(in_channels=2, out_channels=2, pretrained=None)
     assert sum(p.numel() for p in full.parameters()) == 32_639_808
+
+
+def test_public_api_surface():
+    """the names README.md lists under the reference's module layout exist"""
+    import deepinv_b200 as d
+
+    table = {
+        d.physics: "Physics LinearPhysics DecomposablePhysics MRI MultiCoilMRI DynamicMRI SequentialMRI Tomography Blur BlurFFT "
+                   "Downsampling Denoising Inpainting compose stack TensorList GaussianNoise",
+        d.physics.functional: "gaussian_blur bilinear_filter bicubic_filter sinc_filter kaiser_window",
+        d.physics.generator: "RandomMaskGenerator GaussianMaskGenerator EquispacedMaskGenerator MotionBlurGenerator",
+        d.optim: "L2 PnP RED Tikhonov ZeroPrior PGD FISTA ADMM HQS DRS GD DPIR BaseOptim optim_builder create_iterator least_squares "
+                 "conjugate_gradient bicgstab lsqr GraphedIteration GraphedSolve HostStreamedIteration DEQConfig "
+                 "AndersonAccelerationConfig BacktrackingConfig",
+        d.unfolded: "unfolded_builder BaseUnfold DEQ_builder BaseDEQ",
+        d.models: "DRUNet DnCNN",
+        d.sampling: "DDRM DiffPIR",
+    }
+    missing = [f"{m.__name__}.{n}" for m, names in table.items() for n in names.split() if not hasattr(m, n)]
+    assert not missing, missing
