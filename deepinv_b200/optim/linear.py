@@ -93,6 +93,59 @@ def bicgstab(A: Callable, b: torch.Tensor, init: torch.Tensor | None = None, max
     return x
 
 
+def minres(A: Callable, b: torch.Tensor, init: torch.Tensor | None = None, max_iter: int = 100, tol: float = 1e-5,
+           eps: float = 1e-25, verbose: bool = False) -> torch.Tensor:
+    """MINRES (Paige & Saunders 1975) for a symmetric, possibly indefinite operator, batch dimension in parallel
+    (deepinv/optim/linear/minres.py:9-173): Lanczos three-term recurrence + one Givens rotation per step, on the right-hand side
+    normalised per sample; stops when the update is below `tol` relative to the solution, like the reference.  Vector work is
+    `dinvk_batched_dot` / `dinvk_batched_axpy`; the (B,) recurrence scalars stay on the device."""
+    bnorm = _dot(b, b).sqrt()
+    zero_b = bnorm < 1e-10
+    bnorm = torch.where(zero_b, torch.ones_like(bnorm), bnorm)
+    inv = 1.0 / bnorm
+    scale = lambda t, s_: ops.batched_axpy(t, t, s_ - 1.0, 1.0)
+    bn = scale(b, inv)
+    x = torch.zeros_like(b) if init is None else scale(init, inv)
+    z_prev2 = torch.zeros_like(b)
+    z_prev1 = ops.axpbypcz(bn, 1.0, A(x), -1.0)
+    beta_prev = _dot(z_prev1, z_prev1).sqrt().clamp_min(eps)
+    z_prev1 = scale(z_prev1, 1.0 / beta_prev)
+    q = z_prev1
+    one, zero = torch.ones_like(beta_prev), torch.zeros_like(beta_prev)
+    cos2, sin2, cos1, sin1 = one, zero, one, zero
+    s_prev2, s_prev1 = torch.zeros_like(b), torch.zeros_like(b)
+    scale_prev = beta_prev
+    for i in range(int(max_iter)):
+        prod = A(q)
+        alpha = _dot(prod, q)
+        prod = ops.batched_axpy(ops.batched_axpy(prod, z_prev1, alpha, -1.0), z_prev2, beta_prev, -1.0)
+        beta = _dot(prod, prod).sqrt().clamp_min(eps)
+        prod = scale(prod, 1.0 / beta)
+        # apply the two previous rotations to the new tridiagonal column, then the new one
+        subsub = sin2 * beta_prev
+        sub = cos2 * beta_prev
+        diag = alpha * cos1 - sin1 * sub
+        sub = sub * cos1 + sin1 * alpha
+        radius = torch.sqrt(diag * diag + beta * beta)
+        cos, sin = diag / radius, beta / radius
+        diag = diag * cos + sin * beta
+        scale_cur = -scale_prev * sin
+        search = ops.batched_axpy(ops.batched_axpy(q, s_prev1, sub, -1.0), s_prev2, subsub, -1.0)
+        search = scale(search, 1.0 / diag)
+        step = scale_prev * cos
+        x = ops.batched_axpy(x, search, step, 1.0)
+        upd = _dot(search, search).sqrt() * step.abs()
+        if float((upd / _dot(x, x).sqrt()).max()) < tol:
+            if verbose:
+                print("MINRES converged at iteration", i + 1)
+            break
+        z_prev2, z_prev1, q, beta_prev = z_prev1, prod, prod, beta
+        cos2, cos1, sin2, sin1 = cos1, cos, sin1, sin
+        s_prev2, s_prev1, scale_prev = s_prev1, search, scale_cur
+    x = scale(x, torch.where(zero_b, torch.zeros_like(bnorm), bnorm))
+    return x
+
+
 def lsqr(A: Callable, AT: Callable, b: torch.Tensor, eta=0.0, x0: torch.Tensor | None = None, tol: float = 1e-6,
          max_iter: int = 100, verbose: bool = False) -> torch.Tensor:
     r"""LSQR (Paige & Saunders 1982) for min_x ||A x - b||^2 + eta ||x - x0||^2 on rectangular operators, batch dimension in
@@ -167,6 +220,8 @@ def _solve_normal(physics, y, z, init, g, g_batch, max_iter, tol, verbose, kwarg
         H = lambda v: physics.A_adjoint_A(v, **kwargs)
     if solver == "BiCGStab":
         return bicgstab(H, b, init=init, max_iter=max_iter, tol=tol, verbose=verbose)
+    if solver == "minres":
+        return minres(H, b, init=init, max_iter=max_iter, tol=tol, verbose=verbose)
     return conjugate_gradient(H, b, max_iter=max_iter, tol=tol, init=init, verbose=verbose)
 
 
@@ -232,13 +287,12 @@ def least_squares(physics, y: torch.Tensor, z: torch.Tensor | None = None, init:
     (A^T A + I/gamma) x = A^T y + z/gamma  (least_squares.py:148-151); gamma may be a scalar or one value per sample.
     When a gradient w.r.t. y, z or gamma is being tracked the result carries the implicit-differentiation backward of the
     reference's `least_squares_implicit_backward` (least_squares.py:345-469)."""
-    if solver not in ("CG", "cg", "BiCGStab", "lsqr", None):
-        raise NotImplementedError(f"deepinv_b200: solver {solver!r} is outside the accelerated path (CG, BiCGStab, lsqr; "
-                                  "SURVEY §8 a12)")
-    solver = solver if solver in ("BiCGStab", "lsqr") else "CG"
+    if solver not in ("CG", "cg", "BiCGStab", "lsqr", "minres", None):
+        raise ValueError(f"Solver {solver} not recognized. Choose between 'CG', 'lsqr', 'BiCGStab' and 'minres'.")
+    solver = solver if solver in ("BiCGStab", "lsqr", "minres") else "CG"
     kwargs.pop("parallel_dim", None)
     tracked = torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in (y, z, gamma))
-    if tracked and solver == "lsqr":
+    if tracked and solver in ("lsqr", "minres"):
         solver = "CG"  # the implicit-differentiation backward needs the normal-equation solve
     if tracked:
         if z is None:
@@ -256,11 +310,12 @@ def least_squares(physics, y: torch.Tensor, z: torch.Tensor | None = None, init:
                                          else 1.0 / float(gamma))
         return lsqr(lambda v: physics.A(v, **kwargs), lambda v: physics.A_adjoint(v, **kwargs), y, eta=eta, x0=z, tol=tol,
                     max_iter=max_iter, verbose=verbose)
-    if solver == "BiCGStab" and isinstance(y, torch.Tensor):
-        # the reference hands a "complete" system (A^T y has the shape of y) to BiCGStab as A x = y itself — gamma and z do not
-        # enter (least_squares.py:131-134); mirrored so that solver="BiCGStab" returns what the reference returns
+    if solver in ("BiCGStab", "minres") and isinstance(y, torch.Tensor):
+        # the reference hands a "complete" system (A^T y has the shape of y) to BiCGStab / MINRES as A x = y itself — gamma and z
+        # do not enter (least_squares.py:131-134); mirrored so that these solvers return what the reference returns
         probe = physics.A_adjoint(y, **kwargs)
         if probe.shape == y.shape:
-            return bicgstab(lambda v: physics.A(v, **kwargs), y, init=init, max_iter=max_iter, tol=tol, verbose=verbose)
+            fn = bicgstab if solver == "BiCGStab" else minres
+            return fn(lambda v: physics.A(v, **kwargs), y, init=init, max_iter=max_iter, tol=tol, verbose=verbose)
     g, g_batch = _split_gamma(gamma, y0.shape[0])
     return _solve_normal(physics, y, z, init, g, g_batch, max_iter, tol, verbose, kwargs, solver)

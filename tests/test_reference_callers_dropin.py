@@ -188,3 +188,23 @@ def test_lsqr_matches_the_reference_lsqr_on_a_rectangular_operator():
         assert rel_err(got, want) < 1e-4, batched
     cg = dinv.optim.least_squares(phys, y, z=g["x"], init=g["x"], gamma=2.0, solver="CG", max_iter=60, tol=1e-6)
     assert rel_err(dinv.optim.least_squares(phys, y, z=g["x"], gamma=2.0, solver="lsqr", max_iter=60, tol=1e-7), cg) < 1e-3
+
+
+def test_minres_matches_the_reference_minres():
+    """deepinv_b200.optim.minres vs the reference's minres (optim/linear/minres.py): the symmetric system (A^T A + I/gamma) x = b of a
+    rectangular operator through least_squares, and a symmetric complete operator handed over as A x = y"""
+    import deepinv_b200 as dinv
+    from deepinv.optim.linear import least_squares as ref_ls
+
+    g = load_golden("blur_gauss_circular_prox")
+    valid = dinv.physics.Blur(filter=g["filt"], padding="valid", device=DEV)
+    y = valid.A(g["z"])
+    want = ref_ls(valid.A, valid.A_adjoint, y, z=g["x"], init=g["x"], gamma=2.0, parallel_dim=[0], AAT=valid.A_A_adjoint,
+                  ATA=valid.A_adjoint_A, max_iter=30, tol=1e-6, solver="minres")
+    got = dinv.optim.least_squares(valid, y, z=g["x"], init=g["x"], gamma=2.0, solver="minres", max_iter=30, tol=1e-6)
+    assert rel_err(got, want) < 1e-4
+    circ = dinv.physics.Blur(filter=g["filt"], padding="circular", device=DEV)  # symmetric filter: A = A^T, complete system
+    want = ref_ls(circ.A, circ.A_adjoint, g["y"], z=g["z"], init=g["z"], gamma=2.0, parallel_dim=[0], AAT=circ.A_A_adjoint,
+                  ATA=circ.A_adjoint_A, max_iter=15, tol=1e-6, solver="minres")
+    got = dinv.optim.least_squares(circ, g["y"], z=g["z"], init=g["z"], gamma=2.0, solver="minres", max_iter=15, tol=1e-6)
+    assert rel_err(got, want) < 2e-3  # unregularised deblurring: see the BiCGStab case above
