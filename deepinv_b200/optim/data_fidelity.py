@@ -14,6 +14,10 @@ class DataFidelity(nn.Module):
     def forward(self, x, y, physics, *args, **kwargs):
         return self.fn(x, y, physics, *args, **kwargs)
 
+    def prox_conjugate(self, x, y, physics, *args, gamma=1.0, lamb=1.0, **kwargs):
+        """prox of (lamb f)^* by Moreau's identity (potential.py:120-133)"""
+        return x - gamma * self.prox(x / gamma, y, physics, *args, gamma=lamb / gamma, **kwargs)
+
 
 class ZeroFidelity(DataFidelity):
     def fn(self, x, y, physics, *args, **kwargs):

@@ -268,3 +268,44 @@ class GDIteration(OptimIterator):
         else:
             x = x_prev - step * (gg + self.f_step(x_prev, cur_data_fidelity, cur_params, y, physics))
         return {"est": (x,), "cost": self._cost(x, cur_data_fidelity, cur_prior, cur_params, y, physics), "aty": aty}
+
+
+# ---- Chambolle-Pock (primal-dual) ----------------------------------------------------------------------
+class fStepCP(fStep):
+    def forward(self, x, w, cur_data_fidelity, y, physics, cur_params):
+        if self.g_first:
+            return cur_data_fidelity.prox(x - cur_params["stepsize"] * w, y, physics, gamma=cur_params["stepsize"])
+        return cur_data_fidelity.prox_conjugate(x + cur_params["stepsize_dual"] * w, y, physics, gamma=cur_params["stepsize_dual"])
+
+
+class gStepCP(gStep):
+    def forward(self, x, w, cur_prior, cur_params):
+        if self.g_first:
+            return cur_prior.prox_conjugate(x + cur_params["stepsize_dual"] * w, cur_params["g_param"],
+                                            gamma=cur_params["lambda"] * cur_params["stepsize_dual"], lamb=cur_params["lambda"])
+        return cur_prior.prox(x - cur_params["stepsize"] * w, cur_params["g_param"],
+                              gamma=cur_params["stepsize"] * cur_params["lambda"])
+
+
+class CPIteration(OptimIterator):
+    """Chambolle-Pock primal-dual iteration on (x, z, u) = (primal, extrapolated primal, dual) with an optional linear map K
+    (primal_dual_CP.py:12-175):  u <- prox_{sigma F*}(u + sigma K z);  x <- prox_{tau G}(x - tau K^T u);  z <- x + beta (x - x_prev),
+    F / G being the data term and the prior in the order chosen by `g_first`."""
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.g_step = gStepCP(**kwargs)
+        self.f_step = fStepCP(**kwargs)
+
+    def forward(self, X, cur_data_fidelity, cur_prior, cur_params, y, physics, *args, **kwargs):
+        x_prev, z_prev, u_prev = X["est"]
+        K = cur_params.get("K") or (lambda v: v)
+        Kt = cur_params.get("K_adjoint") or (lambda v: v)
+        if self.g_first:
+            u = self.g_step(u_prev, K(z_prev), cur_prior, cur_params)
+            x = self.f_step(x_prev, Kt(u), cur_data_fidelity, y, physics, cur_params)
+        else:
+            u = self.f_step(u_prev, K(z_prev), cur_data_fidelity, y, physics, cur_params)
+            x = self.g_step(x_prev, Kt(u), cur_prior, cur_params)
+        z = x + cur_params["beta"] * (x - x_prev)
+        return {"est": (x, z, u), "cost": self._cost(x, cur_data_fidelity, cur_prior, cur_params, y, physics), "aty": X.get("aty")}

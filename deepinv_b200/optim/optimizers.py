@@ -18,8 +18,8 @@ import torch.nn as nn
 from .data_fidelity import ZeroFidelity
 from dataclasses import dataclass
 
-from .optim_iterators import (ADMMIteration, DRSIteration, FISTAIteration, GDIteration, HQSIteration, OptimIterator,
-                              PGDIteration)
+from .optim_iterators import (ADMMIteration, CPIteration, DRSIteration, FISTAIteration, GDIteration, HQSIteration,
+                              OptimIterator, PGDIteration)
 from .prior import ZeroPrior
 
 
@@ -388,8 +388,33 @@ class GD(_named(GDIteration)):
     """Gradient descent on f + lambda g (optimizers.py:1320-1456)"""
 
 
+class PDCP(BaseOptim):
+    """Primal-dual Chambolle-Pock (optimizers.py:2088-2245): iterates (x, z, u) initialised as (A^T y, A^T y, y)"""
+
+    def __init__(self, data_fidelity=None, prior=None, lambda_reg: float = 1.0, stepsize: float = 1.0, stepsize_dual: float = 1.0,
+                 beta: float = 1.0, K=None, K_adjoint=None, g_param=None, sigma_denoiser=None, max_iter: int = 100,
+                 crit_conv: str = "residual", thres_conv: float = 1e-5, early_stop: bool = False, custom_metrics=None,
+                 custom_init=None, g_first: bool = False, unfold: bool = False, trainable_params=None, cost_fn=None,
+                 params_algo=None, **kwargs):
+        if g_param is None and sigma_denoiser is not None:
+            g_param = sigma_denoiser
+        if params_algo is None:
+            params_algo = {"lambda": lambda_reg, "stepsize": stepsize, "stepsize_dual": stepsize_dual, "g_param": g_param,
+                           "beta": beta, "K": K, "K_adjoint": K_adjoint}
+        if trainable_params is None:
+            trainable_params = ["lambda", "stepsize", "stepsize_dual", "g_param", "beta"]
+        if custom_init is None:
+            def custom_init(y, physics):
+                x0 = physics.A_adjoint(y)
+                return {"est": (x0, x0, y)}
+        super().__init__(CPIteration(g_first=g_first, cost_fn=cost_fn), custom_init=custom_init, data_fidelity=data_fidelity,
+                         prior=prior, params_algo=params_algo, max_iter=max_iter, crit_conv=crit_conv, thres_conv=thres_conv,
+                         early_stop=early_stop, custom_metrics=custom_metrics, unfold=unfold, trainable_params=trainable_params,
+                         **kwargs)
+
+
 _ITERATIONS = {"PGD": PGDIteration, "FISTA": FISTAIteration, "ADMM": ADMMIteration, "HQS": HQSIteration,
-               "DRS": DRSIteration, "GD": GDIteration}
+               "DRS": DRSIteration, "GD": GDIteration, "CP": CPIteration, "PDCP": CPIteration}
 
 
 def create_iterator(iteration, prior=None, cost_fn=None, g_first: bool = False, bregman_potential=None, **kwargs):

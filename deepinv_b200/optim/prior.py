@@ -25,6 +25,10 @@ class Prior(nn.Module):
     def prox(self, x, *args, gamma=1.0, **kwargs):
         raise NotImplementedError
 
+    def prox_conjugate(self, x, *args, gamma=1.0, lamb=1.0, **kwargs):
+        """prox of (lamb g)^* by Moreau's identity (potential.py:120-133): x - gamma prox_{lamb/gamma g}(x / gamma)"""
+        return x - gamma * self.prox(x / gamma, *args, gamma=lamb / gamma, **kwargs)
+
 
 class ZeroPrior(Prior):
     def __init__(self):

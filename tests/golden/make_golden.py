@@ -448,6 +448,13 @@ def anderson_fixtures():
         pgd_bt = PGD(data_fidelity=L2(), prior=Tikhonov(), stepsize=3.0, lambda_reg=0.5, max_iter=10, early_stop=False,
                      backtracking=True)
         out_pgd_bt = pgd_bt(y, phys)
+    from deepinv.optim import PDCP
+
+    with torch.no_grad():
+        cp = PDCP(data_fidelity=L2(), prior=Tikhonov(), lambda_reg=0.3, stepsize=0.6, stepsize_dual=0.8, max_iter=6, early_stop=False)(y, phys)
+        cp_g = PDCP(data_fidelity=L2(), prior=Tikhonov(), lambda_reg=0.3, stepsize=0.6, stepsize_dual=0.8, max_iter=6, early_stop=False,
+                    g_first=True, K=phys.A, K_adjoint=phys.A_adjoint)(y, phys)
+    save("optim_pdcp", cp=cp, cp_gfirst=cp_g)
     save("optim_anderson", x=x, mask=phys.mask, y=y, pgd=pgd, gd=gd, gd_bt=out_bt,
          gd_bt_step=np.float32(gd_bt.params_algo["stepsize"][0]), pgd_bt=out_pgd_bt,
          pgd_bt_step=np.float32(pgd_bt.params_algo["stepsize"][0]), **sd_arrays(den, "sd__"))

@@ -495,6 +495,19 @@ def case_anderson(dev, full=True):
     assert rel_err(pgd(g["y"], phys), g["pgd"]) < 2e-5
 
 
+def case_pdcp(dev):
+    """Chambolle-Pock primal-dual iterations (primal_dual_CP.py): f-first with K = identity, g-first with K = A, vs the reference"""
+    import deepinv_b200 as dinv
+    from deepinv_b200.optim import L2, PDCP, Tikhonov
+
+    g = to_dev(load_golden("optim_anderson"), dev)
+    gp = to_dev(load_golden("optim_pdcp"), dev)
+    phys = dinv.physics.MRI(mask=g["mask"], img_size=(2, 32, 32), device=dev)
+    kwp = dict(data_fidelity=L2(), prior=Tikhonov(), lambda_reg=0.3, stepsize=0.6, stepsize_dual=0.8, max_iter=6, early_stop=False)
+    assert rel_err(PDCP(**kwp)(g["y"], phys), gp["cp"]) < TOL
+    assert rel_err(PDCP(g_first=True, K=phys.A, K_adjoint=phys.A_adjoint, **kwp)(g["y"], phys), gp["cp_gfirst"]) < TOL
+
+
 def case_pnp_blur_admm(dev):
     import deepinv_b200 as dinv
     from deepinv_b200.optim import ADMM, L2, PnP

@@ -80,7 +80,7 @@ def test_public_api_surface():
                    "Downsampling Denoising Inpainting compose stack TensorList GaussianNoise",
         d.physics.functional: "gaussian_blur bilinear_filter bicubic_filter sinc_filter kaiser_window",
         d.physics.generator: "RandomMaskGenerator GaussianMaskGenerator EquispacedMaskGenerator MotionBlurGenerator",
-        d.optim: "L2 PnP RED Tikhonov ZeroPrior PGD FISTA ADMM HQS DRS GD DPIR BaseOptim optim_builder create_iterator least_squares "
+        d.optim: "L2 PnP RED Tikhonov ZeroPrior PGD FISTA ADMM HQS DRS GD PDCP DPIR BaseOptim optim_builder create_iterator least_squares "
                  "conjugate_gradient bicgstab lsqr minres GraphedIteration GraphedSolve HostStreamedIteration DEQConfig "
                  "AndersonAccelerationConfig BacktrackingConfig",
         d.unfolded: "unfolded_builder BaseUnfold DEQ_builder BaseDEQ",

@@ -125,6 +125,10 @@ def test_ddrm_inpainting_and_denoising():
     P.case_ddrm_inpainting(DEV)
 
 
+def test_pdcp():
+    P.case_pdcp(DEV)
+
+
 def test_diffpir():
     P.case_diffpir(DEV)
 
