@@ -289,7 +289,7 @@ class gStepCP(gStep):
 
 class CPIteration(OptimIterator):
     """Chambolle-Pock primal-dual iteration on (x, z, u) = (primal, extrapolated primal, dual) with an optional linear map K
-    (primal_dual_CP.py:12-175):  u <- prox_{sigma F*}(u + sigma K z);  x <- prox_{tau G}(x - tau K^T u);  z <- x + beta (x - x_prev),
+    (primal_dual_CP.py:12-173):  u <- prox_{sigma F*}(u + sigma K z);  x <- prox_{tau G}(x - tau K^T u);  z <- x + beta (x - x_prev),
     F / G being the data term and the prior in the order chosen by `g_first`."""
 
     def __init__(self, **kwargs):

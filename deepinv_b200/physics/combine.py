@@ -1,5 +1,5 @@
 """Combining operators: composition A = A_k ... A_1 (`*`, `compose`) and stacking A = [A_1; ...; A_n] (`stack`)
-(deepinv/physics/forward.py:73-107, 573-601, 865-987, 1365-1560; deepinv/utils/tensorlist.py).
+(deepinv/physics/forward.py:73-107, 573-601, 865-987, 1365-1526; deepinv/utils/tensorlist.py).
 
 Pure host-side plumbing: every `A` / `A_adjoint` below is a sequence of the member operators' kernel launches; `prox_l2`
 and `A_dagger` of a combined linear operator are the CG on those kernels (LinearPhysics), exactly like the reference,
@@ -170,7 +170,7 @@ class StackedPhysics(Physics):
 
 
 class StackedLinearPhysics(StackedPhysics, LinearPhysics):
-    r"""A^T y = sum_i A_i^T y_i (forward.py:1479-1560); A^T A = sum_i A_i^T A_i uses each member's fused normal operator"""
+    r"""A^T y = sum_i A_i^T y_i (forward.py:1479-1526); A^T A = sum_i A_i^T A_i uses each member's fused normal operator"""
 
     def __init__(self, physics_list, reduction="sum", **kwargs):
         StackedPhysics.__init__(self, physics_list, **kwargs)

@@ -1,5 +1,5 @@
 """Cartesian MRI mask generators, sampled ON the device for the whole batch at once (SURVEY §8(f) item 4;
-deepinv/physics/generator/mri.py:15-400, generator/base.py:20-183).
+deepinv/physics/generator/mri.py:15-389, generator/base.py:20-183).
 
 Same classes, constructor arguments, `step(batch_size, seed, img_size)` contract and output shapes/values
 ((B,C,H,W) or (B,C,T,H,W), entries in {0,1}, lines constant along H) as the reference, so the result can be handed to
@@ -132,7 +132,7 @@ class GaussianMaskGenerator(RandomMaskGenerator):
 
 
 class EquispacedMaskGenerator(BaseMaskGenerator):
-    """equispaced columns with a random per-sample offset, sheared across time (generator/mri.py:327-400, after fastMRI)"""
+    """equispaced columns with a random per-sample offset, sheared across time (generator/mri.py:327-389, after fastMRI)"""
 
     def sample_columns(self, rows: int, frames: int, W: int) -> torch.Tensor:
         pad = (W - self.n_center + 1) // 2
