@@ -1,0 +1,72 @@
+"""bench.py's host-side helpers (no GPU): the synthetic Cartesian mask has the RandomMaskGenerator structure the workload names,
+the clock sampler picks the samples inside the timed window (or the replay window when the timed region is too short), and the
+JSON contract keys the driver reads are spelled as in the task statement."""
+import datetime
+import importlib.util
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _bench():
+    spec = importlib.util.spec_from_file_location("bench_module", ROOT / "bench.py")
+    mod = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        sys.argv = argv
+    return mod
+
+
+def test_cartesian_mask_structure():
+    b = _bench()
+    m = b.cartesian_mask(5, 256, 256, 4, seed=0)
+    assert m.shape == (5, 2, 256, 256) and set(m.unique().tolist()) <= {0.0, 1.0}
+    cols = m[:, 0, 0]
+    assert torch.equal(m, cols[:, None, None, :].expand_as(m))                 # lines: constant along H, same on both planes
+    assert torch.all(cols.sum(-1) == 64)                                        # 256 / 4 columns per sample
+    lo = (256 - round(256 * 0.08)) // 2
+    assert torch.all(cols[:, lo: lo + round(256 * 0.08)] == 1)                   # fully sampled centre band (8 % at 4x)
+    assert not torch.equal(cols[0], cols[1])                                    # per-sample masks
+
+
+def test_clock_sampler_selects_the_window():
+    b = _bench()
+    cs = b.ClockSampler(0)
+
+    class Done:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            pass
+
+    cs.p = Done()
+    t0 = datetime.datetime.now()
+    for i in range(12):
+        t = t0 + datetime.timedelta(milliseconds=20 * i)
+        cap = "Active" if i >= 6 else "Not Active"
+        cs.f.write(f"{t.strftime('%Y/%m/%d %H:%M:%S.%f')[:-3]}, {1500 + i}, 1965, {400 + i}.5, 0x4, Not Active, Not Active, Not Active, {cap}\n")
+    cs.f.flush()
+    ms = lambda k: t0 + datetime.timedelta(milliseconds=k)
+    short, probe = ("timed region", ms(50), ms(70)), ("replay", ms(110), ms(230))
+    out = cs.stop([short, probe])
+    assert out["window"] == "replay" and out["samples"] == 6 and out["reasons"] == ["sw_power_cap"] and out["sm_max_mhz"] == 1965.0
+    assert 1506 <= out["sm_mhz"] <= 1511
+
+
+def test_bench_line_contract_of_the_committed_profile():
+    """the last bench line measured on the B200 (profiles/) carries every key of the contract"""
+    line = json.loads((ROOT / "profiles" / "r01_bench_bf16_s3_final.json").read_text())
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in line, k
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(line["cpu_baseline"])
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
+    assert line["clocks"]["samples"] >= 3 and line["clocks"]["window"] == "timed region" and "workload" in line["config"]
