@@ -1,0 +1,602 @@
+// conv_tc32.cu — fp32-grade tensor-core convolutions for the denoisers: split-operand (3 x TF32) tcgen05 implicit GEMM.
+//
+// The reference computes DRUNet / DnCNN in fp32 (deepinv/models/drunet.py:200-263, dncnn.py:121-140).  The bf16 path
+// (conv_tc.cu) is fast but 3e-2 away from it; the CUDA-core path (conv_simt.cu) matches it but runs at 2 % of the tensor
+// peak.  Here every fp32 value v is carried as the pair  hi = tf32(v) (cvt.rna), lo = v - hi (exact), and a product
+// sum is evaluated as  sum a_hi*b_hi  +  sum (a_hi*b_lo + a_lo*b_hi)  with tcgen05.mma kind::tf32 (fp32 accumulate in
+// TMEM): the dropped a_lo*b_lo term is 2^-22 relative.  The two sums live in separate TMEM column ranges ("main" and
+// "corr"), and the accumulators are DRAINED into fp32 registers every `win` pipeline stages (round-to-nearest adds on the
+// CUDA cores) so that the tensor core's accumulator rounding never sees more than a short partial sum.
+//
+// Activation layout in HBM ("split16"): NHWC with channels in blocks of 16, hi and lo interleaved per block:
+//   x[b][y][x][c/16][p][c%16],  p = 0: hi, 1: lo      (fp32 words; 8 bytes per element; a pixel of a 16-channel block is
+//   one 128-byte row = one swizzle row of the K-major UMMA operand).  hi + lo == v exactly, so residual / skip additions
+//   read both words and lose nothing.
+// Weight layout: per 64-row N tile 128 rows [W_hi (64 couts); W_lo (64 couts)], K-major, k = tap*Cin + c, both parts
+//   rounded to tf32.
+// One MMA "k8 step" on a 128-byte A row: steps 0,1 = the 16 hi channels, steps 2,3 = the 16 lo channels.
+//   hi step: A_hi x [W_hi; W_lo]  (N = 128)  -> columns [0,64) main, [64,128) corr
+//   lo step: A_lo x  W_hi         (N =  64)  -> columns [64,128) corr
+//
+// Kernel (persistent, one CTA per SM, 320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 drain/epilogue
+// (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4).
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <mutex>
+
+namespace dinvk {
+namespace t32 {
+
+constexpr int TX = 16, TY = 8;             // pixel tile of one accumulator: 16 x 8 = 128 GEMM rows
+constexpr int A_TILE = 128 * 128;          // one 16-channel block of 128 pixels: 16 KB
+constexpr int B_TILE = 128 * 128;          // [W_hi; W_lo] x 32 channels: 16 KB
+constexpr int STAGE = 2 * A_TILE + B_TILE; // two channel blocks of one tap + their weights
+constexpr int STAGES = 4;
+constexpr int SMEM = STAGES * STAGE + 1024;
+constexpr int THREADS = 320;
+constexpr uint32_t TMEM_COLS = 256;        // 2 accumulator buffers x (64 main + 64 corr)
+
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+  // cute::UMMA::InstrDescriptor: c_format F32 (1) at [4,6), a/b_format TF32 (2) at [7,10) / [10,13), K-major, N>>3, M>>4
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+struct Maps {
+  CUtensorMap a[4];  // activation views: one (3x3, up) or one per tap (2x2 stride-2 down)
+  CUtensorMap b;
+};
+
+struct Params {
+  int B, H, W, Cin, Cout;   // H, W: the pixel grid the GEMM rows tile (3x3: image; down: OUTPUT grid; up: INPUT grid)
+  int ntaps, kc_per_tap;    // kc_per_tap = Cin / 32 (pipeline stages per tap)
+  int dx[9], dy[9], amap[9];
+  int mode;                 // 0: same-grid store; 2: 2x up-scatter (GEMM column = tap*Cout + co)
+  int tiles_x, tiles_y, n_tiles;
+  int relu;
+  int win;                  // drain the accumulators every `win` stages
+  const float* res;         // split16, same shape as out
+  const float* res2;
+  float* out;               // split16 (B, Hout, Wout, Cout)
+  const float* bias;
+};
+
+// split one 16-channel block: v[16] -> 128 bytes [hi16 | lo16]
+__device__ __forceinline__ void store_split16(float* p, const float* v) {
+  float hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { hi[i] = rna_tf32(v[i]); lo[i] = v[i] - hi[i]; }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    uint32_t u[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) u[e] = __float_as_uint(hi[j * 8 + e]);
+    tc::stg256(p + j * 8, u);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    uint32_t u[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) u[e] = __float_as_uint(lo[j * 8 + e]);
+    tc::stg256(p + 16 + j * 8, u);
+  }
+}
+// v[16] += hi + lo of one stored block
+__device__ __forceinline__ void add_split16(const float* p, float* v) {
+  uint32_t h0[8], h1[8], l0[8], l1[8];
+  tc::ldg256(p, h0); tc::ldg256(p + 8, h1); tc::ldg256(p + 16, l0); tc::ldg256(p + 24, l1);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    v[e] += __uint_as_float(h0[e]) + __uint_as_float(l0[e]);
+    v[8 + e] += __uint_as_float(h1[e]) + __uint_as_float(l1[e]);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) conv_tc32_kernel(const __grid_constant__ Maps M, const Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pixel_tiles = P.B * P.tiles_y * P.tiles_x;
+  const int total_tiles = pixel_tiles * P.n_tiles;
+  const int nk = P.ntaps * P.kc_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&M.a[0]);
+    tc::prefetch_tmap(&M.b);
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull_bar[a], 1); tc::mbar_init(&tempty_bar[a], 8); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc<TMEM_COLS>(&tmem_base_smem);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t / pixel_tiles, pt = t - nt * pixel_tiles;
+        const int b = pt / (P.tiles_y * P.tiles_x), r = pt - b * (P.tiles_y * P.tiles_x);
+        const int y0 = (r / P.tiles_x) * TY, x0 = (r % P.tiles_x) * TX;
+        for (int kb = 0; kb < nk; ++kb) {
+          const int tap = kb / P.kc_per_tap, kc = kb - tap * P.kc_per_tap;
+          tc::mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * STAGE;
+          tc::mbar_arrive_expect_tx(&full_bar[s], STAGE);
+          // channel blocks 2kc and 2kc+1: 32 fp32 words each ([hi16 | lo16]) at word offset 32 * block
+          tc::tma_load_4d(sa, &M.a[P.amap[tap]], &full_bar[s], (2 * kc) * 32, x0 + P.dx[tap], y0 + P.dy[tap], b);
+          tc::tma_load_4d(sa + A_TILE, &M.a[P.amap[tap]], &full_bar[s], (2 * kc + 1) * 32, x0 + P.dx[tap], y0 + P.dy[tap], b);
+          tc::tma_load_2d(sa + 2 * A_TILE, &M.b, &full_bar[s], tap * P.Cin + kc * 32, nt * 128);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (converged warp, one elected lane) =====================
+    constexpr uint32_t ID128 = idesc_tf32(128, 128), ID64 = idesc_tf32(128, 64);
+    constexpr uint32_t HI = tc::desc_hi_sw128(1024);
+    const uint32_t smem_lo = tc::smem_u32(smem) >> 4;
+    int s = 0; uint32_t ph = 0;
+    int acc = 0; uint32_t pa = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int in_win = 0;
+      for (int kb = 0; kb < nk; ++kb) {
+        if (in_win == 0) {
+          tc::mbar_wait(&tempty_bar[acc], pa ^ 1);
+          tc::tc_fence_after();
+        }
+        tc::mbar_wait(&full_bar[s], ph);
+        tc::tc_fence_after();
+        const uint32_t d = tmem_base + static_cast<uint32_t>(acc * 128);
+        const uint32_t a0 = smem_lo + static_cast<uint32_t>(s) * (STAGE >> 4);
+        const uint32_t b0 = a0 + (2 * A_TILE >> 4);
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const uint32_t a = a0 + jj * (A_TILE >> 4), b = b0 + jj * 4;  // B: second channel block = +64 bytes inside the row
+            umma_tf32(d, a, HI, b, HI, ID128, (jj | in_win) != 0 ? 1u : 0u);      // hi ch 0-7   x [W_hi; W_lo]
+            umma_tf32(d, a + 2, HI, b + 2, HI, ID128, 1u);                         // hi ch 8-15
+            umma_tf32(d + 64, a + 4, HI, b, HI, ID64, 1u);                         // lo ch 0-7   x W_hi
+            umma_tf32(d + 64, a + 6, HI, b + 2, HI, ID64, 1u);                     // lo ch 8-15
+          }
+          tc::umma_commit(&empty_bar[s]);
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+        ++in_win;
+        if (in_win == P.win || kb == nk - 1) {
+          if (tc::elect_one()) tc::umma_commit(&tfull_bar[acc]);
+          __syncwarp();
+          in_win = 0;
+          if (++acc == 2) { acc = 0; pa ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== drain + epilogue =====================
+    const int q = warp & 3;              // TMEM lane quarter
+    const int g = (warp - 2) >> 2;       // column half: couts [32g, 32g + 32) of the N tile
+    int acc = 0; uint32_t pa = 0;
+    const int nwin = (nk + P.win - 1) / P.win;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nt = t / pixel_tiles, pt = t - nt * pixel_tiles;
+      const int b = pt / (P.tiles_y * P.tiles_x), r = pt - b * (P.tiles_y * P.tiles_x);
+      const int y0 = (r / P.tiles_x) * TY, x0 = (r % P.tiles_x) * TX;
+      const int m = q * 32 + lane;
+      const int y = y0 + m / TX, x = x0 + m % TX;
+      const bool inside = (y < P.H) && (x < P.W);
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      for (int w = 0; w < nwin; ++w) {
+        tc::mbar_wait(&tfull_bar[acc], pa);
+        tc::tc_fence_after();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 128 + g * 32);
+        uint32_t rm[32], rc[32];
+        tc::tmem_ld_32x32b_x32(t_addr, rm);
+        tc::tmem_ld_32x32b_x32(t_addr + 64, rc);
+        tc::tmem_ld_wait();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(rm[i]) + __uint_as_float(rc[i]);
+        if (++acc == 2) { acc = 0; pa ^= 1; }
+      }
+      const int n0 = nt * 64 + g * 32;   // GEMM column of v[0]
+      if (P.bias) {
+        const int cb = P.mode == 2 ? n0 % P.Cout : n0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += __ldg(P.bias + cb + i);
+      }
+      if (P.relu) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      if (inside) {
+        long long o;   // word offset of channel block (n0 / 16) of the output pixel
+        if (P.mode == 2) {
+          const int tap = n0 / P.Cout, co = n0 - tap * P.Cout;
+          o = ((((long long)b * (2 * P.H) + 2 * y + (tap >> 1)) * (2LL * P.W) + 2 * x + (tap & 1)) * P.Cout + co) * 2;
+        } else {
+          o = ((((long long)b * P.H + y) * P.W + x) * P.Cout + n0) * 2;
+        }
+        if (P.res) { add_split16(P.res + o, v); add_split16(P.res + o + 32, v + 16); }
+        if (P.res2) { add_split16(P.res2 + o, v); add_split16(P.res2 + o + 32, v + 16); }
+        store_split16(P.out + o, v);
+        store_split16(P.out + o + 32, v + 16);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Network HEAD (CUDA cores; 0.1 % of the FLOPs, bound by its 8-byte-per-element output write): 3x3 convolution from the
+// reference's NCHW fp32 image (+ optional constant noise-level channel, drunet.py:190-200) to Cout split16 channels.
+// One thread per pixel: its 9*CT inputs sit in registers, the weights in shared memory (every lane reads the same
+// word: broadcast).
+// ---------------------------------------------------------------------------------------------------------------
+struct HeadParams {
+  const float* x; const float* w; const float* bias; float* out;
+  int B, C, H, W, Cout;
+  float fill_scalar; const float* fill_batch; int has_fill; int relu;
+};
+
+template <int CT>
+__global__ void __launch_bounds__(256) head_tc32_kernel(const HeadParams P) {
+  extern __shared__ float sw[];  // [Cout][9*CT] as stored by the module: (Cout, CT, 3, 3) -> index co*9*CT + c*9 + tap
+  for (int i = threadIdx.x; i < P.Cout * 9 * CT; i += blockDim.x) sw[i] = __ldg(P.w + i);
+  __syncthreads();
+  const long long npix = (long long)P.B * P.H * P.W;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const long long HW = (long long)P.H * P.W;
+  const int b = (int)(p / HW);
+  const int rem = (int)(p - (long long)b * HW);
+  const int y = rem / P.W, x = rem - y * P.W;
+  const float fillv = P.has_fill ? (P.fill_batch ? __ldg(P.fill_batch + b) : P.fill_scalar) : 0.f;
+  float in[9 * CT];
+  const float* img = P.x + (long long)b * P.C * HW;
+#pragma unroll
+  for (int c = 0; c < CT; ++c) {
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      const bool inb = (yy >= 0) && (yy < P.H) && (xx >= 0) && (xx < P.W);
+      float val = 0.f;
+      if (inb) val = (c < P.C) ? __ldg(img + (long long)c * HW + (long long)yy * P.W + xx) : fillv;
+      in[c * 9 + tap] = val;
+    }
+  }
+  float* o = P.out + p * P.Cout * 2;
+  for (int c0 = 0; c0 < P.Cout; c0 += 16) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float a = P.bias ? __ldg(P.bias + c0 + i) : 0.f;
+      const float* wr = sw + (c0 + i) * 9 * CT;
+#pragma unroll
+      for (int k = 0; k < 9 * CT; ++k) a = fmaf(in[k], wr[k], a);
+      v[i] = P.relu ? fmaxf(a, 0.f) : a;
+    }
+    store_split16(o + c0 * 2, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Network TAIL (CUDA cores): 3x3 convolution from C split16 channels to Cout <= 4 channels, fp32 NCHW output
+// (+ bias, + optional NCHW term: DnCNN's "+ x", dncnn.py:138).  A CTA stages the (32+2) x (8+2) halo tile as
+// v = hi + lo in shared memory ([position][C + 4] words: 128-bit loads by adjacent pixels are conflict-free).
+// ---------------------------------------------------------------------------------------------------------------
+struct TailParams {
+  const float* x; const float* w; const float* bias; const float* add; float* out;
+  int B, H, W, C, Cout;
+};
+constexpr int TL_TX = 32, TL_TY = 8;
+
+template <int CO>
+__global__ void __launch_bounds__(256) tail_tc32_kernel(const TailParams P) {
+  extern __shared__ __align__(16) float sm[];
+  const int C = P.C, CP = C + 4;
+  float* sx = sm;                                   // (TL_TY+2)*(TL_TX+2) positions x CP
+  float* swt = sm + (TL_TY + 2) * (TL_TX + 2) * CP;  // [co][tap][C]
+  const int tiles_x = (P.W + TL_TX - 1) / TL_TX, tiles_y = (P.H + TL_TY - 1) / TL_TY;
+  const int b = blockIdx.x / (tiles_x * tiles_y), r = blockIdx.x - b * (tiles_x * tiles_y);
+  const int y0 = (r / tiles_x) * TL_TY, x0 = (r % tiles_x) * TL_TX;
+  // weights (Cout, C, 3, 3) -> [co][tap][c]
+  for (int i = threadIdx.x; i < CO * 9 * C; i += blockDim.x) {
+    const int co = i / (9 * C), rem = i - co * 9 * C, tap = rem / C, c = rem - tap * C;
+    swt[i] = __ldg(P.w + ((long long)co * C + c) * 9 + tap);
+  }
+  // halo tile: one float4 of hi + one of lo per (position, 4 channels)
+  const int npos = (TL_TY + 2) * (TL_TX + 2), q4 = C / 4;
+  for (int i = threadIdx.x; i < npos * q4; i += blockDim.x) {
+    const int pos = i / q4, cq = i - pos * q4;
+    const int yy = y0 + pos / (TL_TX + 2) - 1, xx = x0 + pos % (TL_TX + 2) - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (yy >= 0 && yy < P.H && xx >= 0 && xx < P.W) {
+      const int c = cq * 4, blk = c >> 4, i16 = c & 15;
+      const float* src = P.x + (((long long)b * P.H + yy) * P.W + xx) * C * 2 + blk * 32 + i16;
+      const float4 h = __ldg(reinterpret_cast<const float4*>(src));
+      const float4 l = __ldg(reinterpret_cast<const float4*>(src + 16));
+      v = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
+    }
+    *reinterpret_cast<float4*>(sx + pos * CP + cq * 4) = v;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x / TL_TX, tx = threadIdx.x % TL_TX;
+  const int y = y0 + ty, x = x0 + tx;
+  float acc[CO];
+#pragma unroll
+  for (int co = 0; co < CO; ++co) acc[co] = 0.f;
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    const float* px = sx + ((ty + tap / 3) * (TL_TX + 2) + tx + tap % 3) * CP;
+#pragma unroll 4
+    for (int c = 0; c < C; c += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(px + c);
+#pragma unroll
+      for (int co = 0; co < CO; ++co) {
+        const float4 w4 = *reinterpret_cast<const float4*>(swt + (co * 9 + tap) * C + c);
+        acc[co] = fmaf(a.x, w4.x, acc[co]); acc[co] = fmaf(a.y, w4.y, acc[co]);
+        acc[co] = fmaf(a.z, w4.z, acc[co]); acc[co] = fmaf(a.w, w4.w, acc[co]);
+      }
+    }
+  }
+  if (y < P.H && x < P.W) {
+#pragma unroll
+    for (int co = 0; co < CO; ++co) {
+      if (co < P.Cout) {
+        const long long o = (((long long)b * P.Cout + co) * P.H + y) * P.W + x;
+        float val = acc[co] + (P.bias ? __ldg(P.bias + co) : 0.f);
+        if (P.add) val += __ldg(P.add + o);
+        P.out[o] = val;
+      }
+    }
+  }
+}
+
+// split16 -> NCHW fp32 (debug / tests / odd tails): out[b,c,y,x] = hi + lo
+__global__ void __launch_bounds__(256) split16_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int H, int W,
+                                                              long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long HW = (long long)H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long pix = i / C;
+    const int c = (int)(i - pix * C);
+    const long long b = pix / HW, hw = pix - b * HW;
+    const float* s = in + pix * C * 2 + (c >> 4) * 32 + (c & 15);
+    out[(b * C + c) * HW + hw] = __ldg(s) + __ldg(s + 16);
+  }
+}
+// NCHW fp32 -> split16
+__global__ void __launch_bounds__(256) nchw_to_split16_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int H, int W,
+                                                              long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long HW = (long long)H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long pix = i / C;
+    const int c = (int)(i - pix * C);
+    const long long b = pix / HW, hw = pix - b * HW;
+    const float v = __ldg(in + (b * C + c) * HW + hw);
+    const float hi = rna_tf32(v);
+    float* d = out + pix * C * 2 + (c >> 4) * 32 + (c & 15);
+    d[0] = hi;
+    d[16] = v - hi;
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 4-D activation view (words, X, Y, B) of a split16 tensor with arbitrary pixel strides (bytes)
+static int make_act_map(CUtensorMap* m, const void* ptr, int B, int Y, int X, int C, long long sx, long long sy, long long sb, int box_x,
+                        int box_y) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(DINVK_ECUDA, "cuTensorMapEncodeTiled is unavailable");
+  cuuint64_t dims[4] = {(cuuint64_t)C * 2, (cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)sx, (cuuint64_t)sy, (cuuint64_t)sb};
+  cuuint32_t box[4] = {32, (cuuint32_t)box_x, (cuuint32_t)box_y, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(DINVK_ECUDA, "cuTensorMapEncodeTiled(tc32 activations) failed: %d", (int)r);
+  return 0;
+}
+static int make_w_map(CUtensorMap* m, const void* ptr, long long K, long long rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(DINVK_ECUDA, "cuTensorMapEncodeTiled is unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+  cuuint32_t box[2] = {32, 128};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(DINVK_ECUDA, "cuTensorMapEncodeTiled(tc32 weights) failed: %d", (int)r);
+  return 0;
+}
+
+static int default_window() {
+  static int w = -1;
+  if (w < 0) {
+    const char* e = getenv("DINVK_TC32_WINDOW");
+    w = e ? std::max(1, atoi(e)) : 2;
+  }
+  return w;
+}
+
+static int launch(const Maps& M, const Params& P, void* stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return set_error(DINVK_ECUDA, "cudaFuncSetAttribute(conv_tc32): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const long long tiles = (long long)P.B * P.tiles_y * P.tiles_x * P.n_tiles;
+  const int grid = (int)std::min<long long>(tiles, sm_count());
+  count_launch();
+  conv_tc32_kernel<<<grid, THREADS, SMEM, (cudaStream_t)stream>>>(M, P);
+  return DINVK_POST_LAUNCH();
+}
+
+}  // namespace t32
+}  // namespace dinvk
+
+using namespace dinvk;
+
+// kind 0: 3x3 stride 1 zero-pad 1 (weight rows = Cout/64 tiles of 128, K = 9*Cin, k = (ky*3+kx)*Cin + c)
+// kind 1: 2x2 stride 2 (K = 4*Cin, k = (dy*2+dx)*Cin + c), out (B, H/2, W/2, Cout)
+// kind 2: transposed 2x2 stride 2 (K = Cin, GEMM column = (dy*2+dx)*Cout + co), out (B, 2H, 2W, Cout)
+extern "C" int dinvk_conv_tc32(const float* x, const float* weight, const float* bias, const float* res, const float* res2, float* out,
+                               int B, int H, int W, int Cin, int Cout, int kind, int act, int window, void* stream) {
+  using namespace t32;
+  DINVK_CHECK_ARG(x && weight && out, "conv_tc32: null pointer");
+  DINVK_CHECK_ARG(B >= 0 && H >= 1 && W >= 1, "conv_tc32: bad shape");
+  DINVK_CHECK_ARG(kind >= 0 && kind <= 2, "conv_tc32: kind=%d not in 0..2", kind);
+  DINVK_CHECK_ARG(Cin % 32 == 0 && Cin >= 32, "conv_tc32: Cin=%d must be a multiple of 32", Cin);
+  DINVK_CHECK_ARG(Cout % 64 == 0 && Cout >= 64, "conv_tc32: Cout=%d must be a multiple of 64", Cout);
+  DINVK_CHECK_ARG(kind != 1 || (H % 2 == 0 && W % 2 == 0), "conv_tc32: 2x2 stride-2 needs even H, W");
+  DINVK_CHECK_ARG(kind == 0 || (!res && !res2), "conv_tc32: residual inputs are for kind 0 only");
+  if (B == 0) return DINVK_OK;
+  Maps M;
+  Params P;
+  int rc;
+  const long long px = (long long)Cin * 8;  // bytes per input pixel
+  P.B = B; P.Cin = Cin; P.Cout = Cout;
+  P.kc_per_tap = Cin / 32;
+  P.relu = act; P.res = res; P.res2 = res2; P.out = out; P.bias = bias;
+  P.win = window > 0 ? window : default_window();
+  for (int t = 0; t < 9; ++t) { P.dx[t] = 0; P.dy[t] = 0; P.amap[t] = 0; }
+  if (kind == 0) {
+    if ((rc = make_act_map(&M.a[0], x, B, H, W, Cin, px, px * W, px * W * H, TX, TY))) return rc;
+    M.a[1] = M.a[0]; M.a[2] = M.a[0]; M.a[3] = M.a[0];
+    if ((rc = make_w_map(&M.b, weight, 9LL * Cin, 2LL * Cout))) return rc;
+    P.H = H; P.W = W; P.ntaps = 9; P.mode = 0; P.n_tiles = Cout / 64;
+    for (int t = 0; t < 9; ++t) { P.dx[t] = t % 3 - 1; P.dy[t] = t / 3 - 1; }
+  } else if (kind == 1) {
+    const int Ho = H / 2, Wo = W / 2;
+    for (int t = 0; t < 4; ++t) {
+      const char* base = reinterpret_cast<const char*>(x) + ((long long)(t >> 1) * W + (t & 1)) * px;
+      if ((rc = make_act_map(&M.a[t], base, B, Ho, Wo, Cin, 2 * px, 2 * px * W, px * W * H, TX, TY))) return rc;
+      P.amap[t] = t;
+    }
+    if ((rc = make_w_map(&M.b, weight, 4LL * Cin, 2LL * Cout))) return rc;
+    P.H = Ho; P.W = Wo; P.ntaps = 4; P.mode = 0; P.n_tiles = Cout / 64;
+  } else {
+    if ((rc = make_act_map(&M.a[0], x, B, H, W, Cin, px, px * W, px * W * H, TX, TY))) return rc;
+    M.a[1] = M.a[0]; M.a[2] = M.a[0]; M.a[3] = M.a[0];
+    if ((rc = make_w_map(&M.b, weight, (long long)Cin, 8LL * Cout))) return rc;
+    P.H = H; P.W = W; P.ntaps = 1; P.mode = 2; P.n_tiles = 4 * Cout / 64;
+  }
+  P.tiles_x = ceil_div(P.W, TX); P.tiles_y = ceil_div(P.H, TY);
+  return launch(M, P, stream);
+}
+
+extern "C" int dinvk_conv_tc32_head(const float* x_nchw, const float* weight, const float* bias, float* out, int B, int C, int H, int W,
+                                    int Cout, float fill_scalar, const float* fill_batch, int has_fill, int act, void* stream) {
+  using namespace t32;
+  DINVK_CHECK_ARG(x_nchw && weight && out && B >= 0 && C >= 1 && H >= 1 && W >= 1, "conv_tc32_head: bad arguments");
+  const int CT = C + (has_fill ? 1 : 0);
+  DINVK_CHECK_ARG(CT >= 1 && CT <= 4, "conv_tc32_head: %d input channels (incl. noise map) not in 1..4", CT);
+  DINVK_CHECK_ARG(Cout % 16 == 0 && Cout >= 16 && Cout <= 256, "conv_tc32_head: Cout=%d must be a multiple of 16 (<= 256)", Cout);
+  if (B == 0) return DINVK_OK;
+  HeadParams P{x_nchw, weight, bias, out, B, C, H, W, Cout, fill_scalar, fill_batch, has_fill, act};
+  const long long npix = (long long)B * H * W;
+  const unsigned grid = (unsigned)((npix + 255) / 256);
+  const size_t smem = (size_t)Cout * 9 * CT * 4;
+  switch (CT) {
+    case 1: DINVK_LAUNCH(head_tc32_kernel<1>, dim3(grid), dim3(256), smem, stream, P); break;
+    case 2: DINVK_LAUNCH(head_tc32_kernel<2>, dim3(grid), dim3(256), smem, stream, P); break;
+    case 3: DINVK_LAUNCH(head_tc32_kernel<3>, dim3(grid), dim3(256), smem, stream, P); break;
+    default: DINVK_LAUNCH(head_tc32_kernel<4>, dim3(grid), dim3(256), smem, stream, P); break;
+  }
+  return DINVK_POST_LAUNCH();
+}
+
+extern "C" int dinvk_conv_tc32_tail(const float* x, const float* weight, const float* bias, const float* add_nchw, float* out_nchw, int B,
+                                    int H, int W, int Cin, int Cout, void* stream) {
+  using namespace t32;
+  DINVK_CHECK_ARG(x && weight && out_nchw && B >= 0 && H >= 1 && W >= 1, "conv_tc32_tail: bad arguments");
+  DINVK_CHECK_ARG(Cin % 16 == 0 && Cin >= 16 && Cin <= 128, "conv_tc32_tail: Cin=%d must be a multiple of 16 (<= 128)", Cin);
+  DINVK_CHECK_ARG(Cout >= 1 && Cout <= 4, "conv_tc32_tail: Cout=%d not in 1..4", Cout);
+  if (B == 0) return DINVK_OK;
+  TailParams P{x, weight, bias, add_nchw, out_nchw, B, H, W, Cin, Cout};
+  const int tiles = B * ceil_div(H, TL_TY) * ceil_div(W, TL_TX);
+  const int CO = Cout <= 2 ? 2 : 4;
+  const size_t smem = ((size_t)(TL_TY + 2) * (TL_TX + 2) * (Cin + 4) + (size_t)CO * 9 * Cin) * 4;
+  int rc;
+  if (CO == 2) {
+    if ((rc = allow_smem(tail_tc32_kernel<2>, smem))) return rc;
+    DINVK_LAUNCH(tail_tc32_kernel<2>, dim3(tiles), dim3(256), smem, stream, P);
+  } else {
+    if ((rc = allow_smem(tail_tc32_kernel<4>, smem))) return rc;
+    DINVK_LAUNCH(tail_tc32_kernel<4>, dim3(tiles), dim3(256), smem, stream, P);
+  }
+  return DINVK_POST_LAUNCH();
+}
+
+extern "C" int dinvk_split16_to_nchw(const float* in, float* out, int B, int C, int H, int W, void* stream) {
+  using namespace t32;
+  DINVK_CHECK_ARG(in && out && B >= 0 && C % 16 == 0 && C >= 16, "split16_to_nchw: bad arguments");
+  if (B == 0) return DINVK_OK;
+  const long long n = (long long)B * H * W * C;
+  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 16);
+  DINVK_LAUNCH(split16_to_nchw_kernel, dim3(grid), dim3(256), 0, stream, in, out, C, H, W, n);
+  return DINVK_POST_LAUNCH();
+}
+
+extern "C" int dinvk_nchw_to_split16(const float* in, float* out, int B, int C, int H, int W, void* stream) {
+  using namespace t32;
+  DINVK_CHECK_ARG(in && out && B >= 0 && C % 16 == 0 && C >= 16, "nchw_to_split16: bad arguments");
+  if (B == 0) return DINVK_OK;
+  const long long n = (long long)B * H * W * C;
+  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 16);
+  DINVK_LAUNCH(nchw_to_split16_kernel, dim3(grid), dim3(256), 0, stream, in, out, C, H, W, n);
+  return DINVK_POST_LAUNCH();
+}

@@ -32,6 +32,7 @@ class DnCNN(Denoiser):
         self.nl_list = nn.ModuleList([nn.ReLU() for _ in range(depth - 1)])
         self.precision = precision
         self._tc = None
+        self._tc32 = None
         if pretrained is not None:
             if pretrained.startswith("download"):
                 raise RuntimeError("pretrained weights cannot be downloaded here (no network): pass a checkpoint path "
@@ -49,6 +50,11 @@ class DnCNN(Denoiser):
             from .tc_engine import dncnn_forward_bf16
 
             return dncnn_forward_bf16(self, x)
+        if self.precision == "tc32":
+            _no_grad_guard("DnCNN(precision='tc32')", x, self.in_conv.weight)
+            from .tc_engine import dncnn_forward_tc32
+
+            return dncnn_forward_tc32(self, x)
         t = ops.conv_f32_ag(x, self.in_conv.weight, bias=self.in_conv.bias, relu=True)
         for conv in self.conv_list:
             t = ops.conv_f32_ag(t, conv.weight, bias=conv.bias, relu=True)

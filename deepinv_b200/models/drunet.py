@@ -69,6 +69,7 @@ class DRUNet(Denoiser):
         self.dim = 2
         self.precision = precision
         self._tc = None  # tensor-core engine (packed bf16 weights), built lazily
+        self._tc32 = None  # fp32-grade tensor-core engine (packed tf32 hi/lo weights), built lazily
         if pretrained is not None:
             if pretrained.startswith("download"):
                 raise RuntimeError("pretrained weights cannot be downloaded here (no network): pass a checkpoint path "
@@ -106,6 +107,11 @@ class DRUNet(Denoiser):
             from .tc_engine import drunet_forward_bf16
 
             return drunet_forward_bf16(self, x0)
+        if self.precision == "tc32":
+            _no_grad_guard("DRUNet(precision='tc32')", x0, self.m_head.weight)
+            from .tc_engine import drunet_forward_tc32
+
+            return drunet_forward_tc32(self, x0)
         return self._forward_unet_f32(x0)
 
     def forward(self, x: torch.Tensor, sigma) -> torch.Tensor:

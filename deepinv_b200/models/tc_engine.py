@@ -133,3 +133,99 @@ def dncnn_forward_bf16(model, x: torch.Tensor) -> torch.Tensor:
     for w, b in pk.mid:
         t = ops.conv3x3_bf16(t, w, bias=b, relu=True)
     return ops.conv3x3_bf16_tail(t, pk.last[0], pk.cout, bias=pk.last[1], add=x)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# precision="tc32": fp32-grade tensor-core execution (3 x TF32 split operands, csrc/conv_tc32.cu)
+# ---------------------------------------------------------------------------------------------------------
+def _rna_tf32(w: torch.Tensor) -> torch.Tensor:
+    """round to the nearest tf32 value (10-bit mantissa, ties away from zero: the device's cvt.rna.tf32.f32)"""
+    u = w.contiguous().view(torch.int32)
+    return torch.bitwise_and(u + 0x1000, -0x2000).view(torch.float32)
+
+
+def _pack_tc32(wk: torch.Tensor) -> torch.Tensor:
+    """K-major GEMM matrix (rows, K) fp32, rows % 64 == 0 -> (2*rows, K): per 64 rows [hi (64); lo (64)], tf32-rounded"""
+    wk = wk.detach().float().contiguous()
+    rows, K = wk.shape
+    hi = _rna_tf32(wk)
+    lo = _rna_tf32(wk - hi)
+    return torch.cat([hi.view(rows // 64, 64, K), lo.view(rows // 64, 64, K)], dim=1).reshape(2 * rows, K).contiguous()
+
+
+def _pack3x3_tc32(w):   # (Cout, Cin, 3, 3) -> k = (ky*3+kx)*Cin + c
+    return _pack_tc32(w.detach().float().permute(0, 2, 3, 1).reshape(w.shape[0], -1))
+
+
+def _pack_down_tc32(w):  # (Cout, Cin, 2, 2) -> k = (dy*2+dx)*Cin + c
+    return _pack_tc32(w.detach().float().permute(0, 2, 3, 1).reshape(w.shape[0], -1))
+
+
+def _pack_up_tc32(w):    # (Cin, Cout, 2, 2) -> row = (dy*2+dx)*Cout + co
+    return _pack_tc32(w.detach().float().permute(2, 3, 1, 0).reshape(-1, w.shape[0]))
+
+
+class _DrunetPack32:
+    def __init__(self, m):
+        nb = m.nb
+        self.key = _version_key(m)
+        self.nc = [m.m_head.weight.shape[0], m.m_down1[nb].weight.shape[0], m.m_down2[nb].weight.shape[0],
+                   m.m_down3[nb].weight.shape[0]]
+        if any(c % 64 for c in self.nc) or m.m_head.weight.shape[1] > 4 or m.m_tail.weight.shape[0] > 4 or self.nc[0] > 128:
+            raise NotImplementedError("precision='tc32' needs channel counts that are multiples of 64 (tensor-core N/K tiles), at "
+                                      f"most 4 image channels and nc[0] <= 128; got nc={self.nc}; use precision='fp32'")
+        self.head = m.m_head.weight.detach().float().contiguous()
+        self.tail = m.m_tail.weight.detach().float().contiguous()
+        rb = lambda blocks: [(_pack3x3_tc32(b.res[0].weight), _pack3x3_tc32(b.res[2].weight), b.res[0].weight.shape[0]) for b in blocks]
+        self.down = [(rb(list(st)[:nb]), _pack_down_tc32(st[nb].weight), st[nb].weight.shape[0]) for st in (m.m_down1, m.m_down2, m.m_down3)]
+        self.body = rb(list(m.m_body))
+        self.up = [(_pack_up_tc32(st[0].weight), st[0].weight.shape[1], rb(list(st)[1:])) for st in (m.m_up3, m.m_up2, m.m_up1)]
+
+
+def _resblocks32(t, blocks, skip=None):
+    for i, (w0, w1, c) in enumerate(blocks):
+        u = ops.conv_tc32(t, w0, c, relu=True)
+        t = ops.conv_tc32(u, w1, c, res=t, res2=skip if i == len(blocks) - 1 else None)
+    return t
+
+
+def drunet_forward_tc32(model, x0: torch.Tensor) -> torch.Tensor:
+    """x0: (B, C+1, H, W) fp32 (noise map already concatenated) -> (B, C_out, H, W) fp32; same dataflow as the bf16 engine"""
+    pk = model._tc32
+    if pk is None or pk.key != _version_key(model):
+        pk = model._tc32 = _DrunetPack32(model)
+    x1 = ops.conv_tc32_head(x0, pk.head)
+    skips = [x1]
+    t = x1
+    for blocks, wd, cd in pk.down:
+        t = _resblocks32(t, blocks)
+        t = ops.conv_tc32(t, wd, cd, kind=1)
+        skips.append(t)
+    t = _resblocks32(t, pk.body, skip=skips[3])
+    for i, (wu, cu, blocks) in enumerate(pk.up):
+        t = ops.conv_tc32(t, wu, cu, kind=2)
+        t = _resblocks32(t, blocks, skip=skips[2 - i])
+    return ops.conv_tc32_tail(t, pk.tail)
+
+
+class _DncnnPack32:
+    def __init__(self, m):
+        self.key = _version_key(m)
+        nf = m.in_conv.weight.shape[0]
+        if nf % 64 or nf > 128 or m.in_conv.weight.shape[1] > 4 or m.out_conv.weight.shape[0] > 4:
+            raise NotImplementedError("precision='tc32' needs nf in {64, 128} and at most 4 image channels; use precision='fp32'")
+        f32 = lambda b: None if b is None else b.detach().float().contiguous()
+        self.nf = nf
+        self.first = (m.in_conv.weight.detach().float().contiguous(), f32(m.in_conv.bias))
+        self.mid = [(_pack3x3_tc32(c.weight), f32(c.bias)) for c in m.conv_list]
+        self.last = (m.out_conv.weight.detach().float().contiguous(), f32(m.out_conv.bias))
+
+
+def dncnn_forward_tc32(model, x: torch.Tensor) -> torch.Tensor:
+    pk = model._tc32
+    if pk is None or pk.key != _version_key(model):
+        pk = model._tc32 = _DncnnPack32(model)
+    t = ops.conv_tc32_head(x, pk.first[0], bias=pk.first[1], relu=True)
+    for w, b in pk.mid:
+        t = ops.conv_tc32(t, w, pk.nf, bias=b, relu=True)
+    return ops.conv_tc32_tail(t, pk.last[0], bias=pk.last[1], add=x)

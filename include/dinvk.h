@@ -262,6 +262,29 @@ int dinvk_conv2x2_down_bf16(const void* x, const void* xadd, const void* weight,
 int dinvk_conv2x2_up_bf16(const void* x, const void* xadd, const void* weight, void* out,
                           int B, int H, int W, int Cin, int Cout, void* stream);
 
+
+/* fp32-grade tensor-core path (3 x TF32 split operands on tcgen05, TMA-fed; replaces the same ATen / cuDNN calls as
+ * dinvk_conv_f32: deepinv/models/drunet.py:200-263,323-433, dncnn.py:116-140) — every fp32 value v travels as
+ * hi = tf32(v), lo = v - hi; products hi*hi + hi*lo + lo*hi, fp32 accumulation drained to registers every `window`
+ * pipeline stages (0 = library default).  Activation layout "split16": (B,H,W,C/16,2,16) fp32 words, [..,0,:] = hi,
+ * [..,1,:] = lo.  Weights: per 64 output channels 128 K-major rows [W_hi (64); W_lo (64)], both tf32-rounded:
+ *   kind 0 (3x3, pad 1): (2*Cout, 9*Cin), k = (ky*3+kx)*Cin + c
+ *   kind 1 (2x2 stride 2): (2*Cout, 4*Cin), k = (dy*2+dx)*Cin + c;  out (B,H/2,W/2,Cout)
+ *   kind 2 (transposed 2x2 stride 2): (8*Cout, Cin), GEMM column = (dy*2+dx)*Cout + co;  out (B,2H,2W,Cout)
+ *   out = act(conv(x) + bias) + res + res2 (res/res2: split16, kind 0 only).  Cin % 32 == 0, Cout % 64 == 0. */
+int dinvk_conv_tc32(const float* x, const float* weight, const float* bias, const float* res, const float* res2,
+                    float* out, int B, int H, int W, int Cin, int Cout, int kind, int act, int window, void* stream);
+/* head: NCHW fp32 image (+ optional constant noise-level channel) -> split16; weight (Cout, C + has_fill, 3, 3) fp32 */
+int dinvk_conv_tc32_head(const float* x_nchw, const float* weight, const float* bias, float* out, int B, int C, int H,
+                         int W, int Cout, float fill_scalar, const float* fill_batch, int has_fill, int act,
+                         void* stream);
+/* tail: split16 -> NCHW fp32, Cout <= 4;  out = conv3x3(x) + bias + add_nchw;  weight (Cout, Cin, 3, 3) fp32 */
+int dinvk_conv_tc32_tail(const float* x, const float* weight, const float* bias, const float* add_nchw,
+                         float* out_nchw, int B, int H, int W, int Cin, int Cout, void* stream);
+/* layout converters split16 <-> NCHW fp32 (C % 16 == 0) */
+int dinvk_split16_to_nchw(const float* in, float* out, int B, int C, int H, int W, void* stream);
+int dinvk_nchw_to_split16(const float* in, float* out, int B, int C, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
