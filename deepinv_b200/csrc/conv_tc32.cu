@@ -264,6 +264,208 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_kernel(const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// 3x3 convolution with HALO REUSE (the body layers: 97 % of a DRUNet forward).
+//
+// The per-tap kernel above re-reads every activation tile 9 times and every weight tile once per 128 pixels: 107 bytes per
+// clock and SM from L2 against ~50 deliverable — measured 2.0 ms per DRUNet layer where the tensor pipe needs 0.9 ms.
+// Here a CTA owns a 16 x 16-pixel tile = TWO M=128 accumulators (x-halves of 8 columns).  Per 16-channel block ONE TMA box
+// brings the (16+8) x (16+2)-position slab (tile + halo; out-of-range positions zero-filled = the convolution's padding;
+// 24 positions per slab row keep every 8-position group 1024-byte periodic) of [hi16 | lo16] rows into shared memory, and
+// the nine taps are nine shifted UMMA descriptors into it (start + ((ky*24 + kx + 8*half) * 128 B, stride between 8-row
+// groups = one slab row); the 128-byte swizzle is a function of the shared-memory address bits, so the shifted starts
+// need no base offset (validated by the bf16 halo kernel, conv_tc.cu).  A weight tile holds TWO taps of one channel block
+// ([tap even 16 ch | tap odd 16 ch] per row, rows = [W_hi; W_lo]) and is shared by both halves.
+// L2 -> SM traffic: 135 KB per channel block and 4032 tensor-pipe clocks = 33 B/clk.
+// Accumulators: per half 64 main + 64 corr columns, two buffers (512 TMEM columns); a window = `win` taps.
+// ---------------------------------------------------------------------------------------------------------------
+namespace slab {
+constexpr int TXP = 16, TYP = 16;                 // CTA pixel tile
+constexpr int SLAB_X = 24, SLAB_Y = 18;
+constexpr int SLAB_BYTES = SLAB_X * SLAB_Y * 128; // 55296
+constexpr int A_STAGES = 2, B_STAGES = 6;
+constexpr int WT_TILE = 128 * 128;
+constexpr int SMEM_BYTES = A_STAGES * SLAB_BYTES + B_STAGES * WT_TILE + 1024;
+static_assert(SLAB_BYTES % 1024 == 0, "slab stages must stay 1024-byte aligned");
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+constexpr uint32_t TCOLS = 512;               // 2 buffers x 2 halves x (64 main + 64 corr)
+}  // namespace slab
+
+__global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid_constant__ Maps M, const Params P) {
+  using namespace slab;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_b = smem + A_STAGES * SLAB_BYTES;
+  __shared__ __align__(8) uint64_t afull[A_STAGES];
+  __shared__ __align__(8) uint64_t aempty[A_STAGES];
+  __shared__ __align__(8) uint64_t bfull[B_STAGES];
+  __shared__ __align__(8) uint64_t bempty[B_STAGES];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pixel_tiles = P.B * P.tiles_y * P.tiles_x;
+  const int total_tiles = pixel_tiles * P.n_tiles;
+  const int nblk = P.Cin / 16;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&M.a[0]);
+    tc::prefetch_tmap(&M.b);
+    for (int s = 0; s < A_STAGES; ++s) { tc::mbar_init(&afull[s], 1); tc::mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < B_STAGES; ++s) { tc::mbar_init(&bfull[s], 1); tc::mbar_init(&bempty[s], 1); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull_bar[a], 1); tc::mbar_init(&tempty_bar[a], 8); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc<TCOLS>(&tmem_base_smem);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int sa = 0; uint32_t pha = 0;
+      int sb = 0; uint32_t phb = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t / pixel_tiles, pt = t - nt * pixel_tiles;
+        const int b = pt / (P.tiles_y * P.tiles_x), r = pt - b * (P.tiles_y * P.tiles_x);
+        const int y0 = (r / P.tiles_x) * TYP, x0 = (r % P.tiles_x) * TXP;
+        for (int j = 0; j < nblk; ++j) {
+          tc::mbar_wait(&aempty[sa], pha ^ 1);
+          tc::mbar_arrive_expect_tx(&afull[sa], SLAB_BYTES);
+          tc::tma_load_4d(smem + sa * SLAB_BYTES, &M.a[0], &afull[sa], j * 32, x0 - 1, y0 - 1, b);
+          if (++sa == A_STAGES) { sa = 0; pha ^= 1; }
+          for (int tp = 0; tp < 5; ++tp) {
+            tc::mbar_wait(&bempty[sb], phb ^ 1);
+            tc::mbar_arrive_expect_tx(&bfull[sb], WT_TILE);
+            tc::tma_load_2d(smem_b + sb * WT_TILE, &M.b, &bfull[sb], (j * 5 + tp) * 32, nt * 128);
+            if (++sb == B_STAGES) { sb = 0; phb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t ID128 = idesc_tf32(128, 128), ID64 = idesc_tf32(128, 64);
+    constexpr uint32_t HI_A = tc::desc_hi_sw128(SLAB_X * 128);
+    constexpr uint32_t HI_B = tc::desc_hi_sw128(1024);
+    const uint32_t slab_lo0 = tc::smem_u32(smem) >> 4;
+    const uint32_t bt_lo0 = tc::smem_u32(smem_b) >> 4;
+    int sa = 0; uint32_t pha = 0;
+    int sb = 0; uint32_t phb = 0;
+    int acc = 0; uint32_t pa = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int in_win = 0;
+      for (int j = 0; j < nblk; ++j) {
+        tc::mbar_wait(&afull[sa], pha);
+        tc::tc_fence_after();
+        const uint32_t slab_lo = slab_lo0 + static_cast<uint32_t>(sa) * (SLAB_BYTES >> 4);
+#pragma unroll 1
+        for (int tp = 0; tp < 5; ++tp) {
+          tc::mbar_wait(&bfull[sb], phb);
+          tc::tc_fence_after();
+          const uint32_t b_lo = bt_lo0 + static_cast<uint32_t>(sb) * (WT_TILE >> 4);
+#pragma unroll
+          for (int par = 0; par < 2; ++par) {
+            const int tap = 2 * tp + par;
+            if (tap < 9) {
+              if (in_win == 0) {
+                tc::mbar_wait(&tempty_bar[acc], pa ^ 1);
+                tc::tc_fence_after();
+              }
+              const uint32_t d = tmem_base + static_cast<uint32_t>(acc * 256);
+              const uint32_t a_t = slab_lo + static_cast<uint32_t>(((tap / 3) * SLAB_X + (tap % 3)) * 8);
+              const uint32_t b_t = b_lo + par * 4;  // odd tap: +64 bytes inside the weight row
+              if (tc::elect_one()) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const uint32_t a = a_t + h * 64;  // x-half: 8 positions = 1024 bytes
+                  const uint32_t dh = d + h * 128;
+                  umma_tf32(dh, a, HI_A, b_t, HI_B, ID128, in_win != 0 ? 1u : 0u);  // hi ch 0-7  x [W_hi; W_lo]
+                  umma_tf32(dh, a + 2, HI_A, b_t + 2, HI_B, ID128, 1u);             // hi ch 8-15
+                  umma_tf32(dh + 64, a + 4, HI_A, b_t, HI_B, ID64, 1u);             // lo ch 0-7  x W_hi
+                  umma_tf32(dh + 64, a + 6, HI_A, b_t + 2, HI_B, ID64, 1u);         // lo ch 8-15
+                }
+                if (par == 1 || tap == 8) tc::umma_commit(&bempty[sb]);
+                if (tap == 8) tc::umma_commit(&aempty[sa]);
+              }
+              __syncwarp();
+              ++in_win;
+              if (in_win == P.win || (tap == 8 && j == nblk - 1)) {
+                if (tc::elect_one()) tc::umma_commit(&tfull_bar[acc]);
+                __syncwarp();
+                in_win = 0;
+                if (++acc == 2) { acc = 0; pa ^= 1; }
+              }
+            }
+          }
+          if (++sb == B_STAGES) { sb = 0; phb ^= 1; }
+        }
+        if (++sa == A_STAGES) { sa = 0; pha ^= 1; }
+      }
+    }
+  } else {
+    // ===================== drain + epilogue: group g = x-half g, TMEM lane quarter q =====================
+    const int q = warp & 3;
+    const int g = (warp - 2) >> 2;
+    int acc = 0; uint32_t pa = 0;
+    const int ntaps_total = nblk * 9;
+    const int nwin = (ntaps_total + P.win - 1) / P.win;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nt = t / pixel_tiles, pt = t - nt * pixel_tiles;
+      const int b = pt / (P.tiles_y * P.tiles_x), r = pt - b * (P.tiles_y * P.tiles_x);
+      const int y0 = (r / P.tiles_x) * TYP, x0 = (r % P.tiles_x) * TXP;
+      const int m = q * 32 + lane;                 // GEMM row of the half: slab row m / 8, position m % 8
+      const int y = y0 + (m >> 3), x = x0 + 8 * g + (m & 7);
+      const bool inside = (y < P.H) && (x < P.W);
+      float v[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] = 0.f;
+      for (int w = 0; w < nwin; ++w) {
+        tc::mbar_wait(&tfull_bar[acc], pa);
+        tc::tc_fence_after();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 256 + g * 128);
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t rm[32], rc[32];
+          tc::tmem_ld_32x32b_x32(t_addr + c0, rm);
+          tc::tmem_ld_32x32b_x32(t_addr + 64 + c0, rc);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[c0 + i] += __uint_as_float(rm[i]) + __uint_as_float(rc[i]);
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) { acc = 0; pa ^= 1; }
+      }
+      const int n0 = nt * 64;
+      if (P.bias) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] += __ldg(P.bias + n0 + i);
+      }
+      if (P.relu) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      if (inside) {
+        const long long o = ((((long long)b * P.H + y) * P.W + x) * P.Cout + n0) * 2;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (P.res) add_split16(P.res + o + c * 32, v + c * 16);
+          if (P.res2) add_split16(P.res2 + o + c * 32, v + c * 16);
+          store_split16(P.out + o + c * 32, v + c * 16);
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc<TCOLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Network HEAD (CUDA cores; 0.1 % of the FLOPs, bound by its 8-byte-per-element output write): 3x3 convolution from the
 // reference's NCHW fp32 image (+ optional constant noise-level channel, drunet.py:190-200) to Cout split16 channels.
 // One thread per pixel: its 9*CT inputs sit in registers, the weights in shared memory (every lane reads the same
@@ -485,10 +687,51 @@ static int launch(const Maps& M, const Params& P, void* stream) {
   return DINVK_POST_LAUNCH();
 }
 
+static int launch_slab(const Maps& M, const Params& P, void* stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc32_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, slab::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(DINVK_ECUDA, "cudaFuncSetAttribute(conv_tc32_slab): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const long long tiles = (long long)P.B * P.tiles_y * P.tiles_x * P.n_tiles;
+  const int grid = (int)std::min<long long>(tiles, sm_count());
+  count_launch();
+  conv_tc32_slab_kernel<<<grid, THREADS, slab::SMEM_BYTES, (cudaStream_t)stream>>>(M, P);
+  return DINVK_POST_LAUNCH();
+}
+
 }  // namespace t32
 }  // namespace dinvk
 
 using namespace dinvk;
+
+// 3x3 with halo reuse: weight = the "slab pack" (2*Cout, 10*Cin): column ((c/16 * 5 + tap/2) * 2 + tap%2) * 16 + c%16
+// (tap 9 = zeros), rows per 64 output channels [W_hi (64); W_lo (64)];  window counted in taps
+extern "C" int dinvk_conv_tc32_slab(const float* x, const float* weight, const float* bias, const float* res, const float* res2,
+                                    float* out, int B, int H, int W, int Cin, int Cout, int act, int window, void* stream) {
+  using namespace t32;
+  DINVK_CHECK_ARG(x && weight && out, "conv_tc32_slab: null pointer");
+  DINVK_CHECK_ARG(B >= 0 && H >= 1 && W >= 1, "conv_tc32_slab: bad shape");
+  DINVK_CHECK_ARG(Cin % 16 == 0 && Cin >= 16, "conv_tc32_slab: Cin=%d must be a multiple of 16", Cin);
+  DINVK_CHECK_ARG(Cout % 64 == 0 && Cout >= 64, "conv_tc32_slab: Cout=%d must be a multiple of 64", Cout);
+  if (B == 0) return DINVK_OK;
+  Maps M;
+  Params P;
+  int rc;
+  const long long px = (long long)Cin * 8;
+  if ((rc = make_act_map(&M.a[0], x, B, H, W, Cin, px, px * W, px * W * H, slab::SLAB_X, slab::SLAB_Y))) return rc;
+  M.a[1] = M.a[0]; M.a[2] = M.a[0]; M.a[3] = M.a[0];
+  if ((rc = make_w_map(&M.b, weight, 10LL * Cin, 2LL * Cout))) return rc;
+  P.B = B; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout;
+  P.ntaps = 9; P.kc_per_tap = Cin / 16; P.mode = 0; P.n_tiles = Cout / 64;
+  for (int t = 0; t < 9; ++t) { P.dx[t] = t % 3 - 1; P.dy[t] = t / 3 - 1; P.amap[t] = 0; }
+  P.relu = act; P.res = res; P.res2 = res2; P.out = out; P.bias = bias;
+  static const int def_win = getenv("DINVK_TC32_SLAB_WINDOW") ? std::max(1, atoi(getenv("DINVK_TC32_SLAB_WINDOW"))) : 3;
+  P.win = window > 0 ? window : def_win;
+  P.tiles_x = ceil_div(W, slab::TXP); P.tiles_y = ceil_div(H, slab::TYP);
+  return launch_slab(M, P, stream);
+}
 
 // kind 0: 3x3 stride 1 zero-pad 1 (weight rows = Cout/64 tiles of 128, K = 9*Cin, k = (ky*3+kx)*Cin + c)
 // kind 1: 2x2 stride 2 (K = 4*Cin, k = (dy*2+dx)*Cin + c), out (B, H/2, W/2, Cout)

@@ -157,6 +157,16 @@ def _pack3x3_tc32(w):   # (Cout, Cin, 3, 3) -> k = (ky*3+kx)*Cin + c
     return _pack_tc32(w.detach().float().permute(0, 2, 3, 1).reshape(w.shape[0], -1))
 
 
+def _pack3x3_slab_tc32(w):
+    """(Cout, Cin, 3, 3) -> the halo kernel's K order: column ((c/16 * 5 + tap/2) * 2 + tap%2) * 16 + c%16, tap 9 = zeros"""
+    w = w.detach().float()
+    co, ci = w.shape[:2]
+    out = torch.zeros(co, ci // 16, 5, 2, 16, dtype=torch.float32, device=w.device)
+    for tap in range(9):
+        out[:, :, tap // 2, tap % 2, :] = w[:, :, tap // 3, tap % 3].reshape(co, ci // 16, 16)
+    return _pack_tc32(out.reshape(co, 10 * ci))
+
+
 def _pack_down_tc32(w):  # (Cout, Cin, 2, 2) -> k = (dy*2+dx)*Cin + c
     return _pack_tc32(w.detach().float().permute(0, 2, 3, 1).reshape(w.shape[0], -1))
 
@@ -176,7 +186,8 @@ class _DrunetPack32:
                                       f"most 4 image channels and nc[0] <= 128; got nc={self.nc}; use precision='fp32'")
         self.head = m.m_head.weight.detach().float().contiguous()
         self.tail = m.m_tail.weight.detach().float().contiguous()
-        rb = lambda blocks: [(_pack3x3_tc32(b.res[0].weight), _pack3x3_tc32(b.res[2].weight), b.res[0].weight.shape[0]) for b in blocks]
+        rb = lambda blocks: [(_pack3x3_slab_tc32(b.res[0].weight), _pack3x3_slab_tc32(b.res[2].weight), b.res[0].weight.shape[0])
+                             for b in blocks]
         self.down = [(rb(list(st)[:nb]), _pack_down_tc32(st[nb].weight), st[nb].weight.shape[0]) for st in (m.m_down1, m.m_down2, m.m_down3)]
         self.body = rb(list(m.m_body))
         self.up = [(_pack_up_tc32(st[0].weight), st[0].weight.shape[1], rb(list(st)[1:])) for st in (m.m_up3, m.m_up2, m.m_up1)]
@@ -184,8 +195,8 @@ class _DrunetPack32:
 
 def _resblocks32(t, blocks, skip=None):
     for i, (w0, w1, c) in enumerate(blocks):
-        u = ops.conv_tc32(t, w0, c, relu=True)
-        t = ops.conv_tc32(u, w1, c, res=t, res2=skip if i == len(blocks) - 1 else None)
+        u = ops.conv_tc32_slab(t, w0, c, relu=True)
+        t = ops.conv_tc32_slab(u, w1, c, res=t, res2=skip if i == len(blocks) - 1 else None)
     return t
 
 
@@ -217,7 +228,7 @@ class _DncnnPack32:
         f32 = lambda b: None if b is None else b.detach().float().contiguous()
         self.nf = nf
         self.first = (m.in_conv.weight.detach().float().contiguous(), f32(m.in_conv.bias))
-        self.mid = [(_pack3x3_tc32(c.weight), f32(c.bias)) for c in m.conv_list]
+        self.mid = [(_pack3x3_slab_tc32(c.weight), f32(c.bias)) for c in m.conv_list]
         self.last = (m.out_conv.weight.detach().float().contiguous(), f32(m.out_conv.bias))
 
 
@@ -227,5 +238,5 @@ def dncnn_forward_tc32(model, x: torch.Tensor) -> torch.Tensor:
         pk = model._tc32 = _DncnnPack32(model)
     t = ops.conv_tc32_head(x, pk.first[0], bias=pk.first[1], relu=True)
     for w, b in pk.mid:
-        t = ops.conv_tc32(t, w, pk.nf, bias=b, relu=True)
+        t = ops.conv_tc32_slab(t, w, pk.nf, bias=b, relu=True)
     return ops.conv_tc32_tail(t, pk.last[0], bias=pk.last[1], add=x)

@@ -493,6 +493,16 @@ def conv_tc32(x, w, cout: int, *, kind: int = 0, bias=None, res=None, res2=None,
     return out
 
 
+def conv_tc32_slab(x, w, cout: int, *, bias=None, res=None, res2=None, relu: bool = False, window: int = 0) -> torch.Tensor:
+    """3x3 convolution with halo reuse (the body layers); w packed by models.tc_engine._pack3x3_slab_tc32; window in taps"""
+    dev = _require_cuda(x, w)
+    B, H, W, nblk = x.shape[:4]
+    out = torch.empty(B, H, W, cout // 16, 2, 16, dtype=torch.float32, device=dev)
+    check(get_lib().dinvk_conv_tc32_slab(_p(x), _p(w), _p(bias), _p(res), _p(res2), _p(out), B, H, W, nblk * 16, cout, int(relu),
+                                         int(window), _stream(dev)))
+    return out
+
+
 def conv_tc32_head(x, weight, *, bias=None, fill=None, relu: bool = False) -> torch.Tensor:
     """network head: (B,C,H,W) fp32 NCHW (+ constant channel `fill`) -> split16 (B,H,W,Cout/16,2,16); weight (Cout,C[+1],3,3) fp32"""
     dev = _require_cuda(x, weight)

@@ -62,11 +62,39 @@ def test_conv3x3_tc32(shape, window, dev):
     ref32 = F.conv2d(x, w, padding=1)
     out = _from_split(ops.conv_tc32(xs, wp, Cout, window=window))
     e_k, e_ref = rel_err(out.double(), ref64), rel_err(ref32.double(), ref64)
-    assert e_k < 2e-6, (e_k, e_ref)
+    assert e_k < (2e-6 if window != 1000 else 2e-5), (e_k, e_ref)
     if window != 1000:  # (1000 = never drained inside a tile: the tensor core's truncating accumulator shows, ~1e-6)
         assert e_k < max(4 * e_ref, 5e-7), (e_k, e_ref)
     out = _from_split(ops.conv_tc32(xs, wp, Cout, bias=bias.to(dev), res=_to_split(r1, dev), res2=_to_split(r2, dev), relu=True,
                                     window=window))
+    ref = F.relu(F.conv2d(x.double(), w.double(), bias.double(), padding=1)) + r1.double() + r2.double()
+    assert rel_err(out.double(), ref) < (2e-6 if window != 1000 else 2e-5)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64, 32, 48), (1, 64, 128, 16, 16), (2, 128, 128, 24, 40), (1, 256, 256, 8, 16),
+                                   (1, 512, 512, 8, 16), (3, 128, 64, 9, 21), (1, 16, 64, 17, 33), (5, 64, 64, 40, 72)])
+@pytest.mark.parametrize("window", [0, 1, 4, 7])
+def test_conv3x3_tc32_slab(shape, window, dev):
+    """the halo-reuse kernel (16x16-pixel tiles, two accumulators per CTA, nine taps out of one slab)"""
+    from deepinv_b200 import ops
+    from deepinv_b200.models.tc_engine import _pack3x3_slab_tc32
+
+    B, Cin, Cout, H, W = shape
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(B, Cin, H, W, generator=gen).abs()
+    w = torch.randn(Cout, Cin, 3, 3, generator=gen) / (3 * Cin ** 0.5)
+    r1, r2 = torch.randn(B, Cout, H, W, generator=gen), torch.randn(B, Cout, H, W, generator=gen)
+    bias = torch.randn(Cout, generator=gen)
+    wp = _pack3x3_slab_tc32(w.to(dev))
+    xs = _to_split(x, dev)
+    ref64 = F.conv2d(x.double(), w.double(), padding=1)
+    ref32 = F.conv2d(x, w, padding=1)
+    out = _from_split(ops.conv_tc32_slab(xs, wp, Cout, window=window))
+    e_k, e_ref = rel_err(out.double(), ref64), rel_err(ref32.double(), ref64)
+    assert e_k < 2e-6, (e_k, e_ref)
+    assert e_k < max(4 * e_ref, 5e-7), (e_k, e_ref)
+    out = _from_split(ops.conv_tc32_slab(xs, wp, Cout, bias=bias.to(dev), res=_to_split(r1, dev), res2=_to_split(r2, dev), relu=True,
+                                         window=window))
     ref = F.relu(F.conv2d(x.double(), w.double(), bias.double(), padding=1)) + r1.double() + r2.double()
     assert rel_err(out.double(), ref) < 2e-6
 
@@ -74,16 +102,17 @@ def test_conv3x3_tc32(shape, window, dev):
 def test_conv3x3_tc32_positive_sums_no_bias(dev):
     """all-positive weights and activations: a truncating accumulator would shrink every output (negative mean error)"""
     from deepinv_b200 import ops
-    from deepinv_b200.models.tc_engine import _pack3x3_tc32
+    from deepinv_b200.models.tc_engine import _pack3x3_slab_tc32, _pack3x3_tc32
 
     gen = torch.Generator().manual_seed(3)
     x = torch.rand(1, 512, 16, 16, generator=gen) + 0.5
     w = (torch.rand(64, 512, 3, 3, generator=gen) + 0.5) / 4608
     ref64 = F.conv2d(x.double(), w.double(), padding=1)
-    out = _from_split(ops.conv_tc32(_to_split(x, dev), _pack3x3_tc32(w.to(dev)), 64)).double()
-    signed = ((out - ref64) / ref64).mean().item()
-    assert abs(signed) < 2e-7, signed
-    assert rel_err(out, ref64) < 1e-6
+    for fn, pack in ((ops.conv_tc32, _pack3x3_tc32), (ops.conv_tc32_slab, _pack3x3_slab_tc32)):
+        out = _from_split(fn(_to_split(x, dev), pack(w.to(dev)), 64)).double()
+        signed = ((out - ref64) / ref64).mean().item()
+        assert abs(signed) < 4e-7, signed   # (never drained: -3.4e-5 at this K, tools/micro/tf32_probe.cu)
+        assert rel_err(out, ref64) < 1e-6
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 128, 32, 48), (1, 128, 256, 16, 32), (1, 256, 512, 16, 16), (2, 64, 64, 10, 18)])

@@ -11,7 +11,7 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import deepinv_b200 as dinv  # noqa: E402
 from deepinv_b200 import ops  # noqa: E402
-from deepinv_b200.models.tc_engine import _pack3x3_tc32, _pack_down_tc32, _pack_up_tc32  # noqa: E402
+from deepinv_b200.models.tc_engine import _pack3x3_slab_tc32, _pack3x3_tc32, _pack_down_tc32, _pack_up_tc32  # noqa: E402
 
 dev = torch.device("cuda:0")
 args = sys.argv[1:] or ["layers", "net"]
@@ -41,9 +41,16 @@ if "layers" in args:
     for (C, H) in [(64, 256), (128, 128), (256, 64), (512, 32)]:
         x = split_randn(B, H, H, C)
         r = split_randn(B, H, H, C)
-        w = _pack3x3_tc32(torch.randn(C, C, 3, 3, device=dev) / (3 * C ** 0.5))
+        w4 = torch.randn(C, C, 3, 3, device=dev) / (3 * C ** 0.5)
+        w = _pack3x3_tc32(w4)
+        ws = _pack3x3_slab_tc32(w4)
         gf = 2 * B * H * H * C * 9 * C / 1e9
-        for win in windows:
+        for win in (windows if "slab" in args else []):
+            for tag, kw in (("relu", dict(relu=True)), ("res", dict(res=r))):
+                ms = _time(lambda: ops.conv_tc32_slab(x, ws, C, window=win, **kw))
+                print(json.dumps({"op": f"conv3x3 tc32 SLAB {C}->{C} @{H}x{H} B={B} {tag}", "window_taps": win, "us": ms * 1e3,
+                                  "TFLOPs_fp32_equiv": gf / ms}), flush=True)
+        for win in (windows if "tap" in args else []):
             for tag, kw in (("relu", dict(relu=True)), ("res", dict(res=r))):
                 ms = _time(lambda: ops.conv_tc32(x, w, C, window=win, **kw))
                 print(json.dumps({"op": f"conv3x3 tc32 {C}->{C} @{H}x{H} B={B} {tag}", "window": win, "us": ms * 1e3,
