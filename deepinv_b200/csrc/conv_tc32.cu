@@ -80,6 +80,7 @@ struct Params {
   const float* res2;
   float* out;               // split16 (B, Hout, Wout, Cout)
   const float* bias;
+  int dbg;                  // timing experiments only (DINVK_TC32_DBG): 1 no TMA loads, 2 no epilogue memory traffic, 4 no TMEM drains
 };
 
 // split one 16-channel block: v[16] -> 128 bytes [hi16 | lo16]
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_kernel(const __grid_cons
 // need no base offset (validated by the bf16 halo kernel, conv_tc.cu).  A weight tile holds TWO taps of one channel block
 // ([tap even 16 ch | tap odd 16 ch] per row, rows = [W_hi; W_lo]) and is shared by both halves.
 // L2 -> SM traffic: 135 KB per channel block and 4032 tensor-pipe clocks = 33 B/clk.
-// Accumulators: per half 64 main + 64 corr columns, two buffers (512 TMEM columns); a window = `win` taps.
+// Accumulators: per half 64 main + 64 corr columns, two buffers (512 TMEM columns); a window = `win` channel blocks.
 // ---------------------------------------------------------------------------------------------------------------
 namespace slab {
 constexpr int TXP = 16, TYP = 16;                 // CTA pixel tile
@@ -333,13 +334,21 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
         const int y0 = (r / P.tiles_x) * TYP, x0 = (r % P.tiles_x) * TXP;
         for (int j = 0; j < nblk; ++j) {
           tc::mbar_wait(&aempty[sa], pha ^ 1);
-          tc::mbar_arrive_expect_tx(&afull[sa], SLAB_BYTES);
-          tc::tma_load_4d(smem + sa * SLAB_BYTES, &M.a[0], &afull[sa], j * 32, x0 - 1, y0 - 1, b);
+          if (P.dbg & 1) {
+            tc::mbar_arrive(&afull[sa]);
+          } else {
+            tc::mbar_arrive_expect_tx(&afull[sa], SLAB_BYTES);
+            tc::tma_load_4d(smem + sa * SLAB_BYTES, &M.a[0], &afull[sa], j * 32, x0 - 1, y0 - 1, b);
+          }
           if (++sa == A_STAGES) { sa = 0; pha ^= 1; }
           for (int tp = 0; tp < 5; ++tp) {
             tc::mbar_wait(&bempty[sb], phb ^ 1);
-            tc::mbar_arrive_expect_tx(&bfull[sb], WT_TILE);
-            tc::tma_load_2d(smem_b + sb * WT_TILE, &M.b, &bfull[sb], (j * 5 + tp) * 32, nt * 128);
+            if (P.dbg & 1) {
+              tc::mbar_arrive(&bfull[sb]);
+            } else {
+              tc::mbar_arrive_expect_tx(&bfull[sb], WT_TILE);
+              tc::tma_load_2d(smem_b + sb * WT_TILE, &M.b, &bfull[sb], (j * 5 + tp) * 32, nt * 128);
+            }
             if (++sb == B_STAGES) { sb = 0; phb ^= 1; }
           }
         }
@@ -347,6 +356,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // Converged warp, one elected lane issues.  The tap loop is fully unrolled (compile-time tap shifts, one barrier wait and
+    // one commit per weight tile = 16 MMAs): the first version spent ~110 SASS instructions per tap on window / phase
+    // bookkeeping and kept the tensor pipe only 54 % busy (profiles/r02_ncu_tc32_slab_v1.csv).
     constexpr uint32_t ID128 = idesc_tf32(128, 128), ID64 = idesc_tf32(128, 64);
     constexpr uint32_t HI_A = tc::desc_hi_sw128(SLAB_X * 128);
     constexpr uint32_t HI_B = tc::desc_hi_sw128(1024);
@@ -356,53 +368,57 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
     int sb = 0; uint32_t phb = 0;
     int acc = 0; uint32_t pa = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      int in_win = 0;
+      int in_win = 0;  // channel blocks accumulated in the current window
       for (int j = 0; j < nblk; ++j) {
+        if (in_win == 0) {
+          tc::mbar_wait(&tempty_bar[acc], pa ^ 1);
+        }
         tc::mbar_wait(&afull[sa], pha);
         tc::tc_fence_after();
         const uint32_t slab_lo = slab_lo0 + static_cast<uint32_t>(sa) * (SLAB_BYTES >> 4);
-#pragma unroll 1
+        const uint32_t d = tmem_base + static_cast<uint32_t>(acc * 256);
+        const uint32_t fresh = in_win == 0 ? 0u : 1u;
+        const bool last_of_win = (in_win + 1 == P.win) || (j == nblk - 1);
+#pragma unroll
         for (int tp = 0; tp < 5; ++tp) {
           tc::mbar_wait(&bfull[sb], phb);
           tc::tc_fence_after();
           const uint32_t b_lo = bt_lo0 + static_cast<uint32_t>(sb) * (WT_TILE >> 4);
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int par = 0; par < 2; ++par) {
-            const int tap = 2 * tp + par;
-            if (tap < 9) {
-              if (in_win == 0) {
-                tc::mbar_wait(&tempty_bar[acc], pa ^ 1);
-                tc::tc_fence_after();
-              }
-              const uint32_t d = tmem_base + static_cast<uint32_t>(acc * 256);
-              const uint32_t a_t = slab_lo + static_cast<uint32_t>(((tap / 3) * SLAB_X + (tap % 3)) * 8);
-              const uint32_t b_t = b_lo + par * 4;  // odd tap: +64 bytes inside the weight row
-              if (tc::elect_one()) {
+            for (int par = 0; par < 2; ++par) {
+              constexpr int dummy = 0; (void)dummy;
+              const int tap = 2 * tp + par;
+              if (tap < 9) {
+                const uint32_t a_t = slab_lo + static_cast<uint32_t>(((tap / 3) * SLAB_X + (tap % 3)) * 8);
+                const uint32_t b_t = b_lo + par * 4;  // odd tap: +64 bytes inside the weight row
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                   const uint32_t a = a_t + h * 64;  // x-half: 8 positions = 1024 bytes
                   const uint32_t dh = d + h * 128;
-                  umma_tf32(dh, a, HI_A, b_t, HI_B, ID128, in_win != 0 ? 1u : 0u);  // hi ch 0-7  x [W_hi; W_lo]
-                  umma_tf32(dh, a + 2, HI_A, b_t + 2, HI_B, ID128, 1u);             // hi ch 8-15
-                  umma_tf32(dh + 64, a + 4, HI_A, b_t, HI_B, ID64, 1u);             // lo ch 0-7  x W_hi
-                  umma_tf32(dh + 64, a + 6, HI_A, b_t + 2, HI_B, ID64, 1u);         // lo ch 8-15
+                  umma_tf32(dh, a, HI_A, b_t, HI_B, ID128, tap == 0 ? fresh : 1u);   // hi ch 0-7  x [W_hi; W_lo]
+                  umma_tf32(dh, a + 2, HI_A, b_t + 2, HI_B, ID128, 1u);              // hi ch 8-15
+                  umma_tf32(dh + 64, a + 4, HI_A, b_t, HI_B, ID64, 1u);              // lo ch 0-7  x W_hi
+                  umma_tf32(dh + 64, a + 6, HI_A, b_t + 2, HI_B, ID64, 1u);          // lo ch 8-15
                 }
-                if (par == 1 || tap == 8) tc::umma_commit(&bempty[sb]);
-                if (tap == 8) tc::umma_commit(&aempty[sa]);
-              }
-              __syncwarp();
-              ++in_win;
-              if (in_win == P.win || (tap == 8 && j == nblk - 1)) {
-                if (tc::elect_one()) tc::umma_commit(&tfull_bar[acc]);
-                __syncwarp();
-                in_win = 0;
-                if (++acc == 2) { acc = 0; pa ^= 1; }
               }
             }
+            tc::umma_commit(&bempty[sb]);
+            if (tp == 4) {
+              tc::umma_commit(&aempty[sa]);
+              if (last_of_win) tc::umma_commit(&tfull_bar[acc]);
+            }
           }
+          __syncwarp();
           if (++sb == B_STAGES) { sb = 0; phb ^= 1; }
         }
         if (++sa == A_STAGES) { sa = 0; pha ^= 1; }
+        if (last_of_win) {
+          in_win = 0;
+          if (++acc == 2) { acc = 0; pa ^= 1; }
+        } else {
+          ++in_win;
+        }
       }
     }
   } else {
@@ -410,8 +426,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
     const int q = warp & 3;
     const int g = (warp - 2) >> 2;
     int acc = 0; uint32_t pa = 0;
-    const int ntaps_total = nblk * 9;
-    const int nwin = (ntaps_total + P.win - 1) / P.win;
+    const int nwin = (nblk + P.win - 1) / P.win;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int nt = t / pixel_tiles, pt = t - nt * pixel_tiles;
       const int b = pt / (P.tiles_y * P.tiles_x), r = pt - b * (P.tiles_y * P.tiles_x);
@@ -419,6 +434,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
       const int m = q * 32 + lane;                 // GEMM row of the half: slab row m / 8, position m % 8
       const int y = y0 + (m >> 3), x = x0 + 8 * g + (m & 7);
       const bool inside = (y < P.H) && (x < P.W);
+      const long long o = ((((long long)b * P.H + y) * P.W + x) * P.Cout + nt * 64) * 2;  // word offset of this pixel's 64 channels
+      if (inside && P.res) {  // pull the residual lines towards L2 while the tile's MMAs run
+#pragma unroll
+        for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.res + o + k * 32));
+        if (P.res2) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.res2 + o + k * 32));
+        }
+      }
       float v[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) v[i] = 0.f;
@@ -426,6 +450,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
         tc::mbar_wait(&tfull_bar[acc], pa);
         tc::tc_fence_after();
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 256 + g * 128);
+        if (!(P.dbg & 4))
 #pragma unroll
         for (int c0 = 0; c0 < 64; c0 += 32) {
           uint32_t rm[32], rc[32];
@@ -449,13 +474,29 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
 #pragma unroll
         for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
       }
-      if (inside) {
-        const long long o = ((((long long)b * P.H + y) * P.W + x) * P.Cout + n0) * 2;
+      if (inside && !(P.dbg & 2)) {
+        // residual operands: all loads of two channel blocks are issued before the first use (the first version loaded,
+        // added and stored block by block: four dependent HBM round trips per tile and thread)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (P.res) add_split16(P.res + o + c * 32, v + c * 16);
-          if (P.res2) add_split16(P.res2 + o + c * 32, v + c * 16);
-          store_split16(P.out + o + c * 32, v + c * 16);
+        for (int cp = 0; cp < 2; ++cp) {
+          if (P.res) {
+            uint32_t raw[8][8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) tc::ldg256(P.res + o + cp * 64 + k * 8, raw[k]);
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                v[cp * 32 + c2 * 16 + e] += __uint_as_float(raw[c2 * 4][e]) + __uint_as_float(raw[c2 * 4 + 2][e]);
+                v[cp * 32 + c2 * 16 + 8 + e] += __uint_as_float(raw[c2 * 4 + 1][e]) + __uint_as_float(raw[c2 * 4 + 3][e]);
+              }
+          }
+          if (P.res2) {
+            add_split16(P.res2 + o + cp * 64, v + cp * 32);
+            add_split16(P.res2 + o + cp * 64 + 32, v + cp * 32 + 16);
+          }
+          store_split16(P.out + o + cp * 64, v + cp * 32);
+          store_split16(P.out + o + cp * 64 + 32, v + cp * 32 + 16);
         }
       }
     }
@@ -668,7 +709,7 @@ static int default_window() {
   static int w = -1;
   if (w < 0) {
     const char* e = getenv("DINVK_TC32_WINDOW");
-    w = e ? std::max(1, atoi(e)) : 2;
+    w = e ? std::max(1, atoi(e)) : 4;
   }
   return w;
 }
@@ -707,7 +748,7 @@ static int launch_slab(const Maps& M, const Params& P, void* stream) {
 using namespace dinvk;
 
 // 3x3 with halo reuse: weight = the "slab pack" (2*Cout, 10*Cin): column ((c/16 * 5 + tap/2) * 2 + tap%2) * 16 + c%16
-// (tap 9 = zeros), rows per 64 output channels [W_hi (64); W_lo (64)];  window counted in taps
+// (tap 9 = zeros), rows per 64 output channels [W_hi (64); W_lo (64)];  window counted in 16-channel blocks (9 taps, k = 144, each)
 extern "C" int dinvk_conv_tc32_slab(const float* x, const float* weight, const float* bias, const float* res, const float* res2,
                                     float* out, int B, int H, int W, int Cin, int Cout, int act, int window, void* stream) {
   using namespace t32;
@@ -727,9 +768,10 @@ extern "C" int dinvk_conv_tc32_slab(const float* x, const float* weight, const f
   P.ntaps = 9; P.kc_per_tap = Cin / 16; P.mode = 0; P.n_tiles = Cout / 64;
   for (int t = 0; t < 9; ++t) { P.dx[t] = t % 3 - 1; P.dy[t] = t / 3 - 1; P.amap[t] = 0; }
   P.relu = act; P.res = res; P.res2 = res2; P.out = out; P.bias = bias;
-  static const int def_win = getenv("DINVK_TC32_SLAB_WINDOW") ? std::max(1, atoi(getenv("DINVK_TC32_SLAB_WINDOW"))) : 3;
+  static const int def_win = getenv("DINVK_TC32_SLAB_WINDOW") ? std::max(1, atoi(getenv("DINVK_TC32_SLAB_WINDOW"))) : 2;
   P.win = window > 0 ? window : def_win;
   P.tiles_x = ceil_div(W, slab::TXP); P.tiles_y = ceil_div(H, slab::TYP);
+  P.dbg = getenv("DINVK_TC32_DBG") ? atoi(getenv("DINVK_TC32_DBG")) : 0;
   return launch_slab(M, P, stream);
 }
 
@@ -778,6 +820,7 @@ extern "C" int dinvk_conv_tc32(const float* x, const float* weight, const float*
     P.H = H; P.W = W; P.ntaps = 1; P.mode = 2; P.n_tiles = 4 * Cout / 64;
   }
   P.tiles_x = ceil_div(P.W, TX); P.tiles_y = ceil_div(P.H, TY);
+  P.dbg = 0;
   return launch(M, P, stream);
 }
 

@@ -15,6 +15,7 @@ from . import _ffi
 from ._lib import DinvkError, check, get_lib
 
 _ws_cache: dict[tuple, torch.Tensor] = {}
+_ws_retired: list[torch.Tensor] = []  # outgrown workspaces stay alive: a captured CUDA graph may have their address baked in
 
 
 def _require_cuda(*ts: Optional[torch.Tensor]) -> torch.device:
@@ -32,6 +33,10 @@ def _require_cuda(*ts: Optional[torch.Tensor]) -> torch.device:
             raise DinvkError(f"tensors on different devices: {dev} vs {t.device}")
     if dev is None:
         raise DinvkError("no tensor given")
+    if dev.index is not None and dev.index != torch.cuda.current_device():
+        # the library keys its tables by the CURRENT device and launches on the tensors' stream: make them agree (like a
+        # torch op's device guard; stays switched, as `with torch.cuda.device(t.device)` around the caller would leave it)
+        torch.cuda.set_device(dev)
     return dev
 
 
@@ -56,6 +61,8 @@ def workspace(dev: torch.device, nbytes: int, tag: str = "") -> torch.Tensor:
     key = (dev, tag)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            _ws_retired.append(ws)  # never hand the old block back to the allocator (replaying an earlier graph would scribble on it)
         ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
         _ws_cache[key] = ws
     return ws
@@ -494,7 +501,7 @@ def conv_tc32(x, w, cout: int, *, kind: int = 0, bias=None, res=None, res2=None,
 
 
 def conv_tc32_slab(x, w, cout: int, *, bias=None, res=None, res2=None, relu: bool = False, window: int = 0) -> torch.Tensor:
-    """3x3 convolution with halo reuse (the body layers); w packed by models.tc_engine._pack3x3_slab_tc32; window in taps"""
+    """3x3 convolution with halo reuse (the body layers); w packed by models.tc_engine._pack3x3_slab_tc32; window in 16-channel blocks"""
     dev = _require_cuda(x, w)
     B, H, W, nblk = x.shape[:4]
     out = torch.empty(B, H, W, cout // 16, 2, 16, dtype=torch.float32, device=dev)

@@ -185,15 +185,23 @@ def lsqr(A: Callable, AT: Callable, b: torch.Tensor, eta=0.0, x0: torch.Tensor |
         v = ops.batched_axpy(AT(u), v, beta, -1.0)
         alpha = nrm(v)
         v = scale(v, safe_inv(alpha))
+        # every division is guarded per sample: a degenerate sample in the batch (b = 0 or A^T b = 0 with eta = 0, e.g. a
+        # padded all-zero measurement) has rhobar1 = rho = 0 and must stay at its start value instead of turning into NaN
+        # (the reference returns early for it, lsqr.py:150-160, and skips the damped rotation when eta == 0)
         rhobar1 = torch.sqrt(rhobar ** 2 + eta_t)
-        cs1, sn1 = rhobar / rhobar1, damp / rhobar1
+        ok1 = rhobar1 > 0
+        cs1 = torch.where(ok1, rhobar / torch.where(ok1, rhobar1, torch.ones_like(rhobar1)), torch.ones_like(rhobar1))
+        sn1 = torch.where(ok1, damp / torch.where(ok1, rhobar1, torch.ones_like(rhobar1)), torch.zeros_like(rhobar1))
         psi, phibar = sn1 * phibar, cs1 * phibar
         rho = torch.hypot(rhobar1, beta)
-        cs, sn = rhobar1 / rho, beta / rho
+        ok = rho > 0
+        rho_s = torch.where(ok, rho, torch.ones_like(rho))
+        cs = torch.where(ok, rhobar1 / rho_s, torch.ones_like(rho))
+        sn = torch.where(ok, beta / rho_s, torch.zeros_like(rho))
         theta, rhobar = sn * alpha, -cs * alpha
         phi, phibar = cs * phibar, sn * phibar
-        x = ops.batched_axpy(x, w, phi / rho, 1.0)
-        w = ops.batched_axpy(v, w, theta / rho, -1.0)
+        x = ops.batched_axpy(x, w, torch.where(ok, phi / rho_s, torch.zeros_like(rho)), 1.0)
+        w = ops.batched_axpy(v, w, torch.where(ok, theta / rho_s, torch.zeros_like(rho)), -1.0)
         if bool((torch.sqrt(phibar ** 2 + psi ** 2) <= tol * bnorm).all()):
             if verbose:
                 print("LSQR converged at iteration", itn)

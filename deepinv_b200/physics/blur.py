@@ -143,14 +143,16 @@ class BlurFFT(DecomposablePhysics):
         m, a = self.mask, self.angle
         if not cache_hit(self._spec_key, m, a):
             H, W = self.img_size[-2:]
-            half = m[..., 0] * a                       # h^ on the half spectrum (1, C, H, W/2+1)
-            C = half.shape[1]
-            same = C == 1 or bool((half == half[:, :1]).all())
+            half = m[..., 0] * a                       # h^ on the half spectrum (Fb, C, H, W/2+1), Fb = 1 or one filter per sample
+            Fb, C = half.shape[:2]
+            same = Fb == 1 and (C == 1 or bool((half == half[:, :1]).all()))
             hh = half[:, :1] if same else half
             # Hermitian completion: h^[k1, k2] = conj(h^[-k1, W-k2]) for k2 > W/2
             k2 = torch.arange(W // 2 + 1, W, device=m.device)
             src = torch.roll(torch.flip(hh, dims=(-2,)), 1, dims=-2)[..., W - k2]
-            full = torch.cat([hh, torch.conj(src)], dim=-1)[0].contiguous()  # (C', H, W)
+            full = torch.cat([hh, torch.conj(src)], dim=-1).contiguous()  # (Fb, C', H, W); the batch dimension is KEPT
+            if same:
+                full = full[0]
             mag = full.abs()
             pinv = torch.where(mag > 1e-5, 1.0 / mag, torch.zeros_like(mag))
             ang = torch.where(mag > 0, full / mag.clamp_min(1e-38), torch.ones_like(full))
@@ -182,8 +184,13 @@ class BlurFFT(DecomposablePhysics):
         if p1 is not None:
             z1 = torch.zeros(n, 2, H, W, device=x.device)
             z1[:, 0] = p1.float().reshape(n, H, W)
-        t = spec.tensor
-        exp = t.unsqueeze(0).expand(B, *t.shape).reshape(n, *t.shape[1:]).contiguous()
+        # per-sample and / or per-channel filters (the reference broadcasts a (Fb, C', H, W/2+1, 2) mask over the batch,
+        # blur.py:659-692 + forward.py:1080-1116): one multiplier per (sample, channel) image
+        t = spec.tensor                                     # (Fb, C', H, W[, 2])
+        Fb, Cf = t.shape[:2]
+        if Fb not in (1, B) or Cf not in (1, C):
+            raise RuntimeError(f"BlurFFT: filter spectrum of shape {tuple(t.shape[:2])} does not broadcast to a batch of {B} x {C} images")
+        exp = t.expand(B, C, *t.shape[2:]).reshape(n, *t.shape[2:]).contiguous()
         spec_b = ops.MaskSpec(exp, H * W, 0, W, spec.complex)
         out = ops.spectral(z, H, W, fwd=True, inv=True, centered=False, gmode=gmode, mask=spec_b, p1=z1, a1=a1, c=c)
         return out[:, 0].reshape(B, C, H, W)

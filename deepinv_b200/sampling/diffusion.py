@@ -106,7 +106,9 @@ class DiffPIR(nn.Module):
                 t_n = nearest(sigmas[seq[i + 1]])
                 step.update(sac_n=float(sqrt_ac[t_n]), s1m_n=float(sqrt_1m[t_n]))
             plan.append(step)
-        plan[0]["init_std"] = float((sigmas[seq[0]] ** 2 - 4.0 * sigma ** 2).sqrt())
+        # the INITIAL noise level uses the constructor's sigma, like the reference (diffusion.py:469); only rho / the noise
+        # schedule follow the physics' noise model
+        plan[0]["init_std"] = float((sigmas[seq[0]] ** 2 - 4.0 * float(self.sigma) ** 2).sqrt())
         plan[0]["init_div"] = float(sqrt_recip[-1])
         return plan
 

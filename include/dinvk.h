@@ -276,7 +276,7 @@ int dinvk_conv_tc32(const float* x, const float* weight, const float* bias, cons
                     float* out, int B, int H, int W, int Cin, int Cout, int kind, int act, int window, void* stream);
 /* kind 0 with halo reuse (the body layers): one (16+8) x (16+2)-position activation slab per 16-channel block serves all
  * nine taps.  weight: "slab pack" (2*Cout, 10*Cin), column ((c/16 * 5 + tap/2) * 2 + tap%2) * 16 + c%16 (tap 9 = zeros);
- * `window` counted in taps (0 = default 3).  Cin % 16 == 0, Cout % 64 == 0. */
+ * `window` counted in 16-channel blocks of 9 taps (0 = default 2, i.e. k = 288 per accumulation window).  Cin % 16 == 0, Cout % 64 == 0. */
 int dinvk_conv_tc32_slab(const float* x, const float* weight, const float* bias, const float* res, const float* res2,
                          float* out, int B, int H, int W, int Cin, int Cout, int act, int window, void* stream);
 /* head: NCHW fp32 image (+ optional constant noise-level channel) -> split16; weight (Cout, C + has_fill, 3, 3) fp32 */

@@ -258,6 +258,17 @@ def blurfft_fixtures():
         save(tag, x=x, filt=filt, y=y, At=phys.A_adjoint(y), prox=phys.prox_l2(z, y, 1.5), z=z, gamma=np.float32(1.5),
              dagger=phys.A_dagger(y), mask=phys.mask, angle_re=phys.angle.real, angle_im=phys.angle.imag,
              Vt=phys.V_adjoint(x), Ut=phys.U_adjoint(x), AtA=phys.A_adjoint_A(x))
+    # one filter PER SAMPLE (what MotionBlurGenerator.step(batch_size=B) hands out), with and without a channel dimension
+    for tag, (B, C, H, W), fshape in [("blurfft_persample", (3, 2, 12, 14), (3, 1, 5, 5)), ("blurfft_persample_c", (2, 3, 10, 12), (2, 3, 3, 3))]:
+        x = torch.randn(B, C, H, W, generator=g(33))
+        filt = torch.rand(*fshape, generator=g(34)) + 0.1
+        filt = filt / filt.sum(dim=(-2, -1), keepdim=True)
+        phys = BlurFFT(img_size=(C, H, W), filter=filt)
+        y = phys.A(x)
+        z = torch.randn(B, C, H, W, generator=g(35))
+        save(tag, x=x, filt=filt, y=y, At=phys.A_adjoint(y), prox=phys.prox_l2(z, y, 1.5), z=z, gamma=np.float32(1.5),
+             dagger=phys.A_dagger(y), mask=phys.mask, angle_re=phys.angle.real, angle_im=phys.angle.imag,
+             Vt=phys.V_adjoint(x), Ut=phys.U_adjoint(x), AtA=phys.A_adjoint_A(x))
 
 
 def tiny_drunet(cin):

@@ -73,7 +73,7 @@ def test_conv3x3_tc32(shape, window, dev):
 
 @pytest.mark.parametrize("shape", [(2, 64, 64, 32, 48), (1, 64, 128, 16, 16), (2, 128, 128, 24, 40), (1, 256, 256, 8, 16),
                                    (1, 512, 512, 8, 16), (3, 128, 64, 9, 21), (1, 16, 64, 17, 33), (5, 64, 64, 40, 72)])
-@pytest.mark.parametrize("window", [0, 1, 4, 7])
+@pytest.mark.parametrize("window", [0, 1, 2])
 def test_conv3x3_tc32_slab(shape, window, dev):
     """the halo-reuse kernel (16x16-pixel tiles, two accumulators per CTA, nine taps out of one slab)"""
     from deepinv_b200 import ops
@@ -108,11 +108,14 @@ def test_conv3x3_tc32_positive_sums_no_bias(dev):
     x = torch.rand(1, 512, 16, 16, generator=gen) + 0.5
     w = (torch.rand(64, 512, 3, 3, generator=gen) + 0.5) / 4608
     ref64 = F.conv2d(x.double(), w.double(), padding=1)
-    for fn, pack in ((ops.conv_tc32, _pack3x3_tc32), (ops.conv_tc32_slab, _pack3x3_slab_tc32)):
-        out = _from_split(fn(_to_split(x, dev), pack(w.to(dev)), 64)).double()
+    # (never drained: -3.4e-5 at this K, tools/micro/tf32_probe.cu; the bias grows with the MMAs per accumulation window)
+    for fn, pack, kw, lim in ((ops.conv_tc32, _pack3x3_tc32, dict(window=2), 4e-7),            # k = 64 per window
+                              (ops.conv_tc32_slab, _pack3x3_slab_tc32, dict(window=1), 1e-6),  # k = 144
+                              (ops.conv_tc32_slab, _pack3x3_slab_tc32, dict(), 2.5e-6)):       # default: k = 288
+        out = _from_split(fn(_to_split(x, dev), pack(w.to(dev)), 64, **kw)).double()
         signed = ((out - ref64) / ref64).mean().item()
-        assert abs(signed) < 4e-7, signed   # (never drained: -3.4e-5 at this K, tools/micro/tf32_probe.cu)
-        assert rel_err(out, ref64) < 1e-6
+        assert abs(signed) < lim, (kw, signed)
+        assert rel_err(out, ref64) < 1.2 * lim + 2e-7
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 128, 32, 48), (1, 128, 256, 16, 32), (1, 256, 512, 16, 16), (2, 64, 64, 10, 18)])

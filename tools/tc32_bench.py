@@ -48,7 +48,7 @@ if "layers" in args:
         for win in (windows if "slab" in args else []):
             for tag, kw in (("relu", dict(relu=True)), ("res", dict(res=r))):
                 ms = _time(lambda: ops.conv_tc32_slab(x, ws, C, window=win, **kw))
-                print(json.dumps({"op": f"conv3x3 tc32 SLAB {C}->{C} @{H}x{H} B={B} {tag}", "window_taps": win, "us": ms * 1e3,
+                print(json.dumps({"op": f"conv3x3 tc32 SLAB {C}->{C} @{H}x{H} B={B} {tag}", "window_blocks": win, "us": ms * 1e3,
                                   "TFLOPs_fp32_equiv": gf / ms}), flush=True)
         for win in (windows if "tap" in args else []):
             for tag, kw in (("relu", dict(relu=True)), ("res", dict(res=r))):
