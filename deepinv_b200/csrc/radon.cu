@@ -9,9 +9,14 @@
 // every ray / pixel accumulates in a register and the only HBM traffic is the image and the sinogram
 // (50.3 MB per cfg3 call).  These kernels are bound by fp32 issue + L1 gathers, not by HBM.
 //
-// Geometry is evaluated in fp32 exactly like affine_grid/grid_sample(align_corners=True):
-//   lin[k] = linspace(-1,1,P)[k];  g = R_theta (lin[j], lin[i]);  pix = ((g + 1) / 2) * (P - 1);
-//   bilinear weights from floor(pix), zeros outside.  Sinograms are stored ANGLE-major (BC, A, P): this is
+// Geometry: affine_grid/grid_sample(align_corners=True) sample the padded image at
+//   lin[k] = linspace(-1,1,P)[k];  g = R_theta (lin[j], lin[i]);  pix = ((g + 1) / 2) * (P - 1)
+// i.e., in exact arithmetic, pix_x = cx + c (j - cx) + s (i - cx), pix_y = cx - s (j - cx) + c (i - cx), cx = (P-1)/2.  The
+// reference evaluates the first form in fp32: a coordinate of magnitude ~P/2 then carries ~P * 3e-8 of rounding, which is
+// what its results are off by at 512 x 512 (2e-5 .. 4e-5 relative, tests/test_gpu_radon_tiled.py).  The Radon kernels
+// evaluate the second form in fp64 (cos / sin arrive as fp32 (hi, lo) pairs, one DADD per coordinate and step along a
+// sample), so they sit closer to the exact operator than the reference itself; bilinear weights from floor(pix) as fp32,
+// zeros outside.  Sinograms are stored ANGLE-major (BC, A, P): this is
 //   the memory the reference returns as the transposed view (B,C,P,A) (radon.py:291-293).
 #include "common.cuh"
 #ifndef DINVK_EMUL
@@ -28,6 +33,32 @@ struct RadonGeom {
 // torch.linspace(-1, 1, P) in fp32 (symmetric evaluation, ATen RangeFactories)
 __device__ __forceinline__ float lin_at(int k, int P, float step) {
   return (k < P / 2) ? (-1.0f + step * (float)k) : (1.0f - step * (float)(P - 1 - k));
+}
+
+// Sample coordinates in 64-bit FIXED POINT with 45 fractional bits (Q45): with U = 2j - (P-1), V = 2i - (P-1) (integers)
+//   PX(i, j) = cx Q45 + (C45 U + S45 V) / 2,   PY(i, j) = cx Q45 + (C45 V - S45 U) / 2,   C45 = round(cos 2^45), S45 likewise
+// Integer arithmetic is exact and associative: stepping along a ray is PX += S45, PY += C45 and gives bit for bit the value of
+// the closed form, so every tile / kernel family sees the same position for a sample (the owner tile of a sample is decided
+// by floor(px), floor(py)).  cos/sin carry 2^-46 of rounding -> positions are good to ~1e-11 pixels.
+struct Trig45 { long long c, s; };
+__device__ __forceinline__ Trig45 trig45(const float* __restrict__ cos_t, const float* __restrict__ sin_t, int A, int t) {
+  // tables: A fp32 values followed by their A low-order parts (value = hi + lo)
+  const double sc = 35184372088832.0;  // 2^45
+  Trig45 r;
+  r.c = __double2ll_rn(((double)__ldg(cos_t + t) + (double)__ldg(cos_t + A + t)) * sc);
+  r.s = __double2ll_rn(((double)__ldg(sin_t + t) + (double)__ldg(sin_t + A + t)) * sc);
+  return r;
+}
+__device__ __forceinline__ void sample_pos45(const Trig45& T, int P, int j, int i, long long& PX, long long& PY) {
+  const long long U = 2LL * j - (P - 1), V = 2LL * i - (P - 1), CX = (long long)(P - 1) << 44;  // (P-1)/2 in Q45
+  PX = CX + ((T.c * U + T.s * V) >> 1);
+  PY = CX + ((T.c * V - T.s * U) >> 1);
+}
+// integer cell and the two fp32 bilinear weights of one coordinate
+__device__ __forceinline__ void cell_weights(long long Q, int& cell, float& w0, float& w1) {
+  cell = (int)(Q >> 45);
+  w1 = (float)(unsigned)((unsigned long long)Q >> 13) * 2.3283064365386963e-10f;  // top 32 fractional bits * 2^-32
+  w0 = 1.0f - w1;
 }
 
 __device__ __forceinline__ void sample_pos(float c, float s, float xj, float yi, float pm1, float& px, float& py) {
@@ -58,7 +89,6 @@ __global__ void __launch_bounds__(128) radon_fwd_kernel(const float* __restrict_
   if (j >= G.P) return;
   const float c = __ldg(cos_t + t), s = __ldg(sin_t + t);
   const float pm1 = (float)(G.P - 1);
-  const float xj = lin_at(j, G.P, G.step);
   const float* img = x + (long long)bc * G.W * G.W;
   // conservative row range in which the sample can touch the image support [pb-1, pb+W] (both axes):
   // pix_x ~ cx + c (j-cx) + s (i-cx),  pix_y ~ cx - s (j-cx) + c (i-cx)
@@ -81,13 +111,14 @@ __global__ void __launch_bounds__(128) radon_fwd_kernel(const float* __restrict_
   }
   const int i0 = max(0, (int)floorf(i_lo) - 2), i1 = min(G.P - 1, (int)ceilf(i_hi) + 2);
   float acc = 0.f;
-  for (int i = i0; i <= i1; ++i) {
-    const float yi = lin_at(i, G.P, G.step);
-    float px, py;
-    sample_pos(c, s, xj, yi, pm1, px, py);
-    const float fx = floorf(px), fy = floorf(py);
-    const int X0 = (int)fx, Y0 = (int)fy;
-    const float wx1 = px - fx, wy1 = py - fy, wx0 = (fx + 1.0f) - px, wy0 = (fy + 1.0f) - py;
+  const Trig45 tq = trig45(cos_t, sin_t, G.A, t);
+  long long PX, PY;
+  sample_pos45(tq, G.P, j, i0, PX, PY);
+  for (int i = i0; i <= i1; ++i, PX += tq.s, PY += tq.c) {
+    int X0, Y0;
+    float wx0, wx1, wy0, wy1;
+    cell_weights(PX, X0, wx0, wx1);
+    cell_weights(PY, Y0, wy0, wy1);
     if (X0 < G.pb - 1 || X0 >= G.pb + G.W || Y0 < G.pb - 1 || Y0 >= G.pb + G.W) continue;
     const float v00 = img_at(img, G, X0, Y0), v01 = img_at(img, G, X0 + 1, Y0);
     const float v10 = img_at(img, G, X0, Y0 + 1), v11 = img_at(img, G, X0 + 1, Y0 + 1);
@@ -102,8 +133,8 @@ __global__ void __launch_bounds__(128) radon_fwd_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) radon_adj_kernel(const float* __restrict__ sino, float* __restrict__ x, RadonGeom G,
                                                         const float* __restrict__ cos_t, const float* __restrict__ sin_t,
                                                         float scale) {
-  DINVK_DYN_SMEM(float, s_cs);  // cos[A], sin[A]
-  for (int k = threadIdx.x; k < G.A; k += blockDim.x) { s_cs[k] = __ldg(cos_t + k); s_cs[G.A + k] = __ldg(sin_t + k); }
+  DINVK_DYN_SMEM(long long, s_cs);  // cos[A], sin[A] in Q45
+  for (int k = threadIdx.x; k < G.A; k += blockDim.x) { const Trig45 q = trig45(cos_t, sin_t, G.A, k); s_cs[k] = q.c; s_cs[G.A + k] = q.s; }
   __syncthreads();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const int bc = blockIdx.y;
@@ -116,25 +147,28 @@ __global__ void __launch_bounds__(256) radon_adj_kernel(const float* __restrict_
   float acc = 0.f;
   if (active) {
     for (int t = 0; t < G.A; ++t) {
-      const float c = s_cs[t], s = s_cs[G.A + t];
+      Trig45 tq;
+      tq.c = s_cs[t]; tq.s = s_cs[G.A + t];
+      const float c = (float)tq.c * 2.842170943040401e-14f, s = (float)tq.s * 2.842170943040401e-14f;  // * 2^-45
       const int jc = __float2int_rn(cx + c * dx - s * dy), ic = __float2int_rn(cx + s * dx + c * dy);
       const float* srow = sbase + (long long)t * G.P;
 #pragma unroll
       for (int dj = -1; dj <= 1; ++dj) {
         const int j = jc + dj;
         if (j < 0 || j >= G.P) continue;
-        const float xj = lin_at(j, G.P, G.step);
         float wsum = 0.f;
 #pragma unroll
         for (int di = -1; di <= 1; ++di) {
           const int i = ic + di;
           if (i < 0 || i >= G.P) continue;
-          float px, py;
-          sample_pos(c, s, xj, lin_at(i, G.P, G.step), pm1, px, py);
-          const float fx = floorf(px), fy = floorf(py);
-          const int X0 = (int)fx, Y0 = (int)fy;
-          const float wx = (X0 == X) ? ((fx + 1.0f) - px) : ((X0 + 1 == X) ? (px - fx) : 0.f);
-          const float wy = (Y0 == Y) ? ((fy + 1.0f) - py) : ((Y0 + 1 == Y) ? (py - fy) : 0.f);
+          long long PX, PY;
+          sample_pos45(tq, G.P, j, i, PX, PY);
+          int X0, Y0;
+          float wx0, wx1, wy0, wy1;
+          cell_weights(PX, X0, wx0, wx1);
+          cell_weights(PY, Y0, wy0, wy1);
+          const float wx = (X0 == X) ? wx0 : ((X0 + 1 == X) ? wx1 : 0.f);
+          const float wy = (Y0 == Y) ? wy0 : ((Y0 + 1 == Y) ? wy1 : 0.f);
           wsum += wx * wy;
         }
         acc = fmaf(__ldg(srow + j), wsum, acc);
@@ -218,8 +252,14 @@ __global__ void __launch_bounds__(RT_THREADS) radon_tiled_kernel(const float* __
 #else
   extern __shared__ __align__(128) unsigned char rt_raw[];
 #endif
-  float* T = reinterpret_cast<float*>(rt_raw);                 // [RTH][RTW]
-  float* s_cs = T + RTH * RTW;                                  // cos[A], sin[A]
+  // forward: the staged image tile, fp32 [RTH][RTW].  transpose: the tile's accumulator in 32-bit FIXED POINT [RTH][RTW] (scale per tile, see below): an fp32
+  // (or 64-bit) atomicAdd on shared memory is a compare-and-swap loop (SASS ATOMS.CAST.SPIN: the first version's transpose took
+  // 2x the forward), a 32-bit integer add without return value is ONE fire-and-forget ATOMS.ADD, and integer sums do not
+  // depend on the order of the adds (the tile's result is deterministic)
+  float* T = reinterpret_cast<float*>(rt_raw);
+  int* TI = reinterpret_cast<int*>(rt_raw);
+  long long* s_cs = reinterpret_cast<long long*>(rt_raw + (((size_t)RTH * RTW * 4 + 15) & ~(size_t)15));  // cos[A], sin[A], Q45
+  __shared__ unsigned s_absmax;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ty = blockIdx.x / tps, tx = blockIdx.x - ty * tps;
   const int bc = blockIdx.y;
@@ -239,9 +279,10 @@ __global__ void __launch_bounds__(RT_THREADS) radon_tiled_kernel(const float* __
       T[e] = (x >= 0 && x < G.W && y >= 0 && y < G.W) ? __ldg(img + (long long)y * G.W + x) : 0.f;
     }
   } else {
-    for (int e = tid; e < RTH * RTW; e += RT_THREADS) T[e] = 0.f;
+    for (int e = tid; e < RTH * RTW; e += RT_THREADS) TI[e] = 0;
+    if (tid == 0) s_absmax = 0u;
   }
-  for (int k = tid; k < G.A; k += RT_THREADS) { s_cs[k] = __ldg(cos_t + k); s_cs[G.A + k] = __ldg(sin_t + k); }
+  for (int k = tid; k < G.A; k += RT_THREADS) { const Trig45 q = trig45(cos_t, sin_t, G.A, k); s_cs[k] = q.c; s_cs[G.A + k] = q.s; }
   __syncthreads();
   if (!ADJ) {
     if (G.circle) {  // inscribed-disc mask of the image (radon.py:268-279), applied once to the staged tile
@@ -258,15 +299,46 @@ __global__ void __launch_bounds__(RT_THREADS) radon_tiled_kernel(const float* __
   const float pm1 = (float)(G.P - 1), cx = 0.5f * pm1;
   const float fxl = (float)xl, fxu = (float)(xl + xr + 1), fyl = (float)yl, fyu = (float)(yl + yr + 1);
   const long long srow0 = (long long)bc * G.A * G.P;
+  float fx_scale = 1.f;
+  double fx_inv = 1.0;
+  if (ADJ) {
+    // fixed-point scale of this tile: sf = 0.999 * 2^30 / (2 A m), m = max |y| over the rays that can reach the tile (the
+    // bits of a non-negative float order like unsigned integers).  At one angle the bilinear weights of the lattice samples
+    // around a pixel sum to 1 +- 0.1 (a tent function summed over a rotated unit lattice), bounded here by 2: a pixel
+    // collects at most 2 A m, i.e. < 2^30 after scaling — no overflow.  One unit is 2 A m / 2^30 (A = 180: 3.4e-7 m); the
+    // rounding errors of a pixel's ~4 A contributions add up like a random walk to ~8 units: 2.6e-6 m, i.e. 1e-6 .. 2e-6 of the
+    // pixel value for white-noise and for ramp-filtered sinograms — an order of magnitude below the fp32 coordinate noise of
+    // the reference's own transpose at this size, and independent of the order of the adds.
+    unsigned m = 0u;
+    for (int t = warp; t < G.A; t += RT_THREADS / 32) {
+      const float c = (float)s_cs[t] * 2.842170943040401e-14f, s = (float)s_cs[G.A + t] * 2.842170943040401e-14f;
+      const float j00 = c * (fxl - cx) - s * (fyl - cx), j10 = c * (fxu - cx) - s * (fyl - cx);
+      const float j01 = c * (fxl - cx) - s * (fyu - cx), j11 = c * (fxu - cx) - s * (fyu - cx);
+      const int jmin = max(0, (int)floorf(cx + fminf(fminf(j00, j10), fminf(j01, j11))) - 1);
+      const int jmax = min(G.P - 1, (int)ceilf(cx + fmaxf(fmaxf(j00, j10), fmaxf(j01, j11))) + 1);
+      for (int j = jmin + lane; j <= jmax; j += 32) m = max(m, __float_as_uint(fabsf(__ldg(src + srow0 + (long long)t * G.P + j) * scale)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) atomicMax(&s_absmax, m);
+    __syncthreads();
+    const float mf = __uint_as_float(s_absmax);
+    if (mf > 0.f && mf < 3.0e38f) {
+      fx_scale = (0.999f * 1073741824.0f / (float)(2 * G.A)) / mf;
+      if (!(fx_scale < 3.0e38f)) fx_scale = 3.0e38f;   // denormal-sized sinograms
+    }
+    fx_inv = 1.0 / (double)fx_scale;
+  }
   for (int t = warp; t < G.A; t += RT_THREADS / 32) {
-    const float c = s_cs[t], s = s_cs[G.A + t];
+    Trig45 tq;
+    tq.c = s_cs[t]; tq.s = s_cs[G.A + t];
+    const float c = (float)tq.c * 2.842170943040401e-14f, s = (float)tq.s * 2.842170943040401e-14f;
     // ray range of the tile: j ~ cx + c (X - cx) - s (Y - cx) over the corners of [xl, xu+1] x [yl, yu+1]
     const float j00 = c * (fxl - cx) - s * (fyl - cx), j10 = c * (fxu - cx) - s * (fyl - cx);
     const float j01 = c * (fxl - cx) - s * (fyu - cx), j11 = c * (fxu - cx) - s * (fyu - cx);
     const int jmin = max(0, (int)floorf(cx + fminf(fminf(j00, j10), fminf(j01, j11))) - 1);
     const int jmax = min(G.P - 1, (int)ceilf(cx + fmaxf(fmaxf(j00, j10), fmaxf(j01, j11))) + 1);
     for (int j = jmin + lane; j <= jmax; j += 32) {
-      const float xj = lin_at(j, G.P, G.step);
       // steps whose sample can fall in the tile: fxl <= bx + s (i - cx) < fxu and fyl <= by + c (i - cx) < fyu (+- 2 margin)
       float i_lo = 0.f, i_hi = pm1;
       const float bx = cx + c * ((float)j - cx), by = cx - s * ((float)j - cx);
@@ -283,25 +355,27 @@ __global__ void __launch_bounds__(RT_THREADS) radon_tiled_kernel(const float* __
       const int i0 = max(0, (int)floorf(i_lo) - 2), i1 = min(G.P - 1, (int)ceilf(i_hi) + 2);
       float acc = 0.f;
       float yv = 0.f;
-      if (ADJ && i0 <= i1) yv = __ldg(src + srow0 + (long long)t * G.P + j) * scale;
+      if (ADJ && i0 <= i1) yv = (__ldg(src + srow0 + (long long)t * G.P + j) * scale) * fx_scale;
       bool any = false;
-      for (int i = i0; i <= i1; ++i) {
-        const float yi = lin_at(i, G.P, G.step);
-        float px, py;
-        sample_pos(c, s, xj, yi, pm1, px, py);
-        const float fx = floorf(px), fy = floorf(py);
-        const unsigned ux = (unsigned)((int)fx - xl), uy = (unsigned)((int)fy - yl);
+      long long PX, PY;
+      sample_pos45(tq, G.P, j, i0, PX, PY);
+      for (int i = i0; i <= i1; ++i, PX += tq.s, PY += tq.c) {
+        int X0, Y0;
+        float wx0, wx1, wy0, wy1;
+        cell_weights(PX, X0, wx0, wx1);
+        cell_weights(PY, Y0, wy0, wy1);
+        const unsigned ux = (unsigned)(X0 - xl), uy = (unsigned)(Y0 - yl);
         if (ux > (unsigned)xr || uy > (unsigned)yr) continue;
-        const float wx1 = px - fx, wy1 = py - fy, wx0 = (fx + 1.0f) - px, wy0 = (fy + 1.0f) - py;
-        float* tp = T + uy * RTW + ux;
         if (!ADJ) {
+          const float* tp = T + uy * RTW + ux;
           acc += tp[0] * (wx0 * wy0) + tp[1] * (wx1 * wy0) + tp[RTW] * (wx0 * wy1) + tp[RTW + 1] * (wx1 * wy1);
           any = true;
         } else {
-          atomicAdd(tp, yv * (wx0 * wy0));
-          atomicAdd(tp + 1, yv * (wx1 * wy0));
-          atomicAdd(tp + RTW, yv * (wx0 * wy1));
-          atomicAdd(tp + RTW + 1, yv * (wx1 * wy1));
+          int* tp = TI + uy * RTW + ux;
+          atomicAdd(tp, __float2int_rn(yv * (wx0 * wy0)));
+          atomicAdd(tp + 1, __float2int_rn(yv * (wx1 * wy0)));
+          atomicAdd(tp + RTW, __float2int_rn(yv * (wx0 * wy1)));
+          atomicAdd(tp + RTW + 1, __float2int_rn(yv * (wx1 * wy1)));
         }
       }
       if (!ADJ && any) atomicAdd(out + srow0 + (long long)t * G.P + j, acc * scale);
@@ -314,7 +388,7 @@ __global__ void __launch_bounds__(RT_THREADS) radon_tiled_kernel(const float* __
       const int uy = e / RTH, ux = e - uy * RTH;
       const int x = ox + ux, y = oy + uy;
       if (x < 0 || x >= G.W || y < 0 || y >= G.W) continue;
-      float v = T[uy * RTW + ux];
+      float v = (float)((double)TI[uy * RTW + ux] * fx_inv);
       if (G.circle) {
         const float ax = 2.0f * (float)x / (float)(G.W - 1) - 1.0f, ay = 2.0f * (float)y / (float)(G.W - 1) - 1.0f;
         if (!(ax * ax + ay * ay <= 1.0f)) v = 0.f;
@@ -332,7 +406,7 @@ static bool tiled_ok(const void* img, int W, int A) {
 static int launch_tiled(bool adj, const float* x_img, const float* sino_in, float* out, int BC, const RadonGeom& G, const float* cos_t,
                         const float* sin_t, float scale, void* stream) {
   const int tps = (G.W + RT - 1) / RT;
-  const size_t smem = (size_t)RTH * RTW * 4 + (size_t)(2 * G.A + 2) * 4 + 16;
+  const size_t smem = (size_t)RTH * RTW * 4 + 16 + (size_t)(2 * G.A + 2) * 8;
   const size_t out_bytes = adj ? (size_t)BC * G.W * G.W * 4 : (size_t)BC * G.A * G.P * 4;
   if (cudaMemsetAsync(out, 0, out_bytes, (cudaStream_t)stream) != cudaSuccess) return set_error(DINVK_ECUDA, "radon: memset failed");
   int rc;
@@ -449,7 +523,7 @@ extern "C" int dinvk_radon_adj(const float* sino, float* x, int BC, int W, int P
     rc = launch_tiled(true, nullptr, sino, x, BC, G, cos_t, sin_t, scale, stream);
     if (rc >= 0) return rc;
   }
-  DINVK_LAUNCH(radon_adj_kernel, dim3(ceil_div((long long)W * W, 256), BC), dim3(256), 2 * A * sizeof(float), stream, sino, x, G,
+  DINVK_LAUNCH(radon_adj_kernel, dim3(ceil_div((long long)W * W, 256), BC), dim3(256), 2 * A * sizeof(long long), stream, sino, x, G,
                cos_t, sin_t, scale);
   return DINVK_POST_LAUNCH();
 }

@@ -332,7 +332,7 @@ def radon_fwd(x, P: int, cos_t, sin_t, circle: bool, scale: float) -> torch.Tens
     dev = _require_cuda(x, cos_t, sin_t)
     x = _f32c(x)
     B, C, W, _ = x.shape
-    A = cos_t.numel()
+    A = cos_t.shape[-1]
     sino = torch.empty(B, C, A, P, dtype=torch.float32, device=dev)
     if sino.numel() == 0:
         return sino
@@ -359,7 +359,7 @@ def fanbeam(t, W: int, G: int, D: int, cos_t, sin_t, circle: bool, half_len: flo
     dev = _require_cuda(t, cos_t, sin_t)
     t = _f32c(t)
     B, C = t.shape[:2]
-    A = cos_t.numel()
+    A = cos_t.shape[-1]
     out = torch.empty((B, C, W, W) if adjoint else (B, C, A, D), dtype=torch.float32, device=dev)
     if out.numel() == 0:
         return out

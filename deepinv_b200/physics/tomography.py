@@ -86,8 +86,11 @@ class Tomography(LinearPhysics):
     def _trig(self):
         a = self.angles
         if not cache_hit(self._trig_key, a):
-            th = _deg2rad(a.to(torch.float32))
-            self._cos, self._sin = th.cos().contiguous(), th.sin().contiguous()
+            # cos / sin of the (fp32) angles evaluated in fp64 and handed to the kernels as fp32 (hi, lo) pairs, shape (2, A):
+            # the parallel-beam kernels compute sample coordinates in fp64 (csrc/radon.cu header); row 0 alone is the fp32 table
+            th = _deg2rad(a.to(torch.float32).to(torch.float64))
+            split = lambda v: torch.stack([v.float(), (v - v.float().double()).float()]).contiguous()
+            self._cos, self._sin = split(th.cos()), split(th.sin())
             self._trig_key = TensorKey(a)
         return self._cos, self._sin
 

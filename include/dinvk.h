@@ -166,12 +166,15 @@ int dinvk_ddrm_update(float* x_bar_out, const float* x_bar, const float* x_bar_p
  * x    : (BC, W, W) fp32 contiguous (square images)
  * sino : (BC, A, P) fp32, ANGLE-major — the reference returns exactly this memory as the
  *        non-contiguous view (B,C,P,A) (radon.py:291-293); the host wrapper re-views it.
- * P = ceil(sqrt(2)*W) (circle=0) or W (circle=1); cos/sin: A floats each (host computes them in
- * fp32 exactly as the reference does); scale multiplies the result (1/operator_norm).
+ * P = ceil(sqrt(2)*W) (circle=0) or W (circle=1); scale multiplies the result (1/operator_norm).
+ * cos_t / sin_t: 2*A floats each — the A fp32 values cos(theta_t), followed by their A low-order parts
+ *        (cos = hi + lo, evaluated in fp64 on the host from the fp32 angles; pass zeros for plain fp32 tables).
+ *        dinvk_radon_fwd / dinvk_radon_adj evaluate the sample coordinates in fp64 from hi + lo (closer to the exact
+ *        operator than the reference's fp32 affine_grid); dinvk_iradon_bp / dinvk_fanbeam read the first A values only.
  */
 int dinvk_radon_fwd(const float* x, float* sino, int BC, int W, int P, int A, int circle,
                     const float* cos_t, const float* sin_t, float scale, void* stream);
-/* exact transpose of dinvk_radon_fwd (deterministic gather form of the scatter) */
+/* exact transpose of dinvk_radon_fwd (same weights; tiled path: per-tile 32-bit fixed-point accumulation, csrc/radon.cu) */
 int dinvk_radon_adj(const float* sino, float* x, int BC, int W, int P, int A, int circle,
                     const float* cos_t, const float* sin_t, float scale, void* stream);
 /* IRadon back-projection (adjoint_via_backprop=False / FBP geometry), sinogram sampled bilinearly

@@ -206,6 +206,16 @@ static inline float atomicAdd(float* addr, float v) {
 }
 static inline int atomicAdd(int* addr, int v) { return __atomic_fetch_add(addr, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicAdd(unsigned* addr, unsigned v) { return __atomic_fetch_add(addr, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicAdd(unsigned long long* addr, unsigned long long v) { return __atomic_fetch_add(addr, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicMax(unsigned* addr, unsigned v) {
+  unsigned old = __atomic_load_n(addr, __ATOMIC_SEQ_CST);
+  while (old < v && !__atomic_compare_exchange_n(addr, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
+static inline long long __float2ll_rn(float x) { return (long long)__builtin_llrintf(x); }
+static inline long long __double2ll_rn(double x) { return (long long)__builtin_llrint(x); }
+static inline unsigned __float_as_uint(float x) { unsigned u; __builtin_memcpy(&u, &x, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float x; __builtin_memcpy(&x, &u, 4); return x; }
 static inline int atomicAnd(int* addr, int v) { return __atomic_fetch_and(addr, v, __ATOMIC_SEQ_CST); }
 static inline int atomicExch(int* addr, int v) { return __atomic_exchange_n(addr, v, __ATOMIC_SEQ_CST); }
 
@@ -215,6 +225,7 @@ static inline long long min(long long a, long long b) { return a < b ? a : b; }
 static inline long long max(long long a, long long b) { return a > b ? a : b; }
 static inline long min(long a, long b) { return a < b ? a : b; }
 static inline long max(long a, long b) { return a > b ? a : b; }
+static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
