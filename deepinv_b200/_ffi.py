@@ -39,6 +39,7 @@ _SIGNATURES = {
     "dinvk_ramp_filter_workspace_bytes": (c_size_t, [c_int, c_int]),
     "dinvk_ramp_filter": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "dinvk_axpbypcz": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_float, c_void_p, c_float, c_int64, c_void_p]),
+    "dinvk_interleaved_to_planar": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p]),
     "dinvk_batched_axpy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int64, c_void_p]),
     "dinvk_batched_dot": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_size_t, c_void_p]),
     "dinvk_batched_dot_workspace_bytes": (c_size_t, [c_int, c_int64]),

@@ -183,6 +183,32 @@ extern "C" int dinvk_axpbypcz(float* out, const float* x, float a, const float* 
   return DINVK_POST_LAUNCH();
 }
 
+// interleaved complex (B, n) [re, im, re, im, ...] -> planar (B, 2, n): the k-space layout of raw MRI files -> the operators'
+// layout (deepinv/utils/mixins.py:148-156 from_torch_complex: view_as_real + moveaxis + contiguous), one pass
+__global__ void __launch_bounds__(256) interleaved_to_planar_kernel(const float2* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long b = blockIdx.y;
+  const float2* src = in + b * n;
+  float* re = out + b * 2 * n;
+  float* im = re + n;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float2 v = src[i];
+    re[i] = v.x;
+    im[i] = v.y;
+  }
+}
+
+extern "C" int dinvk_interleaved_to_planar(const float* in, float* out, int B, int64_t n_per, void* stream) {
+  DINVK_CHECK_ARG(in && out && B >= 0 && n_per >= 0, "dinvk_interleaved_to_planar: bad arguments");
+  DINVK_CHECK_ARG((reinterpret_cast<uintptr_t>(in) & 7) == 0, "dinvk_interleaved_to_planar: input must be 8-byte aligned");
+  DINVK_CHECK_ARG(B <= 65535, "dinvk_interleaved_to_planar: batch too large");
+  if (B == 0 || n_per == 0) return DINVK_OK;
+  int gx = stream_grid(n_per);
+  gx = std::max(1, std::min(gx, std::max(1, sm_count() * 8 / B)));
+  DINVK_LAUNCH(interleaved_to_planar_kernel, dim3(gx, B), dim3(256), 0, stream, reinterpret_cast<const float2*>(in), out, (long long)n_per);
+  return DINVK_POST_LAUNCH();
+}
+
 extern "C" int dinvk_batched_axpy(float* out, const float* x, const float* y, const float* s, float sa, int B,
                                   int64_t n_per, void* stream) {
   DINVK_CHECK_ARG(out && x && y && s && B >= 0 && n_per >= 0, "dinvk_batched_axpy: bad arguments");

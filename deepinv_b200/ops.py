@@ -552,3 +552,20 @@ def nchw_to_split16(x) -> torch.Tensor:
     out = torch.empty(B, H, W, C // 16, 2, 16, dtype=torch.float32, device=dev)
     check(get_lib().dinvk_nchw_to_split16(_p(x), _p(out), B, C, H, W, _stream(dev)))
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# data input side
+# --------------------------------------------------------------------------------------------
+def interleaved_to_planar(z: torch.Tensor) -> torch.Tensor:
+    """complex64 (B, ...) on the device -> planar fp32 (B, 2, ...) (the reference's from_torch_complex, mixins.py:148-156)"""
+    dev = _require_cuda(z)
+    if z.dtype != torch.complex64:
+        z = z.to(torch.complex64)
+    z = z.contiguous()
+    B = z.shape[0]
+    n = z[0].numel() if B else 0
+    out = torch.empty((B, 2, *z.shape[1:]), dtype=torch.float32, device=dev)
+    if B and n:
+        check(get_lib().dinvk_interleaved_to_planar(_p(torch.view_as_real(z)), _p(out), B, n, _stream(dev)))
+    return out

@@ -159,6 +159,10 @@ int dinvk_ddrm_update(float* x_bar_out, const float* x_bar, const float* x_bar_p
                       float sigma_prev, float sigma_noise, float eta, float etab, float c_sig, float eps,
                       int init, void* stream);
 
+/* interleaved complex (B, n_per) [re, im, ...] -> planar (B, 2, n_per): raw k-space as stored in MRI files -> the operators'
+ * planar layout (deepinv/utils/mixins.py:148-156 from_torch_complex, as used by datasets/fastmri.py:475-478) */
+int dinvk_interleaved_to_planar(const float* in, float* out, int B, int64_t n_per, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Radon (deepinv/physics/functional/radon.py:252-342 forward, autograd transpose of it
  * = tomography.py:322-342, IRadon back-projection radon.py:396-450)

@@ -537,15 +537,41 @@ def diffpir_fixture():
          **sd_arrays(den, "sd__"))
 
 
+def fastmri_fixture():
+    """a synthetic HDF5-shaped fastMRI volume (h5py is absent here: the arrays ARE the file content) and what the reference's
+    own code makes of every slice: MRIMixin.from_torch_complex (datasets/fastmri.py:475-478) and MRISliceTransform.__call__
+    (:719-749) with a file mask / a scalar normalisation"""
+    from deepinv.datasets.fastmri import MRISliceTransform
+    from deepinv.physics.mri import MRIMixin
+
+    gen = np.random.default_rng(0)
+    D, N, H, W = 3, 2, 8, 6
+    ks = (gen.standard_normal((D, N, H, W)) + 1j * gen.standard_normal((D, N, H, W))).astype(np.complex64)
+    rss = gen.random((D, 4, 4)).astype(np.float32)
+    mask = np.array([1, 0, 1, 1, 0, 1], dtype=np.float32)
+    ks1 = (gen.standard_normal((2, 6, 6)) + 1j * gen.standard_normal((2, 6, 6))).astype(np.complex64)
+    out = dict(vol_kspace=ks, vol_rss=rss, vol_mask=mask, vol1_kspace=ks1, acs=np.int64(2))
+    mix = MRIMixin()
+    for d in range(D):
+        k = mix.from_torch_complex(torch.from_numpy(ks[d]).unsqueeze(0)).squeeze(0)
+        t, k2, p = MRISliceTransform()(torch.from_numpy(rss[d]).unsqueeze(0), k, mask=torch.as_tensor(mask), seed="x", metadata={})
+        out[f"k_{d}"], out[f"t_{d}"], out[f"m_{d}"] = k2, t, p["mask"]
+        _, k3, _ = MRISliceTransform(normalize=2.0)(None, k, seed="x", metadata={})
+        out[f"kn_{d}"] = k3
+    for d in range(2):
+        out[f"k1_{d}"] = mix.from_torch_complex(torch.from_numpy(ks1[d]).unsqueeze(0)).squeeze(0)
+    save("fastmri_synth", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm", "optim2", "train", "dynamic", "down", "combine", "maskgen", "mri3d", "fan", "anderson", "diffpir", "inpainting"]
+    which = sys.argv[1:] or ["mri", "multicoil", "tomo", "blur", "blurfft", "model", "optim", "ddrm", "optim2", "train", "dynamic", "down", "combine", "maskgen", "mri3d", "fan", "anderson", "diffpir", "inpainting", "fastmri"]
     table = {"mri": mri_fixtures, "multicoil": multicoil_fixtures, "tomo": tomo_fixtures, "blur": blur_fixtures,
              "blurfft": blurfft_fixtures, "model": model_fixtures, "optim": optim_fixtures, "ddrm": ddrm_fixture,
              "optim2": optim2_fixtures, "train": train_fixtures,
              "dynamic": dynamic_fixtures, "down": down_fixtures,
              "combine": combine_fixtures, "maskgen": maskgen_fixtures,
              "mri3d": mri3d_fixture, "fan": fanbeam_fixtures, "anderson": anderson_fixtures,
-             "diffpir": diffpir_fixture, "inpainting": inpainting_fixture}
+             "diffpir": diffpir_fixture, "inpainting": inpainting_fixture, "fastmri": fastmri_fixture}
     for w in which:
         table[w]()
