@@ -64,12 +64,12 @@ _SIGNATURES = {
     "dinvk_nhwc_bf16_to_nchw_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dinvk_conv2x2_down_bf16": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     "dinvk_conv2x2_up_bf16": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
-    "dinvk_conv_tc32": (c_int, [c_void_p] * 6 + [c_int] * 8 + [c_void_p]),
-    "dinvk_conv_tc32_slab": (c_int, [c_void_p] * 6 + [c_int] * 7 + [c_void_p]),
-    "dinvk_conv_tc32_head": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_float, c_void_p, c_int, c_int, c_void_p]),
-    "dinvk_conv_tc32_tail": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p]),
-    "dinvk_split16_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "dinvk_nchw_to_split16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "dinvk_conv_tc32": (c_int, [c_void_p] * 6 + [c_int] * 9 + [c_void_p, c_void_p]),
+    "dinvk_conv_tc32_slab": (c_int, [c_void_p] * 6 + [c_int] * 8 + [c_void_p, c_void_p]),
+    "dinvk_conv_tc32_head": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_float, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dinvk_conv_tc32_tail": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p, c_void_p]),
+    "dinvk_split16_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dinvk_nchw_to_split16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 

@@ -22,6 +22,7 @@
 // (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4).
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -39,28 +40,69 @@ constexpr int SMEM = STAGES * STAGE + 1024;
 constexpr int THREADS = 320;
 constexpr uint32_t TMEM_COLS = 256;        // 2 accumulator buffers x (64 main + 64 corr)
 
-__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
-  // cute::UMMA::InstrDescriptor: c_format F32 (1) at [4,6), a/b_format TF32 (2) at [7,10) / [10,13), K-major, N>>3, M>>4
-  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      ".reg .b64 da, db;\n\t"
-      "mov.b64 da, {%1, %2};\n\t"
-      "mov.b64 db, {%3, %4};\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 __device__ __forceinline__ float rna_tf32(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
+}
+
+// ---- the two split formats ------------------------------------------------------------------------------------------
+// A 128-byte row block holds CH channels as [hi CH | lo CH].
+//   FmtTF32 ("split16", fp32 words): hi = tf32(v) (cvt.rna), lo = v - hi (exact; the tensor core truncates it to tf32);
+//            kind::tf32, K = 8 per MMA.  No range restriction.
+//   FmtF16  ("split32h", fp16 words): hi = fp16(v), lo = fp16((v - hi) * 2^11) — the low part is scaled so that it sits in
+//            fp16's normal range; the correction accumulators are weighted 2^-11 in the drain.  kind::f16, K = 16 per MMA: the
+//            same 22-bit operands at TWICE the channels per MMA and half the bytes per element.  Range: |v| < 65504 — an
+//            activation beyond it raises the sticky overflow flag and the network tail answers NaN (loud, never silent).
+struct FmtTF32 {
+  using elem = float;
+  static constexpr int CH = 16, EB = 4, ID = 0;
+  static constexpr float CORR = 1.0f;
+  static constexpr CUtensorMapDataType TM = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  // cute::UMMA::InstrDescriptor: c_format F32 (1) at [4,6), a/b_format TF32 (2) at [7,10) / [10,13), K-major, N>>3, M>>4
+  __host__ __device__ static constexpr uint32_t idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+  }
+};
+struct FmtF16 {
+  using elem = __half;
+  static constexpr int CH = 32, EB = 2, ID = 1;
+  static constexpr float CORR = 4.8828125e-4f;  // 2^-11
+  static constexpr CUtensorMapDataType TM = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  // a/b_format F16 (0)
+  __host__ __device__ static constexpr uint32_t idesc(int M, int N) {
+    return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+  }
+};
+
+template <class F>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                     uint32_t accumulate) {
+  if constexpr (F::ID == 0) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 
 struct Maps {
@@ -76,44 +118,72 @@ struct Params {
   int tiles_x, tiles_y, n_tiles;
   int relu;
   int win;                  // drain the accumulators every `win` stages
-  const float* res;         // split16, same shape as out
-  const float* res2;
-  float* out;               // split16 (B, Hout, Wout, Cout)
+  const void* res;          // split layout, same shape as out
+  const void* res2;
+  void* out;                // split layout (B, Hout, Wout, Cout)
+  int* flag;                // sticky overflow flag (FmtF16: an activation left the fp16 range), may be null
   const float* bias;
   int dbg;                  // timing experiments only (DINVK_TC32_DBG): 1 no TMA loads, 2 no epilogue memory traffic, 4 no TMEM drains
 };
 
-// split one 16-channel block: v[16] -> 128 bytes [hi16 | lo16]
-__device__ __forceinline__ void store_split16(float* p, const float* v) {
-  float hi[16], lo[16];
+// one channel block: v[CH] -> 128 bytes [hi CH | lo CH]; returns true if a value left the format's range
+template <class F>
+__device__ __forceinline__ bool store_split(typename F::elem* p, const float* v) {
+  uint32_t u[4][8];
+  bool bad = false;
+  if constexpr (F::ID == 0) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) { hi[i] = rna_tf32(v[i]); lo[i] = v[i] - hi[i]; }
+    for (int i = 0; i < 16; ++i) {
+      const float hi = rna_tf32(v[i]);
+      u[i >> 3][i & 7] = __float_as_uint(hi);
+      u[2 + (i >> 3)][i & 7] = __float_as_uint(v[i] - hi);
+    }
+  } else {
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    uint32_t u[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) u[e] = __float_as_uint(hi[j * 8 + e]);
-    tc::stg256(p + j * 8, u);
+    for (int i = 0; i < 32; i += 2) {
+      const __half h0 = __float2half_rn(v[i]), h1 = __float2half_rn(v[i + 1]);
+      const __half l0 = __float2half_rn((v[i] - __half2float(h0)) * 2048.0f), l1 = __float2half_rn((v[i + 1] - __half2float(h1)) * 2048.0f);
+      bad |= !(fabsf(v[i]) < 65000.0f) || !(fabsf(v[i + 1]) < 65000.0f);
+      u[i >> 4][(i >> 1) & 7] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      u[2 + (i >> 4)][(i >> 1) & 7] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
   }
+  char* pc = reinterpret_cast<char*>(p);
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    uint32_t u[8];
+  for (int k = 0; k < 4; ++k) tc::stg256(pc + 32 * k, u[k]);
+  return bad;
+}
+// v[CH] += hi + lo of one block given as its four 32-byte chunks
+template <class F>
+__device__ __forceinline__ void add_split_raw(const uint32_t (*raw)[8], float* v) {
+  if constexpr (F::ID == 0) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) u[e] = __float_as_uint(lo[j * 8 + e]);
-    tc::stg256(p + 16 + j * 8, u);
+    for (int e = 0; e < 8; ++e) {
+      v[e] += __uint_as_float(raw[0][e]) + __uint_as_float(raw[2][e]);
+      v[8 + e] += __uint_as_float(raw[1][e]) + __uint_as_float(raw[3][e]);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&raw[c][e]));
+        const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&raw[2 + c][e]));
+        v[c * 16 + 2 * e] += h.x + l.x * F::CORR;
+        v[c * 16 + 2 * e + 1] += h.y + l.y * F::CORR;
+      }
   }
 }
-// v[16] += hi + lo of one stored block
-__device__ __forceinline__ void add_split16(const float* p, float* v) {
-  uint32_t h0[8], h1[8], l0[8], l1[8];
-  tc::ldg256(p, h0); tc::ldg256(p + 8, h1); tc::ldg256(p + 16, l0); tc::ldg256(p + 24, l1);
+template <class F>
+__device__ __forceinline__ void add_split(const typename F::elem* p, float* v) {
+  uint32_t raw[4][8];
+  const char* pc = reinterpret_cast<const char*>(p);
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    v[e] += __uint_as_float(h0[e]) + __uint_as_float(l0[e]);
-    v[8 + e] += __uint_as_float(h1[e]) + __uint_as_float(l1[e]);
-  }
+  for (int k = 0; k < 4; ++k) tc::ldg256(pc + 32 * k, raw[k]);
+  add_split_raw<F>(raw, v);
 }
 
+template <class F>
 __global__ void __launch_bounds__(THREADS, 1) conv_tc32_kernel(const __grid_constant__ Maps M, const Params P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -154,17 +224,17 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_kernel(const __grid_cons
           tc::mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * STAGE;
           tc::mbar_arrive_expect_tx(&full_bar[s], STAGE);
-          // channel blocks 2kc and 2kc+1: 32 fp32 words each ([hi16 | lo16]) at word offset 32 * block
-          tc::tma_load_4d(sa, &M.a[P.amap[tap]], &full_bar[s], (2 * kc) * 32, x0 + P.dx[tap], y0 + P.dy[tap], b);
-          tc::tma_load_4d(sa + A_TILE, &M.a[P.amap[tap]], &full_bar[s], (2 * kc + 1) * 32, x0 + P.dx[tap], y0 + P.dy[tap], b);
-          tc::tma_load_2d(sa + 2 * A_TILE, &M.b, &full_bar[s], tap * P.Cin + kc * 32, nt * 128);
+          // channel blocks 2kc and 2kc+1: one 128-byte row ([hi CH | lo CH]) each, at element offset 2 CH * block
+          tc::tma_load_4d(sa, &M.a[P.amap[tap]], &full_bar[s], (2 * kc) * (2 * F::CH), x0 + P.dx[tap], y0 + P.dy[tap], b);
+          tc::tma_load_4d(sa + A_TILE, &M.a[P.amap[tap]], &full_bar[s], (2 * kc + 1) * (2 * F::CH), x0 + P.dx[tap], y0 + P.dy[tap], b);
+          tc::tma_load_2d(sa + 2 * A_TILE, &M.b, &full_bar[s], tap * P.Cin + kc * (2 * F::CH), nt * 128);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (converged warp, one elected lane) =====================
-    constexpr uint32_t ID128 = idesc_tf32(128, 128), ID64 = idesc_tf32(128, 64);
+    constexpr uint32_t ID128 = F::idesc(128, 128), ID64 = F::idesc(128, 64);
     constexpr uint32_t HI = tc::desc_hi_sw128(1024);
     const uint32_t smem_lo = tc::smem_u32(smem) >> 4;
     int s = 0; uint32_t ph = 0;
@@ -185,10 +255,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_kernel(const __grid_cons
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj) {
             const uint32_t a = a0 + jj * (A_TILE >> 4), b = b0 + jj * 4;  // B: second channel block = +64 bytes inside the row
-            umma_tf32(d, a, HI, b, HI, ID128, (jj | in_win) != 0 ? 1u : 0u);      // hi ch 0-7   x [W_hi; W_lo]
-            umma_tf32(d, a + 2, HI, b + 2, HI, ID128, 1u);                         // hi ch 8-15
-            umma_tf32(d + 64, a + 4, HI, b, HI, ID64, 1u);                         // lo ch 0-7   x W_hi
-            umma_tf32(d + 64, a + 6, HI, b + 2, HI, ID64, 1u);                     // lo ch 8-15
+            umma<F>(d, a, HI, b, HI, ID128, (jj | in_win) != 0 ? 1u : 0u);      // hi, first half of the block  x [W_hi; W_lo]
+            umma<F>(d, a + 2, HI, b + 2, HI, ID128, 1u);                         // hi, second half
+            umma<F>(d + 64, a + 4, HI, b, HI, ID64, 1u);                         // lo, first half  x W_hi
+            umma<F>(d + 64, a + 6, HI, b + 2, HI, ID64, 1u);                     // lo, second half
           }
           tc::umma_commit(&empty_bar[s]);
         }
@@ -231,7 +301,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_kernel(const __grid_cons
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(rm[i]) + __uint_as_float(rc[i]);
+        for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(rm[i]) + __uint_as_float(rc[i]) * F::CORR;
         if (++acc == 2) { acc = 0; pa ^= 1; }
       }
       const int n0 = nt * 64 + g * 32;   // GEMM column of v[0]
@@ -245,17 +315,23 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_kernel(const __grid_cons
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
       }
       if (inside) {
-        long long o;   // word offset of channel block (n0 / 16) of the output pixel
+        using E = typename F::elem;
+        constexpr int NB = 32 / F::CH, BS = 2 * F::CH;   // channel blocks held by this thread, elements per block
+        long long o;   // element offset of the channel block of n0 in the output pixel
         if (P.mode == 2) {
           const int tap = n0 / P.Cout, co = n0 - tap * P.Cout;
           o = ((((long long)b * (2 * P.H) + 2 * y + (tap >> 1)) * (2LL * P.W) + 2 * x + (tap & 1)) * P.Cout + co) * 2;
         } else {
           o = ((((long long)b * P.H + y) * P.W + x) * P.Cout + n0) * 2;
         }
-        if (P.res) { add_split16(P.res + o, v); add_split16(P.res + o + 32, v + 16); }
-        if (P.res2) { add_split16(P.res2 + o, v); add_split16(P.res2 + o + 32, v + 16); }
-        store_split16(P.out + o, v);
-        store_split16(P.out + o + 32, v + 16);
+        bool bad = false;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+          if (P.res) add_split<F>(static_cast<const E*>(P.res) + o + c * BS, v + c * F::CH);
+          if (P.res2) add_split<F>(static_cast<const E*>(P.res2) + o + c * BS, v + c * F::CH);
+          bad |= store_split<F>(static_cast<E*>(P.out) + o + c * BS, v + c * F::CH);
+        }
+        if (bad && P.flag) atomicOr(P.flag, 1);
       }
     }
   }
@@ -291,6 +367,7 @@ static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr uint32_t TCOLS = 512;               // 2 buffers x 2 halves x (64 main + 64 corr)
 }  // namespace slab
 
+template <class F>
 __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid_constant__ Maps M, const Params P) {
   using namespace slab;
   extern __shared__ uint8_t smem_raw[];
@@ -307,7 +384,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pixel_tiles = P.B * P.tiles_y * P.tiles_x;
   const int total_tiles = pixel_tiles * P.n_tiles;
-  const int nblk = P.Cin / 16;
+  const int nblk = P.Cin / F::CH;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&M.a[0]);
@@ -338,7 +415,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
             tc::mbar_arrive(&afull[sa]);
           } else {
             tc::mbar_arrive_expect_tx(&afull[sa], SLAB_BYTES);
-            tc::tma_load_4d(smem + sa * SLAB_BYTES, &M.a[0], &afull[sa], j * 32, x0 - 1, y0 - 1, b);
+            tc::tma_load_4d(smem + sa * SLAB_BYTES, &M.a[0], &afull[sa], j * (2 * F::CH), x0 - 1, y0 - 1, b);
           }
           if (++sa == A_STAGES) { sa = 0; pha ^= 1; }
           for (int tp = 0; tp < 5; ++tp) {
@@ -347,7 +424,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
               tc::mbar_arrive(&bfull[sb]);
             } else {
               tc::mbar_arrive_expect_tx(&bfull[sb], WT_TILE);
-              tc::tma_load_2d(smem_b + sb * WT_TILE, &M.b, &bfull[sb], (j * 5 + tp) * 32, nt * 128);
+              tc::tma_load_2d(smem_b + sb * WT_TILE, &M.b, &bfull[sb], (j * 5 + tp) * (2 * F::CH), nt * 128);
             }
             if (++sb == B_STAGES) { sb = 0; phb ^= 1; }
           }
@@ -359,7 +436,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
     // Converged warp, one elected lane issues.  The tap loop is fully unrolled (compile-time tap shifts, one barrier wait and
     // one commit per weight tile = 16 MMAs): the first version spent ~110 SASS instructions per tap on window / phase
     // bookkeeping and kept the tensor pipe only 54 % busy (profiles/r02_ncu_tc32_slab_v1.csv).
-    constexpr uint32_t ID128 = idesc_tf32(128, 128), ID64 = idesc_tf32(128, 64);
+    constexpr uint32_t ID128 = F::idesc(128, 128), ID64 = F::idesc(128, 64);
     constexpr uint32_t HI_A = tc::desc_hi_sw128(SLAB_X * 128);
     constexpr uint32_t HI_B = tc::desc_hi_sw128(1024);
     const uint32_t slab_lo0 = tc::smem_u32(smem) >> 4;
@@ -396,10 +473,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
                 for (int h = 0; h < 2; ++h) {
                   const uint32_t a = a_t + h * 64;  // x-half: 8 positions = 1024 bytes
                   const uint32_t dh = d + h * 128;
-                  umma_tf32(dh, a, HI_A, b_t, HI_B, ID128, tap == 0 ? fresh : 1u);   // hi ch 0-7  x [W_hi; W_lo]
-                  umma_tf32(dh, a + 2, HI_A, b_t + 2, HI_B, ID128, 1u);              // hi ch 8-15
-                  umma_tf32(dh + 64, a + 4, HI_A, b_t, HI_B, ID64, 1u);              // lo ch 0-7  x W_hi
-                  umma_tf32(dh + 64, a + 6, HI_A, b_t + 2, HI_B, ID64, 1u);          // lo ch 8-15
+                  umma<F>(dh, a, HI_A, b_t, HI_B, ID128, tap == 0 ? fresh : 1u);   // hi, first half of the block  x [W_hi; W_lo]
+                  umma<F>(dh, a + 2, HI_A, b_t + 2, HI_B, ID128, 1u);              // hi, second half
+                  umma<F>(dh + 64, a + 4, HI_A, b_t, HI_B, ID64, 1u);              // lo, first half  x W_hi
+                  umma<F>(dh + 64, a + 6, HI_A, b_t + 2, HI_B, ID64, 1u);          // lo, second half
                 }
               }
             }
@@ -434,13 +511,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
       const int m = q * 32 + lane;                 // GEMM row of the half: slab row m / 8, position m % 8
       const int y = y0 + (m >> 3), x = x0 + 8 * g + (m & 7);
       const bool inside = (y < P.H) && (x < P.W);
-      const long long o = ((((long long)b * P.H + y) * P.W + x) * P.Cout + nt * 64) * 2;  // word offset of this pixel's 64 channels
+      using E = typename F::elem;
+      constexpr int NB = 64 / F::CH, BS = 2 * F::CH;   // channel blocks of this thread's 64 couts, elements per block (128 bytes)
+      const long long o = ((((long long)b * P.H + y) * P.W + x) * P.Cout + nt * 64) * 2;  // element offset of this pixel's 64 channels
       if (inside && P.res) {  // pull the residual lines towards L2 while the tile's MMAs run
 #pragma unroll
-        for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.res + o + k * 32));
+        for (int k = 0; k < NB; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const E*>(P.res) + o + k * BS));
         if (P.res2) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.res2 + o + k * 32));
+          for (int k = 0; k < NB; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const E*>(P.res2) + o + k * BS));
         }
       }
       float v[64];
@@ -458,7 +537,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
           tc::tmem_ld_32x32b_x32(t_addr + 64 + c0, rc);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[c0 + i] += __uint_as_float(rm[i]) + __uint_as_float(rc[i]);
+          for (int i = 0; i < 32; ++i) v[c0 + i] += __uint_as_float(rm[i]) + __uint_as_float(rc[i]) * F::CORR;
         }
         tc::tc_fence_before();
         __syncwarp();
@@ -475,29 +554,28 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
         for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
       }
       if (inside && !(P.dbg & 2)) {
-        // residual operands: all loads of two channel blocks are issued before the first use (the first version loaded,
-        // added and stored block by block: four dependent HBM round trips per tile and thread)
+        // residual operands: all loads of half of the channels (256 / 128 bytes) are issued before the first use (the first
+        // version loaded, added and stored block by block: four dependent HBM round trips per tile and thread)
+        constexpr int HB = NB / 2;   // blocks per half
+        bool bad = false;
 #pragma unroll
         for (int cp = 0; cp < 2; ++cp) {
           if (P.res) {
-            uint32_t raw[8][8];
+            uint32_t raw[HB * 4][8];
+            const char* rp = reinterpret_cast<const char*>(static_cast<const E*>(P.res) + o + cp * HB * BS);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) tc::ldg256(P.res + o + cp * 64 + k * 8, raw[k]);
+            for (int k = 0; k < HB * 4; ++k) tc::ldg256(rp + 32 * k, raw[k]);
 #pragma unroll
-            for (int c2 = 0; c2 < 2; ++c2)
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                v[cp * 32 + c2 * 16 + e] += __uint_as_float(raw[c2 * 4][e]) + __uint_as_float(raw[c2 * 4 + 2][e]);
-                v[cp * 32 + c2 * 16 + 8 + e] += __uint_as_float(raw[c2 * 4 + 1][e]) + __uint_as_float(raw[c2 * 4 + 3][e]);
-              }
+            for (int c2 = 0; c2 < HB; ++c2) add_split_raw<F>(raw + 4 * c2, v + (cp * HB + c2) * F::CH);
           }
-          if (P.res2) {
-            add_split16(P.res2 + o + cp * 64, v + cp * 32);
-            add_split16(P.res2 + o + cp * 64 + 32, v + cp * 32 + 16);
+#pragma unroll
+          for (int c2 = 0; c2 < HB; ++c2) {
+            const int c = cp * HB + c2;
+            if (P.res2) add_split<F>(static_cast<const E*>(P.res2) + o + c * BS, v + c * F::CH);
+            bad |= store_split<F>(static_cast<E*>(P.out) + o + c * BS, v + c * F::CH);
           }
-          store_split16(P.out + o + cp * 64, v + cp * 32);
-          store_split16(P.out + o + cp * 64 + 32, v + cp * 32 + 16);
         }
+        if (bad && P.flag) atomicOr(P.flag, 1);
       }
     }
   }
@@ -513,12 +591,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
 // word: broadcast).
 // ---------------------------------------------------------------------------------------------------------------
 struct HeadParams {
-  const float* x; const float* w; const float* bias; float* out;
+  const float* x; const float* w; const float* bias; void* out;
   int B, C, H, W, Cout;
   float fill_scalar; const float* fill_batch; int has_fill; int relu;
+  int* flag;
 };
 
-template <int CT>
+template <class F, int CT>
 __global__ void __launch_bounds__(256) head_tc32_kernel(const HeadParams P) {
   extern __shared__ float sw[];  // [Cout][9*CT] as stored by the module: (Cout, CT, 3, 3) -> index co*9*CT + c*9 + tap
   for (int i = threadIdx.x; i < P.Cout * 9 * CT; i += blockDim.x) sw[i] = __ldg(P.w + i);
@@ -544,19 +623,21 @@ __global__ void __launch_bounds__(256) head_tc32_kernel(const HeadParams P) {
       in[c * 9 + tap] = val;
     }
   }
-  float* o = P.out + p * P.Cout * 2;
-  for (int c0 = 0; c0 < P.Cout; c0 += 16) {
-    float v[16];
+  typename F::elem* o = static_cast<typename F::elem*>(P.out) + p * P.Cout * 2;
+  bool bad = false;
+  for (int c0 = 0; c0 < P.Cout; c0 += F::CH) {
+    float v[F::CH];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < F::CH; ++i) {
       float a = P.bias ? __ldg(P.bias + c0 + i) : 0.f;
       const float* wr = sw + (c0 + i) * 9 * CT;
 #pragma unroll
       for (int k = 0; k < 9 * CT; ++k) a = fmaf(in[k], wr[k], a);
       v[i] = P.relu ? fmaxf(a, 0.f) : a;
     }
-    store_split16(o + c0 * 2, v);
+    bad |= store_split<F>(o + c0 * 2, v);
   }
+  if (bad && P.flag) atomicOr(P.flag, 1);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -565,12 +646,13 @@ __global__ void __launch_bounds__(256) head_tc32_kernel(const HeadParams P) {
 // v = hi + lo in shared memory ([position][C + 4] words: 128-bit loads by adjacent pixels are conflict-free).
 // ---------------------------------------------------------------------------------------------------------------
 struct TailParams {
-  const float* x; const float* w; const float* bias; const float* add; float* out;
+  const void* x; const float* w; const float* bias; const float* add; float* out;
   int B, H, W, C, Cout;
+  const int* flag;   // overflow flag of the network (FmtF16): set -> the output is NaN
 };
 constexpr int TL_TX = 32, TL_TY = 8;
 
-template <int CO>
+template <class F, int CO>
 __global__ void __launch_bounds__(256) tail_tc32_kernel(const TailParams P) {
   extern __shared__ __align__(16) float sm[];
   const int C = P.C, CP = C + 4;
@@ -591,11 +673,18 @@ __global__ void __launch_bounds__(256) tail_tc32_kernel(const TailParams P) {
     const int yy = y0 + pos / (TL_TX + 2) - 1, xx = x0 + pos % (TL_TX + 2) - 1;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (yy >= 0 && yy < P.H && xx >= 0 && xx < P.W) {
-      const int c = cq * 4, blk = c >> 4, i16 = c & 15;
-      const float* src = P.x + (((long long)b * P.H + yy) * P.W + xx) * C * 2 + blk * 32 + i16;
-      const float4 h = __ldg(reinterpret_cast<const float4*>(src));
-      const float4 l = __ldg(reinterpret_cast<const float4*>(src + 16));
-      v = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
+      const int c = cq * 4, blk = c / F::CH, ib = c % F::CH;
+      const typename F::elem* src = static_cast<const typename F::elem*>(P.x) + (((long long)b * P.H + yy) * P.W + xx) * C * 2 + blk * 2 * F::CH + ib;
+      if constexpr (F::ID == 0) {
+        const float4 h = __ldg(reinterpret_cast<const float4*>(src));
+        const float4 l = __ldg(reinterpret_cast<const float4*>(src + F::CH));
+        v = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
+      } else {
+        const uint2 hu = __ldg(reinterpret_cast<const uint2*>(src)), lu = __ldg(reinterpret_cast<const uint2*>(src + F::CH));
+        const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&hu.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&hu.y));
+        const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&lu.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&lu.y));
+        v = make_float4(h0.x + l0.x * F::CORR, h0.y + l0.y * F::CORR, h1.x + l1.x * F::CORR, h1.y + l1.y * F::CORR);
+      }
     }
     *reinterpret_cast<float4*>(sx + pos * CP + cq * 4) = v;
   }
@@ -619,6 +708,7 @@ __global__ void __launch_bounds__(256) tail_tc32_kernel(const TailParams P) {
       }
     }
   }
+  const bool poisoned = P.flag && *reinterpret_cast<const volatile int*>(P.flag) != 0;
   if (y < P.H && x < P.W) {
 #pragma unroll
     for (int co = 0; co < CO; ++co) {
@@ -626,28 +716,31 @@ __global__ void __launch_bounds__(256) tail_tc32_kernel(const TailParams P) {
         const long long o = (((long long)b * P.Cout + co) * P.H + y) * P.W + x;
         float val = acc[co] + (P.bias ? __ldg(P.bias + co) : 0.f);
         if (P.add) val += __ldg(P.add + o);
+        if (poisoned) val = __uint_as_float(0x7fc00000u);   // an activation left the fp16 range somewhere in this network: NaN
         P.out[o] = val;
       }
     }
   }
 }
 
-// split16 -> NCHW fp32 (debug / tests / odd tails): out[b,c,y,x] = hi + lo
-__global__ void __launch_bounds__(256) split16_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int H, int W,
-                                                              long long n) {
+// split layout -> NCHW fp32 (tests / debugging): out[b,c,y,x] = hi + lo
+template <class F>
+__global__ void __launch_bounds__(256) split_to_nchw_kernel(const typename F::elem* __restrict__ in, float* __restrict__ out, int C, int H, int W,
+                                                            long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long HW = (long long)H * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const long long pix = i / C;
     const int c = (int)(i - pix * C);
     const long long b = pix / HW, hw = pix - b * HW;
-    const float* s = in + pix * C * 2 + (c >> 4) * 32 + (c & 15);
-    out[(b * C + c) * HW + hw] = __ldg(s) + __ldg(s + 16);
+    const typename F::elem* s = in + pix * C * 2 + (c / F::CH) * 2 * F::CH + (c % F::CH);
+    out[(b * C + c) * HW + hw] = (float)s[0] + (float)s[F::CH] * F::CORR;
   }
 }
-// NCHW fp32 -> split16
-__global__ void __launch_bounds__(256) nchw_to_split16_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int H, int W,
-                                                              long long n) {
+// NCHW fp32 -> split layout
+template <class F>
+__global__ void __launch_bounds__(256) nchw_to_split_kernel(const float* __restrict__ in, typename F::elem* __restrict__ out, int C, int H, int W,
+                                                            long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long HW = (long long)H * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -655,10 +748,16 @@ __global__ void __launch_bounds__(256) nchw_to_split16_kernel(const float* __res
     const int c = (int)(i - pix * C);
     const long long b = pix / HW, hw = pix - b * HW;
     const float v = __ldg(in + (b * C + c) * HW + hw);
-    const float hi = rna_tf32(v);
-    float* d = out + pix * C * 2 + (c >> 4) * 32 + (c & 15);
-    d[0] = hi;
-    d[16] = v - hi;
+    typename F::elem* d = out + pix * C * 2 + (c / F::CH) * 2 * F::CH + (c % F::CH);
+    if constexpr (F::ID == 0) {
+      const float hi = rna_tf32(v);
+      d[0] = hi;
+      d[F::CH] = v - hi;
+    } else {
+      const __half hi = __float2half_rn(v);
+      d[0] = hi;
+      d[F::CH] = __float2half_rn((v - __half2float(hi)) * 2048.0f);
+    }
   }
 }
 
@@ -679,27 +778,29 @@ static EncodeTiledFn get_encode() {
 }
 
 // 4-D activation view (words, X, Y, B) of a split16 tensor with arbitrary pixel strides (bytes)
+template <class F>
 static int make_act_map(CUtensorMap* m, const void* ptr, int B, int Y, int X, int C, long long sx, long long sy, long long sb, int box_x,
                         int box_y) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_error(DINVK_ECUDA, "cuTensorMapEncodeTiled is unavailable");
   cuuint64_t dims[4] = {(cuuint64_t)C * 2, (cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)sx, (cuuint64_t)sy, (cuuint64_t)sb};
-  cuuint32_t box[4] = {32, (cuuint32_t)box_x, (cuuint32_t)box_y, 1};
+  cuuint32_t box[4] = {(cuuint32_t)(2 * F::CH), (cuuint32_t)box_x, (cuuint32_t)box_y, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(m, F::TM, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(DINVK_ECUDA, "cuTensorMapEncodeTiled(tc32 activations) failed: %d", (int)r);
   return 0;
 }
+template <class F>
 static int make_w_map(CUtensorMap* m, const void* ptr, long long K, long long rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_error(DINVK_ECUDA, "cuTensorMapEncodeTiled is unavailable");
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-  cuuint32_t box[2] = {32, 128};
+  cuuint64_t strides[1] = {(cuuint64_t)K * F::EB};
+  cuuint32_t box[2] = {(cuuint32_t)(2 * F::CH), 128};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(m, F::TM, 2, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(DINVK_ECUDA, "cuTensorMapEncodeTiled(tc32 weights) failed: %d", (int)r);
   return 0;
@@ -714,31 +815,148 @@ static int default_window() {
   return w;
 }
 
+template <class F>
 static int launch(const Maps& M, const Params& P, void* stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc32_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return set_error(DINVK_ECUDA, "cudaFuncSetAttribute(conv_tc32): %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const long long tiles = (long long)P.B * P.tiles_y * P.tiles_x * P.n_tiles;
   const int grid = (int)std::min<long long>(tiles, sm_count());
   count_launch();
-  conv_tc32_kernel<<<grid, THREADS, SMEM, (cudaStream_t)stream>>>(M, P);
+  conv_tc32_kernel<F><<<grid, THREADS, SMEM, (cudaStream_t)stream>>>(M, P);
   return DINVK_POST_LAUNCH();
 }
 
+template <class F>
 static int launch_slab(const Maps& M, const Params& P, void* stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc32_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, slab::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc32_slab_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, slab::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(DINVK_ECUDA, "cudaFuncSetAttribute(conv_tc32_slab): %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const long long tiles = (long long)P.B * P.tiles_y * P.tiles_x * P.n_tiles;
   const int grid = (int)std::min<long long>(tiles, sm_count());
   count_launch();
-  conv_tc32_slab_kernel<<<grid, THREADS, slab::SMEM_BYTES, (cudaStream_t)stream>>>(M, P);
+  conv_tc32_slab_kernel<F><<<grid, THREADS, slab::SMEM_BYTES, (cudaStream_t)stream>>>(M, P);
+  return DINVK_POST_LAUNCH();
+}
+
+// kind 0: 3x3 stride 1 zero-pad 1 (weight rows = Cout/64 tiles of 128, K = 9*Cin, k = (ky*3+kx)*Cin + c)
+// kind 1: 2x2 stride 2 (K = 4*Cin, k = (dy*2+dx)*Cin + c), out (B, H/2, W/2, Cout)
+// kind 2: transposed 2x2 stride 2 (K = Cin, GEMM column = (dy*2+dx)*Cout + co), out (B, 2H, 2W, Cout)
+template <class F>
+static int conv_generic(const void* x, const void* weight, const float* bias, const void* res, const void* res2, void* out, int B, int H,
+                        int W, int Cin, int Cout, int kind, int act, int window, int* flag, void* stream) {
+  DINVK_CHECK_ARG(x && weight && out, "conv_tc32: null pointer");
+  DINVK_CHECK_ARG(B >= 0 && H >= 1 && W >= 1, "conv_tc32: bad shape");
+  DINVK_CHECK_ARG(kind >= 0 && kind <= 2, "conv_tc32: kind=%d not in 0..2", kind);
+  DINVK_CHECK_ARG(Cin % (2 * F::CH) == 0 && Cin >= 2 * F::CH, "conv_tc32: Cin=%d must be a multiple of %d", Cin, 2 * F::CH);
+  DINVK_CHECK_ARG(Cout % 64 == 0 && Cout >= 64, "conv_tc32: Cout=%d must be a multiple of 64", Cout);
+  DINVK_CHECK_ARG(kind != 1 || (H % 2 == 0 && W % 2 == 0), "conv_tc32: 2x2 stride-2 needs even H, W");
+  DINVK_CHECK_ARG(kind == 0 || (!res && !res2), "conv_tc32: residual inputs are for kind 0 only");
+  if (B == 0) return DINVK_OK;
+  Maps M;
+  Params P;
+  int rc;
+  const long long px = (long long)Cin * 2 * F::EB;  // bytes per input pixel
+  P.B = B; P.Cin = Cin; P.Cout = Cout;
+  P.kc_per_tap = Cin / (2 * F::CH);
+  P.relu = act; P.res = res; P.res2 = res2; P.out = out; P.bias = bias; P.flag = flag;
+  P.win = window > 0 ? window : default_window();
+  for (int t = 0; t < 9; ++t) { P.dx[t] = 0; P.dy[t] = 0; P.amap[t] = 0; }
+  if (kind == 0) {
+    if ((rc = make_act_map<F>(&M.a[0], x, B, H, W, Cin, px, px * W, px * W * H, TX, TY))) return rc;
+    M.a[1] = M.a[0]; M.a[2] = M.a[0]; M.a[3] = M.a[0];
+    if ((rc = make_w_map<F>(&M.b, weight, 9LL * Cin, 2LL * Cout))) return rc;
+    P.H = H; P.W = W; P.ntaps = 9; P.mode = 0; P.n_tiles = Cout / 64;
+    for (int t = 0; t < 9; ++t) { P.dx[t] = t % 3 - 1; P.dy[t] = t / 3 - 1; }
+  } else if (kind == 1) {
+    const int Ho = H / 2, Wo = W / 2;
+    for (int t = 0; t < 4; ++t) {
+      const char* base = reinterpret_cast<const char*>(x) + ((long long)(t >> 1) * W + (t & 1)) * px;
+      if ((rc = make_act_map<F>(&M.a[t], base, B, Ho, Wo, Cin, 2 * px, 2 * px * W, px * W * H, TX, TY))) return rc;
+      P.amap[t] = t;
+    }
+    if ((rc = make_w_map<F>(&M.b, weight, 4LL * Cin, 2LL * Cout))) return rc;
+    P.H = Ho; P.W = Wo; P.ntaps = 4; P.mode = 0; P.n_tiles = Cout / 64;
+  } else {
+    if ((rc = make_act_map<F>(&M.a[0], x, B, H, W, Cin, px, px * W, px * W * H, TX, TY))) return rc;
+    M.a[1] = M.a[0]; M.a[2] = M.a[0]; M.a[3] = M.a[0];
+    if ((rc = make_w_map<F>(&M.b, weight, (long long)Cin, 8LL * Cout))) return rc;
+    P.H = H; P.W = W; P.ntaps = 1; P.mode = 2; P.n_tiles = 4 * Cout / 64;
+  }
+  P.tiles_x = ceil_div(P.W, TX); P.tiles_y = ceil_div(P.H, TY);
+  P.dbg = 0;
+  return launch<F>(M, P, stream);
+}
+
+template <class F>
+static int conv_slab(const void* x, const void* weight, const float* bias, const void* res, const void* res2, void* out, int B, int H, int W,
+                     int Cin, int Cout, int act, int window, int* flag, void* stream) {
+  DINVK_CHECK_ARG(x && weight && out, "conv_tc32_slab: null pointer");
+  DINVK_CHECK_ARG(B >= 0 && H >= 1 && W >= 1, "conv_tc32_slab: bad shape");
+  DINVK_CHECK_ARG(Cin % F::CH == 0 && Cin >= F::CH, "conv_tc32_slab: Cin=%d must be a multiple of %d", Cin, F::CH);
+  DINVK_CHECK_ARG(Cout % 64 == 0 && Cout >= 64, "conv_tc32_slab: Cout=%d must be a multiple of 64", Cout);
+  if (B == 0) return DINVK_OK;
+  Maps M;
+  Params P;
+  int rc;
+  const long long px = (long long)Cin * 2 * F::EB;
+  if ((rc = make_act_map<F>(&M.a[0], x, B, H, W, Cin, px, px * W, px * W * H, slab::SLAB_X, slab::SLAB_Y))) return rc;
+  M.a[1] = M.a[0]; M.a[2] = M.a[0]; M.a[3] = M.a[0];
+  if ((rc = make_w_map<F>(&M.b, weight, 10LL * Cin, 2LL * Cout))) return rc;
+  P.B = B; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout;
+  P.ntaps = 9; P.kc_per_tap = Cin / F::CH; P.mode = 0; P.n_tiles = Cout / 64;
+  for (int t = 0; t < 9; ++t) { P.dx[t] = t % 3 - 1; P.dy[t] = t / 3 - 1; P.amap[t] = 0; }
+  P.relu = act; P.res = res; P.res2 = res2; P.out = out; P.bias = bias; P.flag = flag;
+  // accumulation window in channel blocks: ONE block by default = 18 full-scale accumulations (tf32: k = 144, fp16: k = 288).
+  // The tensor core truncates its fp32 accumulator once per MMA; over a plain 20-layer chain (DnCNN) the resulting bias
+  // compounds to 5e-6 with this window and to 1e-5 with twice as many MMAs per window (tools/micro/tf32_probe.cu)
+  static const int def_win = getenv("DINVK_TC32_SLAB_WINDOW") ? std::max(1, atoi(getenv("DINVK_TC32_SLAB_WINDOW"))) : 1;
+  P.win = window > 0 ? window : def_win;
+  P.tiles_x = ceil_div(W, slab::TXP); P.tiles_y = ceil_div(H, slab::TYP);
+  P.dbg = getenv("DINVK_TC32_DBG") ? atoi(getenv("DINVK_TC32_DBG")) : 0;
+  return launch_slab<F>(M, P, stream);
+}
+
+template <class F>
+static int conv_head(const float* x_nchw, const float* weight, const float* bias, void* out, int B, int C, int H, int W, int Cout,
+                     float fill_scalar, const float* fill_batch, int has_fill, int act, int* flag, void* stream) {
+  const int CT = C + (has_fill ? 1 : 0);
+  DINVK_CHECK_ARG(Cout % F::CH == 0 && Cout >= F::CH && Cout <= 256, "conv_tc32_head: Cout=%d must be a multiple of %d (<= 256)", Cout, F::CH);
+  HeadParams P{x_nchw, weight, bias, out, B, C, H, W, Cout, fill_scalar, fill_batch, has_fill, act, flag};
+  const long long npix = (long long)B * H * W;
+  const unsigned grid = (unsigned)((npix + 255) / 256);
+  const size_t smem = (size_t)Cout * 9 * CT * 4;
+  switch (CT) {
+    case 1: DINVK_LAUNCH((head_tc32_kernel<F, 1>), dim3(grid), dim3(256), smem, stream, P); break;
+    case 2: DINVK_LAUNCH((head_tc32_kernel<F, 2>), dim3(grid), dim3(256), smem, stream, P); break;
+    case 3: DINVK_LAUNCH((head_tc32_kernel<F, 3>), dim3(grid), dim3(256), smem, stream, P); break;
+    default: DINVK_LAUNCH((head_tc32_kernel<F, 4>), dim3(grid), dim3(256), smem, stream, P); break;
+  }
+  return DINVK_POST_LAUNCH();
+}
+
+template <class F>
+static int conv_tail(const void* x, const float* weight, const float* bias, const float* add_nchw, float* out_nchw, int B, int H, int W,
+                     int Cin, int Cout, const int* flag, void* stream) {
+  DINVK_CHECK_ARG(Cin % F::CH == 0 && Cin >= F::CH && Cin <= 128, "conv_tc32_tail: Cin=%d must be a multiple of %d (<= 128)", Cin, F::CH);
+  TailParams P{x, weight, bias, add_nchw, out_nchw, B, H, W, Cin, Cout, flag};
+  const int tiles = B * ceil_div(H, TL_TY) * ceil_div(W, TL_TX);
+  const int CO = Cout <= 2 ? 2 : 4;
+  const size_t smem = ((size_t)(TL_TY + 2) * (TL_TX + 2) * (Cin + 4) + (size_t)CO * 9 * Cin) * 4;
+  int rc;
+  if (CO == 2) {
+    if ((rc = allow_smem(tail_tc32_kernel<F, 2>, smem))) return rc;
+    DINVK_LAUNCH((tail_tc32_kernel<F, 2>), dim3(tiles), dim3(256), smem, stream, P);
+  } else {
+    if ((rc = allow_smem(tail_tc32_kernel<F, 4>, smem))) return rc;
+    DINVK_LAUNCH((tail_tc32_kernel<F, 4>), dim3(tiles), dim3(256), smem, stream, P);
+  }
   return DINVK_POST_LAUNCH();
 }
 
@@ -747,142 +965,69 @@ static int launch_slab(const Maps& M, const Params& P, void* stream) {
 
 using namespace dinvk;
 
-// 3x3 with halo reuse: weight = the "slab pack" (2*Cout, 10*Cin): column ((c/16 * 5 + tap/2) * 2 + tap%2) * 16 + c%16
-// (tap 9 = zeros), rows per 64 output channels [W_hi (64); W_lo (64)];  window counted in 16-channel blocks (9 taps, k = 144, each)
-extern "C" int dinvk_conv_tc32_slab(const float* x, const float* weight, const float* bias, const float* res, const float* res2,
-                                    float* out, int B, int H, int W, int Cin, int Cout, int act, int window, void* stream) {
+#define DINVK_FMT_DISPATCH(fmt, call_tf32, call_f16)                                                   \
+  do {                                                                                                 \
+    if ((fmt) == 0) return call_tf32;                                                                  \
+    if ((fmt) == 1) return call_f16;                                                                   \
+    return ::dinvk::set_error(DINVK_EINVAL, "conv_tc32: fmt=%d not in {0 (tf32 split16), 1 (fp16 split32)}", (fmt)); \
+  } while (0)
+
+extern "C" int dinvk_conv_tc32(const void* x, const void* weight, const float* bias, const void* res, const void* res2, void* out, int B,
+                               int H, int W, int Cin, int Cout, int kind, int act, int window, int fmt, int* overflow_flag, void* stream) {
   using namespace t32;
-  DINVK_CHECK_ARG(x && weight && out, "conv_tc32_slab: null pointer");
-  DINVK_CHECK_ARG(B >= 0 && H >= 1 && W >= 1, "conv_tc32_slab: bad shape");
-  DINVK_CHECK_ARG(Cin % 16 == 0 && Cin >= 16, "conv_tc32_slab: Cin=%d must be a multiple of 16", Cin);
-  DINVK_CHECK_ARG(Cout % 64 == 0 && Cout >= 64, "conv_tc32_slab: Cout=%d must be a multiple of 64", Cout);
-  if (B == 0) return DINVK_OK;
-  Maps M;
-  Params P;
-  int rc;
-  const long long px = (long long)Cin * 8;
-  if ((rc = make_act_map(&M.a[0], x, B, H, W, Cin, px, px * W, px * W * H, slab::SLAB_X, slab::SLAB_Y))) return rc;
-  M.a[1] = M.a[0]; M.a[2] = M.a[0]; M.a[3] = M.a[0];
-  if ((rc = make_w_map(&M.b, weight, 10LL * Cin, 2LL * Cout))) return rc;
-  P.B = B; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout;
-  P.ntaps = 9; P.kc_per_tap = Cin / 16; P.mode = 0; P.n_tiles = Cout / 64;
-  for (int t = 0; t < 9; ++t) { P.dx[t] = t % 3 - 1; P.dy[t] = t / 3 - 1; P.amap[t] = 0; }
-  P.relu = act; P.res = res; P.res2 = res2; P.out = out; P.bias = bias;
-  static const int def_win = getenv("DINVK_TC32_SLAB_WINDOW") ? std::max(1, atoi(getenv("DINVK_TC32_SLAB_WINDOW"))) : 2;
-  P.win = window > 0 ? window : def_win;
-  P.tiles_x = ceil_div(W, slab::TXP); P.tiles_y = ceil_div(H, slab::TYP);
-  P.dbg = getenv("DINVK_TC32_DBG") ? atoi(getenv("DINVK_TC32_DBG")) : 0;
-  return launch_slab(M, P, stream);
+  DINVK_FMT_DISPATCH(fmt, conv_generic<FmtTF32>(x, weight, bias, res, res2, out, B, H, W, Cin, Cout, kind, act, window, overflow_flag, stream),
+                     conv_generic<FmtF16>(x, weight, bias, res, res2, out, B, H, W, Cin, Cout, kind, act, window, overflow_flag, stream));
 }
 
-// kind 0: 3x3 stride 1 zero-pad 1 (weight rows = Cout/64 tiles of 128, K = 9*Cin, k = (ky*3+kx)*Cin + c)
-// kind 1: 2x2 stride 2 (K = 4*Cin, k = (dy*2+dx)*Cin + c), out (B, H/2, W/2, Cout)
-// kind 2: transposed 2x2 stride 2 (K = Cin, GEMM column = (dy*2+dx)*Cout + co), out (B, 2H, 2W, Cout)
-extern "C" int dinvk_conv_tc32(const float* x, const float* weight, const float* bias, const float* res, const float* res2, float* out,
-                               int B, int H, int W, int Cin, int Cout, int kind, int act, int window, void* stream) {
+extern "C" int dinvk_conv_tc32_slab(const void* x, const void* weight, const float* bias, const void* res, const void* res2, void* out,
+                                    int B, int H, int W, int Cin, int Cout, int act, int window, int fmt, int* overflow_flag,
+                                    void* stream) {
   using namespace t32;
-  DINVK_CHECK_ARG(x && weight && out, "conv_tc32: null pointer");
-  DINVK_CHECK_ARG(B >= 0 && H >= 1 && W >= 1, "conv_tc32: bad shape");
-  DINVK_CHECK_ARG(kind >= 0 && kind <= 2, "conv_tc32: kind=%d not in 0..2", kind);
-  DINVK_CHECK_ARG(Cin % 32 == 0 && Cin >= 32, "conv_tc32: Cin=%d must be a multiple of 32", Cin);
-  DINVK_CHECK_ARG(Cout % 64 == 0 && Cout >= 64, "conv_tc32: Cout=%d must be a multiple of 64", Cout);
-  DINVK_CHECK_ARG(kind != 1 || (H % 2 == 0 && W % 2 == 0), "conv_tc32: 2x2 stride-2 needs even H, W");
-  DINVK_CHECK_ARG(kind == 0 || (!res && !res2), "conv_tc32: residual inputs are for kind 0 only");
-  if (B == 0) return DINVK_OK;
-  Maps M;
-  Params P;
-  int rc;
-  const long long px = (long long)Cin * 8;  // bytes per input pixel
-  P.B = B; P.Cin = Cin; P.Cout = Cout;
-  P.kc_per_tap = Cin / 32;
-  P.relu = act; P.res = res; P.res2 = res2; P.out = out; P.bias = bias;
-  P.win = window > 0 ? window : default_window();
-  for (int t = 0; t < 9; ++t) { P.dx[t] = 0; P.dy[t] = 0; P.amap[t] = 0; }
-  if (kind == 0) {
-    if ((rc = make_act_map(&M.a[0], x, B, H, W, Cin, px, px * W, px * W * H, TX, TY))) return rc;
-    M.a[1] = M.a[0]; M.a[2] = M.a[0]; M.a[3] = M.a[0];
-    if ((rc = make_w_map(&M.b, weight, 9LL * Cin, 2LL * Cout))) return rc;
-    P.H = H; P.W = W; P.ntaps = 9; P.mode = 0; P.n_tiles = Cout / 64;
-    for (int t = 0; t < 9; ++t) { P.dx[t] = t % 3 - 1; P.dy[t] = t / 3 - 1; }
-  } else if (kind == 1) {
-    const int Ho = H / 2, Wo = W / 2;
-    for (int t = 0; t < 4; ++t) {
-      const char* base = reinterpret_cast<const char*>(x) + ((long long)(t >> 1) * W + (t & 1)) * px;
-      if ((rc = make_act_map(&M.a[t], base, B, Ho, Wo, Cin, 2 * px, 2 * px * W, px * W * H, TX, TY))) return rc;
-      P.amap[t] = t;
-    }
-    if ((rc = make_w_map(&M.b, weight, 4LL * Cin, 2LL * Cout))) return rc;
-    P.H = Ho; P.W = Wo; P.ntaps = 4; P.mode = 0; P.n_tiles = Cout / 64;
-  } else {
-    if ((rc = make_act_map(&M.a[0], x, B, H, W, Cin, px, px * W, px * W * H, TX, TY))) return rc;
-    M.a[1] = M.a[0]; M.a[2] = M.a[0]; M.a[3] = M.a[0];
-    if ((rc = make_w_map(&M.b, weight, (long long)Cin, 8LL * Cout))) return rc;
-    P.H = H; P.W = W; P.ntaps = 1; P.mode = 2; P.n_tiles = 4 * Cout / 64;
-  }
-  P.tiles_x = ceil_div(P.W, TX); P.tiles_y = ceil_div(P.H, TY);
-  P.dbg = 0;
-  return launch(M, P, stream);
+  DINVK_FMT_DISPATCH(fmt, conv_slab<FmtTF32>(x, weight, bias, res, res2, out, B, H, W, Cin, Cout, act, window, overflow_flag, stream),
+                     conv_slab<FmtF16>(x, weight, bias, res, res2, out, B, H, W, Cin, Cout, act, window, overflow_flag, stream));
 }
 
-extern "C" int dinvk_conv_tc32_head(const float* x_nchw, const float* weight, const float* bias, float* out, int B, int C, int H, int W,
-                                    int Cout, float fill_scalar, const float* fill_batch, int has_fill, int act, void* stream) {
+extern "C" int dinvk_conv_tc32_head(const float* x_nchw, const float* weight, const float* bias, void* out, int B, int C, int H, int W,
+                                    int Cout, float fill_scalar, const float* fill_batch, int has_fill, int act, int fmt,
+                                    int* overflow_flag, void* stream) {
   using namespace t32;
   DINVK_CHECK_ARG(x_nchw && weight && out && B >= 0 && C >= 1 && H >= 1 && W >= 1, "conv_tc32_head: bad arguments");
   const int CT = C + (has_fill ? 1 : 0);
   DINVK_CHECK_ARG(CT >= 1 && CT <= 4, "conv_tc32_head: %d input channels (incl. noise map) not in 1..4", CT);
-  DINVK_CHECK_ARG(Cout % 16 == 0 && Cout >= 16 && Cout <= 256, "conv_tc32_head: Cout=%d must be a multiple of 16 (<= 256)", Cout);
   if (B == 0) return DINVK_OK;
-  HeadParams P{x_nchw, weight, bias, out, B, C, H, W, Cout, fill_scalar, fill_batch, has_fill, act};
-  const long long npix = (long long)B * H * W;
-  const unsigned grid = (unsigned)((npix + 255) / 256);
-  const size_t smem = (size_t)Cout * 9 * CT * 4;
-  switch (CT) {
-    case 1: DINVK_LAUNCH(head_tc32_kernel<1>, dim3(grid), dim3(256), smem, stream, P); break;
-    case 2: DINVK_LAUNCH(head_tc32_kernel<2>, dim3(grid), dim3(256), smem, stream, P); break;
-    case 3: DINVK_LAUNCH(head_tc32_kernel<3>, dim3(grid), dim3(256), smem, stream, P); break;
-    default: DINVK_LAUNCH(head_tc32_kernel<4>, dim3(grid), dim3(256), smem, stream, P); break;
-  }
-  return DINVK_POST_LAUNCH();
+  DINVK_FMT_DISPATCH(fmt, conv_head<FmtTF32>(x_nchw, weight, bias, out, B, C, H, W, Cout, fill_scalar, fill_batch, has_fill, act, overflow_flag, stream),
+                     conv_head<FmtF16>(x_nchw, weight, bias, out, B, C, H, W, Cout, fill_scalar, fill_batch, has_fill, act, overflow_flag, stream));
 }
 
-extern "C" int dinvk_conv_tc32_tail(const float* x, const float* weight, const float* bias, const float* add_nchw, float* out_nchw, int B,
-                                    int H, int W, int Cin, int Cout, void* stream) {
+extern "C" int dinvk_conv_tc32_tail(const void* x, const float* weight, const float* bias, const float* add_nchw, float* out_nchw, int B,
+                                    int H, int W, int Cin, int Cout, int fmt, const int* overflow_flag, void* stream) {
   using namespace t32;
   DINVK_CHECK_ARG(x && weight && out_nchw && B >= 0 && H >= 1 && W >= 1, "conv_tc32_tail: bad arguments");
-  DINVK_CHECK_ARG(Cin % 16 == 0 && Cin >= 16 && Cin <= 128, "conv_tc32_tail: Cin=%d must be a multiple of 16 (<= 128)", Cin);
   DINVK_CHECK_ARG(Cout >= 1 && Cout <= 4, "conv_tc32_tail: Cout=%d not in 1..4", Cout);
   if (B == 0) return DINVK_OK;
-  TailParams P{x, weight, bias, add_nchw, out_nchw, B, H, W, Cin, Cout};
-  const int tiles = B * ceil_div(H, TL_TY) * ceil_div(W, TL_TX);
-  const int CO = Cout <= 2 ? 2 : 4;
-  const size_t smem = ((size_t)(TL_TY + 2) * (TL_TX + 2) * (Cin + 4) + (size_t)CO * 9 * Cin) * 4;
-  int rc;
-  if (CO == 2) {
-    if ((rc = allow_smem(tail_tc32_kernel<2>, smem))) return rc;
-    DINVK_LAUNCH(tail_tc32_kernel<2>, dim3(tiles), dim3(256), smem, stream, P);
+  DINVK_FMT_DISPATCH(fmt, conv_tail<FmtTF32>(x, weight, bias, add_nchw, out_nchw, B, H, W, Cin, Cout, overflow_flag, stream),
+                     conv_tail<FmtF16>(x, weight, bias, add_nchw, out_nchw, B, H, W, Cin, Cout, overflow_flag, stream));
+}
+
+template <class F>
+static int split_convert(const void* in, void* out, int B, int C, int H, int W, int to_nchw, void* stream) {
+  using namespace t32;
+  DINVK_CHECK_ARG(in && out && B >= 0 && C % F::CH == 0 && C >= F::CH, "split converter: C=%d must be a multiple of %d", C, F::CH);
+  if (B == 0) return DINVK_OK;
+  const long long n = (long long)B * H * W * C;
+  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 16);
+  if (to_nchw) {
+    DINVK_LAUNCH(split_to_nchw_kernel<F>, dim3(grid), dim3(256), 0, stream, static_cast<const typename F::elem*>(in), static_cast<float*>(out), C, H, W, n);
   } else {
-    if ((rc = allow_smem(tail_tc32_kernel<4>, smem))) return rc;
-    DINVK_LAUNCH(tail_tc32_kernel<4>, dim3(tiles), dim3(256), smem, stream, P);
+    DINVK_LAUNCH(nchw_to_split_kernel<F>, dim3(grid), dim3(256), 0, stream, static_cast<const float*>(in), static_cast<typename F::elem*>(out), C, H, W, n);
   }
   return DINVK_POST_LAUNCH();
 }
 
-extern "C" int dinvk_split16_to_nchw(const float* in, float* out, int B, int C, int H, int W, void* stream) {
-  using namespace t32;
-  DINVK_CHECK_ARG(in && out && B >= 0 && C % 16 == 0 && C >= 16, "split16_to_nchw: bad arguments");
-  if (B == 0) return DINVK_OK;
-  const long long n = (long long)B * H * W * C;
-  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 16);
-  DINVK_LAUNCH(split16_to_nchw_kernel, dim3(grid), dim3(256), 0, stream, in, out, C, H, W, n);
-  return DINVK_POST_LAUNCH();
+extern "C" int dinvk_split16_to_nchw(const void* in, float* out, int B, int C, int H, int W, int fmt, void* stream) {
+  DINVK_FMT_DISPATCH(fmt, split_convert<t32::FmtTF32>(in, out, B, C, H, W, 1, stream), split_convert<t32::FmtF16>(in, out, B, C, H, W, 1, stream));
 }
 
-extern "C" int dinvk_nchw_to_split16(const float* in, float* out, int B, int C, int H, int W, void* stream) {
-  using namespace t32;
-  DINVK_CHECK_ARG(in && out && B >= 0 && C % 16 == 0 && C >= 16, "nchw_to_split16: bad arguments");
-  if (B == 0) return DINVK_OK;
-  const long long n = (long long)B * H * W * C;
-  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 16);
-  DINVK_LAUNCH(nchw_to_split16_kernel, dim3(grid), dim3(256), 0, stream, in, out, C, H, W, n);
-  return DINVK_POST_LAUNCH();
+extern "C" int dinvk_nchw_to_split16(const float* in, void* out, int B, int C, int H, int W, int fmt, void* stream) {
+  DINVK_FMT_DISPATCH(fmt, split_convert<t32::FmtTF32>(in, out, B, C, H, W, 0, stream), split_convert<t32::FmtF16>(in, out, B, C, H, W, 0, stream));
 }

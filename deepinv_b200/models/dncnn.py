@@ -50,8 +50,8 @@ class DnCNN(Denoiser):
             from .tc_engine import dncnn_forward_bf16
 
             return dncnn_forward_bf16(self, x)
-        if self.precision == "tc32":
-            _no_grad_guard("DnCNN(precision='tc32')", x, self.in_conv.weight)
+        if self.precision in ("tc32", "tc32h"):
+            _no_grad_guard(f"DnCNN(precision='{self.precision}')", x, self.in_conv.weight)
             from .tc_engine import dncnn_forward_tc32
 
             return dncnn_forward_tc32(self, x)

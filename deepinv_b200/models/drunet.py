@@ -107,8 +107,8 @@ class DRUNet(Denoiser):
             from .tc_engine import drunet_forward_bf16
 
             return drunet_forward_bf16(self, x0)
-        if self.precision == "tc32":
-            _no_grad_guard("DRUNet(precision='tc32')", x0, self.m_head.weight)
+        if self.precision in ("tc32", "tc32h"):
+            _no_grad_guard(f"DRUNet(precision='{self.precision}')", x0, self.m_head.weight)
             from .tc_engine import drunet_forward_tc32
 
             return drunet_forward_tc32(self, x0)

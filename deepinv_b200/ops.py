@@ -484,73 +484,88 @@ def conv2x2_bf16(x, w2d, cout: int, *, up: bool, xadd=None) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------
-# denoiser convolutions, fp32-grade tensor-core path (3 x TF32 split operands, "split16" activations)
+# denoiser convolutions, fp32-grade tensor-core path (split operands; activations (B,H,W,C/CH,2,CH):
+#   fp32 words, CH = 16  -> fmt 0 (3 x TF32);   fp16 words, CH = 32 -> fmt 1 (3 x FP16, |v| < 65504))
 # --------------------------------------------------------------------------------------------
-def conv_tc32(x, w, cout: int, *, kind: int = 0, bias=None, res=None, res2=None, relu: bool = False, window: int = 0) -> torch.Tensor:
-    """x (B,H,W,Cin/16,2,16) fp32 split16, w packed by models.tc_engine._pack_tc32 -> split16 output
+def _fmt_of(t: torch.Tensor) -> int:
+    return 1 if t.dtype == torch.float16 else 0
+
+
+def _split_empty(B, H, W, C, fmt, dev):
+    ch, dt = (32, torch.float16) if fmt == 1 else (16, torch.float32)
+    return torch.empty(B, H, W, C // ch, 2, ch, dtype=dt, device=dev)
+
+
+def conv_tc32(x, w, cout: int, *, kind: int = 0, bias=None, res=None, res2=None, relu: bool = False, window: int = 0,
+              flag=None) -> torch.Tensor:
+    """x split layout, w packed by models.tc_engine._pack_tc32 -> split output
     kind 0: 3x3 (same grid), 1: 2x2 stride 2 (H/2, W/2), 2: transposed 2x2 stride 2 (2H, 2W);
-    out = act(conv + bias) + res + res2"""
+    out = act(conv + bias) + res + res2;  flag: int32 overflow flag of the network (fp16 format)"""
     dev = _require_cuda(x, w)
+    fmt = _fmt_of(x)
     B, H, W, nblk = x.shape[:4]
-    Cin = nblk * 16
+    Cin = nblk * x.shape[-1]
     Ho, Wo = (H, W) if kind == 0 else ((H // 2, W // 2) if kind == 1 else (2 * H, 2 * W))
-    out = torch.empty(B, Ho, Wo, cout // 16, 2, 16, dtype=torch.float32, device=dev)
+    out = _split_empty(B, Ho, Wo, cout, fmt, dev)
     check(get_lib().dinvk_conv_tc32(_p(x), _p(w), _p(bias), _p(res), _p(res2), _p(out), B, H, W, Cin, cout, kind, int(relu),
-                                    int(window), _stream(dev)))
+                                    int(window), fmt, _p(flag), _stream(dev)))
     return out
 
 
-def conv_tc32_slab(x, w, cout: int, *, bias=None, res=None, res2=None, relu: bool = False, window: int = 0) -> torch.Tensor:
-    """3x3 convolution with halo reuse (the body layers); w packed by models.tc_engine._pack3x3_slab_tc32; window in 16-channel blocks"""
+def conv_tc32_slab(x, w, cout: int, *, bias=None, res=None, res2=None, relu: bool = False, window: int = 0, flag=None) -> torch.Tensor:
+    """3x3 convolution with halo reuse (the body layers); w packed by models.tc_engine._pack3x3_slab_tc32; window in channel blocks"""
     dev = _require_cuda(x, w)
+    fmt = _fmt_of(x)
     B, H, W, nblk = x.shape[:4]
-    out = torch.empty(B, H, W, cout // 16, 2, 16, dtype=torch.float32, device=dev)
-    check(get_lib().dinvk_conv_tc32_slab(_p(x), _p(w), _p(bias), _p(res), _p(res2), _p(out), B, H, W, nblk * 16, cout, int(relu),
-                                         int(window), _stream(dev)))
+    out = _split_empty(B, H, W, cout, fmt, dev)
+    check(get_lib().dinvk_conv_tc32_slab(_p(x), _p(w), _p(bias), _p(res), _p(res2), _p(out), B, H, W, nblk * x.shape[-1], cout, int(relu),
+                                         int(window), fmt, _p(flag), _stream(dev)))
     return out
 
 
-def conv_tc32_head(x, weight, *, bias=None, fill=None, relu: bool = False) -> torch.Tensor:
-    """network head: (B,C,H,W) fp32 NCHW (+ constant channel `fill`) -> split16 (B,H,W,Cout/16,2,16); weight (Cout,C[+1],3,3) fp32"""
+def conv_tc32_head(x, weight, *, bias=None, fill=None, relu: bool = False, fmt: int = 0, flag=None) -> torch.Tensor:
+    """network head: (B,C,H,W) fp32 NCHW (+ constant channel `fill`) -> split layout; weight (Cout,C[+1],3,3) fp32"""
     dev = _require_cuda(x, weight)
     x = _f32c(x)
     B, C, H, W = x.shape
     cout = weight.shape[0]
-    out = torch.empty(B, H, W, cout // 16, 2, 16, dtype=torch.float32, device=dev)
+    out = _split_empty(B, H, W, cout, fmt, dev)
     fill_t = _f32c(fill.reshape(-1)) if torch.is_tensor(fill) else None
     if fill_t is not None and fill_t.numel() == 1:
         fill_t = fill_t.expand(B).contiguous()
     check(get_lib().dinvk_conv_tc32_head(_p(x), _p(_f32c(weight)), _p(bias), _p(out), B, C, H, W, cout,
                                          float(fill) if (fill is not None and fill_t is None) else 0.0,
-                                         _p(fill_t), int(fill is not None), int(relu), _stream(dev)))
+                                         _p(fill_t), int(fill is not None), int(relu), fmt, _p(flag), _stream(dev)))
     return out
 
 
-def conv_tc32_tail(x, weight, *, bias=None, add=None) -> torch.Tensor:
-    """network tail: split16 (B,H,W,Cin/16,2,16) -> (B,Cout,H,W) fp32 NCHW (+ bias + add); weight (Cout,Cin,3,3) fp32, Cout <= 4"""
+def conv_tc32_tail(x, weight, *, bias=None, add=None, flag=None) -> torch.Tensor:
+    """network tail: split layout -> (B,Cout,H,W) fp32 NCHW (+ bias + add); weight (Cout,Cin,3,3) fp32, Cout <= 4;
+    NaN if the network's overflow flag is set"""
     dev = _require_cuda(x, weight)
     B, H, W, nblk = x.shape[:4]
     cout = weight.shape[0]
     out = torch.empty(B, cout, H, W, dtype=torch.float32, device=dev)
-    check(get_lib().dinvk_conv_tc32_tail(_p(x), _p(_f32c(weight)), _p(bias), _p(_f32c(add)), _p(out), B, H, W, nblk * 16, cout,
-                                         _stream(dev)))
+    check(get_lib().dinvk_conv_tc32_tail(_p(x), _p(_f32c(weight)), _p(bias), _p(_f32c(add)), _p(out), B, H, W, nblk * x.shape[-1], cout,
+                                         _fmt_of(x), _p(flag), _stream(dev)))
     return out
 
 
 def split16_to_nchw(x) -> torch.Tensor:
     dev = _require_cuda(x)
     B, H, W, nblk = x.shape[:4]
-    out = torch.empty(B, nblk * 16, H, W, dtype=torch.float32, device=dev)
-    check(get_lib().dinvk_split16_to_nchw(_p(x), _p(out), B, nblk * 16, H, W, _stream(dev)))
+    C = nblk * x.shape[-1]
+    out = torch.empty(B, C, H, W, dtype=torch.float32, device=dev)
+    check(get_lib().dinvk_split16_to_nchw(_p(x), _p(out), B, C, H, W, _fmt_of(x), _stream(dev)))
     return out
 
 
-def nchw_to_split16(x) -> torch.Tensor:
+def nchw_to_split16(x, fmt: int = 0) -> torch.Tensor:
     dev = _require_cuda(x)
     x = _f32c(x)
     B, C, H, W = x.shape
-    out = torch.empty(B, H, W, C // 16, 2, 16, dtype=torch.float32, device=dev)
-    check(get_lib().dinvk_nchw_to_split16(_p(x), _p(out), B, C, H, W, _stream(dev)))
+    out = _split_empty(B, H, W, C, fmt, dev)
+    check(get_lib().dinvk_nchw_to_split16(_p(x), _p(out), B, C, H, W, fmt, _stream(dev)))
     return out
 
 

@@ -270,32 +270,41 @@ int dinvk_conv2x2_up_bf16(const void* x, const void* xadd, const void* weight, v
                           int B, int H, int W, int Cin, int Cout, void* stream);
 
 
-/* fp32-grade tensor-core path (3 x TF32 split operands on tcgen05, TMA-fed; replaces the same ATen / cuDNN calls as
- * dinvk_conv_f32: deepinv/models/drunet.py:200-263,323-433, dncnn.py:116-140) — every fp32 value v travels as
- * hi = tf32(v), lo = v - hi; products hi*hi + hi*lo + lo*hi, fp32 accumulation drained to registers every `window`
- * pipeline stages (0 = library default).  Activation layout "split16": (B,H,W,C/16,2,16) fp32 words, [..,0,:] = hi,
- * [..,1,:] = lo.  Weights: per 64 output channels 128 K-major rows [W_hi (64); W_lo (64)], both tf32-rounded:
+/* fp32-grade tensor-core path (split-operand tcgen05 implicit GEMM, TMA-fed; replaces the same ATen / cuDNN calls as
+ * dinvk_conv_f32: deepinv/models/drunet.py:200-263,323-433, dncnn.py:116-140) — every fp32 value v travels as a pair
+ * (hi, lo) of narrow values, products hi*hi + hi*lo + lo*hi are accumulated in fp32 and drained to registers every `window`
+ * pipeline steps (0 = library default).  Two formats (`fmt`):
+ *   fmt 0 "split16"  (fp32 words):  hi = tf32(v), lo = v - hi;               kind::tf32;  any fp32 range
+ *   fmt 1 "split32h" (fp16 words):  hi = fp16(v), lo = fp16((v - hi) 2^11);  kind::f16 (twice the channels per MMA, half the
+ *         bytes);  |v| < 65504 — an activation beyond it sets *overflow_flag (sticky, may be null) and the tail kernel of a
+ *         network whose flag is set writes NaN: loud, never silent
+ * Activation layout: (B,H,W,C/CH,2,CH) words, CH = 16 (fmt 0) / 32 (fmt 1), [..,0,:] = hi, [..,1,:] = lo.
+ * Weights: per 64 output channels 128 K-major rows [W_hi (64); W_lo (64)] in the same word type (fmt 1: W_lo scaled 2^11):
  *   kind 0 (3x3, pad 1): (2*Cout, 9*Cin), k = (ky*3+kx)*Cin + c
  *   kind 1 (2x2 stride 2): (2*Cout, 4*Cin), k = (dy*2+dx)*Cin + c;  out (B,H/2,W/2,Cout)
  *   kind 2 (transposed 2x2 stride 2): (8*Cout, Cin), GEMM column = (dy*2+dx)*Cout + co;  out (B,2H,2W,Cout)
- *   out = act(conv(x) + bias) + res + res2 (res/res2: split16, kind 0 only).  Cin % 32 == 0, Cout % 64 == 0. */
-int dinvk_conv_tc32(const float* x, const float* weight, const float* bias, const float* res, const float* res2,
-                    float* out, int B, int H, int W, int Cin, int Cout, int kind, int act, int window, void* stream);
-/* kind 0 with halo reuse (the body layers): one (16+8) x (16+2)-position activation slab per 16-channel block serves all
- * nine taps.  weight: "slab pack" (2*Cout, 10*Cin), column ((c/16 * 5 + tap/2) * 2 + tap%2) * 16 + c%16 (tap 9 = zeros);
- * `window` counted in 16-channel blocks of 9 taps (0 = default 2, i.e. k = 288 per accumulation window).  Cin % 16 == 0, Cout % 64 == 0. */
-int dinvk_conv_tc32_slab(const float* x, const float* weight, const float* bias, const float* res, const float* res2,
-                         float* out, int B, int H, int W, int Cin, int Cout, int act, int window, void* stream);
-/* head: NCHW fp32 image (+ optional constant noise-level channel) -> split16; weight (Cout, C + has_fill, 3, 3) fp32 */
-int dinvk_conv_tc32_head(const float* x_nchw, const float* weight, const float* bias, float* out, int B, int C, int H,
-                         int W, int Cout, float fill_scalar, const float* fill_batch, int has_fill, int act,
+ *   out = act(conv(x) + bias) + res + res2 (res/res2: same layout, kind 0 only).  Cin % (2 CH) == 0, Cout % 64 == 0. */
+int dinvk_conv_tc32(const void* x, const void* weight, const float* bias, const void* res, const void* res2, void* out,
+                    int B, int H, int W, int Cin, int Cout, int kind, int act, int window, int fmt, int* overflow_flag,
+                    void* stream);
+/* kind 0 with halo reuse (the body layers): one (16+8) x (16+2)-position activation slab per CH-channel block serves all
+ * nine taps.  weight: "slab pack" (2*Cout, 10*Cin), column ((c/CH * 5 + tap/2) * 2 + tap%2) * CH + c%CH (tap 9 = zeros);
+ * `window` counted in channel blocks of 9 taps (0 = default: one block = 18 full-scale MMA accumulations per window).  Cin % CH == 0, Cout % 64 == 0. */
+int dinvk_conv_tc32_slab(const void* x, const void* weight, const float* bias, const void* res, const void* res2,
+                         void* out, int B, int H, int W, int Cin, int Cout, int act, int window, int fmt,
+                         int* overflow_flag, void* stream);
+/* head: NCHW fp32 image (+ optional constant noise-level channel) -> split layout; weight (Cout, C + has_fill, 3, 3) fp32 */
+int dinvk_conv_tc32_head(const float* x_nchw, const float* weight, const float* bias, void* out, int B, int C, int H,
+                         int W, int Cout, float fill_scalar, const float* fill_batch, int has_fill, int act, int fmt,
+                         int* overflow_flag, void* stream);
+/* tail: split layout -> NCHW fp32, Cout <= 4;  out = conv3x3(x) + bias + add_nchw;  weight (Cout, Cin, 3, 3) fp32;
+ * NaN everywhere if *overflow_flag is set */
+int dinvk_conv_tc32_tail(const void* x, const float* weight, const float* bias, const float* add_nchw,
+                         float* out_nchw, int B, int H, int W, int Cin, int Cout, int fmt, const int* overflow_flag,
                          void* stream);
-/* tail: split16 -> NCHW fp32, Cout <= 4;  out = conv3x3(x) + bias + add_nchw;  weight (Cout, Cin, 3, 3) fp32 */
-int dinvk_conv_tc32_tail(const float* x, const float* weight, const float* bias, const float* add_nchw,
-                         float* out_nchw, int B, int H, int W, int Cin, int Cout, void* stream);
-/* layout converters split16 <-> NCHW fp32 (C % 16 == 0) */
-int dinvk_split16_to_nchw(const float* in, float* out, int B, int C, int H, int W, void* stream);
-int dinvk_nchw_to_split16(const float* in, float* out, int B, int C, int H, int W, void* stream);
+/* layout converters split <-> NCHW fp32 (C % CH == 0) */
+int dinvk_split16_to_nchw(const void* in, float* out, int B, int C, int H, int W, int fmt, void* stream);
+int dinvk_nchw_to_split16(const float* in, void* out, int B, int C, int H, int W, int fmt, void* stream);
 
 #ifdef __cplusplus
 }
