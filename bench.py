@@ -9,8 +9,8 @@
 
 cfg2 (the configuration the metric is quoted on): one "step" = one PnP-PGD iteration over the whole batch — fused L2 data
 step z = x - gamma (A^T A x - A^T y), then x = DRUNet(z, sigma) — through the package's public optimiser API
-(deepinv_b200.optim.PGD.single_iteration).  The denoiser runs at precision="tc32" (3 x TF32 split operands on tcgen05,
-fp32-grade: whole-network error < 1e-5 against the fp32 reference); the line also carries the error of the TIMED
+(deepinv_b200.optim.PGD.single_iteration).  The denoiser runs at precision="tc32h" (3 x FP16 split operands on tcgen05:
+22-bit operands, fp32-grade: whole-network error < 1e-5 against the fp32 reference; "tc32" = the TF32 variant); the line also carries the error of the TIMED
 configuration's K-iteration result against the fp32 CUDA-core path and against the oracle (`parity`), the throughput of the
 fp32 CUDA-core path (`value_fp32`) and of the bf16 tensor-core path with ITS error (`bf16`), per-operator roofline
 fractions with full-size errors against the oracle (`operators`), `cpu_baseline`, clocks sampled during the timed region.
@@ -475,6 +475,8 @@ def run_cfg2(args, world, rank, dev, peaks):
         launches0 = lib.dinvk_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
+        if os.environ.get("DINVK_BENCH_PROFILE"):  # `ncu --profile-from-start off`: only the timed region is captured
+            torch.cuda.profiler.start()
         t_w0 = ClockSampler.now()
         e0.record()
         if graphed is not None:
@@ -483,12 +485,15 @@ def run_cfg2(args, world, rank, dev, peaks):
             for it in range(args.steps):
                 X = iteration(X, it)
             x_hat = X["est"][0]
+        gathered = None
         if world > 1:  # the only collective of the path: gather the final reconstructions
             gathered = torch.empty(world * BATCH, 2, H, W, device=dev)
             dist.all_gather_into_tensor(gathered, x_hat.contiguous())
         e1.record()
         torch.cuda.synchronize()
         t_w1 = ClockSampler.now()
+        if os.environ.get("DINVK_BENCH_PROFILE"):
+            torch.cuda.profiler.stop()
         ms_total = e0.elapsed_time(e1)
         x_hat = x_hat.clone()
         launches = lib.dinvk_launch_count() - launches0
@@ -511,6 +516,25 @@ def run_cfg2(args, world, rank, dev, peaks):
         ms_step = ms_total / args.steps
         images_per_step = BATCH * world
         value = (images_per_step / c["batch"]) * 1000.0 / ms_step  # iterations/s in units of 64-image batches
+
+        # ---- strong scaling: the gathered batch must equal what ONE GPU computes for the whole global batch ---------------
+        shard_check = None
+        if args.verify_shards and world > 1 and args.scaling == "strong":
+            if rank == 0:
+                gen1 = torch.Generator().manual_seed(1234)
+                xg = torch.randn(c["batch"], 2, H, W, generator=gen1)
+                mg = cartesian_mask(c["batch"], H, W, 4, seed=0)
+                pg = dinv.physics.MRI(mask=mg.to(dev), img_size=(2, H, W), device=dev)
+                yg = pg.A(xg.to(dev))
+                Xg = algo.init_iterate_fn(yg, pg)
+                for it in range(args.steps):
+                    Xg = algo.single_iteration(Xg, it, yg, pg)
+                ref_all = Xg["est"][0]
+                shard_check = {"torch_equal": bool(torch.equal(gathered, ref_all)), "max_abs_diff": float((gathered - ref_all).abs().max()),
+                               "what": f"all_gather of {world} shards of {BATCH} images vs the same {c['batch']} images on rank 0 alone, "
+                                       f"{args.steps} iterations (kernels are batch-independent and deterministic)"}
+                del pg, yg, Xg, ref_all
+            dist.barrier()
 
         # ---- e2e: host buffers in, host buffer out, every step ------------------------------------
         xh = x_hat.cpu().pin_memory()
@@ -554,8 +578,8 @@ def run_cfg2(args, world, rank, dev, peaks):
         d2h = out_pin.numel() * 4
 
         # ---- rank 0: parity of the timed configuration, other precisions, rooflines, operators -------------------
-        parity = roof = ops_report = den_report = fp32_report = bf16_report = None
-        if rank == 0:
+        parity = roof = ops_report = den_report = fp32_report = bf16_report = other_report = None
+        if rank == 0 and not args.lean:
             from deepinv_b200 import ops as dops
             from oracle import ref_ops as R
 
@@ -599,6 +623,21 @@ def run_cfg2(args, world, rank, dev, peaks):
             fp32_report = {"value": (BATCH / c["batch"]) * 1000.0 / ms32, "unit": "it/s", "ms_per_step": ms32, "steps": 2,
                            "what": "the same iteration with the fp32 CUDA-core denoiser (precision='fp32'), eager, this rank's batch"}
             del d32, al32, Xf
+            other_report = None
+            if args.precision in ("tc32", "tc32h"):  # the other fp32-grade format, same iteration, eager
+                oprec = "tc32" if args.precision == "tc32h" else "tc32h"
+                torch.manual_seed(0)
+                dox = dinv.models.DRUNet(in_channels=2, out_channels=2, pretrained=None, precision=oprec).to(dev).eval()
+                dox.load_state_dict(den.state_dict())
+                alo = PGD(data_fidelity=L2(), prior=PnP(dox), stepsize=STEPSIZE, sigma_denoiser=SIGMA_DEN, max_iter=2, early_stop=False)
+                Xo = {"est": (x_init.clone(), x_init.clone()), "aty": None}
+                Xo = alo.single_iteration(Xo, 0, y, physics)
+                mso = time_cuda(lambda: alo.single_iteration(Xo, 0, y, physics), 3, warmup=1)
+                xo_k = run_precision(oprec, nchk, args.steps)
+                other_report = {"precision": oprec, "value": (BATCH / c["batch"]) * 1000.0 / mso, "unit": "it/s", "ms_per_step": mso,
+                                "rel_l2_of_K_iteration_result_vs_fp32_path": rel(xo_k, ref32), "images": nchk,
+                                "what": "tc32 = 3 x TF32 (any fp32 range), tc32h = 3 x FP16 (|activations| < 65504, loud overflow); eager loop"}
+                del dox, alo, Xo
             if args.precision != "bf16":
                 torch.manual_seed(0)
                 d16 = dinv.models.DRUNet(in_channels=2, out_channels=2, pretrained=None, precision="bf16").to(dev).eval()
@@ -627,24 +666,28 @@ def run_cfg2(args, world, rank, dev, peaks):
                 traffic = tj.get(args.precision, {}).get("dram_bytes_per_launch") if isinstance(tj.get(args.precision), dict) else None
                 if traffic is None and args.precision == "bf16":
                     traffic = tj.get("dram_bytes_per_launch")
-            if args.precision == "tc32":
+            if args.precision in ("tc32", "tc32h"):
                 from deepinv_b200.models.tc_engine import _pack3x3_slab_tc32
 
-                xa = dops.nchw_to_split16(torch.randn(BATCH, C, H, W, device=dev).abs_())
-                ra = dops.nchw_to_split16(torch.randn(BATCH, C, H, W, device=dev))
-                wa = _pack3x3_slab_tc32(torch.randn(C, C, 3, 3, device=dev) / (3 * C ** 0.5))
+                fmt = 1 if args.precision == "tc32h" else 0
+                xa = dops.nchw_to_split16(torch.randn(BATCH, C, H, W, device=dev).abs_(), fmt)
+                ra = dops.nchw_to_split16(torch.randn(BATCH, C, H, W, device=dev), fmt)
+                wa = _pack3x3_slab_tc32(torch.randn(C, C, 3, 3, device=dev) / (3 * C ** 0.5), fmt)
                 ms_k = time_cuda(lambda: dops.conv_tc32_slab(xa, wa, C, res=ra), 10, warmup=3)
-                bytes_k = 3 * BATCH * H * W * C * 8 + wa.numel() * 4
-                exec_tflops = 3 * gflop_k / ms_k            # three tf32 MMAs per fp32 product
-                tf32_peak = peaks["bf16_tflops"] / 2        # same tensor pipe, K = 8 instead of 16 per instruction
+                bytes_k = 3 * BATCH * H * W * C * 2 * xa.element_size() + wa.numel() * wa.element_size()
+                exec_tflops = 3 * gflop_k / ms_k            # three narrow MMAs per fp32 product
+                # tf32: K = 8 per instruction on the pipe that does K = 16 in bf16 / fp16 -> half the measured bf16 rate
+                tf32_peak = peaks["bf16_tflops"] / (1 if fmt else 2)
                 t_tensor, t_hbm = 3 * gflop_k / tf32_peak, bytes_k / 1e6 / peaks["hbm_gbs"]
                 roof = {"bound": "tensor" if t_tensor >= t_hbm else "hbm",
-                        "kernel": "conv_tc32_slab_kernel: 3x3 conv 64->64, 64x256x256, 3 x TF32 -> fp32 (TMEM + register drain), + residual",
+                        "kernel": f"conv_tc32_slab_kernel<{'FmtF16' if fmt else 'FmtTF32'}>: 3x3 conv 64->64, 64x256x256, 3 x "
+                                  f"{'FP16' if fmt else 'TF32'} -> fp32 (TMEM + register drain), + residual",
                         "achieved": exec_tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": exec_tflops / tf32_peak,
                         "frac_hbm": bytes_k / 1e6 / ms_k / peaks["hbm_gbs"], "traffic": traffic,
-                        "peak_source": peaks["source"] + " bf16 burst / 2 (dense tf32 rate of the same pipe)",
+                        "peak_source": peaks["source"] + (" bf16 burst (kind::f16 runs at the bf16 rate)" if fmt else
+                                                         " bf16 burst / 2 (dense tf32 rate of the same pipe)"),
                         "us_per_launch": ms_k * 1e3, "algorithmic_gflop_per_launch": gflop_k,
-                        "executed_tf32_gflop_per_launch": 3 * gflop_k, "algorithmic_bytes_per_launch": bytes_k,
+                        "executed_mma_gflop_per_launch": 3 * gflop_k, "algorithmic_bytes_per_launch": bytes_k,
                         "fp32_equivalent_TFLOPs": gflop_k / ms_k}
                 del xa, ra, wa
             elif args.precision == "bf16":
@@ -707,7 +750,7 @@ def run_cfg2(args, world, rank, dev, peaks):
     line = None
     if rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not args.lean:
             threads, tried = best_cpu_threads()
             cpu_pgd_iteration_seconds(REF_SAMPLE, threads)
             t = cpu_pgd_iteration_seconds(REF_SAMPLE, threads)
@@ -716,7 +759,8 @@ def run_cfg2(args, world, rank, dev, peaks):
                    "host_cores_logical": hi["logical"], "host_cores_physical": hi["physical"], "threads_tried_s_per_4_images": tried,
                    "sample": f"one PnP-PGD iteration of the oracle on {REF_SAMPLE} of the {c['batch']} images ({t:.2f} s measured, second of "
                              f"two runs), scaled x{c['batch'] / REF_SAMPLE:g} per image; {threads} threads (fastest on a 4-image probe)"}
-        dtype = {"tc32": "f32 (3 x TF32 split-operand tensor-core GEMMs, fp32 accumulate) + f32 operators",
+        dtype = {"tc32h": "f32 (3 x FP16 split-operand tensor-core GEMMs: 22-bit operands, fp32 accumulate) + f32 operators",
+                 "tc32": "f32 (3 x TF32 split-operand tensor-core GEMMs, fp32 accumulate) + f32 operators",
                  "bf16": "bf16 denoiser GEMMs (fp32 accumulate) + f32 operators", "fp32": "f32"}[args.precision]
         line = {
             "metric": c["metric"], "value": value, "unit": c["unit"], "n_gpus": world, "steps": args.steps,
@@ -729,8 +773,10 @@ def run_cfg2(args, world, rank, dev, peaks):
                     "d2h_bytes_per_step": d2h, "steps": n_e2e, "mode": e2e_mode},
             "gpu_launches": int(launches),
             "clocks": clk,
+            "shard_check": shard_check,
             "parity": parity,
             "value_fp32": fp32_report,
+            "other_fp32_grade_format": other_report,
             "bf16": bf16_report,
             "roofline": roof,
             "denoiser": den_report,
@@ -853,7 +899,7 @@ def run_other(args, world, rank, dev, peaks):
     return {
         "metric": c["metric"], "value": value, "unit": c["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 (tc32 denoiser GEMMs)" if args.precision == "tc32" else args.precision, "data": "synthetic",
+        "dtype": f"f32 ({args.precision} denoiser GEMMs)" if args.precision in ("tc32", "tc32h") else args.precision, "data": "synthetic",
         "config": bench_config(args.config, world, "weak"),
         "details": {"denoiser_precision": args.precision, "eager_loop": True, **extra},
         "e2e": {"value": world * per_step_units * 1000.0 / ms_e2e, "unit": c["unit"], "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -873,8 +919,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ.pop("NCCL_DEBUG")  # keep stdout to the one JSON line (NCCL prints its version banner there at VERSION / WARN)
         dist.init_process_group("nccl", device_id=dev)
     peaks = measured_peaks()
     if args.config == "cfg2":
@@ -895,10 +941,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--precision", default=os.environ.get("DINVK_BENCH_PRECISION", "tc32"), choices=["fp32", "bf16", "tc32"])
+    ap.add_argument("--precision", default=os.environ.get("DINVK_BENCH_PRECISION", "tc32h"), choices=["fp32", "bf16", "tc32", "tc32h"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip everything that runs the oracle on the host")
     ap.add_argument("--no-operators", action="store_true", help="skip the cfg3/cfg4/cfg5 operator table")
     ap.add_argument("--no-graph", action="store_true", help="time the eager Python loop instead of CUDA-graph replays")
+    ap.add_argument("--verify-shards", action="store_true", help="strong scaling: compare the gathered result with rank 0 computing the whole batch")
+    ap.add_argument("--lean", action="store_true", help="skip the rank-0 extras (parity, other precisions, rooflines, operators, CPU baseline)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
