@@ -18,8 +18,10 @@
 // A CTA computes a 64x64 output tile; each thread owns 4x4 outputs and slides a 4-wide register window
 // along the filter row (one 128-bit shared load per 16 FMAs per row).  Filters up to ~128x128 fit.
 #include "common.cuh"
+#include "tma_tile.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace dinvk {
 
@@ -29,6 +31,7 @@ struct BlurParams {
   int C, Hin, Win, Hout, Wout, h, w, wp;  // wp = w rounded up to a multiple of 4
   int FB, FC, flip, off_i, off_j, map;    // map: 0 zeros, 1 circular, 2 replicate, 3 reflect
   int PW;                                 // patch row pitch (floats)
+  int shift;                              // zero taps prepended to every filter row (0..3): makes off_j a multiple of 4
   int tiles_x;
 };
 
@@ -41,30 +44,48 @@ __device__ __forceinline__ int map_index(int a, int n, int mode, bool& ok) {
   return ok ? a : 0;
 }
 
-__global__ void __launch_bounds__(256) blur_corr_kernel(const float* __restrict__ in, const float* __restrict__ filt,
+__global__ void __launch_bounds__(256) blur_corr_kernel(const __grid_constant__ tt::TileMap tmap, int use_tma,
+                                                        const float* __restrict__ in, const float* __restrict__ filt,
                                                         float* __restrict__ out, BlurParams P) {
   DINVK_DYN_SMEM(float, smem);
   float* ks = smem;                 // [h][wp]
-  float* patch = smem + P.h * P.wp; // [(BL_T + h - 1)][PW]
+  // [(BL_T + h - 1)][PW], 128-byte aligned at run time (TMA destination; the launch reserves the slack)
+  float* patch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem + P.h * P.wp) + 127) & ~static_cast<uintptr_t>(127));
   const int tid = threadIdx.x;
   const int bc = blockIdx.y;
   const int b = bc / P.C, c = bc - b * P.C;
   const int i0 = (blockIdx.x / P.tiles_x) * BL_T, j0 = (blockIdx.x % P.tiles_x) * BL_T;
   const float* f = filt + ((long long)(P.FB == 1 ? 0 : b) * P.FC + (P.FC == 1 ? 0 : c)) * P.h * P.w;
   for (int idx = tid; idx < P.h * P.wp; idx += 256) {
-    const int u = idx / P.wp, v = idx - u * P.wp;
+    const int u = idx / P.wp, v = idx - u * P.wp - P.shift;   // `shift` leading zero taps: see launch_corr
     float val = 0.f;
-    if (v < P.w) val = P.flip ? __ldg(f + (P.h - 1 - u) * P.w + (P.w - 1 - v)) : __ldg(f + u * P.w + v);
+    if (v >= 0 && v < P.w) val = P.flip ? __ldg(f + (P.h - 1 - u) * P.w + (P.w - 1 - v)) : __ldg(f + u * P.w + v);
     ks[idx] = val;
   }
   const int PH = BL_T + P.h - 1;
   const float* src = in + (long long)bc * P.Hin * P.Win;
-  for (int idx = tid; idx < PH * P.PW; idx += 256) {
-    const int pr = idx / P.PW, pc = idx - pr * P.PW;
-    bool okr, okc;
-    const int gi = map_index(i0 + pr + P.off_i, P.Hin, P.map, okr);
-    const int gj = map_index(j0 + pc + P.off_j, P.Win, P.map, okc);
-    patch[idx] = (okr && okc) ? __ldg(src + (long long)gi * P.Win + gj) : 0.f;
+  // The input tile + halo.  Zero padding (and every tile whose halo stays inside the image, whatever the padding rule) is ONE
+  // tensor-map box load: the copy engine zero-fills out-of-range elements.  Tiles that touch the border under circular /
+  // replicate / reflect padding resolve the rule in index space with the cooperative loop.
+  bool by_tma = false;
+#ifndef DINVK_EMUL
+  if (use_tma) {
+    const int r0 = i0 + P.off_i, c0 = j0 + P.off_j;
+    by_tma = (P.map == 0) || (r0 >= 0 && r0 + PH <= P.Hin && c0 >= 0 && c0 + P.PW <= P.Win);
+    if (by_tma) {   // (uniform over the CTA)
+      __shared__ __align__(8) uint64_t tile_bar;
+      tt::stage_tile(patch, &tmap, &tile_bar, c0, r0, bc, (uint32_t)(PH * P.PW * 4));
+    }
+  }
+#endif
+  if (!by_tma) {
+    for (int idx = tid; idx < PH * P.PW; idx += 256) {
+      const int pr = idx / P.PW, pc = idx - pr * P.PW;
+      bool okr, okc;
+      const int gi = map_index(i0 + pr + P.off_i, P.Hin, P.map, okr);
+      const int gj = map_index(j0 + pc + P.off_j, P.Win, P.map, okc);
+      patch[idx] = (okr && okc) ? __ldg(src + (long long)gi * P.Win + gj) : 0.f;
+    }
   }
   __syncthreads();
 
@@ -152,17 +173,28 @@ __global__ void __launch_bounds__(256) blur_fold_kernel(const float* __restrict_
 static int run_corr(const float* in, const float* filt, float* out, int B, int C, int Hin, int Win, int Hout, int Wout,
                     int FB, int FC, int h, int w, int flip, int off_i, int off_j, int map, void* stream) {
   BlurParams P;
-  P.C = C; P.Hin = Hin; P.Win = Win; P.Hout = Hout; P.Wout = Wout; P.h = h; P.w = w; P.wp = (w + 3) & ~3;
+  // A tensor-map box has to start on a 16-byte boundary of the image row.  Tiles start at multiples of 64 columns, so the patch
+  // origin j0 + off_j is aligned iff off_j is a multiple of 4: prepend shift = off_j mod 4 zero taps to the filter rows and move
+  // the origin left by as much (out[j] = sum_v ks'[v] in[j + v + off_j - shift], ks'[v] = ks[v - shift]): same sums, aligned box.
+  const int shift = ((off_j % 4) + 4) % 4;
+  off_j -= shift;
+  P.shift = shift;
+  P.C = C; P.Hin = Hin; P.Win = Win; P.Hout = Hout; P.Wout = Wout; P.h = h; P.w = w; P.wp = (w + shift + 3) & ~3;
   P.FB = FB; P.FC = FC; P.flip = flip; P.off_i = off_i; P.off_j = off_j; P.map = map;
   P.PW = BL_T + P.wp + 4;  // window reads reach column tx*4 + wp + 3
   P.tiles_x = ceil_div(Wout, BL_T);
-  const size_t smem = sizeof(float) * ((size_t)h * P.wp + (size_t)(BL_T + h - 1) * P.PW);
+  const size_t smem = sizeof(float) * ((size_t)h * P.wp + (size_t)(BL_T + h - 1) * P.PW) + 128;
   if (smem > 200 * 1024) return set_error(DINVK_EUNSUPPORTED, "blur: filter %dx%d too large for the tiled kernel", h, w);
   int rc = allow_smem(blur_corr_kernel, smem);
   if (rc) return rc;
   const long long tiles = (long long)P.tiles_x * ceil_div(Hout, BL_T);
   if ((long long)B * C > 65535 || tiles > 2147483647LL) return set_error(DINVK_EINVAL, "blur: grid too large");
-  DINVK_LAUNCH(blur_corr_kernel, dim3((unsigned)tiles, B * C), dim3(256), smem, stream, in, filt, out, P);
+  tt::TileMap tmap = tt::TileMap();
+  int use_tma = 0;
+#ifndef DINVK_EMUL
+  if (!getenv("DINVK_NO_TMA_STAGING")) use_tma = tt::make_map_f32(&tmap, in, Win, Hin, B * C, P.PW, BL_T + h - 1) ? 1 : 0;
+#endif
+  DINVK_LAUNCH(blur_corr_kernel, dim3((unsigned)tiles, B * C), dim3(256), smem, stream, tmap, use_tma, in, filt, out, P);
   return DINVK_POST_LAUNCH();
 }
 

@@ -19,6 +19,7 @@
 // zeros outside.  Sinograms are stored ANGLE-major (BC, A, P): this is
 //   the memory the reference returns as the transposed view (B,C,P,A) (radon.py:291-293).
 #include "common.cuh"
+#include "tma_tile.cuh"
 #ifndef DINVK_EMUL
 #include <cstdlib>
 #endif
@@ -239,12 +240,16 @@ __global__ void __launch_bounds__(256) iradon_bp_kernel(const float* __restrict_
 // Sample geometry is evaluated with the same fp32 formulas as above.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int RT = 64;    // tile edge (pixels)
-constexpr int RTW = 68;   // staged row pitch / box width (floats; 272 B rows keep the TMA box a multiple of 16 B)
+constexpr int RTW = 76;   // staged row pitch / box width (floats): columns ox-3 .. ox+72 (76 % 32 = 12: rows 12 banks apart, like the 4 of the first 68-float pitch; 72 costs 8 % in bank conflicts) — a tensor-map box must start on a 16-byte
+                          // boundary of the image row, and ox - 3 = 64 tx - 4 is a multiple of 4 (the first attempts, round 1 and
+                          // this round, started the box at ox = 64 tx - 1 and trapped as an illegal instruction)
+constexpr int RXO = 3;    // index of column ox inside a staged row
 constexpr int RTH = 66;   // staged rows
 constexpr int RT_THREADS = 128;
 
 template <bool ADJ>
-__global__ void __launch_bounds__(RT_THREADS) radon_tiled_kernel(const float* __restrict__ src,
+__global__ void __launch_bounds__(RT_THREADS) radon_tiled_kernel(const __grid_constant__ tt::TileMap tmap, int use_tma,
+                                                                 const float* __restrict__ src,
                                                                  float* __restrict__ out, RadonGeom G, const float* __restrict__ cos_t,
                                                                  const float* __restrict__ sin_t, float scale, int tps) {
 #ifdef DINVK_EMUL
@@ -256,9 +261,12 @@ __global__ void __launch_bounds__(RT_THREADS) radon_tiled_kernel(const float* __
   // (or 64-bit) atomicAdd on shared memory is a compare-and-swap loop (SASS ATOMS.CAST.SPIN: the first version's transpose took
   // 2x the forward), a 32-bit integer add without return value is ONE fire-and-forget ATOMS.ADD, and integer sums do not
   // depend on the order of the adds (the tile's result is deterministic)
-  float* T = reinterpret_cast<float*>(rt_raw);
-  int* TI = reinterpret_cast<int*>(rt_raw);
-  long long* s_cs = reinterpret_cast<long long*>(rt_raw + (((size_t)RTH * RTW * 4 + 15) & ~(size_t)15));  // cos[A], sin[A], Q45
+  // (the tile is the destination of a tensor-map copy: 128-byte aligned at run time — the declared alignment of a dynamic
+  // shared array is not honoured beyond 16 bytes when the kernel also has static shared variables; the launch reserves the slack)
+  unsigned char* rt_al = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(rt_raw) + 127) & ~static_cast<uintptr_t>(127));
+  float* T = reinterpret_cast<float*>(rt_al);
+  int* TI = reinterpret_cast<int*>(rt_al);
+  long long* s_cs = reinterpret_cast<long long*>(rt_al + (((size_t)RTH * RTW * 4 + 15) & ~(size_t)15));  // cos[A], sin[A], Q45
   __shared__ unsigned s_absmax;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ty = blockIdx.x / tps, tx = blockIdx.x - ty * tps;
@@ -271,12 +279,21 @@ __global__ void __launch_bounds__(RT_THREADS) radon_tiled_kernel(const float* __
   const int yr = (ty == tps - 1) ? (G.W - 1 - oy) : (RT - 1);
 
   if (!ADJ) {
-    // stage the tile once (coalesced rows; explicit zeros outside the image = the reference's zero padding)
-    const float* img = src + (long long)bc * G.W * G.W;
-    for (int e = tid; e < RTH * RTW; e += RT_THREADS) {
-      const int uy = e / RTW, ux = e - uy * RTW;
-      const int x = ox + ux, y = oy + uy;
-      T[e] = (x >= 0 && x < G.W && y >= 0 && y < G.W) ? __ldg(img + (long long)y * G.W + x) : 0.f;
+    // stage the tile once; zeros outside the image = the reference's zero padding (radon.py:262-266)
+#ifndef DINVK_EMUL
+    if (use_tma) {
+      // ONE tensor-map box load (68 x 66 fp32, origin (ox, oy) may be -1): the copy engine zero-fills what lies outside the image
+      __shared__ __align__(8) uint64_t tile_bar;
+      tt::stage_tile(T, &tmap, &tile_bar, ox - RXO, oy, bc, RTH * RTW * 4);
+    } else
+#endif
+    {
+      const float* img = src + (long long)bc * G.W * G.W;
+      for (int e = tid; e < RTH * RTW; e += RT_THREADS) {
+        const int uy = e / RTW, ux = e - uy * RTW;
+        const int x = ox - RXO + ux, y = oy + uy;
+        T[e] = (x >= 0 && x < G.W && y >= 0 && y < G.W) ? __ldg(img + (long long)y * G.W + x) : 0.f;
+      }
     }
   } else {
     for (int e = tid; e < RTH * RTW; e += RT_THREADS) TI[e] = 0;
@@ -288,7 +305,7 @@ __global__ void __launch_bounds__(RT_THREADS) radon_tiled_kernel(const float* __
     if (G.circle) {  // inscribed-disc mask of the image (radon.py:268-279), applied once to the staged tile
       for (int e = tid; e < RTH * RTW; e += RT_THREADS) {
         const int uy = e / RTW, ux = e - uy * RTW;
-        const int x = ox + ux, y = oy + uy;
+        const int x = ox - RXO + ux, y = oy + uy;
         const float ax = 2.0f * (float)x / (float)(G.W - 1) - 1.0f, ay = 2.0f * (float)y / (float)(G.W - 1) - 1.0f;
         if (!(ax * ax + ay * ay <= 1.0f)) T[e] = 0.f;
       }
@@ -367,11 +384,11 @@ __global__ void __launch_bounds__(RT_THREADS) radon_tiled_kernel(const float* __
         const unsigned ux = (unsigned)(X0 - xl), uy = (unsigned)(Y0 - yl);
         if (ux > (unsigned)xr || uy > (unsigned)yr) continue;
         if (!ADJ) {
-          const float* tp = T + uy * RTW + ux;
+          const float* tp = T + uy * RTW + ux + RXO;
           acc += tp[0] * (wx0 * wy0) + tp[1] * (wx1 * wy0) + tp[RTW] * (wx0 * wy1) + tp[RTW + 1] * (wx1 * wy1);
           any = true;
         } else {
-          int* tp = TI + uy * RTW + ux;
+          int* tp = TI + uy * RTW + ux + RXO;
           atomicAdd(tp, __float2int_rn(yv * (wx0 * wy0)));
           atomicAdd(tp + 1, __float2int_rn(yv * (wx1 * wy0)));
           atomicAdd(tp + RTW, __float2int_rn(yv * (wx0 * wy1)));
@@ -388,7 +405,7 @@ __global__ void __launch_bounds__(RT_THREADS) radon_tiled_kernel(const float* __
       const int uy = e / RTH, ux = e - uy * RTH;
       const int x = ox + ux, y = oy + uy;
       if (x < 0 || x >= G.W || y < 0 || y >= G.W) continue;
-      float v = (float)((double)TI[uy * RTW + ux] * fx_inv);
+      float v = (float)((double)TI[uy * RTW + ux + RXO] * fx_inv);
       if (G.circle) {
         const float ax = 2.0f * (float)x / (float)(G.W - 1) - 1.0f, ay = 2.0f * (float)y / (float)(G.W - 1) - 1.0f;
         if (!(ax * ax + ay * ay <= 1.0f)) v = 0.f;
@@ -406,16 +423,21 @@ static bool tiled_ok(const void* img, int W, int A) {
 static int launch_tiled(bool adj, const float* x_img, const float* sino_in, float* out, int BC, const RadonGeom& G, const float* cos_t,
                         const float* sin_t, float scale, void* stream) {
   const int tps = (G.W + RT - 1) / RT;
-  const size_t smem = (size_t)RTH * RTW * 4 + 16 + (size_t)(2 * G.A + 2) * 8;
+  const size_t smem = (size_t)RTH * RTW * 4 + 16 + (size_t)(2 * G.A + 2) * 8 + 128;
   const size_t out_bytes = adj ? (size_t)BC * G.W * G.W * 4 : (size_t)BC * G.A * G.P * 4;
   if (cudaMemsetAsync(out, 0, out_bytes, (cudaStream_t)stream) != cudaSuccess) return set_error(DINVK_ECUDA, "radon: memset failed");
   int rc;
+  tt::TileMap tmap = tt::TileMap();
+  int use_tma = 0;
+#ifndef DINVK_EMUL
+  if (!adj && !getenv("DINVK_NO_TMA_STAGING")) use_tma = tt::make_map_f32(&tmap, x_img, G.W, G.W, BC, RTW, RTH) ? 1 : 0;
+#endif
   if (adj) {
     if ((rc = allow_smem(radon_tiled_kernel<true>, smem))) return rc;
-    DINVK_LAUNCH(radon_tiled_kernel<true>, dim3(tps * tps, BC), dim3(RT_THREADS), smem, stream, sino_in, out, G, cos_t, sin_t, scale, tps);
+    DINVK_LAUNCH(radon_tiled_kernel<true>, dim3(tps * tps, BC), dim3(RT_THREADS), smem, stream, tmap, use_tma, sino_in, out, G, cos_t, sin_t, scale, tps);
   } else {
     if ((rc = allow_smem(radon_tiled_kernel<false>, smem))) return rc;
-    DINVK_LAUNCH(radon_tiled_kernel<false>, dim3(tps * tps, BC), dim3(RT_THREADS), smem, stream, x_img, out, G, cos_t, sin_t, scale, tps);
+    DINVK_LAUNCH(radon_tiled_kernel<false>, dim3(tps * tps, BC), dim3(RT_THREADS), smem, stream, tmap, use_tma, x_img, out, G, cos_t, sin_t, scale, tps);
   }
   return DINVK_POST_LAUNCH();
 }
