@@ -380,7 +380,9 @@ def ramp_filter(sino_am) -> torch.Tensor:
         two = torch.cat([sino_am.reshape(1, P), torch.zeros(1, P, device=dev)], 0)
         return ramp_filter(two.reshape(1, 1, 2, P))[..., :1, :].reshape(sino_am.shape)
     out = torch.empty_like(sino_am)
-    check(get_lib().dinvk_ramp_filter(_p(sino_am), _p(out), rows, P, None, 0, _stream(dev)))
+    lib = get_lib()
+    ws = workspace(dev, int(lib.dinvk_ramp_filter_workspace_bytes(rows, P)), "ramp")
+    check(lib.dinvk_ramp_filter(_p(sino_am), _p(out), rows, P, _p(ws), ws.numel(), _stream(dev)))
     return out
 
 

@@ -119,7 +119,13 @@ int dinvk_fft_prepare(int n, int centered);
 /* Ramp filter of filtered back-projection (deepinv/physics/functional/radon.py:79-162): `rows` (>= 2)
  * signals of length N (contiguous, one per row — the angle-major sinogram memory (B*C*A, P)), each
  * zero-padded to L = max(64, 2^ceil(log2(2N))), multiplied by 2*rfft(f) with f the reference's spatial ramp
- * kernel (built by the library in double from the closed form, :151-162), inverse-transformed, cropped to N. */
+ * kernel (built by the library in double from the closed form, :151-162), inverse-transformed, cropped to N.
+ * Default (N <= 8192): the SAME linear filter evaluated exactly in the spatial domain with fp64 accumulation (the padded
+ * circular convolution is a linear one on the N valid samples and the kernel has a closed form) — the result is the filter to
+ * fp32 rounding, where an fp32 FFT leaves ~4e-6 (a sinogram row is ~100x larger than its filtered version).  DINVK_RAMP_FFT=1
+ * selects the FFT form; there, with a workspace of dinvk_ramp_filter_workspace_bytes(rows, N) the row means are removed before the fp32 transform and their
+ * exact response (mean x filter(box), built in double) is added back: the result is the same linear filter, an order of
+ * magnitude closer to its exact value (the transform's rounding noise scales with the norm of what it is given). */
 size_t dinvk_ramp_filter_workspace_bytes(int rows, int N);
 int dinvk_ramp_filter(const float* sino, float* out, int rows, int N,
                       void* workspace, size_t workspace_bytes, void* stream);

@@ -324,7 +324,9 @@ def ramp_filter(y: torch.Tensor) -> torch.Tensor:
     """AbstractFilter.forward + RampFilter along dim -2 of (B,C,N,A) (radon.py:79-173)"""
     N = y.shape[-2]
     L = max(64, int(2 ** (2 * torch.tensor(N)).float().log2().ceil()))
-    n = torch.cat([torch.arange(1, L / 2 + 1, 2), torch.arange(L / 2 - 1, 0, -2)])
+    # (the index vector takes the dtype of y: in the fp32 evaluation nothing changes, and an fp64 evaluation — the yardstick of
+    # the full-size parity tests — gets the kernel coefficients in fp64 instead of fp32-rounded ones)
+    n = torch.cat([torch.arange(1, L / 2 + 1, 2), torch.arange(L / 2 - 1, 0, -2)]).to(y.dtype)
     f = torch.zeros(L, dtype=y.dtype)
     f[0] = 0.25
     f[1::2] = -1 / (torch.pi * n) ** 2
