@@ -652,6 +652,107 @@ __global__ void __launch_bounds__(256) head_tc32_kernel(const HeadParams P) {
   if (bad && P.flag) atomicOr(P.flag, 1);
 }
 
+// HEAD for Cout = 64: lanes = output channels.  A warp owns 32 consecutive pixels of two image rows; lane l computes
+// channels (2l, 2l+1) of every pixel with its 2 * 9 * CT weights in registers.  The 3 x 3 x CT inputs of the 32 pixels
+// are loaded once (lane i holds column x0 + i of the three rows; lanes 0 / 1 also hold the two halo columns) and
+// broadcast by shuffles while the warp slides along the row.  A pixel's 64 channels leave as four coalesced
+// 64-byte (fp16) / 128-byte (tf32) segments: [hi | lo] of each channel block.  (The thread-per-pixel version above
+// stores 128 bytes per lane at a 256-byte stride and reads its weights through the shared-memory pipe: 0.9 ms.)
+template <class F, int CT>
+__global__ void __launch_bounds__(256) head64_tc32_kernel(const HeadParams P) {
+  using E = typename F::elem;
+  constexpr int R = 2;   // output rows per warp: rows y0, y0 + 1 share two of their three input rows (6 instead of 9 shuffles per pixel)
+  const int lane = threadIdx.x & 31;
+  const int segs = (P.W + 31) / 32, rows2 = (P.H + R - 1) / R;
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= (long long)P.B * rows2 * segs) return;
+  const int b = (int)(wid / ((long long)rows2 * segs)), rem = (int)(wid - (long long)b * rows2 * segs);
+  const int y0 = (rem / segs) * R, x0 = (rem % segs) * 32;
+  float w0[CT * 9], w1[CT * 9];
+#pragma unroll
+  for (int k = 0; k < CT * 9; ++k) {
+    w0[k] = __ldg(P.w + (long long)(2 * lane) * CT * 9 + k);
+    w1[k] = __ldg(P.w + (long long)(2 * lane + 1) * CT * 9 + k);
+  }
+  const float b0 = P.bias ? __ldg(P.bias + 2 * lane) : 0.f, b1 = P.bias ? __ldg(P.bias + 2 * lane + 1) : 0.f;
+  const float fillv = P.has_fill ? (P.fill_batch ? __ldg(P.fill_batch + b) : P.fill_scalar) : 0.f;
+  const long long HW = (long long)P.H * P.W;
+  const float* img = P.x + (long long)b * P.C * HW;
+  // mid[c][r]: column x0 + lane of input row y0 - 1 + r; edge[c][r]: lane 0 holds column x0 - 1, lane 1 column x0 + 32
+  float mid[CT][R + 2], edge[CT][R + 2];
+  const int xe = lane == 0 ? x0 - 1 : x0 + 32;
+#pragma unroll
+  for (int c = 0; c < CT; ++c)
+#pragma unroll
+    for (int r = 0; r < R + 2; ++r) {
+      const int yy = y0 + r - 1;
+      const bool rowin = yy >= 0 && yy < P.H;
+      const int xm = x0 + lane;
+      float m = 0.f, e = 0.f;
+      if (rowin && xm < P.W) m = c < P.C ? __ldg(img + (long long)c * HW + (long long)yy * P.W + xm) : fillv;
+      if (rowin && lane < 2 && xe >= 0 && xe < P.W) e = c < P.C ? __ldg(img + (long long)c * HW + (long long)yy * P.W + xe) : fillv;
+      mid[c][r] = m; edge[c][r] = e;
+    }
+  const int eo = ((2 * lane) / F::CH) * 2 * F::CH + (2 * lane) % F::CH;
+  E* orow = static_cast<E*>(P.out) + (((long long)b * P.H + y0) * P.W + x0) * 128 + eo;
+  const long long rstride = (long long)P.W * 128;
+  bool bad = false;
+  // sliding window of the three columns around pixel p
+  float cl[CT][R + 2], cc[CT][R + 2], cr[CT][R + 2], last[CT][R + 2];
+#pragma unroll
+  for (int c = 0; c < CT; ++c)
+#pragma unroll
+    for (int r = 0; r < R + 2; ++r) {
+      cl[c][r] = __shfl_sync(0xffffffffu, edge[c][r], 0);
+      cc[c][r] = __shfl_sync(0xffffffffu, mid[c][r], 0);
+      last[c][r] = __shfl_sync(0xffffffffu, edge[c][r], 1);
+    }
+  const int npx = min(32, P.W - x0);
+#pragma unroll 1
+  for (int p = 0; p < npx; ++p) {
+#pragma unroll
+    for (int c = 0; c < CT; ++c)
+#pragma unroll
+      for (int r = 0; r < R + 2; ++r) {
+        const float nm = __shfl_sync(0xffffffffu, mid[c][r], (p + 1) & 31);
+        cr[c][r] = p == 31 ? last[c][r] : nm;
+      }
+#pragma unroll
+    for (int ro = 0; ro < R; ++ro) {
+      float a0 = b0, a1 = b1;
+#pragma unroll
+      for (int c = 0; c < CT; ++c)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          a0 = fmaf(w0[c * 9 + ky * 3 + 0], cl[c][ro + ky], a0); a1 = fmaf(w1[c * 9 + ky * 3 + 0], cl[c][ro + ky], a1);
+          a0 = fmaf(w0[c * 9 + ky * 3 + 1], cc[c][ro + ky], a0); a1 = fmaf(w1[c * 9 + ky * 3 + 1], cc[c][ro + ky], a1);
+          a0 = fmaf(w0[c * 9 + ky * 3 + 2], cr[c][ro + ky], a0); a1 = fmaf(w1[c * 9 + ky * 3 + 2], cr[c][ro + ky], a1);
+        }
+      if (P.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+      if (y0 + ro < P.H) {
+        E* o = orow + ro * rstride + (long long)p * 128;
+        if constexpr (F::ID == 0) {
+          const float h0 = rna_tf32(a0), h1 = rna_tf32(a1);
+          *reinterpret_cast<float2*>(o) = make_float2(h0, h1);
+          *reinterpret_cast<float2*>(o + F::CH) = make_float2(a0 - h0, a1 - h1);
+        } else {
+          const __half2 h = __floats2half2_rn(a0, a1);
+          const float2 hf = __half22float2(h);
+          const __half2 l = __floats2half2_rn((a0 - hf.x) * 2048.0f, (a1 - hf.y) * 2048.0f);
+          bad |= !(fmaxf(fabsf(a0), fabsf(a1)) < 65000.0f);
+          *reinterpret_cast<__half2*>(o) = h;
+          *reinterpret_cast<__half2*>(o + F::CH) = l;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CT; ++c)
+#pragma unroll
+      for (int r = 0; r < R + 2; ++r) { cl[c][r] = cc[c][r]; cc[c][r] = cr[c][r]; }
+  }
+  if (bad && P.flag) atomicOr(P.flag, 1);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Network TAIL (CUDA cores): 3x3 convolution from C split16 channels to Cout <= 4 channels, fp32 NCHW output
 // (+ bias, + optional NCHW term: DnCNN's "+ x", dncnn.py:138).  A CTA stages the (32+2) x (8+2) halo tile as
@@ -733,6 +834,146 @@ __global__ void __launch_bounds__(256) tail_tc32_kernel(const TailParams P) {
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TAIL for C = 64 (every DRUNet / DnCNN of the reference): lanes = channels.  A warp owns a strip of WT = 16 / CO output
+// columns and walks TL_RC output rows downwards; lane l carries channels (2l, 2l+1): its 2 * 9 * CO weights stay in
+// registers for the whole kernel, an input pixel is ONE coalesced 256-byte (fp16) / 512-byte (tf32) row per warp, read
+// once per strip (no shared memory, no staging phase), and contributes to the 3 x 3 outputs around it.  The per-lane
+// partial sums of an output row (WT * CO = 16 values) are summed across the 32 lanes by a transposing butterfly
+// (8 + 4 + 2 + 1 + 1 shuffles: each step halves the values a lane keeps), after which lane 2v owns value v.
+// The first version (thread = pixel, halo tile and weights in shared memory: tail_tc32_kernel) spent 3 LDS.128 per
+// 8 FMAs and took 1.4 ms for 64 x 256^2; this one is bound by its 1152 FMAs per pixel.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TL_RC = 64;  // output rows per warp (the 2 * 9 * CO weight loads and the two halo rows are per warp)
+
+template <int N>
+__device__ __forceinline__ void halve_across(float (&a)[16], int upper, int offset) {
+#pragma unroll
+  for (int j = 0; j < N / 2; ++j) {
+    const float send = upper ? a[j] : a[j + N / 2];
+    const float keep = upper ? a[j + N / 2] : a[j];
+    a[j] = keep + __shfl_xor_sync(0xffffffffu, send, offset);
+  }
+}
+
+// input row r of the strip: the lane's two channels of the WT + 2 columns xs - 1 .. xs + WT (zero outside the image = the padding)
+template <class F, int WT>
+__device__ __forceinline__ void tail_load_row(const typename F::elem* img, bool rowin, int r, int xs, int W, float (&v0)[WT + 2],
+                                              float (&v1)[WT + 2]) {
+  using E = typename F::elem;
+#pragma unroll
+  for (int i = 0; i < WT + 2; ++i) {
+    const int x = xs - 1 + i;
+    v0[i] = 0.f; v1[i] = 0.f;
+    if (rowin && x >= 0 && x < W) {
+      const E* q = img + ((long long)r * W + x) * 128;
+      if constexpr (F::ID == 0) {
+        const float2 h = __ldg(reinterpret_cast<const float2*>(q)), l = __ldg(reinterpret_cast<const float2*>(q + F::CH));
+        v0[i] = h.x + l.x; v1[i] = h.y + l.y;
+      } else {
+        const uint32_t hu = __ldg(reinterpret_cast<const uint32_t*>(q)), lu = __ldg(reinterpret_cast<const uint32_t*>(q + F::CH));
+        const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hu)), l = __half22float2(*reinterpret_cast<const __half2*>(&lu));
+        v0[i] = fmaf(l.x, F::CORR, h.x); v1[i] = fmaf(l.y, F::CORR, h.y);
+      }
+    }
+  }
+}
+// input row t (image row r0 - 1 + t) feeds output rows t + 1, t, t - 1 (ky = 0, 1, 2); PH = t % 3 names the accumulator slots;
+// afterwards output row t - 1 is complete: summed over the lanes, written, its slot cleared
+template <int CO, int PH>
+__device__ __forceinline__ void tail_row(const TailParams& P, int t, int tmax, int b, int r0, int xs, int lane, bool poisoned,
+                                         const float (&w0)[CO][9], const float (&w1)[CO][9], float (&acc)[3][16],
+                                         const float (&v0)[16 / CO + 2], const float (&v1)[16 / CO + 2]) {
+  constexpr int WT = 16 / CO;
+  if (t > tmax) return;
+  const int r = r0 - 1 + t;
+  if (r >= 0 && r < P.H) {
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      constexpr int S0 = (PH + 1) % 3, S1 = PH, S2 = (PH + 2) % 3;
+      float* a = ky == 0 ? acc[S0] : (ky == 1 ? acc[S1] : acc[S2]);
+#pragma unroll
+      for (int co = 0; co < CO; ++co)
+#pragma unroll
+        for (int j = 0; j < WT; ++j) {
+          float s = a[co * WT + j];
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            s = fmaf(w0[co][ky * 3 + kx], v0[j + kx], s);
+            s = fmaf(w1[co][ky * 3 + kx], v1[j + kx], s);
+          }
+          a[co * WT + j] = s;
+        }
+    }
+  }
+  constexpr int SD = (PH + 2) % 3;
+  const int y = r0 + t - 2;
+  if (t >= 2 && y < P.H) {
+    float red[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) red[i] = acc[SD][i];
+    halve_across<16>(red, lane & 16, 16);
+    halve_across<8>(red, lane & 8, 8);
+    halve_across<4>(red, lane & 4, 4);
+    halve_across<2>(red, lane & 2, 2);
+    const float tot = red[0] + __shfl_xor_sync(0xffffffffu, red[0], 1);
+    const int vi = lane >> 1, co = vi / WT, x = xs + vi % WT;
+    if (!(lane & 1) && co < P.Cout && x < P.W) {
+      const long long o = (((long long)b * P.Cout + co) * P.H + y) * P.W + x;
+      float val = tot + (P.bias ? __ldg(P.bias + co) : 0.f);
+      if (P.add) val += __ldg(P.add + o);
+      if (poisoned) val = __uint_as_float(0x7fc00000u);
+      P.out[o] = val;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[SD][i] = 0.f;
+}
+
+template <class F, int CO>
+__global__ void __launch_bounds__(256) tail64_tc32_kernel(const TailParams P) {
+  using E = typename F::elem;
+  constexpr int WT = 16 / CO;
+  const int lane = threadIdx.x & 31;
+  const int strips = (P.W + WT - 1) / WT, chunks = (P.H + TL_RC - 1) / TL_RC;
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= (long long)P.B * strips * chunks) return;
+  const int b = (int)(wid / (strips * chunks)), rem = (int)(wid - (long long)b * strips * chunks);
+  const int r0 = (rem / strips) * TL_RC, xs = (rem % strips) * WT;
+  // channel pair of this lane inside a pixel's 2 * 64 elements: block (2l) / CH, offset (2l) % CH; lo = hi + CH
+  const int eo = ((2 * lane) / F::CH) * 2 * F::CH + (2 * lane) % F::CH;
+  float w0[CO][9], w1[CO][9];
+#pragma unroll
+  for (int co = 0; co < CO; ++co)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const bool live = co < P.Cout;
+      w0[co][t] = live ? __ldg(P.w + ((long long)co * 64 + 2 * lane) * 9 + t) : 0.f;
+      w1[co][t] = live ? __ldg(P.w + ((long long)co * 64 + 2 * lane + 1) * 9 + t) : 0.f;
+    }
+  float acc[3][16];  // [output row slot][co * WT + j]
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[s][i] = 0.f;
+  const bool poisoned = P.flag && *reinterpret_cast<const volatile int*>(P.flag) != 0;
+  const E* img = static_cast<const E*>(P.x) + (long long)b * P.H * P.W * 128 + eo;
+  const int tmax = min(TL_RC, P.H - r0) + 1;  // last input row index (t) that matters
+  // (issuing the loads of row t + 1 before row t is accumulated was measured: 2.2 ms instead of 1.1 — the extra live registers
+  // cost more warps than the overlap gains)
+  float c0[WT + 2], c1[WT + 2];
+#define TL_LOAD(T, A0, A1) tail_load_row<F, WT>(img, (T) <= tmax && r0 - 1 + (T) >= 0 && r0 - 1 + (T) < P.H, r0 - 1 + (T), xs, P.W, A0, A1)
+#define TL_ROW(PH, T, A0, A1) tail_row<CO, PH>(P, T, tmax, b, r0, xs, lane, poisoned, w0, w1, acc, A0, A1)
+#pragma unroll 1
+  for (int t = 0; t <= tmax; t += 3) {
+    TL_LOAD(t, c0, c1); TL_ROW(0, t, c0, c1);
+    TL_LOAD(t + 1, c0, c1); TL_ROW(1, t + 1, c0, c1);
+    TL_LOAD(t + 2, c0, c1); TL_ROW(2, t + 2, c0, c1);
+  }
+#undef TL_LOAD
+#undef TL_ROW
 }
 
 // split layout -> NCHW fp32 (tests / debugging): out[b,c,y,x] = hi + lo
@@ -942,6 +1183,18 @@ static int conv_head(const float* x_nchw, const float* weight, const float* bias
   DINVK_CHECK_ARG(Cout % F::CH == 0 && Cout >= F::CH && Cout <= 256, "conv_tc32_head: Cout=%d must be a multiple of %d (<= 256)", Cout, F::CH);
   HeadParams P{x_nchw, weight, bias, out, B, C, H, W, Cout, fill_scalar, fill_batch, has_fill, act, flag};
   const long long npix = (long long)B * H * W;
+  static const bool old_head = getenv("DINVK_TC32_OLD_HEAD") != nullptr;
+  if (Cout == 64 && CT >= 1 && CT <= 4 && !old_head) {
+    const long long warps = (long long)B * ceil_div(H, 2) * ceil_div(W, 32);
+    const unsigned g = (unsigned)((warps + 7) / 8);
+    switch (CT) {
+      case 1: DINVK_LAUNCH((head64_tc32_kernel<F, 1>), dim3(g), dim3(256), 0, stream, P); break;
+      case 2: DINVK_LAUNCH((head64_tc32_kernel<F, 2>), dim3(g), dim3(256), 0, stream, P); break;
+      case 3: DINVK_LAUNCH((head64_tc32_kernel<F, 3>), dim3(g), dim3(256), 0, stream, P); break;
+      default: DINVK_LAUNCH((head64_tc32_kernel<F, 4>), dim3(g), dim3(256), 0, stream, P); break;
+    }
+    return DINVK_POST_LAUNCH();
+  }
   const unsigned grid = (unsigned)((npix + 255) / 256);
   const size_t smem = (size_t)Cout * ((9 * CT + 3) & ~3) * 4;
   switch (CT) {
@@ -958,6 +1211,16 @@ static int conv_tail(const void* x, const float* weight, const float* bias, cons
                      int Cin, int Cout, const int* flag, void* stream) {
   DINVK_CHECK_ARG(Cin % F::CH == 0 && Cin >= F::CH && Cin <= 128, "conv_tc32_tail: Cin=%d must be a multiple of %d (<= 128)", Cin, F::CH);
   TailParams P{x, weight, bias, add_nchw, out_nchw, B, H, W, Cin, Cout, flag};
+  static const bool old_tail = getenv("DINVK_TC32_OLD_TAIL") != nullptr;
+  if (Cin == 64 && Cout >= 1 && Cout <= 4 && !old_tail) {
+    const int co = Cout == 3 ? 4 : Cout, wt = 16 / co;
+    const long long warps = (long long)B * ceil_div(W, wt) * ceil_div(H, TL_RC);
+    const unsigned grid = (unsigned)((warps + 7) / 8);
+    if (co == 1) DINVK_LAUNCH((tail64_tc32_kernel<F, 1>), dim3(grid), dim3(256), 0, stream, P);
+    else if (co == 2) DINVK_LAUNCH((tail64_tc32_kernel<F, 2>), dim3(grid), dim3(256), 0, stream, P);
+    else DINVK_LAUNCH((tail64_tc32_kernel<F, 4>), dim3(grid), dim3(256), 0, stream, P);
+    return DINVK_POST_LAUNCH();
+  }
   const int tiles = B * ceil_div(H, TL_TY) * ceil_div(W, TL_TX);
   const int CO = Cout <= 2 ? 2 : 4;
   const size_t smem = ((size_t)(TL_TY + 2) * (TL_TX + 2) * (Cin + 4) + (size_t)CO * 9 * Cin) * 4;

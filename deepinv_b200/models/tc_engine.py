@@ -36,7 +36,7 @@ def _pack_up(w: torch.Tensor) -> torch.Tensor:
 
 
 def _version_key(model) -> tuple:
-    return tuple((p.data_ptr(), p._version) for p in model.parameters())
+    return tuple((id(p), p.data_ptr(), p._version) for p in model.parameters())
 
 
 def _pad64(c: int) -> int:
@@ -222,6 +222,8 @@ def drunet_forward_tc32(model, x0: torch.Tensor) -> torch.Tensor:
     if pk is None or pk.key != (_version_key(model), fmt):
         pk = model._tc32 = _DrunetPack32(model, fmt)
     f = pk.flag if fmt == 1 else None
+    if f is not None:
+        f.zero_()   # the flag is per call: an out-of-range input poisons its own output, not the model
     x1 = ops.conv_tc32_head(x0, pk.head, fmt=fmt, flag=f)
     skips = [x1]
     t = x1
@@ -257,6 +259,8 @@ def dncnn_forward_tc32(model, x: torch.Tensor) -> torch.Tensor:
     if pk is None or pk.key != (_version_key(model), fmt):
         pk = model._tc32 = _DncnnPack32(model, fmt)
     f = pk.flag if fmt == 1 else None
+    if f is not None:
+        f.zero_()
     t = ops.conv_tc32_head(x, pk.first[0], bias=pk.first[1], relu=True, fmt=fmt, flag=f)
     for w, b in pk.mid:
         t = ops.conv_tc32_slab(t, w, pk.nf, bias=b, relu=True, flag=f)
@@ -264,7 +268,7 @@ def dncnn_forward_tc32(model, x: torch.Tensor) -> torch.Tensor:
 
 
 def tc_overflow(model) -> bool:
-    """True if an activation of a precision='tc32h' forward left the fp16 range since the engine was built (the outputs of the
-    affected and of all later calls are NaN); host-synchronising read of the sticky device flag"""
+    """True if an activation of the LAST precision='tc32h' forward left the fp16 range (that call's output is NaN, every kernel
+    after the overflow having seen the raised flag); host-synchronising read of the device flag, which each forward clears"""
     pk = getattr(model, "_tc32", None)
     return bool(pk is not None and pk.fmt == 1 and int(pk.flag.item()) != 0)

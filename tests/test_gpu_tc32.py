@@ -159,14 +159,20 @@ def test_head_and_tail_tc32(fmt, dev):
     out = _from_split(ops.conv_tc32_head(x.to(dev), wh4.to(dev), fill=sig.to(dev), fmt=fmt))
     x4 = torch.cat([x, sig.view(2, 1, 1, 1).expand(2, 1, 24, 40)], 1)
     assert rel_err(out.double(), F.conv2d(x4.double(), wh4.double(), padding=1)) < 1e-6
-    # tail
-    t = torch.randn(2, 64, 19, 37, generator=gen)
-    for cout in (1, 2, 3):
-        wt = torch.randn(cout, 64, 3, 3, generator=gen) / 24
-        bt = torch.randn(cout, generator=gen)
-        add = torch.randn(2, cout, 19, 37, generator=gen)
-        out = ops.conv_tc32_tail(_to_split(t, dev, fmt), wt.to(dev), bias=bt.to(dev), add=add.to(dev)).cpu()
-        assert rel_err(out.double(), F.conv2d(t.double(), wt.double(), bt.double(), padding=1) + add.double()) < 1e-6
+    # several row segments per image (W > 32), a partial one
+    x = torch.randn(1, 2, 9, 70, generator=gen)
+    wh2 = torch.randn(64, 2, 3, 3, generator=gen) / 4
+    out = _from_split(ops.conv_tc32_head(x.to(dev), wh2.to(dev), fmt=fmt))
+    assert rel_err(out.double(), F.conv2d(x.double(), wh2.double(), padding=1)) < 1e-6
+    # tail: strips of 16 / 8 / 4 columns, row chunks of 32 (one chunk, and three with a partial last one)
+    for Ht, Wt in ((19, 37), (70, 45)):
+        t = torch.randn(2, 64, Ht, Wt, generator=gen)
+        for cout in (1, 2, 3, 4):
+            wt = torch.randn(cout, 64, 3, 3, generator=gen) / 24
+            bt = torch.randn(cout, generator=gen)
+            add = torch.randn(2, cout, Ht, Wt, generator=gen)
+            out = ops.conv_tc32_tail(_to_split(t, dev, fmt), wt.to(dev), bias=bt.to(dev), add=add.to(dev)).cpu()
+            assert rel_err(out.double(), F.conv2d(t.double(), wt.double(), bt.double(), padding=1) + add.double()) < 1e-6
 
 
 @pytest.mark.parametrize("precision", ["tc32", "tc32h"])
@@ -244,7 +250,7 @@ def test_split32h_roundtrip_and_range(dev):
 
 
 def test_tc32h_overflow_is_loud(dev):
-    """an activation beyond the fp16 range raises the sticky flag and the network answers NaN — never a silently wrong image"""
+    """an activation beyond the fp16 range raises the call's overflow flag and the network answers NaN — never a silently wrong image"""
     import deepinv_b200 as dinv
     from deepinv_b200.models.tc_engine import tc_overflow
 
@@ -256,5 +262,7 @@ def test_tc32h_overflow_is_loud(dev):
         assert torch.isfinite(ok).all() and not tc_overflow(m)
         bad = m(x * 3e6, 0.05)
         assert torch.isnan(bad).all() and tc_overflow(m)
+        again = m(x, 0.05)       # the flag is per call: the next in-range input is served normally
+        assert torch.equal(again, ok) and not tc_overflow(m)
         m.precision = "tc32"     # the tf32 format has the full fp32 range
         assert torch.isfinite(m(x * 3e6, 0.05)).all()
