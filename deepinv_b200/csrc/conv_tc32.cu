@@ -123,6 +123,9 @@ struct Params {
   void* out;                // split layout (B, Hout, Wout, Cout)
   int* flag;                // sticky overflow flag (FmtF16: an activation left the fp16 range), may be null
   const float* bias;
+  int nt_inner;             // tile order: the N tiles (64 output channels each) of a pixel tile are consecutive work items, so that the
+                            // CTAs that share its activation slab run at the same time and all but the first read it from L2
+                            // (0 = all pixel tiles of N tile 0 first: every activation byte crosses HBM n_tiles times; DINVK_TC32_NT_OUTER=1)
   int dbg;                  // timing experiments only (DINVK_TC32_DBG): 1 no TMA loads, 2 no epilogue memory traffic, 4 no TMEM drains
 };
 
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_kernel(const __grid_cons
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int nt = t / pixel_tiles, pt = t - nt * pixel_tiles;
+        const int pt = P.nt_inner ? t / P.n_tiles : t % pixel_tiles, nt = P.nt_inner ? t - pt * P.n_tiles : t / pixel_tiles;
         const int b = pt / (P.tiles_y * P.tiles_x), r = pt - b * (P.tiles_y * P.tiles_x);
         const int y0 = (r / P.tiles_x) * TY, x0 = (r % P.tiles_x) * TX;
         for (int kb = 0; kb < nk; ++kb) {
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_kernel(const __grid_cons
     int acc = 0; uint32_t pa = 0;
     const int nwin = (nk + P.win - 1) / P.win;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int nt = t / pixel_tiles, pt = t - nt * pixel_tiles;
+      const int pt = P.nt_inner ? t / P.n_tiles : t % pixel_tiles, nt = P.nt_inner ? t - pt * P.n_tiles : t / pixel_tiles;
       const int b = pt / (P.tiles_y * P.tiles_x), r = pt - b * (P.tiles_y * P.tiles_x);
       const int y0 = (r / P.tiles_x) * TY, x0 = (r % P.tiles_x) * TX;
       const int m = q * 32 + lane;
@@ -406,7 +409,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
       int sa = 0; uint32_t pha = 0;
       int sb = 0; uint32_t phb = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int nt = t / pixel_tiles, pt = t - nt * pixel_tiles;
+        const int pt = P.nt_inner ? t / P.n_tiles : t % pixel_tiles, nt = P.nt_inner ? t - pt * P.n_tiles : t / pixel_tiles;
         const int b = pt / (P.tiles_y * P.tiles_x), r = pt - b * (P.tiles_y * P.tiles_x);
         const int y0 = (r / P.tiles_x) * TYP, x0 = (r % P.tiles_x) * TXP;
         for (int j = 0; j < nblk; ++j) {
@@ -505,7 +508,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
     int acc = 0; uint32_t pa = 0;
     const int nwin = (nblk + P.win - 1) / P.win;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int nt = t / pixel_tiles, pt = t - nt * pixel_tiles;
+      const int pt = P.nt_inner ? t / P.n_tiles : t % pixel_tiles, nt = P.nt_inner ? t - pt * P.n_tiles : t / pixel_tiles;
       const int b = pt / (P.tiles_y * P.tiles_x), r = pt - b * (P.tiles_y * P.tiles_x);
       const int y0 = (r / P.tiles_x) * TYP, x0 = (r % P.tiles_x) * TXP;
       const int m = q * 32 + lane;                 // GEMM row of the half: slab row m / 8, position m % 8
@@ -846,7 +849,7 @@ __global__ void __launch_bounds__(256) tail_tc32_kernel(const TailParams P) {
 // The first version (thread = pixel, halo tile and weights in shared memory: tail_tc32_kernel) spent 3 LDS.128 per
 // 8 FMAs and took 1.4 ms for 64 x 256^2; this one is bound by its 1152 FMAs per pixel.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int TL_RC = 64;  // output rows per warp (the 2 * 9 * CO weight loads and the two halo rows are per warp)
+constexpr int TL_RC = 32;  // output rows per warp
 
 template <int N>
 __device__ __forceinline__ void halve_across(float (&a)[16], int upper, int offset) {
@@ -858,26 +861,41 @@ __device__ __forceinline__ void halve_across(float (&a)[16], int upper, int offs
   }
 }
 
-// input row r of the strip: the lane's two channels of the WT + 2 columns xs - 1 .. xs + WT (zero outside the image = the padding)
+// input row r of the strip: the lane's two channels (raw hi / lo words) of the WT + 2 columns xs - 1 .. xs + WT.  The loads are
+// UNCONDITIONAL (clamped addresses; out-of-image values are zeroed when they are converted) and fill plain register arrays, so
+// that all 2 (WT + 2) of them are in flight together — the first version converted each pixel right after its two loads and
+// ran one memory round trip per pixel: 2.0 ms instead of the 1.1 ms of the version before it.
+template <class F> struct TailRaw { using type = uint32_t; };
+template <> struct TailRaw<FmtTF32> { using type = float2; };
+
 template <class F, int WT>
-__device__ __forceinline__ void tail_load_row(const typename F::elem* img, bool rowin, int r, int xs, int W, float (&v0)[WT + 2],
-                                              float (&v1)[WT + 2]) {
-  using E = typename F::elem;
+__device__ __forceinline__ void tail_load_raw(const typename F::elem* img, int r, int xs, int H, int W, typename TailRaw<F>::type (&rh)[WT + 2],
+                                              typename TailRaw<F>::type (&rl)[WT + 2]) {
+  using R = typename TailRaw<F>::type;
+  const int rc = min(max(r, 0), H - 1);
+#pragma unroll
+  for (int i = 0; i < WT + 2; ++i) {
+    const int xc = min(max(xs - 1 + i, 0), W - 1);
+    const typename F::elem* q = img + ((long long)rc * W + xc) * 128;
+    rh[i] = __ldg(reinterpret_cast<const R*>(q));
+    rl[i] = __ldg(reinterpret_cast<const R*>(q + F::CH));
+  }
+}
+template <class F, int WT>
+__device__ __forceinline__ void tail_convert(bool rowin, int xs, int W, const typename TailRaw<F>::type (&rh)[WT + 2],
+                                             const typename TailRaw<F>::type (&rl)[WT + 2], float (&v0)[WT + 2], float (&v1)[WT + 2]) {
 #pragma unroll
   for (int i = 0; i < WT + 2; ++i) {
     const int x = xs - 1 + i;
-    v0[i] = 0.f; v1[i] = 0.f;
-    if (rowin && x >= 0 && x < W) {
-      const E* q = img + ((long long)r * W + x) * 128;
-      if constexpr (F::ID == 0) {
-        const float2 h = __ldg(reinterpret_cast<const float2*>(q)), l = __ldg(reinterpret_cast<const float2*>(q + F::CH));
-        v0[i] = h.x + l.x; v1[i] = h.y + l.y;
-      } else {
-        const uint32_t hu = __ldg(reinterpret_cast<const uint32_t*>(q)), lu = __ldg(reinterpret_cast<const uint32_t*>(q + F::CH));
-        const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hu)), l = __half22float2(*reinterpret_cast<const __half2*>(&lu));
-        v0[i] = fmaf(l.x, F::CORR, h.x); v1[i] = fmaf(l.y, F::CORR, h.y);
-      }
+    const bool in = rowin && x >= 0 && x < W;
+    float a, b;
+    if constexpr (F::ID == 0) {
+      a = rh[i].x + rl[i].x; b = rh[i].y + rl[i].y;
+    } else {
+      const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&rh[i])), l = __half22float2(*reinterpret_cast<const __half2*>(&rl[i]));
+      a = fmaf(l.x, F::CORR, h.x); b = fmaf(l.y, F::CORR, h.y);
     }
+    v0[i] = in ? a : 0.f; v1[i] = in ? b : 0.f;
   }
 }
 // input row t (image row r0 - 1 + t) feeds output rows t + 1, t, t - 1 (ky = 0, 1, 2); PH = t % 3 names the accumulator slots;
@@ -961,16 +979,23 @@ __global__ void __launch_bounds__(256) tail64_tc32_kernel(const TailParams P) {
   const bool poisoned = P.flag && *reinterpret_cast<const volatile int*>(P.flag) != 0;
   const E* img = static_cast<const E*>(P.x) + (long long)b * P.H * P.W * 128 + eo;
   const int tmax = min(TL_RC, P.H - r0) + 1;  // last input row index (t) that matters
-  // (issuing the loads of row t + 1 before row t is accumulated was measured: 2.2 ms instead of 1.1 — the extra live registers
-  // cost more warps than the overlap gains)
+  // the raw words of row t + 1 are requested before row t is converted and accumulated
+  using RW = typename TailRaw<F>::type;
+  RW ah[WT + 2], al[WT + 2], bh[WT + 2], bl[WT + 2];
   float c0[WT + 2], c1[WT + 2];
-#define TL_LOAD(T, A0, A1) tail_load_row<F, WT>(img, (T) <= tmax && r0 - 1 + (T) >= 0 && r0 - 1 + (T) < P.H, r0 - 1 + (T), xs, P.W, A0, A1)
-#define TL_ROW(PH, T, A0, A1) tail_row<CO, PH>(P, T, tmax, b, r0, xs, lane, poisoned, w0, w1, acc, A0, A1)
+#define TL_LOAD(T, RH, RL) if ((T) <= tmax) tail_load_raw<F, WT>(img, r0 - 1 + (T), xs, P.H, P.W, RH, RL)
+#define TL_ROW(PH, T, RH, RL)                                                                                                    \
+  tail_convert<F, WT>((T) <= tmax && r0 - 1 + (T) >= 0 && r0 - 1 + (T) < P.H, xs, P.W, RH, RL, c0, c1);                          \
+  tail_row<CO, PH>(P, T, tmax, b, r0, xs, lane, poisoned, w0, w1, acc, c0, c1)
+  TL_LOAD(0, ah, al);
 #pragma unroll 1
-  for (int t = 0; t <= tmax; t += 3) {
-    TL_LOAD(t, c0, c1); TL_ROW(0, t, c0, c1);
-    TL_LOAD(t + 1, c0, c1); TL_ROW(1, t + 1, c0, c1);
-    TL_LOAD(t + 2, c0, c1); TL_ROW(2, t + 2, c0, c1);
+  for (int t = 0; t <= tmax; t += 6) {
+    TL_LOAD(t + 1, bh, bl); TL_ROW(0, t, ah, al);
+    TL_LOAD(t + 2, ah, al); TL_ROW(1, t + 1, bh, bl);
+    TL_LOAD(t + 3, bh, bl); TL_ROW(2, t + 2, ah, al);
+    TL_LOAD(t + 4, ah, al); TL_ROW(0, t + 3, bh, bl);
+    TL_LOAD(t + 5, bh, bl); TL_ROW(1, t + 4, ah, al);
+    TL_LOAD(t + 6, ah, al); TL_ROW(2, t + 5, bh, bl);
   }
 #undef TL_LOAD
 #undef TL_ROW
@@ -1144,6 +1169,9 @@ static int conv_generic(const void* x, const void* weight, const float* bias, co
   }
   P.tiles_x = ceil_div(P.W, TX); P.tiles_y = ceil_div(P.H, TY);
   P.dbg = 0;
+  // every 2x2 layer gains from sharing the activation tile between its N tiles (down 64 -> 128: 402 -> 297 us, up 256 -> 128: 415 -> 263 us):
+  // with the N tile outermost each activation byte crossed HBM n_tiles (2 .. 8) times
+  P.nt_inner = getenv("DINVK_TC32_NT_OUTER") ? 0 : 1;
   return launch<F>(M, P, stream);
 }
 
@@ -1173,6 +1201,9 @@ static int conv_slab(const void* x, const void* weight, const float* bias, const
   P.win = window > 0 ? window : def_win;
   P.tiles_x = ceil_div(W, slab::TXP); P.tiles_y = ceil_div(H, slab::TYP);
   P.dbg = getenv("DINVK_TC32_DBG") ? atoi(getenv("DINVK_TC32_DBG")) : 0;
+  // measured (profiles/r02_tc32h_nt_order.txt): with 2 N tiles the shared slab pays (128 -> 128: 731 -> 710 us), with 4 or 8 the CTAs of a
+  // pixel tile stream 4 or 8 different weight groups at once and the order that keeps ONE group hot wins (512 -> 512 + residual: 773 vs 803 us)
+  P.nt_inner = (P.n_tiles <= 2 && !getenv("DINVK_TC32_NT_OUTER")) ? 1 : 0;
   return launch_slab<F>(M, P, stream);
 }
 

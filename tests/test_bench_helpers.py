@@ -62,7 +62,7 @@ def test_clock_sampler_selects_the_window():
 
 def test_bench_line_contract_of_the_committed_profile():
     """the last bench line measured on the B200 (profiles/) carries every key of the contract"""
-    line = json.loads((ROOT / "profiles" / "r02_bench_tc32h_b.json").read_text())
+    line = json.loads((ROOT / "profiles" / "r02_final_bench.json").read_text())
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
         assert k in line, k
