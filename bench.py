@@ -210,7 +210,10 @@ def best_cpu_threads() -> tuple[int, dict]:
 def bench_config(cfg: str, world: int, scaling: str) -> dict:
     c = CONFIGS[cfg]
     per_gpu = c["batch"] // world if scaling == "strong" else c["batch"]
-    return {"workload": c["workload"], "global_batch": per_gpu * world, "parallelism": f"dp{world}"}
+    workload = c["workload"]
+    if scaling == "strong" and world > 1:   # the SAME batch split over the ranks: say so in the workload name
+        workload = workload.replace(f"batch={c['batch']} per GPU", f"batch={c['batch']} in total ({per_gpu} per GPU)")
+    return {"workload": workload, "global_batch": per_gpu * world, "parallelism": f"dp{world}"}
 
 
 def run_reference(args):
