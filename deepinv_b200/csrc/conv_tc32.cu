@@ -123,11 +123,19 @@ struct Params {
   void* out;                // split layout (B, Hout, Wout, Cout)
   int* flag;                // sticky overflow flag (FmtF16: an activation left the fp16 range), may be null
   const float* bias;
-  int nt_inner;             // tile order: the N tiles (64 output channels each) of a pixel tile are consecutive work items, so that the
-                            // CTAs that share its activation slab run at the same time and all but the first read it from L2
-                            // (0 = all pixel tiles of N tile 0 first: every activation byte crosses HBM n_tiles times; DINVK_TC32_NT_OUTER=1)
+  int ngrp;                 // work-item order: `ngrp` N tiles (64 output channels each) of a pixel tile are ADJACENT work items, so that
+                            // the CTAs that share its activations run at the same time and all but the first read them from L2
+                            // (1 = all pixel tiles of N tile 0 first: every activation byte crosses HBM n_tiles times); divides n_tiles
   int dbg;                  // timing experiments only (DINVK_TC32_DBG): 1 no TMA loads, 2 no epilogue memory traffic, 4 no TMEM drains
 };
+
+// work item t -> (pixel tile, N tile): t = ((nt / g) * pixel_tiles + pt) * g + nt % g, g = P.ngrp
+__device__ __forceinline__ void tile_index(const Params& P, int pixel_tiles, int t, int& pt, int& nt) {
+  const int u = t / P.ngrp, lo = t - u * P.ngrp;
+  const int hi = u / pixel_tiles;
+  pt = u - hi * pixel_tiles;
+  nt = hi * P.ngrp + lo;
+}
 
 // one channel block: v[CH] -> 128 bytes [hi CH | lo CH]; returns true if a value left the format's range
 template <class F>
@@ -219,7 +227,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_kernel(const __grid_cons
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int pt = P.nt_inner ? t / P.n_tiles : t % pixel_tiles, nt = P.nt_inner ? t - pt * P.n_tiles : t / pixel_tiles;
+        int pt, nt; tile_index(P, pixel_tiles, t, pt, nt);
         const int b = pt / (P.tiles_y * P.tiles_x), r = pt - b * (P.tiles_y * P.tiles_x);
         const int y0 = (r / P.tiles_x) * TY, x0 = (r % P.tiles_x) * TX;
         for (int kb = 0; kb < nk; ++kb) {
@@ -283,7 +291,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_kernel(const __grid_cons
     int acc = 0; uint32_t pa = 0;
     const int nwin = (nk + P.win - 1) / P.win;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int pt = P.nt_inner ? t / P.n_tiles : t % pixel_tiles, nt = P.nt_inner ? t - pt * P.n_tiles : t / pixel_tiles;
+      int pt, nt; tile_index(P, pixel_tiles, t, pt, nt);
       const int b = pt / (P.tiles_y * P.tiles_x), r = pt - b * (P.tiles_y * P.tiles_x);
       const int y0 = (r / P.tiles_x) * TY, x0 = (r % P.tiles_x) * TX;
       const int m = q * 32 + lane;
@@ -409,7 +417,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
       int sa = 0; uint32_t pha = 0;
       int sb = 0; uint32_t phb = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int pt = P.nt_inner ? t / P.n_tiles : t % pixel_tiles, nt = P.nt_inner ? t - pt * P.n_tiles : t / pixel_tiles;
+        int pt, nt; tile_index(P, pixel_tiles, t, pt, nt);
         const int b = pt / (P.tiles_y * P.tiles_x), r = pt - b * (P.tiles_y * P.tiles_x);
         const int y0 = (r / P.tiles_x) * TYP, x0 = (r % P.tiles_x) * TXP;
         for (int j = 0; j < nblk; ++j) {
@@ -508,7 +516,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
     int acc = 0; uint32_t pa = 0;
     const int nwin = (nblk + P.win - 1) / P.win;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int pt = P.nt_inner ? t / P.n_tiles : t % pixel_tiles, nt = P.nt_inner ? t - pt * P.n_tiles : t / pixel_tiles;
+      int pt, nt; tile_index(P, pixel_tiles, t, pt, nt);
       const int b = pt / (P.tiles_y * P.tiles_x), r = pt - b * (P.tiles_y * P.tiles_x);
       const int y0 = (r / P.tiles_x) * TYP, x0 = (r % P.tiles_x) * TXP;
       const int m = q * 32 + lane;                 // GEMM row of the half: slab row m / 8, position m % 8
@@ -1171,7 +1179,7 @@ static int conv_generic(const void* x, const void* weight, const float* bias, co
   P.dbg = 0;
   // every 2x2 layer gains from sharing the activation tile between its N tiles (down 64 -> 128: 402 -> 297 us, up 256 -> 128: 415 -> 263 us):
   // with the N tile outermost each activation byte crossed HBM n_tiles (2 .. 8) times
-  P.nt_inner = getenv("DINVK_TC32_NT_OUTER") ? 0 : 1;
+  P.ngrp = getenv("DINVK_TC32_NT_OUTER") ? 1 : P.n_tiles;
   return launch<F>(M, P, stream);
 }
 
@@ -1201,9 +1209,15 @@ static int conv_slab(const void* x, const void* weight, const float* bias, const
   P.win = window > 0 ? window : def_win;
   P.tiles_x = ceil_div(W, slab::TXP); P.tiles_y = ceil_div(H, slab::TYP);
   P.dbg = getenv("DINVK_TC32_DBG") ? atoi(getenv("DINVK_TC32_DBG")) : 0;
-  // measured (profiles/r02_tc32h_nt_order.txt): with 2 N tiles the shared slab pays (128 -> 128: 731 -> 710 us), with 4 or 8 the CTAs of a
-  // pixel tile stream 4 or 8 different weight groups at once and the order that keeps ONE group hot wins (512 -> 512 + residual: 773 vs 803 us)
-  P.nt_inner = (P.n_tiles <= 2 && !getenv("DINVK_TC32_NT_OUTER")) ? 1 : 0;
+  // measured (profiles/r02_tc32h_nt_order.txt): with 2 N tiles the shared slab pays (128 -> 128: 731 -> 710 us); with all 4 or 8 N tiles of a
+  // pixel tile adjacent its CTAs stream 4 or 8 different weight groups at once and the order that keeps ONE group hot wins
+  // (512 -> 512 + residual: 773 vs 803 us) — hence groups of at most 2 (DINVK_TC32_NT_GROUP overrides: 1 = N tile outermost)
+  {
+    static const int env_g = getenv("DINVK_TC32_NT_GROUP") ? atoi(getenv("DINVK_TC32_NT_GROUP")) : 0;
+    int g = env_g > 0 ? env_g : (P.n_tiles <= 2 ? P.n_tiles : 1);
+    while (g > 1 && P.n_tiles % g) --g;
+    P.ngrp = std::max(1, std::min(g, P.n_tiles));
+  }
   return launch_slab<F>(M, P, stream);
 }
 
