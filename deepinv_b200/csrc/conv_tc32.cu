@@ -475,7 +475,6 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
           if (tc::elect_one()) {
 #pragma unroll
             for (int par = 0; par < 2; ++par) {
-              constexpr int dummy = 0; (void)dummy;
               const int tap = 2 * tp + par;
               if (tap < 9) {
                 const uint32_t a_t = slab_lo + static_cast<uint32_t>(((tap / 3) * SLAB_X + (tap % 3)) * 8);
