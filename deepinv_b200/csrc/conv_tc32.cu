@@ -21,11 +21,21 @@
 // Kernel (persistent, one CTA per SM, 320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 drain/epilogue
 // (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4).
 #include "common.cuh"
+#ifndef DINVK_EMUL
 #include "tc_ptx.cuh"
 #include <cuda_fp16.h>
+#else
+// host emulation (tests/emul): only the CUDA-core kernels of this file exist there — head, tail, layout converters; the 32-byte
+// vector accesses of the store path are plain copies
+namespace dinvk { namespace tc {
+inline void ldg256(const void* p, uint32_t (&r)[8]) { std::memcpy(r, p, 32); }
+inline void stg256(void* p, const uint32_t (&r)[8]) { std::memcpy(p, r, 32); }
+} }
+#endif
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 namespace dinvk {
@@ -41,9 +51,13 @@ constexpr int THREADS = 320;
 constexpr uint32_t TMEM_COLS = 256;        // 2 accumulator buffers x (64 main + 64 corr)
 
 __device__ __forceinline__ float rna_tf32(float x) {
+#ifndef DINVK_EMUL
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
+#else
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);   // round to nearest, ties away: what cvt.rna does
+#endif
 }
 
 // ---- the two split formats ------------------------------------------------------------------------------------------
@@ -58,23 +72,28 @@ struct FmtTF32 {
   using elem = float;
   static constexpr int CH = 16, EB = 4, ID = 0;
   static constexpr float CORR = 1.0f;
+#ifndef DINVK_EMUL
   static constexpr CUtensorMapDataType TM = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   // cute::UMMA::InstrDescriptor: c_format F32 (1) at [4,6), a/b_format TF32 (2) at [7,10) / [10,13), K-major, N>>3, M>>4
   __host__ __device__ static constexpr uint32_t idesc(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
   }
+#endif
 };
 struct FmtF16 {
   using elem = __half;
   static constexpr int CH = 32, EB = 2, ID = 1;
   static constexpr float CORR = 4.8828125e-4f;  // 2^-11
+#ifndef DINVK_EMUL
   static constexpr CUtensorMapDataType TM = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   // a/b_format F16 (0)
   __host__ __device__ static constexpr uint32_t idesc(int M, int N) {
     return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
   }
+#endif
 };
 
+#ifndef DINVK_EMUL
 template <class F>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
                                      uint32_t accumulate) {
@@ -137,6 +156,7 @@ __device__ __forceinline__ void tile_index(const Params& P, int pixel_tiles, int
   nt = hi * P.ngrp + lo;
 }
 
+#endif  // !DINVK_EMUL
 // one channel block: v[CH] -> 128 bytes [hi CH | lo CH]; returns true if a value left the format's range
 template <class F>
 __device__ __forceinline__ bool store_split(typename F::elem* p, const float* v) {
@@ -194,6 +214,7 @@ __device__ __forceinline__ void add_split(const typename F::elem* p, float* v) {
   add_split_raw<F>(raw, v);
 }
 
+#ifndef DINVK_EMUL
 template <class F>
 __global__ void __launch_bounds__(THREADS, 1) conv_tc32_kernel(const __grid_constant__ Maps M, const Params P) {
   extern __shared__ uint8_t smem_raw[];
@@ -594,6 +615,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc32_slab_kernel(const __grid
   if (warp == 2) tc::tmem_dealloc<TCOLS>(tmem_base);
 }
 
+#endif  // !DINVK_EMUL
 // ---------------------------------------------------------------------------------------------------------------
 // Network HEAD (CUDA cores; 0.1 % of the FLOPs, bound by its 8-byte-per-element output write): 3x3 convolution from the
 // reference's NCHW fp32 image (+ optional constant noise-level channel, drunet.py:190-200) to Cout split16 channels.
@@ -612,7 +634,11 @@ __global__ void __launch_bounds__(256) head_tc32_kernel(const HeadParams P) {
   // weights [Cout][KP] in shared memory, KP = 9*CT rounded up to a multiple of 4: one 128-bit broadcast load feeds four FMAs
   // (the first version read one word per FMA and was bound by the shared-memory pipe: 1.0 ms instead of the 0.3 ms its writes take)
   constexpr int KR = 9 * CT, KP = (KR + 3) & ~3;
+#ifndef DINVK_EMUL
   extern __shared__ __align__(16) float sw[];  // module layout (Cout, CT, 3, 3) -> sw[co * KP + c * 9 + tap], zero padded
+#else
+  float* sw = reinterpret_cast<float*>(::emul::dyn_smem());
+#endif
   for (int i = threadIdx.x; i < P.Cout * KP; i += blockDim.x) {
     const int co = i / KP, k = i - co * KP;
     sw[i] = k < KR ? __ldg(P.w + co * KR + k) : 0.f;
@@ -777,7 +803,11 @@ constexpr int TL_TX = 32, TL_TY = 8;
 
 template <class F, int CO>
 __global__ void __launch_bounds__(256) tail_tc32_kernel(const TailParams P) {
+#ifndef DINVK_EMUL
   extern __shared__ __align__(16) float sm[];
+#else
+  float* sm = reinterpret_cast<float*>(::emul::dyn_smem());
+#endif
   const int C = P.C, CP = C + 4;
   float* sx = sm;                                   // (TL_TY+2)*(TL_TX+2) positions x CP
   float* swt = sm + (TL_TY + 2) * (TL_TX + 2) * CP;  // [co][tap][C]
@@ -1046,6 +1076,7 @@ __global__ void __launch_bounds__(256) nchw_to_split_kernel(const float* __restr
   }
 }
 
+#ifndef DINVK_EMUL
 // ---- host side -------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1220,6 +1251,7 @@ static int conv_slab(const void* x, const void* weight, const float* bias, const
   return launch_slab<F>(M, P, stream);
 }
 
+#endif  // !DINVK_EMUL
 template <class F>
 static int conv_head(const float* x_nchw, const float* weight, const float* bias, void* out, int B, int C, int H, int W, int Cout,
                      float fill_scalar, const float* fill_batch, int has_fill, int act, int* flag, void* stream) {
@@ -1291,6 +1323,7 @@ using namespace dinvk;
     return ::dinvk::set_error(DINVK_EINVAL, "conv_tc32: fmt=%d not in {0 (tf32 split16), 1 (fp16 split32)}", (fmt)); \
   } while (0)
 
+#ifndef DINVK_EMUL
 extern "C" int dinvk_conv_tc32(const void* x, const void* weight, const float* bias, const void* res, const void* res2, void* out, int B,
                                int H, int W, int Cin, int Cout, int kind, int act, int window, int fmt, int* overflow_flag, void* stream) {
   using namespace t32;
@@ -1306,6 +1339,7 @@ extern "C" int dinvk_conv_tc32_slab(const void* x, const void* weight, const flo
                      conv_slab<FmtF16>(x, weight, bias, res, res2, out, B, H, W, Cin, Cout, act, window, overflow_flag, stream));
 }
 
+#endif  // !DINVK_EMUL
 extern "C" int dinvk_conv_tc32_head(const float* x_nchw, const float* weight, const float* bias, void* out, int B, int C, int H, int W,
                                     int Cout, float fill_scalar, const float* fill_batch, int has_fill, int act, int fmt,
                                     int* overflow_flag, void* stream) {

@@ -24,7 +24,8 @@ SANITIZE = os.environ.get("DINVK_EMUL_SANITIZE") in ("1", "thread")
 TSAN = os.environ.get("DINVK_EMUL_SANITIZE") == "thread"
 OUT = HERE / "_build" / ("libdinvk_emul_tsan.so" if TSAN else "libdinvk_emul_asan.so" if SANITIZE else "libdinvk_emul.so")
 # SIMT-only translation units (the tcgen05/TMA kernels cannot be emulated)
-SOURCES = ["core.cu", "spectral.cu", "elementwise.cu", "radon.cu", "blur.cu", "conv_simt.cu"]
+# conv_tc32.cu: only its CUDA-core kernels (network head / tail, layout converters); the tcgen05 / TMA parts are compiled out
+SOURCES = ["core.cu", "spectral.cu", "elementwise.cu", "radon.cu", "blur.cu", "conv_simt.cu", "conv_tc32.cu"]
 
 
 def build() -> Path:

@@ -219,6 +219,23 @@ static inline float __uint_as_float(unsigned u) { float x; __builtin_memcpy(&x, 
 static inline int atomicAnd(int* addr, int v) { return __atomic_fetch_and(addr, v, __ATOMIC_SEQ_CST); }
 static inline int atomicExch(int* addr, int v) { return __atomic_exchange_n(addr, v, __ATOMIC_SEQ_CST); }
 
+static inline int atomicOr(int* addr, int v) { return __atomic_fetch_or(addr, v, __ATOMIC_SEQ_CST); }
+
+// fp16 (cuda_fp16.h subset used by the split32h format): IEEE binary16 through the compiler's _Float16, round-to-nearest-even
+struct uint2 { unsigned x, y; };
+struct __half {
+  _Float16 v;
+  __half() = default;
+  __half(float f) : v((_Float16)f) {}
+  explicit operator float() const { return (float)v; }
+};
+struct __half2 { __half x, y; };
+static inline __half __float2half_rn(float f) { return __half(f); }
+static inline float __half2float(__half h) { return (float)h.v; }
+static inline unsigned short __half_as_ushort(__half h) { unsigned short u; __builtin_memcpy(&u, &h.v, 2); return u; }
+static inline __half2 __floats2half2_rn(float a, float b) { __half2 r; r.x = __half(a); r.y = __half(b); return r; }
+static inline float2 __half22float2(__half2 h) { return float2{(float)h.x.v, (float)h.y.v}; }
+
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline long long min(long long a, long long b) { return a < b ? a : b; }
