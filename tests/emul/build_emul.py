@@ -24,14 +24,17 @@ SANITIZE = os.environ.get("DINVK_EMUL_SANITIZE") in ("1", "thread")
 TSAN = os.environ.get("DINVK_EMUL_SANITIZE") == "thread"
 OUT = HERE / "_build" / ("libdinvk_emul_tsan.so" if TSAN else "libdinvk_emul_asan.so" if SANITIZE else "libdinvk_emul.so")
 # SIMT-only translation units (the tcgen05/TMA kernels cannot be emulated)
-# conv_tc32.cu: only its CUDA-core kernels (network head / tail, layout converters); the tcgen05 / TMA parts are compiled out
-SOURCES = ["core.cu", "spectral.cu", "elementwise.cu", "radon.cu", "blur.cu", "conv_simt.cu", "conv_tc32.cu"]
+SOURCES = ["core.cu", "spectral.cu", "elementwise.cu", "radon.cu", "blur.cu", "conv_simt.cu"]
+# conv_tc32.cu enters through tests/emul/conv_tc32_model.cu: its CUDA-core kernels (network head / tail, layout converters) as they
+# are — the tcgen05 / TMA parts are compiled out — plus a test-only scalar model of the tensor-core layers behind the same C ABI
+EXTRA = [HERE / "conv_tc32_model.cu"]
 
 
 def build() -> Path:
-    srcs = [CSRC / s for s in SOURCES if (CSRC / s).exists()]
+    srcs = [CSRC / s for s in SOURCES if (CSRC / s).exists()] + EXTRA
+    assert (CSRC / "conv_tc32.cu").exists()
     h = hashlib.sha256()
-    for f in sorted(srcs + list(CSRC.glob("*.cuh")) + [HERE / "cuda_emul.h", ROOT / "include" / "dinvk.h", Path(__file__)]):
+    for f in sorted(srcs + [CSRC / "conv_tc32.cu"] + list(CSRC.glob("*.cuh")) + [HERE / "cuda_emul.h", ROOT / "include" / "dinvk.h", Path(__file__)]):
         h.update(f.read_bytes())
     stamp = OUT.with_suffix(".stamp")
     if OUT.exists() and stamp.exists() and stamp.read_text() == h.hexdigest():

@@ -132,3 +132,61 @@ def test_head_fp16_overflow_raises_the_flag():
     flag.zero_()
     head(x * 1e-3, w, 1, flag=flag)
     assert int(flag) == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The package's fp32-grade denoiser ENGINES on the host: tc_engine.py (weight packing, ResBlock / skip wiring, per-call overflow
+# flag) driving the emulated head / tail kernels and the scalar model of the tensor-core layers (tests/emul/conv_tc32_model.cu),
+# against the oracle's fp32 networks (drunet.py:200-263, dncnn.py:116-140).  What this pins is the HOST logic; the tcgen05 kernels
+# behind the same ABI are compared with the same oracle on the B200 (tests/test_gpu_tc32.py).
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.fixture()
+def emul_backend(monkeypatch):
+    from deepinv_b200 import ops
+
+    lib = emul_lib()
+
+    def check(rc):
+        assert rc == 0, lib.dinvk_last_error()
+
+    monkeypatch.setattr(ops, "_require_cuda", lambda *ts: torch.device("cpu"))
+    monkeypatch.setattr(ops, "_stream", lambda dev: None)
+    monkeypatch.setattr(ops, "get_lib", lambda: lib)
+    monkeypatch.setattr(ops, "check", check)
+    ops._ws_cache.clear()
+    yield
+    ops._ws_cache.clear()
+
+
+@pytest.mark.parametrize("precision", ["tc32", "tc32h"])
+def test_drunet_engine_on_the_model(precision, emul_backend):
+    import deepinv_b200 as dinv
+    from deepinv_b200.models.tc_engine import tc_overflow
+    from oracle import ref_ops as R
+
+    torch.manual_seed(0)
+    m = dinv.models.DRUNet(in_channels=2, out_channels=2, nb=1, pretrained=None, precision=precision).eval()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = torch.randn(1, 2, 16, 16)
+    with torch.no_grad():
+        out = m(x, 0.07)
+        ref = R.drunet_forward(x, 0.07, sd, nb=1)
+        assert rel_err(out, ref) < 1e-5 and not tc_overflow(m)
+        per = m(x, torch.tensor([0.07]))                  # per-sample noise level: the head's fill channel from a device vector
+        assert rel_err(per, ref) < 1e-5
+        if precision == "tc32h":                          # out-of-range input: that call answers NaN, the next one is served normally
+            assert torch.isnan(m(x * 3e6, 0.07)).all() and tc_overflow(m)
+            assert torch.equal(m(x, 0.07), out) and not tc_overflow(m)
+
+
+@pytest.mark.parametrize("precision", ["tc32", "tc32h"])
+def test_dncnn_engine_on_the_model(precision, emul_backend):
+    import deepinv_b200 as dinv
+    from oracle import ref_ops as R
+
+    torch.manual_seed(1)
+    m = dinv.models.DnCNN(in_channels=1, out_channels=1, depth=4, nf=64, pretrained=None, precision=precision).eval()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = torch.randn(2, 1, 9, 12)
+    with torch.no_grad():
+        assert rel_err(m(x, 0.1), R.dncnn_forward(x, sd, depth=4)) < 1e-5
