@@ -190,3 +190,27 @@ def test_dncnn_engine_on_the_model(precision, emul_backend):
     x = torch.randn(2, 1, 9, 12)
     with torch.no_grad():
         assert rel_err(m(x, 0.1), R.dncnn_forward(x, sd, depth=4)) < 1e-5
+
+
+def test_pnp_pgd_loop_with_the_tc32h_engine(emul_backend):
+    """the benchmark's loop in miniature on the host: PnP-PGD on single-coil MRI (emulated spectral kernels) with the tc32h DRUNet
+    engine (emulated head / tail + model layers), 3 iterations, against the oracle's loop (pgd.py:137-168)"""
+    import deepinv_b200 as dinv
+    from deepinv_b200.optim import L2, PGD, PnP
+    from oracle import ref_ops as R
+
+    torch.manual_seed(0)
+    B, H, W = 1, 16, 16
+    x = torch.randn(B, 2, H, W)
+    cols = (torch.rand(B, 1, 1, W) > 0.6).float()
+    cols[..., W // 2 - 2: W // 2 + 2] = 1
+    mask = cols.expand(B, 2, H, W).contiguous()
+    den = dinv.models.DRUNet(in_channels=2, out_channels=2, nb=1, pretrained=None, precision="tc32h").eval()
+    sd = {k: v.detach().clone() for k, v in den.state_dict().items()}
+    y = R.mri_A(x, mask)
+    with torch.no_grad():
+        ref = R.pgd(y, lambda v: R.mri_A(v, mask), lambda v: R.mri_At(v, mask), lambda v, s: R.drunet_forward(v, s, sd, nb=1), 1.0, 0.05, 3)
+        physics = dinv.physics.MRI(mask=mask, img_size=(2, H, W), device="cpu")
+        algo = PGD(data_fidelity=L2(), prior=PnP(den), stepsize=1.0, sigma_denoiser=0.05, max_iter=3, early_stop=False)
+        out = algo(y, physics)
+    assert rel_err(out, ref) < 1e-5
