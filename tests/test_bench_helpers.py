@@ -87,3 +87,22 @@ def test_binding_roofline_picks_the_algorithmic_bound():
     assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - 1000.0 / 1695.9) < 1e-9
     for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert k in r
+
+
+def test_gpu_session_scripts_parse():
+    """the shell drivers of the GPU sessions (tools/*.sh) are only ever executed on the B200 box: at least their syntax is checked here"""
+    import subprocess
+
+    for sh in sorted((ROOT / "tools").glob("*.sh")):
+        r = subprocess.run(["bash", "-n", str(sh)], capture_output=True, text=True)
+        assert r.returncode == 0, (sh.name, r.stderr)
+
+
+def test_bench_config_names_the_split_under_strong_scaling():
+    import bench
+
+    weak = bench.bench_config("cfg2", 4, "weak")
+    strong = bench.bench_config("cfg2", 4, "strong")
+    assert weak["global_batch"] == 256 and "batch=64 per GPU" in weak["workload"]
+    assert strong["global_batch"] == 64 and "16 per GPU" in strong["workload"] and "per GPU" in strong["workload"]
+    assert bench.bench_config("cfg2", 1, "strong") == bench.bench_config("cfg2", 1, "weak")
