@@ -94,9 +94,9 @@ def test_head_other_widths_use_the_thread_per_pixel_kernel(fmt):
 
 @pytest.mark.parametrize("fmt", [0, 1])
 @pytest.mark.parametrize("cout", [1, 2, 3, 4])
-@pytest.mark.parametrize("shape", [(2, 7, 19), (1, 37, 9)])
+@pytest.mark.parametrize("shape", [(2, 7, 19), (1, 37, 9), (1, 70, 10)])
 def test_tail_lanes_are_channels(fmt, cout, shape):
-    """Cin = 64: strips of 16 / 8 / 4 columns x 32-row chunks (one partial chunk, two chunks), + bias + the NCHW addend"""
+    """Cin = 64: strips of 16 / 8 / 4 columns x 32-row chunks (one partial chunk, two chunks, three chunks), + bias + the NCHW addend"""
     B, H, W = shape
     gen = torch.Generator().manual_seed(100 * cout + fmt)
     t = torch.randn(B, 64, H, W, generator=gen)
